@@ -1,0 +1,163 @@
+/*
+ * ltgan.h -- C ABI of the B200-native Long-Tail-GAN hot path (libltgan.so).
+ *
+ * The reference (ash-shar/Long-Tail-GAN) has no native boundary: its hot path is a TensorFlow-1 graph driven by
+ * `sess.run` from Codes/train.py and Codes/test.py. Each entry point below replaces the TF ops (and the host NumPy
+ * loops) cited next to it; the Python host layer in long-tail-gan_b200/ binds them with ctypes and keeps the
+ * reference's plugin surface (generator.py / discriminator.py / sample.py / eval_functions.py signatures).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns all buffers, kernels allocate nothing
+ *   - `stream` is a cudaStream_t passed as void*; all ops are asynchronous and stream-ordered (CUDA-graph capturable)
+ *   - return 0 on success, negative on error (LTG_ERR_*); ltg_last_error() describes the last failure of this thread
+ *   - bf16 tensors are row-major with the stated pitch ("ld", in elements); a pitch must be a multiple of 8 elements
+ *   - H = 600 (hidden), L = 200 (latent) are the VAE-CF sizes hard-coded by generator.py:13
+ *   - randomness is stateless Philox4x32-10 keyed by (seed, stream id, step, element index); `*_step_dev` arguments
+ *     are optional device words added to the scalar step so that a captured CUDA graph can be replayed
+ */
+#ifndef LTGAN_H_
+#define LTGAN_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LTG_H 600
+#define LTG_L 200
+
+/* slots of the per-step fp32 scalar buffer (`scal`, at least LTG_NSCAL floats, zeroed by the caller per step) */
+enum {
+  LTG_S_KL_SUM = 0,   /* sum_u KL_u                      MultiVAE.py:161-162 (before the batch mean) */
+  LTG_S_NLL_SUM = 1,  /* sum_u -sum_i x_ui log_softmax   MultiVAE.py:110-112 (before the batch mean) */
+  LTG_S_SUM_P = 2,    /* sum over sampled (u,i) of softmax prob   train.py:145-149 */
+  LTG_S_SUM_Y = 3,    /* sum over valid generated pairs of y      train.py:155 */
+  LTG_S_CNT = 4,      /* number of valid generated pairs (sampled_cnt)  train.py:251,316 */
+  LTG_S_D_LOSS = 5,   /* d_loss  train.py:142 */
+  LTG_S_DB4 = 6,      /* grad of d_b4 */
+  LTG_S_LR_T = 8,     /* Adam: lr*sqrt(1-b2^t)/(1-b1^t), written by ltg_step_advance */
+  LTG_S_ANNEAL = 9,   /* KL anneal weight of this G step, written by ltg_step_advance */
+  LTG_NSCAL = 16
+};
+
+/* ---- runtime -------------------------------------------------------------------------------------------------- */
+const char* ltg_last_error(void);
+int ltg_version(void);
+/* One-time per process and device: resolves cuTensorMapEncodeTiled, opts kernels into large shared memory. */
+int ltg_init(void);
+
+/* Persistent step state (device): words[0] = rng step, words[1] = Adam step t (shared by D and G updates, F6),
+ * words[2] = G-update count (KL anneal, train.py:319-324). ltg_step_advance bumps the counters on the device and
+ * writes LTG_S_LR_T / LTG_S_ANNEAL into `scal`, so a captured graph needs no host values.
+ *   kind: 0 = phase-A (rng only), 1 = D update (rng + Adam t), 2 = G update (rng + Adam t + anneal count)      */
+int ltg_step_advance(uint32_t* words, float* scal, int kind, float lr, float beta1, float beta2,
+                     float anneal_cap, float total_anneal_steps, void* stream);
+
+/* ---- generic bf16 tensor-core GEMM (tcgen05/TMA/TMEM) ------------------------------------------------------------
+ * D[M,N] = alpha * A * B^T with A given as [M,K] (a_mn=0, pitch lda) or stored transposed [K,M] (a_mn=1), B likewise
+ * ([N,K] or [K,N]); epilogue: +bias[N], act (0 none / 1 tanh), dropout(keep) keyed by idx=row*rng_ld+col, outputs fp32
+ * and/or bf16, `atomic` = split-K accumulation into a zeroed fp32 buffer; column `aux_col` is diverted to aux_out[row].
+ * bn in {64,128,256}. Building block of every dense layer below (tf.matmul sites: MultiVAE.py:152,169;
+ * discriminator.py:25-55) and their autodiff transposes (train.py:163-164).                                        */
+int ltg_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int N, int K, int splits, int bn,
+                  float* out_f32, int ld_f32, void* out_bf16, int ld_bf16, const float* bias, int act, float alpha, int atomic,
+                  float keep, uint64_t seed, uint32_t rng_stream, uint32_t rng_step, const uint32_t* rng_step_dev, int rng_ld,
+                  int aux_col, float* aux_out, void* stream);
+
+/* ---- a3: encoder (MultiVAE.py:148-155): l2_normalize + dropout + x*W_q0 + b + tanh, as a CSR gather-sum -----------
+ * indptr[B+1] (absolute offsets into indices/values), values may be NULL (all ones). uid0 = global id of row 0 (RNG key).
+ * Writes h1 (bf16 [B, ld_h1]) and coef[nnz] = x_ui * rsqrt(max(|x_u|^2,1e-12)) * mask/keep at the same offsets as indices. */
+int ltg_enc_gather_fwd(const int32_t* indptr, const int32_t* indices, const float* values, int B, int n_items, int64_t uid0,
+                       const void* W_enc_bf16, const float* b_q0, float keep, uint64_t seed, uint32_t step,
+                       const uint32_t* step_dev, void* h1_bf16, int ld_h1, float* coef, void* stream);
+
+/* ---- a3/a4: latent head (MultiVAE.py:157-162,178-181): KL, std, reparameterisation ---------------------------------
+ * mulv fp32 [B, 2L] = [mu | logvar]. eps may be NULL (Philox Box-Muller keyed by uid). Writes z bf16 [B, ld_z],
+ * zmu fp32 [B, L] = z - mu, adds sum_u KL_u to scal[LTG_S_KL_SUM].                                                    */
+int ltg_latent_fwd(const float* mulv, const float* eps, int B, int64_t uid0, float is_training, uint64_t seed, uint32_t step,
+                   const uint32_t* step_dev, void* z_bf16, int ld_z, float* zmu, float* scal, void* stream);
+/* backward of the above + anneal*KL: dmulv bf16 [B, ld] and bias grad db_q1[2L] (zeroed by caller).
+ * anneal is read from scal[LTG_S_ANNEAL] when anneal < 0.                                                              */
+int ltg_latent_bwd(const float* dz, const float* mulv, const float* zmu, int B, int B_global, float anneal, const float* scal,
+                   void* dmulv_bf16, int ld, float* db_q1, void* stream);
+
+/* dx = dy * (1 - y^2) for y = tanh(.) stored as bf16 [B, ld_y]; outputs bf16 and/or fp32; column sums -> dbias (atomic). */
+int ltg_tanh_bwd(const float* dy, int ld_dy, const void* y_bf16, int ld_y, int B, int N, void* dx_bf16, int ld_dxb,
+                 float* dx_f32, int ld_dxf, float* dbias, void* stream);
+
+/* ---- a5/a6: decoder + catalog softmax (MultiVAE.py:169,108-112,143) -------------------------------------------------
+ * logits = h2 * W_dec + b_dec through the tcgen05 GEMM with the softmax-statistics epilogue: bf16 logits stash
+ * [B, ld_logits] (NULL = statistics only) and partial (max,sumexp) per 256-column block: partial[nblk(256)][B].       */
+int ltg_dec_logits_fwd(const void* h2_bf16, int ld_h2, const void* WdT_bf16, const float* b_dec, int B, int n_items,
+                       void* logits_bf16, int ld_logits, float* partial, void* stream);
+/* Row pass: lse[B]; nll: scal[NLL_SUM] += -sum_i x_ui (logit_ui - lse_u); sampled-probability sum per user s_u[B] and
+ * scal[SUM_P] (train.py:145-149). samp_* may be NULL (VAE-only / evaluation). xw[B] = sum_i x_ui.                       */
+int ltg_dec_row_stats(const float* partial, int n_blocks, const void* logits_bf16, int ld_logits, int B,
+                      const int32_t* indptr, const int32_t* indices, const float* values,
+                      const int32_t* samp_ptr, const int32_t* samp_items, const int32_t* samp_valid,
+                      float* lse, float* xw, float* s_u, float* scal, void* stream);
+/* softmax probabilities (generator_out, MultiVAE.py:143) materialised as fp32 [B, ld_out] -- compatibility path only. */
+int ltg_dec_probs(const void* logits_bf16, int ld_logits, const float* lse, int B, int n_items, float* out, int ld_out, void* stream);
+/* d g_loss / d logits (train.py:155 + MultiVAE.py:110-119 under autodiff), Appendix A of SURVEY.md:
+ *   dl_ui = pi_ui (xw_u/Bg + lam*Ybar*s_u) - x_ui/Bg - lam*Ybar*pi_ui*m_ui,  Ybar = scal[SUM_Y]/scal[CNT]
+ * dense pass then sparse fix-ups; bf16 [B, ld]. lam = GANLAMBDA (0 disables the adversarial term).                     */
+int ltg_dec_dlogits(const void* logits_bf16, int ld, const float* lse, const float* xw, const float* s_u, int B, int n_items,
+                    int B_global, float lam, const float* scal,
+                    const int32_t* indptr, const int32_t* indices, const float* values,
+                    const int32_t* samp_ptr, const int32_t* samp_items, const int32_t* samp_valid,
+                    void* dl_bf16, void* stream);
+
+/* ---- a13: TF-semantics Adam (train.py:160-164; F6 shared step, F7 dense) ------------------------------------------
+ * p,m,v fp32 updated in place; g fp32; optional bf16 shadow with the same layout. lr_t < 0: read scal[LTG_S_LR_T].    */
+int ltg_adam(float* p, float* m, float* v, const float* g, void* shadow_bf16, int64_t n, float lr_t, const float* scal,
+             float beta1, float beta2, float eps, void* stream);
+/* Encoder weight W_q0 [n_items, H]: gradient is never materialised -- row i is rebuilt from the batch CSC
+ * (csc_ptr[n_items+1], csc_row[nnz] = batch row, csc_pos[nnz] = offset into coef) as sum coef*dh1pre[row,:], then Adam. */
+int ltg_enc_adam(float* p, float* m, float* v, void* shadow_bf16, int n_items, const int32_t* csc_ptr, const int32_t* csc_row,
+                 const int32_t* csc_pos, const float* coef, const float* dh1pre, int ld_dh1, float lr_t, const float* scal,
+                 float beta1, float beta2, float eps, void* stream);
+/* Dense gradient of W_q0 (parity checks / data-parallel all-reduce path): dW[i,:] = sum coef*dh1pre[row,:].             */
+int ltg_enc_wgrad(float* dW, int n_items, const int32_t* csc_ptr, const int32_t* csc_row, const int32_t* csc_pos,
+                  const float* coef, const float* dh1pre, int ld_dh1, void* stream);
+
+/* ---- a9/a10: niche sampling + pair construction (sample.py:40-67, train.py:212-251) --------------------------------
+ * Per user u: candidates cand[cand_ptr[u]..), draw n_u = samp_ptr[u+1]-samp_ptr[u] items without replacement with
+ * probability proportional to softmax(logits)[u, cand] (Gumbel-top-k == numpy's successive draw in distribution, F9),
+ * emit them in ascending item order at slots samp_ptr[u].., each paired with a uniformly drawn popular item of the user
+ * (pop_ptr/pop_items), valid[slot] = both ids in the item-feature table (item_valid[n_items] bytes, F10).
+ * scal[LTG_S_CNT] += number of valid pairs.                                                                             */
+int ltg_sample_pairs(const void* logits_bf16, int ld_logits, int B, int n_items, int64_t uid0,
+                     const int32_t* cand_ptr, const int32_t* cand_items, const int32_t* samp_ptr,
+                     const int32_t* pop_ptr, const int32_t* pop_items, const uint8_t* item_valid,
+                     uint64_t seed, uint32_t step, const uint32_t* step_dev,
+                     int32_t* samp_items, int32_t* samp_partner, int32_t* samp_valid, float* scal, int max_cand, void* stream);
+
+/* ---- a11/a12: discriminator (discriminator.py:14-55, train.py:142) --------------------------------------------------
+ * Frozen embedding gather (F5): rows of E_bf16 [n_items, 128] (cols 100.. are zero) -> Xp, Xn bf16 [P, 128].            */
+int ltg_disc_gather(const void* E_bf16, const int32_t* pop_ids, const int32_t* niche_ids, int P, void* Xp, void* Xn, void* stream);
+/* Head: s = Y3*w4 + b4, y = sigmoid(s); label[row]: 0 real, 1 generated, <0 ignored.
+ * Accumulates scal[D_LOSS], scal[SUM_Y] (generated rows), and when dz3 != NULL the backward seed:
+ * dz3 bf16 [P, ld] = ds*w4*dact(Y3), dw4[h3] += Y3^T ds, scal[DB4] += sum ds, db3[h3] += colsum(dz3).                    */
+int ltg_disc_head(const void* Y3_bf16, int ld, int P, int h3, const float* w4, const float* b4, const int32_t* label,
+                  float keep, float* y_out, float* scal, void* dz3_bf16, float* dw4, float* db3, void* stream);
+/* dz = dH * dact(Hact) for a dropout(tanh) layer stored post-dropout in bf16; column sums -> dbias (atomic).             */
+int ltg_drop_tanh_bwd(const float* dH, int ld_dh, const void* Hact_bf16, int ld_h, int P, int N, float keep,
+                      void* dz_bf16, int ld_dz, float* dbias, void* stream);
+
+/* ---- a16/a17: ranking metrics (eval_functions.py:11-62, train.py:341) -----------------------------------------------
+ * Per row: scores (fp32 or bf16, pitch ld) with the row's seen items (seen_ptr/seen_items, may be NULL) forced to -inf,
+ * exact top-k (k <= 128; ties: lowest index first) sorted by score descending -> topk_idx [n, k] (may be NULL),
+ * dcg[n] (fp64, as the reference's NumPy) = sum_{r<k} held(top_r)/log2(r+2), hits[n, n_rk] = |top-rk[j] AND heldout| for up to 4 recall cut-offs rk[j] <= k.
+ * held_ptr/held_items: CSR of the held-out interactions (sorted within row).                                            */
+int ltg_topk_metrics(const void* scores, int is_bf16, int64_t ld, int n_rows, int n_items,
+                     const int32_t* seen_ptr, const int32_t* seen_items, const int32_t* held_ptr, const int32_t* held_items,
+                     int k, const int32_t* rk_host, int n_rk, int32_t* topk_idx, double* dcg, int32_t* hits, void* stream);
+
+/* ---- misc ------------------------------------------------------------------------------------------------------------ */
+/* fp32 -> bf16 with optional re-pitch: dst[r*ld_dst + c] = src[r*ld_src + c]                                             */
+int ltg_cast_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows, int64_t cols, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LTGAN_H_ */

@@ -1,0 +1,164 @@
+// a11/a12: discriminator pieces that are not GEMMs (discriminator.py:14-55, train.py:142).
+//   - frozen embedding gather (F5)
+//   - head: fc2 (h3 -> 1) + sigmoid + both loss terms + backward seed
+//   - backward through dropout(tanh(.)) layers stored post-dropout in bf16
+// The three dense layers run on the tcgen05 GEMM (gemm_ops.cu) with the bias+tanh+dropout epilogue.
+#include "ltg_common.cuh"
+#include "../../include/ltgan.h"
+
+namespace {
+
+// bf16 embedding rows are padded from h0=100 to 128 columns (256 B = 16 uint4 per row)
+
+__global__ void disc_gather_kernel(const uint4* __restrict__ E, const int32_t* __restrict__ pop, const int32_t* __restrict__ niche, int P,
+                                   uint4* __restrict__ Xp, uint4* __restrict__ Xn) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte vector each; 16 per row
+  const int64_t row = t >> 4;
+  const int v = (int)(t & 15);
+  if (row >= P) return;
+  Xp[row * 16 + v] = __ldg(E + (size_t)pop[row] * 16 + v);
+  Xn[row * 16 + v] = __ldg(E + (size_t)niche[row] * 16 + v);
+}
+
+// derivative of y = dropout(tanh(a)) w.r.t. a, recovered from the stored y: mask/keep * (1 - tanh^2)
+__device__ __forceinline__ float dact_drop_tanh(float y, float keep, bool drop) {
+  if (!drop) return 1.0f - y * y;
+  if (y == 0.f) return 0.f;
+  const float t = y * keep;
+  return (1.0f - t * t) / keep;
+}
+
+constexpr int HEAD_ROWS = 32;      // rows per CTA
+constexpr int HEAD_THREADS = 256;  // 8 warps x 4 rows
+constexpr int HEAD_MAXH3 = 512;
+
+__global__ void __launch_bounds__(HEAD_THREADS)
+disc_head_kernel(const __nv_bfloat16* __restrict__ Y3, int ld, int P, int h3, const float* __restrict__ w4, const float* __restrict__ b4,
+                 const int32_t* __restrict__ label, float keep, float* __restrict__ y_out, float* __restrict__ scal,
+                 __nv_bfloat16* __restrict__ dz3, float* __restrict__ dw4, float* __restrict__ db3) {
+  __shared__ float s_w4[HEAD_MAXH3];
+  __shared__ float s_dw4[HEAD_MAXH3];
+  __shared__ float s_db3[HEAD_MAXH3];
+  __shared__ float s_acc[3];  // d_loss, sum_y, db4
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool bwd = dz3 != nullptr;
+  const bool drop = keep > 0.f && keep < 1.f;
+  for (int j = tid; j < h3; j += HEAD_THREADS) { s_w4[j] = w4[j]; s_dw4[j] = 0.f; s_db3[j] = 0.f; }
+  if (tid < 3) s_acc[tid] = 0.f;
+  __syncthreads();
+  const float bias = b4[0];
+  float loss = 0.f, sumy = 0.f, sds = 0.f;
+  for (int rr = warp; rr < HEAD_ROWS; rr += HEAD_THREADS / 32) {
+    const int row = blockIdx.x * HEAD_ROWS + rr;
+    if (row >= P) break;
+    const int lab = label[row];
+    const __nv_bfloat16* yr = Y3 + (size_t)row * ld;
+    float s = 0.f;
+    for (int j = lane; j < h3; j += 32) s = fmaf(__bfloat162float(yr[j]), s_w4[j], s);
+    s = warp_sum(s) + bias;
+    const float y = 1.0f / (1.0f + __expf(-s));
+    if (lane == 0 && y_out != nullptr) y_out[row] = y;
+    // -log(sigmoid(s)) = softplus(-s) ; -log(1 - sigmoid(s)) = softplus(s)     train.py:142
+    // label < 0 (pair dropped by the validity filter, train.py:240-243): no loss, zero gradient row
+    const float sp = (lab == 0) ? -s : s;
+    const float l = lab < 0 ? 0.f : fmaxf(sp, 0.f) + log1pf(__expf(-fabsf(sp)));
+    const float ds = lab < 0 ? 0.f : ((lab == 0) ? (y - 1.0f) : y);
+    if (lane == 0) { loss += l; if (lab == 1) sumy += y; sds += ds; }
+    if (bwd) {
+      __nv_bfloat16* dr = dz3 + (size_t)row * ld;
+      for (int j = lane; j < h3; j += 32) {
+        const float yv = __bfloat162float(yr[j]);
+        const float d = ds * s_w4[j] * dact_drop_tanh(yv, keep, drop);
+        dr[j] = __float2bfloat16(d);
+        atomicAdd(&s_dw4[j], yv * ds);
+        atomicAdd(&s_db3[j], d);
+      }
+    }
+  }
+  if (lane == 0) { atomicAdd(&s_acc[0], loss); atomicAdd(&s_acc[1], sumy); atomicAdd(&s_acc[2], sds); }
+  __syncthreads();
+  if (tid == 0) {
+    atomicAdd(scal + LTG_S_D_LOSS, s_acc[0]);
+    atomicAdd(scal + LTG_S_SUM_Y, s_acc[1]);
+    if (bwd) atomicAdd(scal + LTG_S_DB4, s_acc[2]);
+  }
+  if (bwd) {
+    for (int j = tid; j < h3; j += HEAD_THREADS) {
+      if (dw4 != nullptr) atomicAdd(dw4 + j, s_dw4[j]);
+      if (db3 != nullptr) atomicAdd(db3 + j, s_db3[j]);
+    }
+  }
+}
+
+constexpr int COLSUM_ROWS = 32;
+
+__global__ void drop_tanh_bwd_kernel(const float* __restrict__ dH, int ld_dh, const __nv_bfloat16* __restrict__ Hact, int ld_h, int P, int N,
+                                     float keep, __nv_bfloat16* __restrict__ dz, int ld_dz, float* __restrict__ db) {
+  const bool drop = keep > 0.f && keep < 1.f;
+  const int r0 = blockIdx.x * COLSUM_ROWS;
+  const int r1 = min(P, r0 + COLSUM_ROWS);
+  for (int c = threadIdx.x; c < N; c += blockDim.x) {
+    float cs = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      const float y = __bfloat162float(Hact[(size_t)r * ld_h + c]);
+      const float o = dH[(size_t)r * ld_dh + c] * dact_drop_tanh(y, keep, drop);
+      dz[(size_t)r * ld_dz + c] = __float2bfloat16(o);
+      cs += o;
+    }
+    if (db != nullptr) atomicAdd(db + c, cs);
+  }
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ src, int64_t ld_src, __nv_bfloat16* __restrict__ dst, int64_t ld_dst,
+                                 int64_t rows, int64_t cols) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t r = i / cols, c = i - r * cols;
+    dst[r * ld_dst + c] = __float2bfloat16(src[r * ld_src + c]);
+  }
+}
+
+}  // namespace
+
+extern "C" int ltg_disc_gather(const void* E_bf16, const int32_t* pop_ids, const int32_t* niche_ids, int P, void* Xp, void* Xn, void* stream) {
+  LTG_REQUIRE(E_bf16 && pop_ids && niche_ids && Xp && Xn);
+  if (P <= 0) return LTG_OK;
+  const int64_t n = (int64_t)P * 16;
+  disc_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(E_bf16), pop_ids, niche_ids, P,
+                                                                                     reinterpret_cast<uint4*>(Xp), reinterpret_cast<uint4*>(Xn));
+  LTG_CHECK_LAUNCH();
+  return LTG_OK;
+}
+
+extern "C" int ltg_disc_head(const void* Y3_bf16, int ld, int P, int h3, const float* w4, const float* b4, const int32_t* label,
+                             float keep, float* y_out, float* scal, void* dz3_bf16, float* dw4, float* db3, void* stream) {
+  LTG_REQUIRE(Y3_bf16 && w4 && b4 && label && scal);
+  LTG_REQUIRE(h3 > 0 && h3 <= HEAD_MAXH3 && ld >= h3);
+  if (P <= 0) return LTG_OK;
+  disc_head_kernel<<<(P + HEAD_ROWS - 1) / HEAD_ROWS, HEAD_THREADS, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(Y3_bf16), ld, P, h3, w4, b4, label, keep, y_out, scal, reinterpret_cast<__nv_bfloat16*>(dz3_bf16),
+      dw4, db3);
+  LTG_CHECK_LAUNCH();
+  return LTG_OK;
+}
+
+extern "C" int ltg_drop_tanh_bwd(const float* dH, int ld_dh, const void* Hact_bf16, int ld_h, int P, int N, float keep,
+                                 void* dz_bf16, int ld_dz, float* dbias, void* stream) {
+  LTG_REQUIRE(dH && Hact_bf16 && dz_bf16);
+  if (P <= 0) return LTG_OK;
+  drop_tanh_bwd_kernel<<<(P + COLSUM_ROWS - 1) / COLSUM_ROWS, 256, 0, (cudaStream_t)stream>>>(
+      dH, ld_dh, reinterpret_cast<const __nv_bfloat16*>(Hact_bf16), ld_h, P, N, keep, reinterpret_cast<__nv_bfloat16*>(dz_bf16), ld_dz, dbias);
+  LTG_CHECK_LAUNCH();
+  return LTG_OK;
+}
+
+extern "C" int ltg_cast_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows, int64_t cols, void* stream) {
+  LTG_REQUIRE(src && dst);
+  if (rows <= 0 || cols <= 0) return LTG_OK;
+  int64_t blocks = (rows * cols + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  cast_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, ld_src, reinterpret_cast<__nv_bfloat16*>(dst), ld_dst, rows, cols);
+  LTG_CHECK_LAUNCH();
+  return LTG_OK;
+}

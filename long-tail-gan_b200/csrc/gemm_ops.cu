@@ -1,0 +1,59 @@
+// Instantiations of the tcgen05 GEMM: the generic entry point and the decoder forward with the
+// softmax-statistics epilogue.
+#include "gemm_sm100.cuh"
+#include "../../include/ltgan.h"
+
+using namespace ltg;
+
+template <int BN>
+static int dispatch_major(const __nv_bfloat16* A, int lda, int a_mn, const __nv_bfloat16* B, int ldb, int b_mn, int M, int N, int K,
+                          int splits, const EpiStore::Params& ep, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch_gemm<BN, false, false, EpiStore>(A, lda, B, ldb, M, N, K, splits, ep, st);
+  if (!a_mn && b_mn) return launch_gemm<BN, false, true, EpiStore>(A, lda, B, ldb, M, N, K, splits, ep, st);
+  if (a_mn && !b_mn) return launch_gemm<BN, true, false, EpiStore>(A, lda, B, ldb, M, N, K, splits, ep, st);
+  return launch_gemm<BN, true, true, EpiStore>(A, lda, B, ldb, M, N, K, splits, ep, st);
+}
+
+extern "C" int ltg_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int N, int K, int splits, int bn,
+                             float* out_f32, int ld_f32, void* out_bf16, int ld_bf16, const float* bias, int act, float alpha, int atomic,
+                             float keep, uint64_t seed, uint32_t rng_stream, uint32_t rng_step, const uint32_t* rng_step_dev, int rng_ld,
+                             int aux_col, float* aux_out, void* stream) {
+  LTG_REQUIRE(A != nullptr && B != nullptr);
+  LTG_REQUIRE(out_f32 != nullptr || out_bf16 != nullptr);
+  LTG_REQUIRE(!atomic || (out_f32 != nullptr && out_bf16 == nullptr && act == 0 && bias == nullptr));
+  LTG_REQUIRE(splits <= 1 || atomic);
+  LTG_REQUIRE(aux_col < 0 || aux_out != nullptr);
+  const bool drop = keep > 0.f && keep < 1.f;
+  LTG_REQUIRE(!drop || (rng_ld % 4 == 0 && rng_ld >= N));
+  EpiStore::Params ep;
+  ep.out_f32 = out_f32; ep.ld_f32 = ld_f32;
+  ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); ep.ld_bf16 = ld_bf16;
+  ep.bias = bias; ep.act = act; ep.atomic = atomic; ep.alpha = alpha;
+  ep.keep = keep; ep.seed = seed; ep.rng_stream = rng_stream; ep.rng_step = rng_step; ep.rng_step_dev = rng_step_dev; ep.rng_ld = rng_ld;
+  ep.aux_col = aux_col; ep.aux_out = aux_out;
+  const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(A);
+  const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(B);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (bn) {
+    case 64: return dispatch_major<64>(a, lda, a_mn, b, ldb, b_mn, M, N, K, splits, ep, st);
+    case 128: return dispatch_major<128>(a, lda, a_mn, b, ldb, b_mn, M, N, K, splits, ep, st);
+    case 256: return dispatch_major<256>(a, lda, a_mn, b, ldb, b_mn, M, N, K, splits, ep, st);
+    default:
+      ltg_set_last_error("bn must be 64, 128 or 256", __FILE__, __LINE__);
+      return LTG_ERR_ARG;
+  }
+}
+
+extern "C" int ltg_dec_logits_fwd(const void* h2_bf16, int ld_h2, const void* WdT_bf16, const float* b_dec, int B, int n_items,
+                                  void* logits_bf16, int ld_logits, float* partial, void* stream) {
+  LTG_REQUIRE(h2_bf16 != nullptr && WdT_bf16 != nullptr && b_dec != nullptr && partial != nullptr);
+  LTG_REQUIRE(logits_bf16 == nullptr || ld_logits >= n_items);
+  EpiLogitsStats::Params ep;
+  ep.logits = reinterpret_cast<__nv_bfloat16*>(logits_bf16);
+  ep.ld = ld_logits;
+  ep.bias = b_dec;
+  ep.partial = reinterpret_cast<float2*>(partial);
+  return launch_gemm<256, false, false, EpiLogitsStats>(reinterpret_cast<const __nv_bfloat16*>(h2_bf16), ld_h2,
+                                                        reinterpret_cast<const __nv_bfloat16*>(WdT_bf16), LTG_H, B, n_items, LTG_H, 1,
+                                                        ep, (cudaStream_t)stream);
+}

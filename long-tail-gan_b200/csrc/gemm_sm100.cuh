@@ -1,0 +1,514 @@
+// Warp-specialised tcgen05 / TMA / TMEM GEMM for sm_100a, bf16 operands, fp32 accumulate.
+//
+//   D[M,N] = A[M,K] * B[N,K]^T          (each operand either K-major or MN-major in HBM)
+//
+// One persistent CTA per SM, 192 threads:
+//   warp 0      TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx-count)
+//   warp 1      MMA issuer     (one elected lane issues tcgen05.mma 128xBNx16, fp32 accumulators in TMEM,
+//                               tcgen05.commit releases smem slots / publishes the accumulator)
+//   warps 2..5  epilogue       (tcgen05.ld 32x32b: thread == accumulator row; the Epi functor consumes
+//                               32-column chunks, so row-wise reductions such as the catalog softmax
+//                               statistics are thread-local)
+// The TMEM accumulator is double buffered (2*BN columns) so the epilogue of tile i overlaps the
+// mainloop of tile i+1. Split-K is supported (tile index carries the split; Epi decides how to merge).
+//
+// Operand layouts ("major"), as seen by the tensor core:
+//   K-major  operand X[MN][K]  (K contiguous in HBM): TMA box {64 k, rows}, smem rows of 128 B,
+//            UMMA descriptor SWIZZLE_128B, SBO = 1024 B, k-step advances the start address by 32 B.
+//   MN-major operand X[K][MN]  (MN contiguous in HBM): TMA boxes {64 mn, 64 k} (8 KB each),
+//            UMMA descriptor SWIZZLE_128B, LBO = 8 KB (next 64-wide MN chunk), SBO = 1 KB
+//            (next 8 k), k-step (16 k) advances the start address by 2 KB.
+// The second form is what lets the backward GEMMs (dgrad over the catalog, wgrad over the batch)
+// read the very same HBM tensors the forward wrote, with no transposed copies.
+#pragma once
+#include <cuda.h>
+#include "ltg_common.cuh"
+
+namespace ltg {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+// ----------------------------------------------------------------------------------------------
+// PTX wrappers
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, issued by ONE thread for the CTA.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Arrive on an mbarrier once every previously issued tcgen05.mma of this thread has retired.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives row (lane base + t).
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ----------------------------------------------------------------------------------------------
+// UMMA descriptors (cute/arch/mma_sm100_desc.hpp documents the bit fields)
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t umma_desc_base() {
+  // version = 1 (bits 46..47), layout = SWIZZLE_128B (2, bits 61..63), SBO = 1024 B (bits 32..45)
+  return ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)(1024 >> 4) << 32);
+}
+__device__ __forceinline__ uint64_t umma_desc_k(uint32_t saddr) {  // K-major, LBO ignored (=1)
+  return umma_desc_base() | ((uint64_t)1 << 16) | (uint64_t)((saddr & 0x3FFFF) >> 4);
+}
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  return umma_desc_base() | ((uint64_t)(lbo_bytes >> 4) << 16) | (uint64_t)((saddr & 0x3FFFF) >> 4);
+}
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4)                    // D format fp32
+         | (1u << 7) | (1u << 10)     // A, B = bf16
+         | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16)
+         | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Problem description
+// ----------------------------------------------------------------------------------------------
+struct GemmShape {
+  int M, N, K;
+  int m_blocks, n_blocks, k_blocks;  // 128-row blocks, BN-col blocks, 64-deep k blocks
+  int splits, kb_per_split;          // split-K: split s covers k blocks [s*kb_per_split, ...)
+};
+
+template <int BN>
+__host__ __device__ constexpr int gemm_stages() {
+  constexpr int per_stage = GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2;
+  constexpr int s = 196608 / per_stage;
+  return s > 8 ? 8 : s;
+}
+
+template <int BN>
+__host__ __device__ constexpr size_t gemm_smem_bytes() {
+  return (size_t)gemm_stages<BN>() * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 1024 /*align slack*/ + 256 /*barriers*/;
+}
+
+// ----------------------------------------------------------------------------------------------
+// The kernel. Epi: struct with `Params`, ctor(const Params&, row, n0, n_blk, split, shape),
+// `chunk(col0, v[32])`, `finish()`.
+// ----------------------------------------------------------------------------------------------
+template <int BN, bool A_MN, bool B_MN, class Epi>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ GemmShape shape, const __grid_constant__ typename Epi::Params ep) {
+  constexpr int STAGES = gemm_stages<BN>();
+  constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  constexpr int B_BYTES = BN * GEMM_BK * 2;
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  constexpr uint32_t IDESC = umma_idesc(GEMM_BM, BN, A_MN, B_MN);
+  static_assert(BN % 64 == 0 && BN <= 256, "BN must be 64, 128, 192 or 256");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));
+  uint64_t* full_bar = bars;                  // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;        // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;    // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = shape.m_blocks * shape.n_blocks * shape.splits;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m_blk = t % shape.m_blocks;
+        const int rest = t / shape.m_blocks;
+        const int n_blk = rest % shape.n_blocks;
+        const int split = rest / shape.n_blocks;
+        const int kb0 = split * shape.kb_per_split;
+        const int kb1 = min(shape.k_blocks, kb0 + shape.kb_per_split);
+        const int m0 = m_blk * GEMM_BM, n0 = n_blk * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
+          uint8_t* sa = smem_a + stage * A_BYTES;
+          uint8_t* sb = smem_b + stage * B_BYTES;
+          const int k0 = kb * GEMM_BK;
+          if constexpr (A_MN) {
+#pragma unroll
+            for (int j = 0; j < GEMM_BM / 64; ++j) tma_load_2d(sa + j * 8192, &tmA, &full_bar[stage], m0 + j * 64, k0);
+          } else {
+            tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);
+          }
+          if constexpr (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, &full_bar[stage], n0 + j * 64, k0);
+          } else {
+            tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int split = (t / shape.m_blocks) / shape.n_blocks;
+        const int kb0 = split * shape.kb_per_split;
+        const int kb1 = min(shape.k_blocks, kb0 + shape.kb_per_split);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem_a + stage * A_BYTES);
+          const uint32_t sb = smem_u32(smem_b + stage * B_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            const uint64_t da = A_MN ? umma_desc_mn(sa + k * 2048, 8192) : umma_desc_k(sa + k * 32);
+            const uint64_t db = B_MN ? umma_desc_mn(sb + k * 2048, 8192) : umma_desc_k(sb + k * 32);
+            umma_bf16(tmem_d, da, db, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+          if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (4 warps, one TMEM sub-partition each) =====================
+    const int sub = warp & 3;  // hardware rule: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m_blk = t % shape.m_blocks;
+      const int rest = t / shape.m_blocks;
+      const int n_blk = rest % shape.n_blocks;
+      const int split = rest / shape.n_blocks;
+      const int n0 = n_blk * BN;
+      const int row = m_blk * GEMM_BM + sub * 32 + lane;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      Epi epi(ep, row, n0, n_blk, split, shape);
+      const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        if (n0 + c >= shape.N) break;  // warp-uniform
+        float v[32];
+        tmem_ld32(taddr + c, v);
+        epi.chunk(n0 + c, v);
+      }
+      epi.finish();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Epilogues
+// ----------------------------------------------------------------------------------------------
+
+// Generic: out = dropout(act(alpha*acc + bias[col])) -> fp32 and/or bf16, or fp32 atomic accumulate (split-K).
+// A designated column (`aux_col`) can be diverted to `aux_out[row]` (used to get column sums for free
+// from a ones-column in the B operand).
+struct EpiStore {
+  struct Params {
+    float* out_f32; int ld_f32;
+    __nv_bfloat16* out_bf16; int ld_bf16;
+    const float* bias;      // [N] or null
+    int act;                // 0 none, 1 tanh
+    int atomic;             // 1: red.add into out_f32 (which the caller zeroed)
+    float alpha;
+    float keep;             // dropout keep prob; >= 1 or <= 0 disables
+    uint64_t seed; uint32_t rng_stream, rng_step; const uint32_t* rng_step_dev; int rng_ld;  // element idx = row*rng_ld + col
+    int aux_col; float* aux_out;  // aux_col < 0 disables
+  };
+  const Params& p;
+  int row, M, N;
+  uint32_t thr, step;
+  float inv_keep;
+  __device__ EpiStore(const Params& p_, int row_, int, int, int, const GemmShape& s) : p(p_), row(row_), M(s.M), N(s.N) {
+    const bool drop = p.keep > 0.f && p.keep < 1.f;
+    step = p.rng_step + ((drop && p.rng_step_dev != nullptr) ? *p.rng_step_dev : 0u);
+    thr = drop ? ltg_keep_threshold(p.keep) : 0xFFFFFFFFu;
+    inv_keep = drop ? 1.0f / p.keep : 1.0f;
+  }
+  __device__ void chunk(int col0, float (&v)[32]) {
+    if (row >= M) return;
+    const bool drop = p.keep > 0.f && p.keep < 1.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      float x = v[i] * p.alpha;
+      const int col = col0 + i;
+      if (p.bias != nullptr && col < N) x += __ldg(p.bias + col);
+      if (p.act == 1) x = tanhf(x);
+      v[i] = x;
+    }
+    if (drop) {
+      // rng idx = row*rng_ld + col; col0 % 32 == 0 and rng_ld % 4 == 0, so 4 consecutive cols share one Philox block
+      const uint64_t base = (uint64_t)row * (uint64_t)p.rng_ld + (uint64_t)col0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint64_t blk = (base >> 2) + q;
+        Philox4 r = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), p.rng_stream, step, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+        v[4 * q + 0] = r.x < thr ? v[4 * q + 0] * inv_keep : 0.f;
+        v[4 * q + 1] = r.y < thr ? v[4 * q + 1] * inv_keep : 0.f;
+        v[4 * q + 2] = r.z < thr ? v[4 * q + 2] * inv_keep : 0.f;
+        v[4 * q + 3] = r.w < thr ? v[4 * q + 3] * inv_keep : 0.f;
+      }
+    }
+    if (p.aux_col >= col0 && p.aux_col < col0 + 32) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i == p.aux_col) {
+          if (p.atomic) atomicAdd(p.aux_out + row, v[i]); else p.aux_out[row] = v[i];
+        }
+    }
+    const int nlim = (p.aux_col >= 0 && p.aux_col < N) ? p.aux_col : N;  // columns >= aux_col are not part of `out`
+    if (p.out_f32 != nullptr) {
+      float* o = p.out_f32 + (size_t)row * p.ld_f32 + col0;
+      if (p.atomic) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (col0 + i < nlim) atomicAdd(o + i, v[i]);
+      } else if (col0 + 32 <= nlim && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (col0 + i < nlim) o[i] = v[i];
+      }
+    }
+    if (p.out_bf16 != nullptr) {
+      __nv_bfloat16* o = p.out_bf16 + (size_t)row * p.ld_bf16 + col0;
+      if (col0 + 32 <= nlim && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 u;
+          u.x = pack_bf16x2(v[i], v[i + 1]); u.y = pack_bf16x2(v[i + 2], v[i + 3]);
+          u.z = pack_bf16x2(v[i + 4], v[i + 5]); u.w = pack_bf16x2(v[i + 6], v[i + 7]);
+          *reinterpret_cast<uint4*>(o + i) = u;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (col0 + i < nlim) o[i] = __float2bfloat16(v[i]);
+      }
+    }
+  }
+  __device__ void finish() {}
+};
+
+// Decoder forward: logits = acc + b_dec -> bf16 stash, plus per-(n-block,row) softmax partials
+// (row max, sum exp(x - max)) so the [B, I] logits never exist in fp32 in HBM.
+// Restates MultiVAE.py:169 (matmul + bias) and the reductions inside log_softmax/softmax (108, 143).
+struct EpiLogitsStats {
+  struct Params {
+    __nv_bfloat16* logits; int ld;   // [M, ld] bf16 (may be null: statistics only)
+    const float* bias;               // [N]
+    float2* partial;                 // [n_blocks, M] (max, sumexp)
+  };
+  const Params& p;
+  int row, M, N, n_blk;
+  float mx, sum;
+  __device__ EpiLogitsStats(const Params& p_, int row_, int, int n_blk_, int, const GemmShape& s)
+      : p(p_), row(row_), M(s.M), N(s.N), n_blk(n_blk_), mx(-INFINITY), sum(0.f) {}
+  __device__ void chunk(int col0, float (&v)[32]) {
+    if (row >= M) return;
+    float cmax = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int col = col0 + i;
+      float x = (col < N) ? v[i] + __ldg(p.bias + col) : -INFINITY;
+      v[i] = x;
+      cmax = fmaxf(cmax, x);
+    }
+    const float nm = fmaxf(mx, cmax);  // finite: every processed chunk has col0 < N
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s += __expf(v[i] - nm);
+    sum = sum * __expf(mx - nm) + s;
+    mx = nm;
+    if (p.logits != nullptr) {
+      __nv_bfloat16* o = p.logits + (size_t)row * p.ld + col0;
+      if (col0 + 32 <= N && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 u;
+          u.x = pack_bf16x2(v[i], v[i + 1]); u.y = pack_bf16x2(v[i + 2], v[i + 3]);
+          u.z = pack_bf16x2(v[i + 4], v[i + 5]); u.w = pack_bf16x2(v[i + 6], v[i + 7]);
+          *reinterpret_cast<uint4*>(o + i) = u;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (col0 + i < N) o[i] = __float2bfloat16(v[i]);
+      }
+    }
+  }
+  __device__ void finish() {
+    if (row < M) p.partial[(size_t)n_blk * M + row] = make_float2(mx, sum);
+  }
+};
+
+// ----------------------------------------------------------------------------------------------
+// Host side: tensor maps + launch
+// ----------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled ltg_get_encode_tiled();
+
+// bf16 2-D tensor [outer][inner] with row pitch ld (elements), box {box_inner (=64), box_outer}, 128B swizzle, zero OOB fill.
+inline int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer) {
+  PFN_encodeTiled fn = ltg_get_encode_tiled();
+  if (fn == nullptr) return LTG_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ((ld * 2) & 15) != 0) {
+    ltg_set_last_error("TMA operand must be 16-byte aligned with a 16-byte-multiple pitch", __FILE__, __LINE__);
+    return LTG_ERR_ARG;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    ltg_set_last_error("cuTensorMapEncodeTiled failed", __FILE__, __LINE__);
+    return LTG_ERR_DRIVER;
+  }
+  return LTG_OK;
+}
+
+int ltg_num_sms();
+
+// A: [M,K] (a_mn=false, pitch lda over K) or stored [K,M] (a_mn=true, pitch lda over M). Same for B with N.
+template <int BN, bool A_MN, bool B_MN, class Epi>
+int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, int M, int N, int K, int splits,
+                const typename Epi::Params& ep, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return LTG_OK;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (A_MN) rc = make_tmap_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, 64);
+  else rc = make_tmap_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, GEMM_BM);
+  if (rc) return rc;
+  if (B_MN) rc = make_tmap_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, 64);
+  else rc = make_tmap_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, BN);
+  if (rc) return rc;
+  GemmShape s;
+  s.M = M; s.N = N; s.K = K;
+  s.m_blocks = (M + GEMM_BM - 1) / GEMM_BM;
+  s.n_blocks = (N + BN - 1) / BN;
+  s.k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
+  if (splits < 1) splits = 1;
+  if (splits > s.k_blocks) splits = s.k_blocks;
+  s.kb_per_split = (s.k_blocks + splits - 1) / splits;
+  s.splits = (s.k_blocks + s.kb_per_split - 1) / s.kb_per_split;  // no empty split
+  const int tiles = s.m_blocks * s.n_blocks * s.splits;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, Epi>;
+  static bool attr_set = false;  // per instantiation
+  const size_t smem = gemm_smem_bytes<BN>();
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { ltg_set_last_error(cudaGetErrorString(e), __FILE__, __LINE__); return LTG_ERR_CUDA; }
+    attr_set = true;
+  }
+  const int grid = tiles < ltg_num_sms() ? tiles : ltg_num_sms();
+  kern<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, s, ep);
+  LTG_CHECK_LAUNCH();
+  return LTG_OK;
+}
+
+}  // namespace ltg

@@ -1,0 +1,137 @@
+// Shared device/host helpers for the Long-Tail-GAN sm_100a kernels.
+// Everything here is header-only; each .cu includes it.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#define LTG_OK 0
+#define LTG_ERR_ARG -1
+#define LTG_ERR_CUDA -2
+#define LTG_ERR_DRIVER -3
+
+#define LTG_CHECK_LAUNCH()                                   \
+  do {                                                       \
+    cudaError_t e__ = cudaGetLastError();                    \
+    if (e__ != cudaSuccess) {                                \
+      ltg_set_last_error(cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return LTG_ERR_CUDA;                                   \
+    }                                                        \
+  } while (0)
+
+#define LTG_REQUIRE(cond)                                    \
+  do {                                                       \
+    if (!(cond)) {                                           \
+      ltg_set_last_error("bad argument: " #cond, __FILE__, __LINE__); \
+      return LTG_ERR_ARG;                                    \
+    }                                                        \
+  } while (0)
+
+void ltg_set_last_error(const char* msg, const char* file, int line);
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10, stateless. key = (seed_lo, seed_hi); counter = (c0, c1, c2, c3).
+// The numpy mirror lives in oracle/philox.py and tests/ check bit equality of the streams.
+// ---------------------------------------------------------------------------------------------
+struct Philox4 {
+  uint32_t x, y, z, w;
+};
+
+__host__ __device__ __forceinline__ uint32_t ltg_mulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                         uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = ltg_mulhi32(M0, c0), lo0 = M0 * c0;
+    uint32_t hi1 = ltg_mulhi32(M1, c2), lo1 = M1 * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0;
+    uint32_t n1 = lo1;
+    uint32_t n2 = hi0 ^ c3 ^ k1;
+    uint32_t n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  Philox4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+  return o;
+}
+
+// RNG stream ids (counter word c2). Shared with oracle/philox.py.
+#define LTG_STREAM_ENC_DROPOUT 1u
+#define LTG_STREAM_EPS 2u
+#define LTG_STREAM_DISC_DROPOUT 3u   // + layer index (0: pop branch, 1: niche branch, 2: fc1)
+#define LTG_STREAM_SAMPLE 8u
+#define LTG_STREAM_PARTNER 9u
+
+// One Bernoulli(keep) bit for element `idx` of stream `stream` at step `step`.
+// Four consecutive idx share one Philox block (word idx&3).
+__device__ __forceinline__ uint32_t ltg_rand_u32(uint64_t seed, uint32_t stream, uint32_t step, uint64_t idx) {
+  uint64_t blk = idx >> 2;
+  Philox4 r = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), stream, step, (uint32_t)seed, (uint32_t)(seed >> 32));
+  uint32_t w = (uint32_t)(idx & 3);
+  return w == 0 ? r.x : (w == 1 ? r.y : (w == 2 ? r.z : r.w));
+}
+
+// keep-threshold: element kept iff u32 < thr, thr = floor(keep * 2^32) clipped.
+__host__ __device__ __forceinline__ uint32_t ltg_keep_threshold(float keep) {
+  double t = (double)keep * 4294967296.0;
+  if (t >= 4294967295.0) return 0xFFFFFFFFu;
+  if (t <= 0.0) return 0u;
+  return (uint32_t)t;
+}
+
+// uniform strictly inside (0,1): ((u32 >> 8) + 0.5) * 2^-24 (exact in fp32)
+__device__ __forceinline__ float ltg_u01(uint32_t r) { return ((float)(r >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+// ---------------------------------------------------------------------------------------------
+// small numeric helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
+  __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&v);
+  return __bfloat1622float2(h);
+}
+__device__ __forceinline__ float bf16_to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// 16-byte streaming load (read-once data: keep it out of L1)
+__device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float4 ld_stream_f4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream_f4(float* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}

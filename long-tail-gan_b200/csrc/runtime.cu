@@ -1,0 +1,82 @@
+// Runtime glue of libltgan.so: error reporting, driver entry points, device step state.
+#include <stdio.h>
+#include <string.h>
+#include "gemm_sm100.cuh"
+#include "../../include/ltgan.h"
+
+static thread_local char g_err[512] = "";
+
+void ltg_set_last_error(const char* msg, const char* file, int line) {
+  snprintf(g_err, sizeof(g_err), "%s (%s:%d)", msg, file, line);
+}
+
+namespace ltg {
+
+PFN_encodeTiled ltg_get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn != nullptr) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || p == nullptr) {
+    ltg_set_last_error("cuTensorMapEncodeTiled not available from the CUDA driver", __FILE__, __LINE__);
+    return nullptr;
+  }
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+int ltg_num_sms() {
+  static int n = 0;
+  if (n > 0) return n;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  return n;
+}
+
+}  // namespace ltg
+
+extern "C" const char* ltg_last_error(void) { return g_err; }
+extern "C" int ltg_version(void) { return 100; }
+
+extern "C" int ltg_init(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { ltg_set_last_error(cudaGetErrorString(e), __FILE__, __LINE__); return LTG_ERR_CUDA; }
+  int major = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10) { ltg_set_last_error("libltgan requires an sm_100a (B200) device", __FILE__, __LINE__); return LTG_ERR_CUDA; }
+  if (ltg::ltg_get_encode_tiled() == nullptr) return LTG_ERR_DRIVER;
+  ltg::ltg_num_sms();
+  return LTG_OK;
+}
+
+// words[0] rng step, words[1] Adam t, words[2] G-update count.
+__global__ void step_advance_kernel(uint32_t* words, float* scal, int kind, float lr, double beta1, double beta2,
+                                    float anneal_cap, float total_anneal_steps) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  words[0] += 1;
+  if (kind >= 1) {
+    const uint32_t t = ++words[1];
+    // TF1 AdamOptimizer: lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t)   [ext, SURVEY F6]
+    const double b1t = pow(beta1, (double)t), b2t = pow(beta2, (double)t);
+    scal[LTG_S_LR_T] = (float)((double)lr * sqrt(1.0 - b2t) / (1.0 - b1t));
+  }
+  if (kind == 2) {
+    // train.py:319-324: anneal from the pre-increment update_count
+    const uint32_t c = words[2];
+    float a = anneal_cap;
+    if (total_anneal_steps > 0.f) a = fminf(anneal_cap, (float)c / total_anneal_steps);
+    scal[LTG_S_ANNEAL] = a;
+    words[2] = c + 1;
+  }
+}
+
+extern "C" int ltg_step_advance(uint32_t* words, float* scal, int kind, float lr, float beta1, float beta2,
+                                float anneal_cap, float total_anneal_steps, void* stream) {
+  LTG_REQUIRE(words != nullptr && scal != nullptr);
+  step_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(words, scal, kind, lr, (double)beta1, (double)beta2, anneal_cap, total_anneal_steps);
+  LTG_CHECK_LAUNCH();
+  return LTG_OK;
+}

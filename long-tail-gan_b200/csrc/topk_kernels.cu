@@ -1,0 +1,196 @@
+// a16/a17: exact per-row top-k and the ranking metrics built on it
+// (eval_functions.py:11-38 NDCG@k, 40-62 Recall@k; the seen-item mask of train.py:341 / test.py:149).
+//
+// One CTA per user row. The row's seen items become a bitmap in shared memory (one bit per catalog
+// item), scores are mapped to order-preserving uint32 keys, and the k-th largest key is found with a
+// 4-pass 8-bit radix select that streams the row from L2/HBM (nothing but the bitmap is staged, so
+// the same kernel serves a 1,000-item and a 1,000,000-item catalog). Ties at the threshold are
+// resolved by lowest item index with a second radix select over the indices, which runs only when
+// the threshold key is actually shared. The k winners are then sorted (bitonic, 128 lanes) by
+// (score desc, index asc) and tested against the held-out CSR row by binary search.
+#include "ltg_common.cuh"
+#include "../../include/ltgan.h"
+
+namespace {
+
+constexpr int TK_THREADS = 256;
+constexpr int TK_MAXK = 128;
+
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+template <bool BF16>
+__device__ __forceinline__ uint32_t load_key(const void* row, int i, const uint32_t* bitmap) {
+  if (bitmap[i >> 5] & (1u << (i & 31))) return f2ord(-INFINITY);
+  float f;
+  if (BF16) f = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(row)[i]);
+  else f = reinterpret_cast<const float*>(row)[i];
+  return f2ord(f);
+}
+
+// Finds, among elements whose `key(i)` passes `pred`, the value with 1-based rank k from the top of
+// an arbitrary 32-bit quantity `val(i)`. Returns the value; *count_eq receives how many elements share it
+// and *k_rem the rank remaining inside that group.
+template <class ValFn>
+__device__ uint32_t radix_select_desc(int n, uint32_t k, ValFn val, uint32_t* s_hist, uint32_t* s_sel, uint32_t* count_eq, uint32_t* k_rem) {
+  uint32_t prefix = 0, pmask = 0;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += TK_THREADS) s_hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += TK_THREADS) {
+      uint32_t v; const bool ok = val(i, v);
+      if (ok && (v & pmask) == prefix) atomicAdd(&s_hist[(v >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t acc = 0; int d = 255;
+      for (; d > 0; --d) {
+        if (acc + s_hist[d] >= k) break;
+        acc += s_hist[d];
+      }
+      s_sel[0] = (uint32_t)d; s_sel[1] = k - acc; s_sel[2] = s_hist[d];
+    }
+    __syncthreads();
+    prefix |= s_sel[0] << shift;
+    pmask |= 255u << shift;
+    k = s_sel[1];
+    *count_eq = s_sel[2];
+    __syncthreads();
+  }
+  *k_rem = k;
+  return prefix;
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(TK_THREADS)
+topk_metrics_kernel(const void* __restrict__ scores, int64_t ld, int n_items,
+                    const int32_t* __restrict__ seen_ptr, const int32_t* __restrict__ seen_items,
+                    const int32_t* __restrict__ held_ptr, const int32_t* __restrict__ held_items,
+                    int k, int4 rk, int n_rk, int32_t* __restrict__ topk_idx, double* __restrict__ dcg, int32_t* __restrict__ hits) {
+  extern __shared__ uint32_t s_bitmap[];  // [(n_items+31)/32]
+  __shared__ uint32_t s_hist[256];
+  __shared__ uint32_t s_sel[3];
+  __shared__ unsigned long long s_win[TK_MAXK];
+  __shared__ int s_nwin;
+  __shared__ double s_dcg[TK_MAXK / 32];
+  __shared__ int s_hits[4];
+
+  const int u = blockIdx.x;
+  const int tid = threadIdx.x;
+  const void* row = BF16 ? (const void*)(reinterpret_cast<const __nv_bfloat16*>(scores) + (size_t)u * ld)
+                         : (const void*)(reinterpret_cast<const float*>(scores) + (size_t)u * ld);
+  const int words = (n_items + 31) >> 5;
+  for (int w = tid; w < words; w += TK_THREADS) s_bitmap[w] = 0u;
+  if (tid < TK_MAXK) s_win[tid] = 0ull;
+  if (tid == 0) s_nwin = 0;
+  if (tid < 4) s_hits[tid] = 0;
+  __syncthreads();
+  if (seen_ptr != nullptr)
+    for (int j = seen_ptr[u] + tid; j < seen_ptr[u + 1]; j += TK_THREADS) {
+      const int it = seen_items[j];
+      atomicOr(&s_bitmap[it >> 5], 1u << (it & 31));
+    }
+  __syncthreads();
+
+  const int kk = min(k, n_items);
+  uint32_t cnt_eq = 0, k_rem = 0;
+  const uint32_t T = radix_select_desc(n_items, (uint32_t)kk,
+      [&](int i, uint32_t& v) { v = load_key<BF16>(row, i, s_bitmap); return true; }, s_hist, s_sel, &cnt_eq, &k_rem);
+  // ties at the threshold: keep the k_rem lowest indices among the cnt_eq elements equal to T
+  uint32_t idx_thr = 0xFFFFFFFFu;  // compare on ~idx: take eq elements with ~idx >= idx_thr_inv
+  uint32_t inv_thr = 0u;
+  if (cnt_eq != k_rem) {
+    uint32_t c2 = 0, k2 = 0;
+    inv_thr = radix_select_desc(n_items, k_rem,
+        [&](int i, uint32_t& v) { v = ~(uint32_t)i; return load_key<BF16>(row, i, s_bitmap) == T; }, s_hist, s_sel, &c2, &k2);
+  }
+  (void)idx_thr;
+  // collect winners (unordered), then sort
+  for (int i = tid; i < n_items; i += TK_THREADS) {
+    const uint32_t key = load_key<BF16>(row, i, s_bitmap);
+    if (key > T || (key == T && ~(uint32_t)i >= inv_thr)) {
+      const int slot = atomicAdd(&s_nwin, 1);
+      if (slot < TK_MAXK) s_win[slot] = ((unsigned long long)key << 32) | (unsigned long long)(~(uint32_t)i);
+    }
+  }
+  __syncthreads();
+  // bitonic sort, descending, 128 entries (unused entries are 0 = smallest)
+  for (int size = 2; size <= TK_MAXK; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (tid < TK_MAXK) {
+        const int j = tid ^ stride;
+        if (j > tid) {
+          const unsigned long long a = s_win[tid], b = s_win[j];
+          const bool desc = (tid & size) == 0;
+          if ((a < b) == desc) { s_win[tid] = b; s_win[j] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // metrics
+  double term = 0.0;
+  if (tid < kk) {
+    const int idx = (int)(~(uint32_t)(s_win[tid] & 0xFFFFFFFFull));
+    if (topk_idx != nullptr) topk_idx[(size_t)u * k + tid] = idx;
+    int lo = held_ptr[u], hi = held_ptr[u + 1];
+    bool hit = false;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      const int v = held_items[mid];
+      if (v == idx) { hit = true; break; }
+      if (v < idx) lo = mid + 1; else hi = mid;
+    }
+    if (hit) {
+      term = 1.0 / log2((double)(tid + 2));  // eval_functions.py:25
+      if (n_rk > 0 && tid < rk.x) atomicAdd(&s_hits[0], 1);
+      if (n_rk > 1 && tid < rk.y) atomicAdd(&s_hits[1], 1);
+      if (n_rk > 2 && tid < rk.z) atomicAdd(&s_hits[2], 1);
+      if (n_rk > 3 && tid < rk.w) atomicAdd(&s_hits[3], 1);
+    }
+  } else if (tid < k && topk_idx != nullptr) {
+    topk_idx[(size_t)u * k + tid] = -1;
+  }
+  if (tid < TK_MAXK) {
+    term = warp_sum_d(term);
+    if ((tid & 31) == 0) s_dcg[tid >> 5] = term;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    dcg[u] = s_dcg[0] + s_dcg[1] + s_dcg[2] + s_dcg[3];
+    for (int j = 0; j < n_rk; ++j) hits[(size_t)u * n_rk + j] = s_hits[j];
+  }
+}
+
+}  // namespace
+
+extern "C" int ltg_topk_metrics(const void* scores, int is_bf16, int64_t ld, int n_rows, int n_items,
+                                const int32_t* seen_ptr, const int32_t* seen_items, const int32_t* held_ptr, const int32_t* held_items,
+                                int k, const int32_t* rk_host, int n_rk, int32_t* topk_idx, double* dcg, int32_t* hits, void* stream) {
+  LTG_REQUIRE(scores && held_ptr && held_items && dcg);
+  LTG_REQUIRE(k >= 1 && k <= TK_MAXK && n_rk >= 0 && n_rk <= 4 && (n_rk == 0 || (rk_host != nullptr && hits != nullptr)));
+  LTG_REQUIRE(seen_ptr == nullptr || seen_items != nullptr);
+  if (n_rows <= 0) return LTG_OK;
+  int4 rk = make_int4(0, 0, 0, 0);
+  int* rkp = reinterpret_cast<int*>(&rk);
+  for (int j = 0; j < n_rk; ++j) { LTG_REQUIRE(rk_host[j] >= 1 && rk_host[j] <= k); rkp[j] = rk_host[j]; }
+  const size_t smem = (size_t)((n_items + 31) / 32) * 4;
+  LTG_REQUIRE(smem <= 200 * 1024);
+  static size_t opted[2] = {40 * 1024, 40 * 1024};
+  if (smem > opted[is_bf16 ? 1 : 0]) {
+    cudaError_t e = is_bf16 ? cudaFuncSetAttribute(topk_metrics_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                            : cudaFuncSetAttribute(topk_metrics_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { ltg_set_last_error(cudaGetErrorString(e), __FILE__, __LINE__); return LTG_ERR_CUDA; }
+    opted[is_bf16 ? 1 : 0] = smem;
+  }
+  if (is_bf16)
+    topk_metrics_kernel<true><<<n_rows, TK_THREADS, smem, (cudaStream_t)stream>>>(scores, ld, n_items, seen_ptr, seen_items, held_ptr, held_items, k,
+                                                                                 rk, n_rk, topk_idx, dcg, hits);
+  else
+    topk_metrics_kernel<false><<<n_rows, TK_THREADS, smem, (cudaStream_t)stream>>>(scores, ld, n_items, seen_ptr, seen_items, held_ptr, held_items, k,
+                                                                                  rk, n_rk, topk_idx, dcg, hits);
+  LTG_CHECK_LAUNCH();
+  return LTG_OK;
+}

@@ -1,0 +1,412 @@
+// MultiVAE-side kernels that are not GEMMs: CSR encoder gather, latent head, activation backward,
+// catalog-softmax row statistics, d(loss)/d(logits).
+#include "ltg_common.cuh"
+#include "../../include/ltgan.h"
+
+namespace {
+
+constexpr int H = LTG_H;
+constexpr int L = LTG_L;
+constexpr int HV = H / 8;  // 75 16-byte vectors per bf16 weight row
+
+// ---------------------------------------------------------------------------------------------
+// a3: encoder. One CTA per user; the CTA first turns the CSR row into (item, coef) pairs in shared
+// memory (norm, Philox dropout bit per nonzero), then 75 threads each own one 16-byte column slice
+// of the 1200-byte bf16 W_q0 rows and stream the surviving rows with 4 loads in flight.
+// Restates MultiVAE.py:148 (l2_normalize), 149 (dropout), 152-155 (matmul + bias + tanh).
+// ---------------------------------------------------------------------------------------------
+constexpr int ENC_THREADS = 96;
+constexpr int ENC_CHUNK = 512;
+
+__global__ void __launch_bounds__(ENC_THREADS)
+enc_gather_fwd_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
+                      int n_items, int64_t uid0, const uint4* __restrict__ W, const float* __restrict__ bias, float keep,
+                      uint64_t seed, uint32_t step, const uint32_t* __restrict__ step_dev, __nv_bfloat16* __restrict__ h1,
+                      int ld_h1, float* __restrict__ coef) {
+  __shared__ int s_item[ENC_CHUNK];
+  __shared__ float s_coef[ENC_CHUNK];
+  __shared__ float s_red[ENC_THREADS / 32];
+  const int u = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int beg = indptr[u], end = indptr[u + 1];
+  if (step_dev != nullptr) step += *step_dev;
+
+  // squared norm of the row (values == NULL: binary row)
+  float ss = 0.f;
+  if (values != nullptr) {
+    for (int j = beg + tid; j < end; j += ENC_THREADS) { float v = values[j]; ss += v * v; }
+    ss = warp_sum(ss);
+    if ((tid & 31) == 0) s_red[tid >> 5] = ss;
+    __syncthreads();
+    ss = s_red[0] + s_red[1] + s_red[2];
+    __syncthreads();
+  } else {
+    ss = (float)(end - beg);
+  }
+  const float rs = rsqrtf(fmaxf(ss, 1e-12f));
+  const bool drop = keep > 0.f && keep < 1.f;
+  const uint32_t thr = drop ? ltg_keep_threshold(keep) : 0xFFFFFFFFu;
+  const float scale = drop ? rs / keep : rs;
+
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+
+  for (int c0 = beg; c0 < end; c0 += ENC_CHUNK) {
+    const int cnt = min(ENC_CHUNK, end - c0);
+    for (int j = tid; j < cnt; j += ENC_THREADS) {
+      const int item = indices[c0 + j];
+      const float val = values != nullptr ? values[c0 + j] : 1.0f;
+      float c = val * scale;
+      if (drop) {
+        const uint32_t r = ltg_rand_u32(seed, LTG_STREAM_ENC_DROPOUT, step, (uint64_t)(uid0 + u) * (uint64_t)n_items + (uint64_t)item);
+        if (r >= thr) c = 0.f;
+      }
+      s_item[j] = item;
+      s_coef[j] = c;
+      coef[c0 + j] = c;
+    }
+    __syncthreads();
+    if (tid < HV) {
+      int j = 0;
+      for (; j + 4 <= cnt; j += 4) {
+        uint4 w[4]; float c[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          c[q] = s_coef[j + q];
+          w[q] = make_uint4(0, 0, 0, 0);
+          if (c[q] != 0.f) w[q] = __ldg(W + (size_t)s_item[j + q] * HV + tid);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float2 a = unpack_bf16x2(w[q].x), b = unpack_bf16x2(w[q].y), d = unpack_bf16x2(w[q].z), e = unpack_bf16x2(w[q].w);
+          acc[0] = fmaf(c[q], a.x, acc[0]); acc[1] = fmaf(c[q], a.y, acc[1]);
+          acc[2] = fmaf(c[q], b.x, acc[2]); acc[3] = fmaf(c[q], b.y, acc[3]);
+          acc[4] = fmaf(c[q], d.x, acc[4]); acc[5] = fmaf(c[q], d.y, acc[5]);
+          acc[6] = fmaf(c[q], e.x, acc[6]); acc[7] = fmaf(c[q], e.y, acc[7]);
+        }
+      }
+      for (; j < cnt; ++j) {
+        const float c = s_coef[j];
+        if (c != 0.f) {
+          const uint4 w = __ldg(W + (size_t)s_item[j] * HV + tid);
+          float2 a = unpack_bf16x2(w.x), b = unpack_bf16x2(w.y), d = unpack_bf16x2(w.z), e = unpack_bf16x2(w.w);
+          acc[0] = fmaf(c, a.x, acc[0]); acc[1] = fmaf(c, a.y, acc[1]);
+          acc[2] = fmaf(c, b.x, acc[2]); acc[3] = fmaf(c, b.y, acc[3]);
+          acc[4] = fmaf(c, d.x, acc[4]); acc[5] = fmaf(c, d.y, acc[5]);
+          acc[6] = fmaf(c, e.x, acc[6]); acc[7] = fmaf(c, e.y, acc[7]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (tid < HV) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias) + tid * 2);
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias) + tid * 2 + 1);
+    uint4 o;
+    o.x = pack_bf16x2(tanhf(acc[0] + b0.x), tanhf(acc[1] + b0.y));
+    o.y = pack_bf16x2(tanhf(acc[2] + b0.z), tanhf(acc[3] + b0.w));
+    o.z = pack_bf16x2(tanhf(acc[4] + b1.x), tanhf(acc[5] + b1.y));
+    o.w = pack_bf16x2(tanhf(acc[6] + b1.z), tanhf(acc[7] + b1.w));
+    *reinterpret_cast<uint4*>(h1 + (size_t)u * ld_h1 + tid * 8) = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a3/a4: latent head. MultiVAE.py:157-162 (mu/logvar split, std, KL) and 178-181 (reparameterise).
+// ---------------------------------------------------------------------------------------------
+__global__ void latent_fwd_kernel(const float* __restrict__ mulv, const float* __restrict__ eps, int B, int64_t uid0, float is_training,
+                                  uint64_t seed, uint32_t step, const uint32_t* __restrict__ step_dev,
+                                  __nv_bfloat16* __restrict__ z, int ld_z, float* __restrict__ zmu, float* __restrict__ scal) {
+  __shared__ float s_red[8];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  float kl = 0.f;
+  if (idx < B * L) {
+    const int u = idx / L, j = idx - u * L;
+    const float mu = mulv[(size_t)u * 2 * L + j];
+    const float lv = mulv[(size_t)u * 2 * L + L + j];
+    const float ev = expf(lv);
+    kl = 0.5f * (-lv + ev + mu * mu - 1.0f);
+    float e = 0.f;
+    if (is_training != 0.f) {
+      if (eps != nullptr) {
+        e = eps[idx];
+      } else {
+        if (step_dev != nullptr) step += *step_dev;
+        const uint64_t g = (uint64_t)(uid0 + u) * (uint64_t)L + (uint64_t)j;
+        Philox4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), LTG_STREAM_EPS, step, (uint32_t)seed, (uint32_t)(seed >> 32));
+        const float u1 = ltg_u01(r.x), u2 = ltg_u01(r.y);
+        e = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+      }
+    }
+    const float d = is_training * e * expf(0.5f * lv);
+    zmu[idx] = d;
+    z[(size_t)u * ld_z + j] = __float2bfloat16(mu + d);
+  }
+  kl = warp_sum(kl);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = kl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
+    atomicAdd(scal + LTG_S_KL_SUM, t);
+  }
+}
+
+// rows are tiled by 32 per block; every thread owns columns (strided) and sums its column over the tile,
+// then issues one atomic per column per block for the bias gradient.
+constexpr int COLSUM_ROWS = 32;
+
+__global__ void latent_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ mulv, const float* __restrict__ zmu, int B,
+                                  float inv_bg, float anneal, const float* __restrict__ scal, __nv_bfloat16* __restrict__ dmulv, int ld,
+                                  float* __restrict__ db) {
+  if (anneal < 0.f) anneal = scal[LTG_S_ANNEAL];
+  const int r0 = blockIdx.x * COLSUM_ROWS;
+  const int r1 = min(B, r0 + COLSUM_ROWS);
+  for (int c = threadIdx.x; c < 2 * L; c += blockDim.x) {
+    float cs = 0.f;
+    const bool is_mu = c < L;
+    const int j = is_mu ? c : c - L;
+    for (int r = r0; r < r1; ++r) {
+      const float g = dz[(size_t)r * L + j];
+      float o;
+      if (is_mu) {
+        o = g + anneal * mulv[(size_t)r * 2 * L + j] * inv_bg;
+      } else {
+        const float lv = mulv[(size_t)r * 2 * L + L + j];
+        o = g * zmu[(size_t)r * L + j] * 0.5f + anneal * 0.5f * (expf(lv) - 1.0f) * inv_bg;
+      }
+      dmulv[(size_t)r * ld + c] = __float2bfloat16(o);
+      cs += o;
+    }
+    if (db != nullptr) atomicAdd(db + c, cs);
+  }
+}
+
+__global__ void tanh_bwd_kernel(const float* __restrict__ dy, int ld_dy, const __nv_bfloat16* __restrict__ y, int ld_y, int B, int N,
+                                __nv_bfloat16* __restrict__ dxb, int ld_dxb, float* __restrict__ dxf, int ld_dxf, float* __restrict__ db) {
+  const int r0 = blockIdx.x * COLSUM_ROWS;
+  const int r1 = min(B, r0 + COLSUM_ROWS);
+  for (int c = threadIdx.x; c < N; c += blockDim.x) {
+    float cs = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      const float t = __bfloat162float(y[(size_t)r * ld_y + c]);
+      const float o = dy[(size_t)r * ld_dy + c] * (1.0f - t * t);
+      if (dxb != nullptr) dxb[(size_t)r * ld_dxb + c] = __float2bfloat16(o);
+      if (dxf != nullptr) dxf[(size_t)r * ld_dxf + c] = o;
+      cs += o;
+    }
+    if (db != nullptr) atomicAdd(db + c, cs);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a6: row statistics of the catalog softmax. One warp per user.
+// ---------------------------------------------------------------------------------------------
+__global__ void dec_row_stats_kernel(const float2* __restrict__ partial, int n_blocks, const __nv_bfloat16* __restrict__ logits, int ld, int B,
+                                     const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
+                                     const int32_t* __restrict__ samp_ptr, const int32_t* __restrict__ samp_items,
+                                     const int32_t* __restrict__ samp_valid, float* __restrict__ lse_out, float* __restrict__ xw_out,
+                                     float* __restrict__ su_out, float* __restrict__ scal) {
+  const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (u >= B) return;
+  float mx = -INFINITY;
+  for (int b = lane; b < n_blocks; b += 32) mx = fmaxf(mx, partial[(size_t)b * B + u].x);
+  mx = warp_max(mx);
+  float s = 0.f;
+  for (int b = lane; b < n_blocks; b += 32) {
+    const float2 p = partial[(size_t)b * B + u];
+    s += p.y * __expf(p.x - mx);
+  }
+  s = warp_sum(s);
+  const float lse = mx + logf(s);
+  const __nv_bfloat16* row = logits + (size_t)u * ld;
+  float nll = 0.f, xw = 0.f;
+  if (indptr != nullptr) {
+    for (int j = indptr[u] + lane; j < indptr[u + 1]; j += 32) {
+      const float v = values != nullptr ? values[j] : 1.0f;
+      nll -= v * (__bfloat162float(row[indices[j]]) - lse);
+      xw += v;
+    }
+    nll = warp_sum(nll);
+    xw = warp_sum(xw);
+  }
+  float sp = 0.f;
+  if (samp_ptr != nullptr) {
+    for (int j = samp_ptr[u] + lane; j < samp_ptr[u + 1]; j += 32)
+      if (samp_valid[j] > 0) sp += __expf(__bfloat162float(row[samp_items[j]]) - lse);
+    sp = warp_sum(sp);
+  }
+  if (lane == 0) {
+    lse_out[u] = lse;
+    if (xw_out != nullptr) xw_out[u] = xw;
+    if (su_out != nullptr) su_out[u] = sp;
+    if (indptr != nullptr) atomicAdd(scal + LTG_S_NLL_SUM, nll);
+    if (samp_ptr != nullptr) atomicAdd(scal + LTG_S_SUM_P, sp);
+  }
+}
+
+__global__ void dec_probs_kernel(const __nv_bfloat16* __restrict__ logits, int ld, const float* __restrict__ lse, int n_items,
+                                 float* __restrict__ out, int ld_out) {
+  const int u = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n_items) out[(size_t)u * ld_out + c] = __expf(__bfloat162float(logits[(size_t)u * ld + c]) - lse[u]);
+}
+
+// dense part of d g_loss / d logits: dl = pi * a_u, 8 bf16 per thread.
+__global__ void dlogits_dense_kernel(const uint4* __restrict__ logits, int ld8, const float* __restrict__ lse, const float* __restrict__ xw,
+                                     const float* __restrict__ s_u, int n_items, float inv_bg, float lam, const float* __restrict__ scal,
+                                     uint4* __restrict__ dl) {
+  const int u = blockIdx.y;
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= ld8) return;
+  float ybar = 0.f;
+  if (lam != 0.f) {
+    const float cnt = scal[LTG_S_CNT];
+    ybar = cnt > 0.f ? scal[LTG_S_SUM_Y] / cnt : 0.f;
+  }
+  const float a = xw[u] * inv_bg + lam * ybar * (s_u != nullptr ? s_u[u] : 0.f);
+  const float l = lse[u];
+  const uint4 x = ld_nc_v4(logits + (size_t)u * ld8 + v);
+  const uint32_t xi[4] = {x.x, x.y, x.z, x.w};
+  uint32_t o[4];
+  const int c0 = v * 8;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float2 f = unpack_bf16x2(xi[q]);
+    const float p0 = (c0 + 2 * q < n_items) ? __expf(f.x - l) * a : 0.f;
+    const float p1 = (c0 + 2 * q + 1 < n_items) ? __expf(f.y - l) * a : 0.f;
+    o[q] = pack_bf16x2(p0, p1);
+  }
+  dl[(size_t)u * ld8 + v] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// sparse fix-ups: -x_ui/Bg at the user's interactions, -lam*Ybar*pi_ui at the sampled (valid) items. One warp per user.
+__global__ void dlogits_sparse_kernel(const __nv_bfloat16* __restrict__ logits, int ld, const float* __restrict__ lse, int B, float inv_bg,
+                                      float lam, const float* __restrict__ scal, const int32_t* __restrict__ indptr,
+                                      const int32_t* __restrict__ indices, const float* __restrict__ values,
+                                      const int32_t* __restrict__ samp_ptr, const int32_t* __restrict__ samp_items,
+                                      const int32_t* __restrict__ samp_valid, __nv_bfloat16* __restrict__ dl) {
+  const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (u >= B) return;
+  __nv_bfloat16* drow = dl + (size_t)u * ld;
+  for (int j = indptr[u] + lane; j < indptr[u + 1]; j += 32) {
+    const int i = indices[j];
+    const float v = values != nullptr ? values[j] : 1.0f;
+    drow[i] = __float2bfloat16(__bfloat162float(drow[i]) - v * inv_bg);
+  }
+  if (lam != 0.f && samp_ptr != nullptr) {
+    __syncwarp();
+    const float cnt = scal[LTG_S_CNT];
+    const float ybar = cnt > 0.f ? scal[LTG_S_SUM_Y] / cnt : 0.f;
+    const float l = lse[u];
+    const __nv_bfloat16* row = logits + (size_t)u * ld;
+    for (int j = samp_ptr[u] + lane; j < samp_ptr[u + 1]; j += 32) {
+      if (samp_valid[j] > 0) {
+        const int i = samp_items[j];
+        const float pi = __expf(__bfloat162float(row[i]) - l);
+        drow[i] = __float2bfloat16(__bfloat162float(drow[i]) - lam * ybar * pi);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" int ltg_enc_gather_fwd(const int32_t* indptr, const int32_t* indices, const float* values, int B, int n_items, int64_t uid0,
+                                  const void* W_enc_bf16, const float* b_q0, float keep, uint64_t seed, uint32_t step,
+                                  const uint32_t* step_dev, void* h1_bf16, int ld_h1, float* coef, void* stream) {
+  LTG_REQUIRE(indptr && indices && W_enc_bf16 && b_q0 && h1_bf16 && coef);
+  LTG_REQUIRE(ld_h1 % 8 == 0 && ld_h1 >= H);
+  if (B <= 0) return LTG_OK;
+  enc_gather_fwd_kernel<<<B, ENC_THREADS, 0, (cudaStream_t)stream>>>(indptr, indices, values, n_items, uid0,
+                                                                      reinterpret_cast<const uint4*>(W_enc_bf16), b_q0, keep, seed, step, step_dev,
+                                                                      reinterpret_cast<__nv_bfloat16*>(h1_bf16), ld_h1, coef);
+  LTG_CHECK_LAUNCH();
+  return LTG_OK;
+}
+
+extern "C" int ltg_latent_fwd(const float* mulv, const float* eps, int B, int64_t uid0, float is_training, uint64_t seed, uint32_t step,
+                              const uint32_t* step_dev, void* z_bf16, int ld_z, float* zmu, float* scal, void* stream) {
+  LTG_REQUIRE(mulv && z_bf16 && zmu && scal);
+  if (B <= 0) return LTG_OK;
+  const int n = B * L;
+  latent_fwd_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mulv, eps, B, uid0, is_training, seed, step, step_dev,
+                                                                        reinterpret_cast<__nv_bfloat16*>(z_bf16), ld_z, zmu, scal);
+  LTG_CHECK_LAUNCH();
+  return LTG_OK;
+}
+
+extern "C" int ltg_latent_bwd(const float* dz, const float* mulv, const float* zmu, int B, int B_global, float anneal, const float* scal,
+                              void* dmulv_bf16, int ld, float* db_q1, void* stream) {
+  LTG_REQUIRE(dz && mulv && zmu && dmulv_bf16);
+  LTG_REQUIRE(anneal >= 0.f || scal != nullptr);
+  if (B <= 0) return LTG_OK;
+  latent_bwd_kernel<<<(B + COLSUM_ROWS - 1) / COLSUM_ROWS, 256, 0, (cudaStream_t)stream>>>(
+      dz, mulv, zmu, B, 1.0f / (float)B_global, anneal, scal, reinterpret_cast<__nv_bfloat16*>(dmulv_bf16), ld, db_q1);
+  LTG_CHECK_LAUNCH();
+  return LTG_OK;
+}
+
+extern "C" int ltg_tanh_bwd(const float* dy, int ld_dy, const void* y_bf16, int ld_y, int B, int N, void* dx_bf16, int ld_dxb,
+                            float* dx_f32, int ld_dxf, float* dbias, void* stream) {
+  LTG_REQUIRE(dy && y_bf16);
+  if (B <= 0) return LTG_OK;
+  tanh_bwd_kernel<<<(B + COLSUM_ROWS - 1) / COLSUM_ROWS, 256, 0, (cudaStream_t)stream>>>(
+      dy, ld_dy, reinterpret_cast<const __nv_bfloat16*>(y_bf16), ld_y, B, N, reinterpret_cast<__nv_bfloat16*>(dx_bf16), ld_dxb, dx_f32,
+      ld_dxf, dbias);
+  LTG_CHECK_LAUNCH();
+  return LTG_OK;
+}
+
+extern "C" int ltg_dec_row_stats(const float* partial, int n_blocks, const void* logits_bf16, int ld_logits, int B,
+                                 const int32_t* indptr, const int32_t* indices, const float* values,
+                                 const int32_t* samp_ptr, const int32_t* samp_items, const int32_t* samp_valid,
+                                 float* lse, float* xw, float* s_u, float* scal, void* stream) {
+  LTG_REQUIRE(partial && lse && scal);
+  LTG_REQUIRE((indptr == nullptr && samp_ptr == nullptr) || logits_bf16 != nullptr);
+  if (B <= 0) return LTG_OK;
+  const int threads = 128;
+  dec_row_stats_kernel<<<(B * 32 + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float2*>(partial), n_blocks, reinterpret_cast<const __nv_bfloat16*>(logits_bf16), ld_logits, B, indptr, indices,
+      values, samp_ptr, samp_items, samp_valid, lse, xw, s_u, scal);
+  LTG_CHECK_LAUNCH();
+  return LTG_OK;
+}
+
+extern "C" int ltg_dec_probs(const void* logits_bf16, int ld_logits, const float* lse, int B, int n_items, float* out, int ld_out, void* stream) {
+  LTG_REQUIRE(logits_bf16 && lse && out);
+  if (B <= 0) return LTG_OK;
+  dim3 grid((n_items + 255) / 256, B);
+  dec_probs_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(logits_bf16), ld_logits, lse, n_items, out, ld_out);
+  LTG_CHECK_LAUNCH();
+  return LTG_OK;
+}
+
+extern "C" int ltg_dec_dlogits(const void* logits_bf16, int ld, const float* lse, const float* xw, const float* s_u, int B, int n_items,
+                               int B_global, float lam, const float* scal,
+                               const int32_t* indptr, const int32_t* indices, const float* values,
+                               const int32_t* samp_ptr, const int32_t* samp_items, const int32_t* samp_valid,
+                               void* dl_bf16, void* stream) {
+  LTG_REQUIRE(logits_bf16 && lse && xw && dl_bf16 && indptr && indices);
+  LTG_REQUIRE(ld % 8 == 0 && ld >= n_items);
+  LTG_REQUIRE(lam == 0.f || scal != nullptr);
+  if (B <= 0) return LTG_OK;
+  const int ld8 = ld / 8;
+  dim3 grid((ld8 + 255) / 256, B);
+  const float inv_bg = 1.0f / (float)B_global;
+  dlogits_dense_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(logits_bf16), ld8, lse, xw, s_u, n_items, inv_bg,
+                                                                lam, scal, reinterpret_cast<uint4*>(dl_bf16));
+  LTG_CHECK_LAUNCH();
+  const int threads = 128;
+  dlogits_sparse_kernel<<<(B * 32 + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(logits_bf16), ld, lse, B, inv_bg, lam, scal, indptr, indices, values, samp_ptr, samp_items,
+      samp_valid, reinterpret_cast<__nv_bfloat16*>(dl_bf16));
+  LTG_CHECK_LAUNCH();
+  return LTG_OK;
+}
