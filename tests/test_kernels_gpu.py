@@ -1,0 +1,506 @@
+"""GPU parity tests of the individual CUDA kernels, called through the C ABI (ops.py -> libltgan.so), against the
+CPU oracle (oracle/) or a plain torch fp32 restatement of the same op on the same seeded inputs.
+Tolerances: bit-exact for integer/index work and RNG bits; bf16-operand/fp32-accumulate GEMMs within 2e-2 of the
+fp32 product of the *bf16-rounded* operands scaled by sqrt(K) (the rounding of the inputs is shared)."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ltgan_oracle as orc  # noqa: E402
+from oracle import philox  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    pkg = importlib.import_module("long-tail-gan_b200")
+    pkg._lib.build()
+    o = importlib.import_module("long-tail-gan_b200.ops")
+    o.init()
+    return o
+
+
+def dev(x, dtype=None):
+    t = torch.as_tensor(x)
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda().contiguous()
+
+
+def rand_csr(rng, B, I, mean_nnz, min_nnz=1):
+    indptr = [0]
+    idx = []
+    for _ in range(B):
+        n = int(np.clip(rng.poisson(mean_nnz), min_nnz, I))
+        it = np.sort(rng.choice(I, size=n, replace=False))
+        idx.append(it)
+        indptr.append(indptr[-1] + n)
+    return np.asarray(indptr, dtype=np.int32), np.concatenate(idx).astype(np.int32)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# tcgen05 GEMM
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("bn", [64, 128, 256])
+def test_gemm_layouts(ops, a_mn, b_mn, bn):
+    torch.manual_seed(1)
+    M, N, K = 500, 600, 456  # ragged in every dimension (K tail handled by TMA zero fill)
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    Bm = torch.randn(N, K, device="cuda").bfloat16()
+    ref = A.float() @ Bm.float().t()
+    # physical layouts with padded pitches (multiples of 8 elements)
+    if a_mn:
+        Ap = torch.zeros(K, 504, device="cuda", dtype=torch.bfloat16); Ap[:, :M] = A.t()
+    else:
+        Ap = torch.zeros(M, 456 + 8, device="cuda", dtype=torch.bfloat16); Ap[:, :K] = A
+    if b_mn:
+        Bp = torch.zeros(K, 608, device="cuda", dtype=torch.bfloat16); Bp[:, :N] = Bm.t()
+    else:
+        Bp = torch.zeros(N, 456 + 8, device="cuda", dtype=torch.bfloat16); Bp[:, :K] = Bm
+    out = torch.full((M, 608), float("nan"), device="cuda")
+    outb = torch.zeros(M, 608, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(Ap, Bp, M, N, K, a_mn=a_mn, b_mn=b_mn, bn=bn, out_f32=out, out_bf16=outb)
+    torch.cuda.synchronize()
+    err = (out[:, :N] - ref).abs().max().item()
+    assert err < 2e-2 * np.sqrt(K), err
+    assert torch.isnan(out[:, N:]).all()  # nothing written outside N
+    assert (outb[:, :N].float() - ref).abs().max().item() < 0.02 * ref.abs().max().item() + 0.1
+
+
+def test_gemm_splitk_bias_act_aux(ops):
+    torch.manual_seed(2)
+    M, N, K = 300, 200, 4100
+    A = (torch.randn(M, K, device="cuda") * 0.05).bfloat16()
+    Bm = (torch.randn(N, K + 4, device="cuda") * 0.05).bfloat16()[:, :K]
+    Bp = torch.zeros(N, K + 4, device="cuda", dtype=torch.bfloat16); Bp[:, :K] = Bm
+    Ap = torch.zeros(M, K + 4, device="cuda", dtype=torch.bfloat16); Ap[:, :K] = A
+    ref = A.float() @ Bm.float().t()
+    out = torch.zeros(M, N, device="cuda")
+    ops.gemm(Ap, Bp, M, N, K, splits=16, bn=128, out_f32=out, atomic=True, alpha=0.5)
+    torch.cuda.synchronize()
+    assert (out - 0.5 * ref).abs().max().item() < 5e-3
+    # bias + tanh, bf16 out, aux column diverted
+    bias = torch.randn(N, device="cuda")
+    outb = torch.zeros(M, 208, device="cuda", dtype=torch.bfloat16)
+    aux = torch.zeros(M, device="cuda")
+    ops.gemm(Ap, Bp, M, N, K, bn=64, out_bf16=outb, bias=bias, act=1, aux_col=N - 1, aux_out=aux)
+    torch.cuda.synchronize()
+    want = torch.tanh(ref + bias)
+    assert (outb[:, :N - 1].float() - want[:, :N - 1]).abs().max().item() < 1e-2
+    assert (aux - want[:, N - 1]).abs().max().item() < 1e-2
+    assert (outb[:, N - 1:] == 0).all()
+
+
+def test_gemm_dropout_epilogue_bits(ops):
+    torch.manual_seed(3)
+    M, N, K = 260, 150, 128
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    Bm = torch.randn(N, K, device="cuda").bfloat16()
+    ref = torch.tanh(A.float() @ Bm.float().t())
+    out = torch.zeros(M, 152, device="cuda")
+    seed, step, keep = 0x1234567811, 7, 0.7
+    step_dev = torch.tensor([3], dtype=torch.int32, device="cuda")
+    ops.gemm(A, Bm, M, N, K, bn=128, out_f32=out, act=1, keep=keep, seed=seed, rng_stream=philox.STREAM_DISC_DROPOUT, rng_step=step,
+             rng_step_dev=step_dev, rng_ld=152)
+    torch.cuda.synchronize()
+    idx = (np.arange(M, dtype=np.uint64)[:, None] * np.uint64(152) + np.arange(N, dtype=np.uint64)[None, :])
+    mask = philox.keep_mask(seed, philox.STREAM_DISC_DROPOUT, step + 3, idx, keep)
+    got = out[:, :N].cpu().numpy()
+    assert ((got != 0) == (mask & (ref.cpu().numpy() != 0))).all()  # RNG bits identical
+    want = ref.cpu().numpy() * mask / np.float32(keep)
+    assert np.abs(got - want).max() < 2e-2
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# encoder gather, latent head, decoder statistics
+# ----------------------------------------------------------------------------------------------------------------
+def test_enc_gather_fwd_matches_oracle(ops):
+    rng = np.random.RandomState(0)
+    B, I = 37, 1000
+    indptr, indices = rand_csr(rng, B, I, 20)
+    indptr[-1]  # noqa
+    # one long row to cross the 512-nnz chunk boundary
+    W = (rng.randn(I, 600) * 0.05).astype(np.float32)
+    b = (rng.randn(600) * 0.01).astype(np.float32)
+    Wb = dev(W).bfloat16()
+    seed, step, keep, uid0 = 42, 5, 0.75, 1000
+    h1 = torch.zeros(B, 600, device="cuda", dtype=torch.bfloat16)
+    coef = torch.zeros(len(indices), device="cuda")
+    ops.enc_gather_fwd(dev(indptr), dev(indices), None, B, I, uid0, Wb, dev(b), keep, seed, step, None, h1, coef)
+    torch.cuda.synchronize()
+    X = np.zeros((B, I), dtype=np.float32)
+    rows = np.repeat(np.arange(B), np.diff(indptr))
+    X[rows, indices] = 1.0
+    idx = (np.uint64(uid0) + np.arange(B, dtype=np.uint64))[:, None] * np.uint64(I) + np.arange(I, dtype=np.uint64)[None, :]
+    mask = philox.keep_mask(seed, philox.STREAM_ENC_DROPOUT, step, idx, keep)
+    params = [Wb.float().cpu(), None, None, None, torch.from_numpy(b)]
+    Xt = torch.from_numpy(X)
+    h = Xt * torch.rsqrt(torch.clamp((Xt * Xt).sum(1, keepdim=True), min=1e-12)) * torch.from_numpy(mask).float() / keep
+    want = torch.tanh(h @ params[0] + params[4])
+    assert (h1.float().cpu() - want).abs().max().item() < 1e-2
+    # coefficients: exact mask bits, values to fp32 rounding
+    want_coef = h.numpy()[rows, indices]
+    got_coef = coef.cpu().numpy()
+    assert ((got_coef != 0) == (want_coef != 0)).all()
+    assert np.abs(got_coef - want_coef).max() < 1e-6
+
+
+def test_enc_gather_long_row_and_values(ops):
+    rng = np.random.RandomState(1)
+    I = 3000
+    n = 1300  # > 2 chunks of 512
+    indices = np.sort(rng.choice(I, n, replace=False)).astype(np.int32)
+    indptr = np.asarray([0, n, n, n + 0], dtype=np.int32)  # second and third rows empty
+    vals = rng.randint(1, 3, size=n).astype(np.float32)
+    W = (rng.randn(I, 600) * 0.05).astype(np.float32)
+    Wb = dev(W).bfloat16()
+    b = np.zeros(600, dtype=np.float32)
+    h1 = torch.zeros(3, 600, device="cuda", dtype=torch.bfloat16)
+    coef = torch.zeros(n, device="cuda")
+    ops.enc_gather_fwd(dev(indptr), dev(indices), dev(vals), 3, I, 0, Wb, dev(b), 1.0, 1, 0, None, h1, coef)
+    torch.cuda.synchronize()
+    x = np.zeros(I, dtype=np.float32); x[indices] = vals
+    want = np.tanh((x / np.sqrt((x * x).sum())) @ Wb.float().cpu().numpy())
+    assert np.abs(h1[0].float().cpu().numpy() - want).max() < 1e-2
+    assert (h1[1:].float().abs().max().item()) == 0.0  # empty rows: tanh(0 + 0)
+
+
+def test_latent_fwd_bwd(ops):
+    torch.manual_seed(5)
+    B, L = 45, 200
+    mulv = torch.randn(B, 2 * L, device="cuda") * 0.3
+    eps = torch.randn(B, L, device="cuda")
+    z = torch.zeros(B, L, device="cuda", dtype=torch.bfloat16)
+    zmu = torch.zeros(B, L, device="cuda")
+    scal = torch.zeros(16, device="cuda")
+    ops.latent_fwd(mulv, eps, B, 0, 1.0, 0, 0, None, z, zmu, scal)
+    torch.cuda.synchronize()
+    mu, lv = mulv[:, :L], mulv[:, L:]
+    kl = (0.5 * (-lv + lv.exp() + mu ** 2 - 1)).sum()
+    assert abs(scal[0].item() - kl.item()) < 1e-3 * abs(kl.item())
+    want_z = mu + eps * (0.5 * lv).exp()
+    assert (z.float() - want_z).abs().max().item() < 2e-2
+    assert (zmu - eps * (0.5 * lv).exp()).abs().max().item() < 1e-5
+    # philox eps stream matches the numpy mirror
+    ops.latent_fwd(mulv, None, B, 11, 1.0, 99, 4, None, z, zmu, scal)
+    torch.cuda.synchronize()
+    idx = (np.uint64(11) + np.arange(B, dtype=np.uint64))[:, None] * np.uint64(L) + np.arange(L, dtype=np.uint64)[None, :]
+    e = philox.normal_eps(99, 4, idx)
+    got_e = (zmu / (0.5 * lv).exp()).cpu().numpy()
+    assert np.abs(got_e - e).max() < 1e-3
+    # backward
+    dz = torch.randn(B, L, device="cuda")
+    dm = torch.zeros(B, 2 * L, device="cuda", dtype=torch.bfloat16)
+    db = torch.zeros(2 * L, device="cuda")
+    ops.latent_fwd(mulv, eps, B, 0, 1.0, 0, 0, None, z, zmu, scal)
+    ops.latent_bwd(dz, mulv, zmu, B, B, 0.2, None, dm, db)
+    torch.cuda.synchronize()
+    mulv_r = mulv.clone().requires_grad_(True)
+    mu_r, lv_r = mulv_r[:, :L], mulv_r[:, L:]
+    loss = ((mu_r + eps * (0.5 * lv_r).exp()) * dz).sum() + 0.2 * (0.5 * (-lv_r + lv_r.exp() + mu_r ** 2 - 1)).sum(1).mean()
+    g, = torch.autograd.grad(loss, mulv_r)
+    assert (dm.float() - g).abs().max().item() < 2e-2
+    assert (db - g.sum(0)).abs().max().item() < 5e-2
+
+
+def test_decoder_logits_stats_and_dlogits(ops):
+    torch.manual_seed(6)
+    rng = np.random.RandomState(6)
+    B, I = 70, 1203
+    ld = 1208
+    h2 = (torch.randn(B, 600, device="cuda") * 0.5).bfloat16()
+    WdT = (torch.randn(I, 600, device="cuda") * 0.08).bfloat16()
+    bd = torch.randn(I, device="cuda") * 0.1
+    logits = torch.zeros(B, ld, device="cuda", dtype=torch.bfloat16)
+    nblk = (I + 255) // 256
+    partial = torch.zeros(nblk, B, 2, device="cuda")
+    ops.dec_logits_fwd(h2, WdT, bd, B, I, logits, partial)
+    ref = h2.float() @ WdT.float().t() + bd
+    torch.cuda.synchronize()
+    assert (logits[:, :I].float() - ref).abs().max().item() < 0.03 * ref.abs().max().item()
+    indptr, indices = rand_csr(rng, B, I, 15)
+    # sampled lists
+    n_s = rng.randint(0, 6, size=B)
+    samp_ptr = np.concatenate([[0], np.cumsum(n_s)]).astype(np.int32)
+    samp_items = np.concatenate([np.sort(rng.choice(I, n, replace=False)) for n in n_s] + [np.zeros(0, dtype=np.int64)]).astype(np.int32)
+    samp_valid = (rng.rand(len(samp_items)) < 0.8).astype(np.int32)
+    lse = torch.zeros(B, device="cuda"); xw = torch.zeros(B, device="cuda"); su = torch.zeros(B, device="cuda")
+    scal = torch.zeros(16, device="cuda")
+    ops.dec_row_stats(partial, nblk, logits, B, dev(indptr), dev(indices), None, dev(samp_ptr), dev(samp_items), dev(samp_valid), lse, xw,
+                      su, scal)
+    torch.cuda.synchronize()
+    want_lse = torch.logsumexp(ref, dim=1)
+    assert (lse - want_lse).abs().max().item() < 2e-3
+    X = torch.zeros(B, I); X[np.repeat(np.arange(B), np.diff(indptr)), indices] = 1.0
+    lsm = torch.log_softmax(logits[:, :I].float().cpu(), dim=1)
+    want_nll = -(lsm * X).sum().item()
+    assert abs(scal[ops.S_NLL_SUM].item() - want_nll) < 1e-3 * abs(want_nll)
+    probs = torch.softmax(logits[:, :I].float().cpu(), dim=1)
+    m = torch.zeros(B, I)
+    rows_s = np.repeat(np.arange(B), n_s)
+    m[rows_s[samp_valid > 0], samp_items[samp_valid > 0]] = 1.0
+    want_sp = (probs * m).sum().item()
+    assert abs(scal[ops.S_SUM_P].item() - want_sp) < 2e-3 * abs(want_sp) + 1e-6
+    # dlogits against autograd of the reference formula (on the stashed logits)
+    lam = 1.0
+    scal[ops.S_SUM_Y] = 3.3; scal[ops.S_CNT] = 7.0
+    dl = torch.zeros(B, ld, device="cuda", dtype=torch.bfloat16)
+    ops.dec_dlogits(logits, lse, xw, su, B, I, B, lam, scal, dev(indptr), dev(indices), None, dev(samp_ptr), dev(samp_items),
+                    dev(samp_valid), dl)
+    torch.cuda.synchronize()
+    lg = logits[:, :I].float().cpu().requires_grad_(True)
+    ls = torch.log_softmax(lg, dim=1)
+    pr = torch.softmax(lg, dim=1)
+    loss = -(ls * X).sum(1).mean() - lam * (3.3 / 7.0) * (pr * m).sum()
+    g, = torch.autograd.grad(loss, lg)
+    err = (dl[:, :I].float().cpu() - g).abs().max().item()
+    assert err < 1e-2 * g.abs().max().item() + 1e-6, err
+    assert (dl[:, I:] == 0).all()
+    # probabilities (compat path)
+    out = torch.zeros(B, I, device="cuda")
+    ops.dec_probs(logits, lse, B, I, out)
+    torch.cuda.synchronize()
+    assert (out.cpu() - probs).abs().max().item() < 1e-3 * probs.max().item() + 1e-7
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Adam, encoder sparse gradient
+# ----------------------------------------------------------------------------------------------------------------
+def test_adam_matches_tf_formula(ops):
+    torch.manual_seed(7)
+    n = 600 * 37 + 3
+    p = torch.randn(n, device="cuda"); m = torch.randn(n, device="cuda") * 0.01; v = torch.rand(n, device="cuda") * 1e-4
+    g = torch.randn(n, device="cuda") * 0.1
+    p0, m0, v0 = p.cpu().clone(), m.cpu().clone(), v.cpu().clone()
+    sh = torch.zeros(n + 5, device="cuda", dtype=torch.bfloat16)[:n]
+    lr_t = orc.tf_adam_lr_t(1e-4, 17)
+    ops.adam(p, m, v, g, sh, lr_t=lr_t)
+    torch.cuda.synchronize()
+    orc.tf_adam_step(p0, m0, v0, g.cpu(), lr_t)
+    assert (p.cpu() - p0).abs().max().item() < 1e-6
+    assert (m.cpu() - m0).abs().max().item() < 1e-7
+    assert (v.cpu() - v0).abs().max().item() < 1e-9
+    assert (sh.float().cpu() - p0).abs().max().item() < 2e-2
+    # lr_t from the device step state
+    words = torch.zeros(4, dtype=torch.int32, device="cuda"); scal = torch.zeros(16, device="cuda")
+    for _ in range(3):
+        ops.step_advance(words, scal, 2, 1e-4)
+    torch.cuda.synchronize()
+    assert words.cpu().tolist()[:3] == [3, 3, 3]
+    assert abs(scal[ops.S_LR_T].item() - orc.tf_adam_lr_t(1e-4, 3)) < 1e-10
+    assert abs(scal[ops.S_ANNEAL].item() - orc.anneal_value(2)) < 1e-9
+
+
+def test_enc_wgrad_and_enc_adam(ops):
+    rng = np.random.RandomState(8)
+    B, I = 50, 400
+    indptr, indices = rand_csr(rng, B, I, 12)
+    nnz = len(indices)
+    coef = (rng.rand(nnz).astype(np.float32)) * (rng.rand(nnz) < 0.75)
+    dh1 = rng.randn(B, 600).astype(np.float32)
+    rows = np.repeat(np.arange(B), np.diff(indptr))
+    order = np.lexsort((rows, indices))
+    csc_ptr = np.zeros(I + 1, dtype=np.int32); np.add.at(csc_ptr, indices + 1, 1); csc_ptr = np.cumsum(csc_ptr).astype(np.int32)
+    csc_row = rows[order].astype(np.int32); csc_pos = order.astype(np.int32)
+    dW = torch.full((I, 600), float("nan"), device="cuda")
+    ops.enc_wgrad(dW, I, dev(csc_ptr), dev(csc_row), dev(csc_pos), dev(coef), dev(dh1))
+    torch.cuda.synchronize()
+    Xc = np.zeros((B, I), dtype=np.float32); Xc[rows, indices] = coef
+    want = Xc.T @ dh1
+    assert np.abs(dW.cpu().numpy() - want).max() < 1e-4
+    p = torch.randn(I, 600, device="cuda"); m = torch.zeros(I, 600, device="cuda"); v = torch.zeros(I, 600, device="cuda")
+    m += 0.01  # rows without gradient must still move (dense Adam, F7)
+    p0, m0, v0 = p.cpu().clone(), m.cpu().clone(), v.cpu().clone()
+    p_init = p.cpu().clone()
+    sh = torch.zeros(I, 600, device="cuda", dtype=torch.bfloat16)
+    ops.enc_adam(p, m, v, sh, I, dev(csc_ptr), dev(csc_row), dev(csc_pos), dev(coef), dev(dh1), lr_t=1e-3)
+    torch.cuda.synchronize()
+    orc.tf_adam_step(p0, m0, v0, torch.from_numpy(want), 1e-3)
+    assert (p.cpu() - p0).abs().max().item() < 1e-5
+    assert (sh.float().cpu() - p0).abs().max().item() < 2e-2
+    untouched = np.diff(csc_ptr) == 0
+    assert untouched.any() and (p.cpu()[untouched] != p_init[untouched]).all()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# sampler
+# ----------------------------------------------------------------------------------------------------------------
+def _sampler_inputs(rng, B, I, ld):
+    logits = (rng.randn(B, ld) * 1.5).astype(np.float32)
+    niche = np.arange(I // 10, I)  # 90% of the catalog is "niche"
+    cand, n_s, pops = [], [], []
+    for u in range(B):
+        n = int(rng.randint(0, 12)) if u % 7 else 0
+        own = np.sort(rng.choice(niche, n, replace=False))
+        others = np.setdiff1d(niche, own)
+        extra = rng.choice(others, max(2 * n, 10 - n), replace=False)
+        cand.append(np.sort(np.concatenate([own, extra])).astype(np.int32))
+        n_s.append(n)
+        pops.append(rng.choice(I // 10, size=rng.randint(1, 8), replace=False).astype(np.int32))
+    return logits, cand, np.asarray(n_s), pops
+
+
+def test_sampler_matches_gumbel_topk_oracle_bit_exact(ops):
+    rng = np.random.RandomState(9)
+    B, I, ld = 64, 1000, 1000
+    logits, cand, n_s, pops = _sampler_inputs(rng, B, I, ld)
+    lg = dev(logits).bfloat16()
+    cand_ptr = np.concatenate([[0], np.cumsum([len(c) for c in cand])]).astype(np.int32)
+    samp_ptr = np.concatenate([[0], np.cumsum(n_s)]).astype(np.int32)
+    pop_ptr = np.concatenate([[0], np.cumsum([len(p) for p in pops])]).astype(np.int32)
+    valid = np.ones(I, dtype=np.uint8); valid[[418, 447, 595]] = 0
+    K = int(samp_ptr[-1])
+    si = torch.full((K,), -7, dtype=torch.int32, device="cuda"); sp = torch.full((K,), -7, dtype=torch.int32, device="cuda")
+    sv = torch.full((K,), -7, dtype=torch.int32, device="cuda")
+    scal = torch.zeros(16, device="cuda")
+    seed, step, uid0 = 777, 3, 500
+    ops.sample_pairs(lg, B, I, uid0, dev(cand_ptr), dev(np.concatenate(cand)), dev(samp_ptr), dev(pop_ptr), dev(np.concatenate(pops)),
+                     dev(valid), seed, step, None, si, sp, sv, scal, int(max(len(c) for c in cand)))
+    torch.cuda.synchronize()
+    si, sp, sv = si.cpu().numpy(), sp.cpu().numpy(), sv.cpu().numpy()
+    lgf = lg.float().cpu().numpy()
+    nvalid = 0
+    for u in range(B):
+        s0, s1 = samp_ptr[u], samp_ptr[u + 1]
+        if s1 == s0:
+            continue
+        idx = np.uint64(uid0 + u) * np.uint64(I) + cand[u].astype(np.uint64)
+        # device computes -log(-log(u)) with fast intrinsics; compare sets, allowing only near-ties to differ
+        want = orc.gumbel_topk_sample(cand[u], lgf[u], n_s[u], philox.gumbel(seed, step, idx))
+        got = si[s0:s1]
+        assert (np.diff(got) > 0).all()
+        if not np.array_equal(got, want):
+            keys = lgf[u][cand[u]] + philox.gumbel(seed, step, idx)
+            kth = np.sort(keys)[::-1][n_s[u] - 1:n_s[u] + 1]
+            assert abs(kth[0] - kth[1]) < 1e-4, (u, got, want)
+        r = philox.rand_u32(seed, philox.STREAM_PARTNER, step, np.uint64(uid0 + u) * np.uint64(I) + got.astype(np.uint64))
+        want_p = pops[u][((r.astype(np.uint64) * np.uint64(len(pops[u]))) >> np.uint64(32)).astype(np.int64)]
+        assert np.array_equal(sp[s0:s1], want_p)
+        want_v = (valid[got] & valid[want_p]).astype(np.int32)
+        assert np.array_equal(sv[s0:s1], want_v)
+        nvalid += int(want_v.sum())
+    assert scal[ops.S_CNT].item() == nvalid
+
+
+def test_sampler_distribution_chi_square(ops):
+    """Distributional parity with sample.py:54 (np.random.choice without replacement): per-item inclusion counts of the
+    device sampler vs the oracle's restatement over many draws (chi-square, alpha = 1e-3)."""
+    from scipy import stats
+    rng = np.random.RandomState(10)
+    I = 64
+    cand = np.sort(rng.choice(np.arange(8, I), 9, replace=False)).astype(np.int32)
+    n_draw = 3
+    logit_row = (rng.randn(I) * 1.2).astype(np.float32)
+    R = 20000  # users all sharing the same candidate set / logits, distinct RNG keys
+    lg = dev(np.tile(logit_row, (R, 1))).bfloat16()
+    cand_ptr = (np.arange(R + 1) * len(cand)).astype(np.int32)
+    samp_ptr = (np.arange(R + 1) * n_draw).astype(np.int32)
+    pop_ptr = np.arange(R + 1).astype(np.int32)
+    si = torch.zeros(R * n_draw, dtype=torch.int32, device="cuda"); sp = torch.zeros_like(si); sv = torch.zeros_like(si)
+    scal = torch.zeros(16, device="cuda")
+    ops.sample_pairs(lg, R, I, 0, dev(cand_ptr), dev(np.tile(cand, R)), dev(samp_ptr), dev(pop_ptr), dev(np.zeros(R, dtype=np.int32)),
+                     dev(np.ones(I, dtype=np.uint8)), 2024, 1, None, si, sp, sv, scal, len(cand))
+    torch.cuda.synchronize()
+    got = np.bincount(si.cpu().numpy(), minlength=I)[cand]
+    p = np.exp(lg[0].float().cpu().numpy()[cand].astype(np.float64)); p /= p.sum()
+    ref_rng = np.random.RandomState(11)
+    ref = np.zeros(I, dtype=np.int64)
+    for _ in range(R):
+        _, ids = orc.sample_from_generator_new(cand, p, n_draw, I, ref_rng)
+        ref[ids] += 1
+    ref = ref[cand]
+    chi2, pval, _, _ = stats.chi2_contingency(np.stack([got, ref]))
+    assert pval > 1e-3, (pval, got, ref)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# top-k metrics
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_topk_metrics_exact(ops, dtype):
+    from scipy import sparse
+    rng = np.random.RandomState(12)
+    n, I, k = 57, 2500, 100
+    scores = rng.randn(n, I).astype(np.float32)
+    scores[3, :] = 0.25           # a fully tied row
+    scores[4, ::2] = 1.0          # half the row tied at the top
+    t = dev(scores)
+    if dtype == "bf16":
+        t = t.bfloat16()
+        scores = t.float().cpu().numpy()
+    seen_ptr, seen_items = rand_csr(rng, n, I, 30)
+    held_ptr, held_items = rand_csr(rng, n, I, 10, min_nnz=0)
+    topk = torch.zeros(n, k, dtype=torch.int32, device="cuda")
+    dcg = torch.zeros(n, dtype=torch.float64, device="cuda")
+    hits = torch.zeros(n, 2, dtype=torch.int32, device="cuda")
+    ops.topk_metrics(t, n, I, dev(seen_ptr), dev(seen_items), dev(held_ptr), dev(held_items), k, [20, 50], topk, dcg, hits)
+    torch.cuda.synchronize()
+    masked = scores.copy()
+    masked[np.repeat(np.arange(n), np.diff(seen_ptr)), seen_items] = -np.inf
+    want = orc.topk_indices(masked, k)
+    assert np.array_equal(topk.cpu().numpy(), want)  # bit-exact index lists (ties: lowest index first)
+    held = sparse.csr_matrix((np.ones(len(held_items)), held_items, held_ptr), shape=(n, I))
+    tp = 1.0 / np.log2(np.arange(2, k + 2))
+    want_dcg = (held[np.arange(n)[:, None], want].toarray() * tp).sum(1)
+    assert np.abs(dcg.cpu().numpy() - want_dcg).max() < 1e-12
+    for j, kk in enumerate((20, 50)):
+        want_hits = held[np.arange(n)[:, None], want[:, :kk]].toarray().sum(1)
+        assert np.array_equal(hits.cpu().numpy()[:, j], want_hits.astype(np.int32))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# discriminator pieces
+# ----------------------------------------------------------------------------------------------------------------
+def test_disc_gather_head_and_backward(ops):
+    torch.manual_seed(13)
+    I, P, h3, ld = 500, 333, 300, 304
+    E = torch.zeros(I, 128, device="cuda", dtype=torch.bfloat16); E[:, :100] = (torch.randn(I, 100, device="cuda") * 0.1).bfloat16()
+    pop = torch.randint(0, I, (P,), dtype=torch.int32, device="cuda"); niche = torch.randint(0, I, (P,), dtype=torch.int32, device="cuda")
+    Xp = torch.zeros(P, 128, device="cuda", dtype=torch.bfloat16); Xn = torch.zeros_like(Xp)
+    ops.disc_gather(E, pop, niche, P, Xp, Xn)
+    torch.cuda.synchronize()
+    assert torch.equal(Xp, E[pop.long()]) and torch.equal(Xn, E[niche.long()])
+    keep = 0.7
+    t3 = torch.tanh(torch.randn(P, h3, device="cuda"))
+    mask = (torch.rand(P, h3, device="cuda") < keep)
+    Y3 = torch.zeros(P, ld, device="cuda", dtype=torch.bfloat16); Y3[:, :h3] = (t3 * mask / keep).bfloat16()
+    w4 = torch.randn(h3, device="cuda") * 0.1; b4 = torch.tensor([0.05], device="cuda")
+    label = torch.randint(-1, 2, (P,), dtype=torch.int32, device="cuda")
+    y = torch.zeros(P, device="cuda"); scal = torch.zeros(16, device="cuda")
+    dz3 = torch.full((P, ld), 7.0, device="cuda", dtype=torch.bfloat16); dz3[:, h3:] = 0
+    dw4 = torch.zeros(h3, device="cuda"); db3 = torch.zeros(h3, device="cuda")
+    ops.disc_head(Y3, P, h3, w4, b4, label, keep, y, scal, dz3, dw4, db3)
+    torch.cuda.synchronize()
+    Yf = Y3[:, :h3].float()
+    a = Yf.clone().requires_grad_(True); w4r = w4.clone().requires_grad_(True); b4r = b4.clone().requires_grad_(True)
+    yr = torch.sigmoid(a @ w4r + b4r)
+    real, gen = label == 0, label == 1
+    loss = -torch.log(yr[real]).sum() - torch.log(1 - yr[gen]).sum()
+    ga, gw, gb = torch.autograd.grad(loss, [a, w4r, b4r])
+    assert (y - yr).abs().max().item() < 1e-5
+    assert abs(scal[ops.S_D_LOSS].item() - loss.item()) < 1e-3 * abs(loss.item())
+    assert abs(scal[ops.S_SUM_Y].item() - yr[gen].sum().item()) < 1e-3
+    assert abs(scal[ops.S_DB4].item() - gb.item()) < 1e-3
+    assert (dw4 - gw).abs().max().item() < 1e-3
+    dact = torch.where(Yf != 0, (1 - (Yf * keep) ** 2) / keep, torch.zeros_like(Yf))
+    want_dz3 = ga * dact
+    assert (dz3[:, :h3].float() - want_dz3).abs().max().item() < 1e-2 * want_dz3.abs().max().item() + 1e-6
+    assert (db3 - want_dz3.sum(0)).abs().max().item() < 2e-2
+    assert (dz3[label.long() < 0][:, :h3] == 0).all()
+    # backward through a dropout(tanh) layer
+    dH = torch.randn(P, 416, device="cuda")
+    Hact = torch.zeros(P, 416, device="cuda", dtype=torch.bfloat16); Hact[:, :h3] = Y3[:, :h3]
+    dz = torch.zeros(P, 416, device="cuda", dtype=torch.bfloat16); db = torch.zeros(h3, device="cuda")
+    ops.drop_tanh_bwd(dH, Hact, P, h3, keep, dz, db)
+    torch.cuda.synchronize()
+    want = dH[:, :h3] * dact
+    assert (dz[:, :h3].float() - want).abs().max().item() < 2e-2 * want.abs().max().item()
+    assert (db - want.sum(0)).abs().max().item() < 5e-2
