@@ -32,9 +32,8 @@ enum {
   LTG_S_NLL_SUM = 1,  /* sum_u -sum_i x_ui log_softmax   MultiVAE.py:110-112 (before the batch mean) */
   LTG_S_SUM_P = 2,    /* sum over sampled (u,i) of softmax prob   train.py:145-149 */
   LTG_S_SUM_Y = 3,    /* sum over valid generated pairs of y      train.py:155 */
-  LTG_S_CNT = 4,      /* number of valid generated pairs (sampled_cnt)  train.py:251,316 */
+  LTG_S_CNT = 4,      /* number of valid generated pairs (sampled_cnt)  train.py:251,316; counted by ltg_disc_head */
   LTG_S_D_LOSS = 5,   /* d_loss  train.py:142 */
-  LTG_S_DB4 = 6,      /* grad of d_b4 */
   LTG_S_LR_T = 8,     /* Adam: lr*sqrt(1-b2^t)/(1-b1^t), written by ltg_step_advance */
   LTG_S_ANNEAL = 9,   /* KL anneal weight of this G step, written by ltg_step_advance */
   LTG_NSCAL = 16
@@ -124,22 +123,22 @@ int ltg_enc_wgrad(float* dW, int n_items, const int32_t* csc_ptr, const int32_t*
  * Per user u: candidates cand[cand_ptr[u]..), draw n_u = samp_ptr[u+1]-samp_ptr[u] items without replacement with
  * probability proportional to softmax(logits)[u, cand] (Gumbel-top-k == numpy's successive draw in distribution, F9),
  * emit them in ascending item order at slots samp_ptr[u].., each paired with a uniformly drawn popular item of the user
- * (pop_ptr/pop_items), valid[slot] = both ids in the item-feature table (item_valid[n_items] bytes, F10).
- * scal[LTG_S_CNT] += number of valid pairs.                                                                             */
+ * (pop_ptr/pop_items), valid[slot] = +1 if both ids are in the item-feature table (item_valid[n_items] bytes, F10), else -1.
+ * *cnt (int32, may be NULL) += number of valid pairs.                                                                            */
 int ltg_sample_pairs(const void* logits_bf16, int ld_logits, int B, int n_items, int64_t uid0,
                      const int32_t* cand_ptr, const int32_t* cand_items, const int32_t* samp_ptr,
                      const int32_t* pop_ptr, const int32_t* pop_items, const uint8_t* item_valid,
                      uint64_t seed, uint32_t step, const uint32_t* step_dev,
-                     int32_t* samp_items, int32_t* samp_partner, int32_t* samp_valid, float* scal, int max_cand, void* stream);
+                     int32_t* samp_items, int32_t* samp_partner, int32_t* samp_valid, int32_t* cnt, int max_cand, void* stream);
 
 /* ---- a11/a12: discriminator (discriminator.py:14-55, train.py:142) --------------------------------------------------
  * Frozen embedding gather (F5): rows of E_bf16 [n_items, 128] (cols 100.. are zero) -> Xp, Xn bf16 [P, 128].            */
 int ltg_disc_gather(const void* E_bf16, const int32_t* pop_ids, const int32_t* niche_ids, int P, void* Xp, void* Xn, void* stream);
 /* Head: s = Y3*w4 + b4, y = sigmoid(s); label[row]: 0 real, 1 generated, <0 ignored.
- * Accumulates scal[D_LOSS], scal[SUM_Y] (generated rows), and when dz3 != NULL the backward seed:
- * dz3 bf16 [P, ld] = ds*w4*dact(Y3), dw4[h3] += Y3^T ds, scal[DB4] += sum ds, db3[h3] += colsum(dz3).                    */
+ * Accumulates scal[D_LOSS], scal[SUM_Y] and scal[CNT] (generated rows), and when dz3 != NULL the backward seed:
+ * dz3 bf16 [P, ld] = ds*w4*dact(Y3), dw4[h3] += Y3^T ds, *db4 += sum ds, db3[h3] += colsum(dz3).                    */
 int ltg_disc_head(const void* Y3_bf16, int ld, int P, int h3, const float* w4, const float* b4, const int32_t* label,
-                  float keep, float* y_out, float* scal, void* dz3_bf16, float* dw4, float* db3, void* stream);
+                  float keep, float* y_out, float* scal, void* dz3_bf16, float* dw4, float* db3, float* db4, void* stream);
 /* dz = dH * dact(Hact) for a dropout(tanh) layer stored post-dropout in bf16; column sums -> dbias (atomic).             */
 int ltg_drop_tanh_bwd(const float* dH, int ld_dh, const void* Hact_bf16, int ld_h, int P, int N, float keep,
                       void* dz_bf16, int ld_dz, float* dbias, void* stream);

@@ -96,7 +96,7 @@ SIGNATURES = {
     "ltg_enc_wgrad": (_I, [_P, _I, _P, _P, _P, _P, _P, _I, _P]),
     "ltg_sample_pairs": (_I, [_P, _I, _I, _I, _I64, _P, _P, _P, _P, _P, _P, _U64, _U32, _P, _P, _P, _P, _P, _I, _P]),
     "ltg_disc_gather": (_I, [_P, _P, _P, _I, _P, _P, _P]),
-    "ltg_disc_head": (_I, [_P, _I, _I, _I, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P]),
+    "ltg_disc_head": (_I, [_P, _I, _I, _I, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P]),
     "ltg_drop_tanh_bwd": (_I, [_P, _I, _P, _I, _I, _I, _F, _P, _I, _P, _P]),
     "ltg_topk_metrics": (_I, [_P, _I, _I64, _I, _I, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _P]),
     "ltg_cast_bf16": (_I, [_P, _I64, _P, _I64, _I64, _I64, _P]),

@@ -35,19 +35,19 @@ constexpr int HEAD_MAXH3 = 512;
 __global__ void __launch_bounds__(HEAD_THREADS)
 disc_head_kernel(const __nv_bfloat16* __restrict__ Y3, int ld, int P, int h3, const float* __restrict__ w4, const float* __restrict__ b4,
                  const int32_t* __restrict__ label, float keep, float* __restrict__ y_out, float* __restrict__ scal,
-                 __nv_bfloat16* __restrict__ dz3, float* __restrict__ dw4, float* __restrict__ db3) {
+                 __nv_bfloat16* __restrict__ dz3, float* __restrict__ dw4, float* __restrict__ db3, float* __restrict__ db4) {
   __shared__ float s_w4[HEAD_MAXH3];
   __shared__ float s_dw4[HEAD_MAXH3];
   __shared__ float s_db3[HEAD_MAXH3];
-  __shared__ float s_acc[3];  // d_loss, sum_y, db4
+  __shared__ float s_acc[4];  // d_loss, sum_y, db4, cnt
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool bwd = dz3 != nullptr;
   const bool drop = keep > 0.f && keep < 1.f;
   for (int j = tid; j < h3; j += HEAD_THREADS) { s_w4[j] = w4[j]; s_dw4[j] = 0.f; s_db3[j] = 0.f; }
-  if (tid < 3) s_acc[tid] = 0.f;
+  if (tid < 4) s_acc[tid] = 0.f;
   __syncthreads();
   const float bias = b4[0];
-  float loss = 0.f, sumy = 0.f, sds = 0.f;
+  float loss = 0.f, sumy = 0.f, sds = 0.f, ngen = 0.f;
   for (int rr = warp; rr < HEAD_ROWS; rr += HEAD_THREADS / 32) {
     const int row = blockIdx.x * HEAD_ROWS + rr;
     if (row >= P) break;
@@ -63,7 +63,7 @@ disc_head_kernel(const __nv_bfloat16* __restrict__ Y3, int ld, int P, int h3, co
     const float sp = (lab == 0) ? -s : s;
     const float l = lab < 0 ? 0.f : fmaxf(sp, 0.f) + log1pf(__expf(-fabsf(sp)));
     const float ds = lab < 0 ? 0.f : ((lab == 0) ? (y - 1.0f) : y);
-    if (lane == 0) { loss += l; if (lab == 1) sumy += y; sds += ds; }
+    if (lane == 0) { loss += l; if (lab == 1) { sumy += y; ngen += 1.f; } sds += ds; }
     if (bwd) {
       __nv_bfloat16* dr = dz3 + (size_t)row * ld;
       for (int j = lane; j < h3; j += 32) {
@@ -75,12 +75,13 @@ disc_head_kernel(const __nv_bfloat16* __restrict__ Y3, int ld, int P, int h3, co
       }
     }
   }
-  if (lane == 0) { atomicAdd(&s_acc[0], loss); atomicAdd(&s_acc[1], sumy); atomicAdd(&s_acc[2], sds); }
+  if (lane == 0) { atomicAdd(&s_acc[0], loss); atomicAdd(&s_acc[1], sumy); atomicAdd(&s_acc[2], sds); atomicAdd(&s_acc[3], ngen); }
   __syncthreads();
   if (tid == 0) {
     atomicAdd(scal + LTG_S_D_LOSS, s_acc[0]);
     atomicAdd(scal + LTG_S_SUM_Y, s_acc[1]);
-    if (bwd) atomicAdd(scal + LTG_S_DB4, s_acc[2]);
+    atomicAdd(scal + LTG_S_CNT, s_acc[3]);
+    if (bwd && db4 != nullptr) atomicAdd(db4, s_acc[2]);
   }
   if (bwd) {
     for (int j = tid; j < h3; j += HEAD_THREADS) {
@@ -132,13 +133,13 @@ extern "C" int ltg_disc_gather(const void* E_bf16, const int32_t* pop_ids, const
 }
 
 extern "C" int ltg_disc_head(const void* Y3_bf16, int ld, int P, int h3, const float* w4, const float* b4, const int32_t* label,
-                             float keep, float* y_out, float* scal, void* dz3_bf16, float* dw4, float* db3, void* stream) {
+                             float keep, float* y_out, float* scal, void* dz3_bf16, float* dw4, float* db3, float* db4, void* stream) {
   LTG_REQUIRE(Y3_bf16 && w4 && b4 && label && scal);
   LTG_REQUIRE(h3 > 0 && h3 <= HEAD_MAXH3 && ld >= h3);
   if (P <= 0) return LTG_OK;
   disc_head_kernel<<<(P + HEAD_ROWS - 1) / HEAD_ROWS, HEAD_THREADS, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(Y3_bf16), ld, P, h3, w4, b4, label, keep, y_out, scal, reinterpret_cast<__nv_bfloat16*>(dz3_bf16),
-      dw4, db3);
+      dw4, db3, db4);
   LTG_CHECK_LAUNCH();
   return LTG_OK;
 }

@@ -30,7 +30,7 @@ sample_pairs_kernel(const __nv_bfloat16* __restrict__ logits, int ld, int n_item
                     const int32_t* __restrict__ pop_ptr, const int32_t* __restrict__ pop_items, const uint8_t* __restrict__ item_valid,
                     uint64_t seed, uint32_t step, const uint32_t* __restrict__ step_dev,
                     int32_t* __restrict__ samp_items, int32_t* __restrict__ samp_partner, int32_t* __restrict__ samp_valid,
-                    float* __restrict__ scal) {
+                    int32_t* __restrict__ cnt_out) {
   extern __shared__ uint32_t s_keys[];  // [max_cand]
   __shared__ uint32_t s_hist[256];
   __shared__ uint32_t s_sel[2];          // digit, remaining-k
@@ -130,7 +130,7 @@ sample_pairs_kernel(const __nv_bfloat16* __restrict__ logits, int ld, int n_item
       const int ok = (partner >= 0 && item_valid[item] && item_valid[partner]) ? 1 : 0;  // train.py:240-243
       samp_items[slot] = item;
       samp_partner[slot] = partner >= 0 ? partner : 0;
-      samp_valid[slot] = ok;
+      samp_valid[slot] = ok ? 1 : -1;
       if (ok) atomicAdd(&s_nvalid, 1);
     }
     __syncthreads();
@@ -139,9 +139,9 @@ sample_pairs_kernel(const __nv_bfloat16* __restrict__ logits, int ld, int n_item
   }
   // slots that could not be filled (n < nslots)
   for (int j = n + tid; j < nslots; j += SAMP_THREADS) {
-    samp_items[s0 + j] = 0; samp_partner[s0 + j] = 0; samp_valid[s0 + j] = 0;
+    samp_items[s0 + j] = 0; samp_partner[s0 + j] = 0; samp_valid[s0 + j] = -1;
   }
-  if (tid == 0 && s_nvalid > 0) atomicAdd(scal + LTG_S_CNT, (float)s_nvalid);
+  if (tid == 0 && s_nvalid > 0 && cnt_out != nullptr) atomicAdd(cnt_out, s_nvalid);
 }
 
 }  // namespace
@@ -150,9 +150,9 @@ extern "C" int ltg_sample_pairs(const void* logits_bf16, int ld_logits, int B, i
                                 const int32_t* cand_ptr, const int32_t* cand_items, const int32_t* samp_ptr,
                                 const int32_t* pop_ptr, const int32_t* pop_items, const uint8_t* item_valid,
                                 uint64_t seed, uint32_t step, const uint32_t* step_dev,
-                                int32_t* samp_items, int32_t* samp_partner, int32_t* samp_valid, float* scal, int max_cand, void* stream) {
+                                int32_t* samp_items, int32_t* samp_partner, int32_t* samp_valid, int32_t* cnt, int max_cand, void* stream) {
   LTG_REQUIRE(logits_bf16 && cand_ptr && cand_items && samp_ptr && pop_ptr && pop_items && item_valid);
-  LTG_REQUIRE(samp_items && samp_partner && samp_valid && scal);
+  LTG_REQUIRE(samp_items && samp_partner && samp_valid);
   LTG_REQUIRE(max_cand >= 0 && (size_t)max_cand * 4 <= 200 * 1024);
   if (B <= 0) return LTG_OK;
   const size_t smem = (size_t)(max_cand > 0 ? max_cand : 1) * sizeof(uint32_t);
@@ -164,7 +164,7 @@ extern "C" int ltg_sample_pairs(const void* logits_bf16, int ld_logits, int B, i
   }
   sample_pairs_kernel<<<B, SAMP_THREADS, smem, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(logits_bf16), ld_logits, n_items, uid0, cand_ptr, cand_items, samp_ptr, pop_ptr, pop_items,
-      item_valid, seed, step, step_dev, samp_items, samp_partner, samp_valid, scal);
+      item_valid, seed, step, step_dev, samp_items, samp_partner, samp_valid, cnt);
   LTG_CHECK_LAUNCH();
   return LTG_OK;
 }

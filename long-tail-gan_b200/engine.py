@@ -1,0 +1,351 @@
+"""The GAN step of Long-Tail-GAN on one B200: phase A (generator inference + niche sampling + pair construction),
+D update, G update and ranking evaluation, as sequences of CUDA kernels launched through the C ABI.
+
+This replaces the body of the reference's epoch loop (Codes/train.py:192-348) and test loop (Codes/test.py:138-171):
+every `sess.run` site becomes one method below, the host NumPy loops (train.py:212-251) become ltg_sample_pairs, and
+the dense fp32/fp64 feeds (X, generated_tags mask) become CSR / index lists that stay on the device.
+
+Device-resident step state (`words`, `scal`) makes every method CUDA-graph capturable: nothing the kernels need comes
+from the host after the launch arguments are fixed (RNG step, Adam bias correction and KL anneal are advanced on the
+device by ltg_step_advance). `GanEngine.run_*` therefore capture one graph per (phase, batch) on first use and replay it.
+"""
+import numpy as np
+import torch
+
+from . import ops
+from .generator import H, L
+
+
+def _pad(n, q):
+    return (n + q - 1) // q * q
+
+
+class TrainData(object):
+    """Everything phase A/D/G need about the training users, resident on the device, plus per-batch index structures.
+
+    Host inputs (NumPy, int32 CSR-style):
+      indptr/indices           training interactions (data_processing.load_train_data)
+      pop_ptr/pop_items        the user's popular items (train_GAN_popular.csv order), `train.py:91`
+      n_niche[u]               number of niche items of the user (= number of draws, train.py:227)
+      cand_ptr/cand_items      sorted candidate set USER_TAGS_TO_SAMPLE (data_processing.py:170-224)
+      real_ptr/real_niche/real_pop   precomputed real pairs (data_processing.py:227-271)
+      eligible[u]              user has both popular and niche items (train.py:213)
+      item_valid[i]            item is in ITEM_FEATURE_DICT (data_processing.py:40-70)
+    """
+
+    def __init__(self, n_items, indptr, indices, pop_ptr, pop_items, n_niche, cand_ptr, cand_items, real_ptr, real_niche, real_pop,
+                 eligible, item_valid, batch_size, device="cuda", uid_start=0):
+        self.n_items = int(n_items)
+        self.N = len(indptr) - 1
+        self.batch_size = int(batch_size)
+        self.device = torch.device(device)
+        self.uid_start = int(uid_start)
+        i32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(self.device)  # noqa: E731
+        self.h_indptr = np.asarray(indptr, dtype=np.int64)
+        self.h_indices = np.asarray(indices, dtype=np.int32)
+        self.indptr = i32(indptr); self.indices = i32(indices)
+        self.pop_ptr = i32(pop_ptr); self.pop_items = i32(pop_items if len(pop_items) else np.zeros(1))
+        self.cand_ptr = i32(cand_ptr); self.cand_items = i32(cand_items if len(cand_items) else np.zeros(1))
+        self.item_valid = torch.as_tensor(np.ascontiguousarray(item_valid, dtype=np.uint8)).to(self.device)
+        self.coef = torch.zeros(max(1, len(indices)), dtype=torch.float32, device=self.device)
+        eligible = np.asarray(eligible, dtype=bool)
+        n_draw = np.where(eligible, np.asarray(n_niche, dtype=np.int64), 0)
+        cand_len = np.diff(np.asarray(cand_ptr, dtype=np.int64))
+        n_draw = np.minimum(n_draw, cand_len)
+        real_ptr = np.asarray(real_ptr, dtype=np.int64)
+        self.batches = []
+        for b0 in range(0, self.N, self.batch_size):
+            b1 = min(self.N, b0 + self.batch_size)
+            self.batches.append(self._make_batch(b0, b1, n_draw, real_ptr, real_niche, real_pop, cand_len))
+        self.max_B = max(bt["B"] for bt in self.batches)
+        self.max_P = max(bt["P"] for bt in self.batches)
+        self.max_K = max(bt["K"] for bt in self.batches)
+
+    def _make_batch(self, b0, b1, n_draw, real_ptr, real_niche, real_pop, cand_len):
+        B = b1 - b0
+        dev = self.device
+        e0, e1 = int(self.h_indptr[b0]), int(self.h_indptr[b1])
+        idx = self.h_indices[e0:e1].astype(np.int64)
+        rows = np.repeat(np.arange(B, dtype=np.int64), np.diff(self.h_indptr[b0:b1 + 1]))
+        order = np.lexsort((rows, idx))  # item-major, then batch row
+        csc_ptr = np.zeros(self.n_items + 1, dtype=np.int64)
+        np.add.at(csc_ptr, idx + 1, 1)
+        csc_ptr = np.cumsum(csc_ptr)
+        samp_ptr = np.concatenate([[0], np.cumsum(n_draw[b0:b1])])
+        K = int(samp_ptr[-1])
+        r0, r1 = int(real_ptr[b0]), int(real_ptr[b1])
+        Pr = r1 - r0
+        P = Pr + K
+        pair_pop = np.zeros(max(P, 1), dtype=np.int32); pair_niche = np.zeros(max(P, 1), dtype=np.int32)
+        label = np.full(max(P, 1), -1, dtype=np.int32)
+        pair_pop[:Pr] = real_pop[r0:r1]; pair_niche[:Pr] = real_niche[r0:r1]; label[:Pr] = 0
+        t = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(dev)  # noqa: E731
+        return dict(b0=b0, B=B, uid0=self.uid_start + b0, nnz=e1 - e0, Pr=Pr, K=K, P=P,
+                    csc_ptr=t(csc_ptr), csc_row=t(rows[order]), csc_pos=t(order + e0), samp_ptr=t(samp_ptr),
+                    pair_pop=t(pair_pop), pair_niche=t(pair_niche), label=t(label),
+                    cnt=torch.zeros(1, dtype=torch.int32, device=dev),
+                    max_cand=int(cand_len[b0:b1].max()) if B > 0 else 0)
+
+
+class GanEngine(object):
+    """Owns the workspaces and runs phase A / D / G / evaluation for one (vae, discriminator) pair."""
+
+    def __init__(self, vae, disc, max_B, max_P=1, seed=0, lr=1e-4, lam=1.0, keep_vae=0.75, keep_d=0.7, total_anneal_steps=20000,
+                 anneal_cap=0.2, B_global=None, use_graphs=True):
+        ops.init()
+        self.vae, self.disc = vae, disc
+        self.I = vae.n_items
+        self.ld = _pad(self.I, 8)
+        self.nblk = (self.I + 255) // 256
+        self.seed, self.lr, self.lam = int(seed), float(lr), float(lam)
+        self.keep_vae, self.keep_d = float(keep_vae), float(keep_d)
+        self.total_anneal_steps, self.anneal_cap = float(total_anneal_steps), float(anneal_cap)
+        self.B_global = B_global
+        self.use_graphs = use_graphs
+        self.device = vae.device
+        self.max_B, self.max_P = int(max_B), int(max(1, max_P))
+        self.words = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self.scal = torch.zeros(ops.NSCAL, dtype=torch.float32, device=self.device)
+        self._graphs = {}
+        self._alloc()
+        self.dgrad_splits = 8
+        self.eps_inject = None  # optional [B, L] fp32 tensor used instead of the Philox normal (parity tests)
+
+    def _alloc(self):
+        dev, B, P, I, ld = self.device, self.max_B, self.max_P, self.I, self.ld
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        d = self.disc
+        # VAE activations
+        self.h1 = torch.zeros(B, H, **bf)
+        self.mulv = torch.zeros(B, 2 * L, **f32)
+        self.z = torch.zeros(B, L, **bf)
+        self.zmu = torch.zeros(B, L, **f32)
+        self.h2 = torch.zeros(B, 608, **bf)
+        self.h2[:, H] = 1.0  # ones column: wgrad's column 600 becomes the decoder-bias gradient
+        self.logits = torch.zeros(B, ld, **bf)
+        self.dl = torch.zeros(B, ld, **bf)
+        self.partial = torch.zeros(self.nblk, B, 2, **f32)
+        self.lse = torch.zeros(B, **f32); self.xw = torch.zeros(B, **f32); self.su = torch.zeros(B, **f32)
+        self.dWdT = torch.zeros(I, H, **f32)
+        self.dh2pre = torch.zeros(B, H, **bf)
+        self.dmulv = torch.zeros(B, 2 * L, **bf)
+        self.dh1pre = torch.zeros(B, H, **f32)
+        # fp32 accumulators that must be zero at the start of a G step: one arena, one memset
+        self.zero_g = torch.zeros(B * H + B * L + B * H, **f32)
+        self.dh2 = self.zero_g[: B * H].view(B, H)
+        self.dz = self.zero_g[B * H: B * H + B * L].view(B, L)
+        self.dh1 = self.zero_g[B * H + B * L:].view(B, H)
+        # discriminator
+        self.Xp = torch.zeros(P, 128, **bf); self.Xn = torch.zeros(P, 128, **bf)
+        self.Hd = torch.zeros(P, d.k3, **bf)
+        self.Y3 = torch.zeros(P, d.ld3, **bf)
+        self.y = torch.zeros(P, **f32)
+        self.dz3 = torch.zeros(P, d.ld3, **bf)
+        self.dH = torch.zeros(P, d.k3, **f32)
+        self.dz12 = torch.zeros(P, d.k3, **bf)
+
+    # ------------------------------------------------------------------------------------------------------------
+    # building blocks
+    # ------------------------------------------------------------------------------------------------------------
+    def _vae_forward(self, data, bt, is_training, keep, stash=True, indptr=None, indices=None, coef=None, uid0=None, B=None):
+        """MultiVAE.forward_pass (MultiVAE.py:175-186) up to the logits and their softmax statistics."""
+        v = self.vae
+        B = bt["B"] if B is None else B
+        indptr = data.indptr[bt["b0"]: bt["b0"] + B + 1] if indptr is None else indptr
+        indices = data.indices if indices is None else indices
+        coef = data.coef if coef is None else coef
+        uid0 = bt["uid0"] if uid0 is None else uid0
+        ops.enc_gather_fwd(indptr, indices, None, B, self.I, uid0, v.W_q0_b, v.view("b_q0"), keep, self.seed, 0, self.words, self.h1, coef)
+        ops.gemm(self.h1, v.view("W_q1", "b"), B, 2 * L, H, b_mn=True, bn=64, out_f32=self.mulv, bias=v.view("b_q1"))
+        ops.latent_fwd(self.mulv, self.eps_inject if is_training else None, B, uid0, 1.0 if is_training else 0.0, self.seed, 0,
+                       self.words, self.z, self.zmu, self.scal)
+        ops.gemm(self.z, v.view("W_p0", "b"), B, H, L, b_mn=True, bn=64, out_bf16=self.h2, bias=v.view("b_p0"), act=1)
+        ops.dec_logits_fwd(self.h2, v.WdT_b, v.view("b_p1"), B, self.I, self.logits if stash else None, self.partial)
+        return indptr, indices
+
+    def _disc_forward(self, pop, niche, label, P, backward):
+        """discriminator.py:16-55 on P pairs (real and generated share the weights, so they run as one batch)."""
+        d = self.disc
+        seed, kd = self.seed, self.keep_d
+        st = ops.STREAM_DISC_DROPOUT
+        ops.disc_gather(d.E_b, pop, niche, P, self.Xp, self.Xn)
+        b12 = d.view("b12")
+        ops.gemm(self.Xp, d.view("W1", "b"), P, d.h1, d.h0, lda=128, b_mn=True, bn=64, out_bf16=self.Hd, ld_bf16=d.k3, bias=b12, act=1,
+                 keep=kd, seed=seed, rng_stream=st, rng_step_dev=self.words, rng_ld=d.ld1)
+        ops.gemm(self.Xn, d.view("W2", "b"), P, d.h2, d.h0, lda=128, b_mn=True, bn=64, out_bf16=self.Hd[:, d.off2:], ld_bf16=d.k3,
+                 bias=b12[d.off2:], act=1, keep=kd, seed=seed, rng_stream=st + 1, rng_step_dev=self.words, rng_ld=d.ld2)
+        ops.gemm(self.Hd, d.view("W3", "b"), P, d.h3, d.k3, b_mn=True, bn=64, out_bf16=self.Y3, bias=d.view("b3"), act=1, keep=kd, seed=seed,
+                 rng_stream=st + 2, rng_step_dev=self.words, rng_ld=d.ld3)
+        if backward:
+            ops.disc_head(self.Y3, P, d.h3, d.view("w4"), d.view("b4"), label, kd, self.y, self.scal, self.dz3, d.view("w4", "g"),
+                          d.view("b3", "g"), d.view("b4", "g"))
+        else:
+            ops.disc_head(self.Y3, P, d.h3, d.view("w4"), d.view("b4"), label, kd, self.y, self.scal)
+
+    # ------------------------------------------------------------------------------------------------------------
+    # phase A: train.py:192-269
+    # ------------------------------------------------------------------------------------------------------------
+    def phase_a(self, data, bi):
+        bt = data.batches[bi]
+        B = bt["B"]
+        self.scal.zero_()
+        ops.step_advance(self.words, self.scal, 0, self.lr, anneal_cap=self.anneal_cap, total_anneal_steps=self.total_anneal_steps)
+        # train.py:200: sess.run(generator_out) with default placeholders: dropout 0.75 (F4), is_training 0
+        self._vae_forward(data, bt, False, self.keep_vae)
+        bt["cnt"].zero_()
+        if bt["K"] > 0:
+            Pr = bt["Pr"]
+            ops.sample_pairs(self.logits, B, self.I, bt["uid0"], data.cand_ptr[bt["b0"]: bt["b0"] + B + 1], data.cand_items, bt["samp_ptr"],
+                             data.pop_ptr[bt["b0"]: bt["b0"] + B + 1], data.pop_items, data.item_valid, self.seed, 0, self.words,
+                             bt["pair_niche"][Pr:], bt["pair_pop"][Pr:], bt["label"][Pr:], bt["cnt"], bt["max_cand"])
+
+    # ------------------------------------------------------------------------------------------------------------
+    # D update: train.py:300
+    # ------------------------------------------------------------------------------------------------------------
+    def d_step(self, data, bi):
+        bt = data.batches[bi]
+        d = self.disc
+        P = bt["P"]
+        self.scal.zero_()
+        d.arena_g.zero_()
+        ops.step_advance(self.words, self.scal, 1, self.lr, anneal_cap=self.anneal_cap, total_anneal_steps=self.total_anneal_steps)
+        self._disc_forward(bt["pair_pop"], bt["pair_niche"], bt["label"], P, True)
+        sp = max(1, min(32, P // 512))
+        # dW3 = Hd^T dz3 ; dH = dz3 W3^T ; dz12 = dH * dact ; dW1 = Xp^T dz1 ; dW2 = Xn^T dz2     (autodiff of discriminator.py:25-55)
+        ops.gemm(self.Hd, self.dz3, d.k3, d.h3, P, a_mn=True, b_mn=True, splits=sp, bn=64, out_f32=d.view("W3", "g"), atomic=True)
+        ops.gemm(self.dz3, d.view("W3", "b"), P, d.k3, d.h3, bn=64, out_f32=self.dH)
+        ops.drop_tanh_bwd(self.dH, self.Hd, P, d.k3, self.keep_d, self.dz12, d.view("b12", "g"))
+        ops.gemm(self.Xp, self.dz12, d.h0, d.h1, P, a_mn=True, b_mn=True, splits=sp, bn=64, out_f32=d.view("W1", "g"), atomic=True)
+        ops.gemm(self.Xn, self.dz12[:, d.off2:], d.h0, d.h2, P, a_mn=True, b_mn=True, ldb=d.k3, splits=sp, bn=64,
+                 out_f32=d.view("W2", "g"), atomic=True)
+        ops.adam(d.arena, d.arena_m, d.arena_v, d.arena_g, d.arena_b, scal=self.scal)
+
+    # ------------------------------------------------------------------------------------------------------------
+    # G update: train.py:326
+    # ------------------------------------------------------------------------------------------------------------
+    def g_step(self, data, bi, update=True):
+        bt = data.batches[bi]
+        v = self.vae
+        B, Pr, K = bt["B"], bt["Pr"], bt["K"]
+        Bg = B if self.B_global is None else self.B_global
+        self.scal.zero_()
+        self.zero_g.zero_()
+        v.small_g.zero_()
+        ops.step_advance(self.words, self.scal, 2, self.lr, anneal_cap=self.anneal_cap, total_anneal_steps=self.total_anneal_steps)
+        indptr, indices = self._vae_forward(data, bt, True, self.keep_vae)
+        lam = self.lam if K > 0 else 0.0
+        samp = (bt["samp_ptr"], bt["pair_niche"][Pr:], bt["label"][Pr:]) if K > 0 else (None, None, None)
+        if K > 0:
+            # y_generated with fresh dropout masks (keep_prob 0.7 is fed in the G step too, train.py:326)
+            self._disc_forward(bt["pair_pop"][Pr:], bt["pair_niche"][Pr:], bt["label"][Pr:], K, False)
+        ops.dec_row_stats(self.partial, self.nblk, self.logits, B, indptr, indices, None, samp[0], samp[1], samp[2], self.lse, self.xw,
+                          self.su, self.scal)
+        ops.dec_dlogits(self.logits, self.lse, self.xw, self.su, B, self.I, Bg, lam, self.scal, indptr, indices, None, samp[0], samp[1],
+                        samp[2], self.dl)
+        # decoder backward: dh2 = dl W_p1^T (split-K over the catalog), dW_p1^T = dl^T [h2 | 1]
+        ops.gemm(self.dl, v.WdT_b, B, H, self.I, b_mn=True, splits=self.dgrad_splits, bn=128, out_f32=self.dh2, atomic=True)
+        ops.gemm(self.dl, self.h2, self.I, H + 1, B, a_mn=True, b_mn=True, bn=128, out_f32=self.dWdT, ld_f32=H, aux_col=H,
+                 aux_out=v.view("b_p1", "g"))
+        ops.tanh_bwd(self.dh2, self.h2, B, H, dx_bf16=self.dh2pre, dbias=v.view("b_p0", "g"))
+        ops.gemm(self.dh2pre, v.view("W_p0", "b"), B, L, H, bn=64, out_f32=self.dz)
+        ops.gemm(self.z, self.dh2pre, L, H, B, a_mn=True, b_mn=True, bn=64, out_f32=v.view("W_p0", "g"))
+        ops.latent_bwd(self.dz, self.mulv, self.zmu, B, Bg, -1.0, self.scal, self.dmulv, v.view("b_q1", "g"))
+        ops.gemm(self.dmulv, v.view("W_q1", "b"), B, H, 2 * L, bn=64, out_f32=self.dh1)
+        ops.gemm(self.h1, self.dmulv, H, 2 * L, B, a_mn=True, b_mn=True, bn=64, out_f32=v.view("W_q1", "g"))
+        ops.tanh_bwd(self.dh1, self.h1, B, H, dx_f32=self.dh1pre, dbias=v.view("b_q0", "g"))
+        if update:
+            ops.enc_adam(v.W_q0, v.W_q0_m, v.W_q0_v, v.W_q0_b, self.I, bt["csc_ptr"], bt["csc_row"], bt["csc_pos"], data.coef,
+                         self.dh1pre, scal=self.scal)
+            ops.adam(v.WdT, v.WdT_m, v.WdT_v, self.dWdT, v.WdT_b, scal=self.scal)
+            ops.adam(v.small, v.small_m, v.small_v, v.small_g, v.small_b, scal=self.scal)
+
+    # ------------------------------------------------------------------------------------------------------------
+    # graph capture / replay
+    # ------------------------------------------------------------------------------------------------------------
+    def _run(self, key, fn):
+        if not self.use_graphs:
+            fn()
+            return
+        g = self._graphs.get(key)
+        if g is None:
+            fn()  # eager warm-up (also opts kernels into their shared-memory sizes outside of capture)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()  # capture only: the eager call above already performed this step
+            self._graphs[key] = g
+            return
+        g.replay()
+
+    def run_phase_a(self, data, bi):
+        self._run(("a", id(data), bi), lambda: self.phase_a(data, bi))
+
+    def run_d_step(self, data, bi):
+        self._run(("d", id(data), bi), lambda: self.d_step(data, bi))
+
+    def run_g_step(self, data, bi):
+        self._run(("g", id(data), bi), lambda: self.g_step(data, bi))
+
+    # ------------------------------------------------------------------------------------------------------------
+    # losses of the last step (host reads; train.py:303,329 print them once per sub-epoch)
+    # ------------------------------------------------------------------------------------------------------------
+    def last_losses(self, B, B_global=None):
+        s = self.scal.detach().cpu().numpy().astype(np.float64)
+        Bg = B if B_global is None else B_global
+        neg_ll = s[ops.S_NLL_SUM] / Bg
+        kl = s[ops.S_KL_SUM] / Bg
+        anneal = s[ops.S_ANNEAL]
+        vae_loss = neg_ll + anneal * kl
+        cnt = s[ops.S_CNT]
+        gan = -(self.lam / cnt) * s[ops.S_SUM_P] * s[ops.S_SUM_Y] if cnt > 0 else 0.0
+        return dict(neg_ll=neg_ll, KL=kl, anneal=anneal, vae_loss=vae_loss, gan_loss=gan, g_loss=vae_loss + gan, d_loss=s[ops.S_D_LOSS],
+                    cnt=cnt, sum_p=s[ops.S_SUM_P], sum_y=s[ops.S_SUM_Y])
+
+    # ------------------------------------------------------------------------------------------------------------
+    # evaluation: train.py:333-348, test.py:138-173 + eval_functions.py
+    # ------------------------------------------------------------------------------------------------------------
+    def evaluate(self, tr_indptr, tr_indices, te_indptr, te_indices, k=100, recall_ks=(20, 50), batch=None, uid_start=0, keep=None):
+        """Scores every eval user from its fold-in interactions, masks them, ranks, and returns the per-user lists
+        (ndcg@k, recall@rk...) over users with a non-empty held-out set, exactly like eval_functions.py."""
+        dev = self.device
+        N = len(tr_indptr) - 1
+        batch = self.max_B if batch is None else min(batch, self.max_B)
+        keep = self.keep_vae if keep is None else keep
+        trp = torch.as_tensor(np.ascontiguousarray(tr_indptr, dtype=np.int32)).to(dev)
+        tri = torch.as_tensor(np.ascontiguousarray(tr_indices, dtype=np.int32)).to(dev)
+        tep = torch.as_tensor(np.ascontiguousarray(te_indptr, dtype=np.int32)).to(dev)
+        tei = torch.as_tensor(np.ascontiguousarray(te_indices if len(te_indices) else np.zeros(1), dtype=np.int32)).to(dev)
+        coef = torch.zeros(max(1, len(tr_indices)), dtype=torch.float32, device=dev)
+        scores = torch.zeros(batch, self.ld, dtype=torch.float32, device=dev)
+        dcg = torch.zeros(N, dtype=torch.float64, device=dev)
+        hits = torch.zeros(N, len(recall_ks), dtype=torch.int32, device=dev)
+        v = self.vae
+        for b0 in range(0, N, batch):
+            B = min(batch, N - b0)
+            self.scal.zero_()
+            ops.step_advance(self.words, self.scal, 0, self.lr)
+            ip = trp[b0: b0 + B + 1]
+            ops.enc_gather_fwd(ip, tri, None, B, self.I, uid_start + b0, v.W_q0_b, v.view("b_q0"), keep, self.seed, 0, self.words,
+                               self.h1, coef)
+            ops.gemm(self.h1, v.view("W_q1", "b"), B, 2 * L, H, b_mn=True, bn=64, out_f32=self.mulv, bias=v.view("b_q1"))
+            ops.latent_fwd(self.mulv, None, B, uid_start + b0, 0.0, self.seed, 0, self.words, self.z, self.zmu, self.scal)
+            ops.gemm(self.z, v.view("W_p0", "b"), B, H, L, b_mn=True, bn=64, out_bf16=self.h2, bias=v.view("b_p0"), act=1)
+            # fp32 logits: softmax is monotone per row, so ranking the logits equals ranking generator_out
+            ops.gemm(self.h2, v.WdT_b, B, self.I, H, bn=256, out_f32=scores, bias=v.view("b_p1"))
+            ops.topk_metrics(scores, B, self.I, ip, tri, tep[b0: b0 + B + 1], tei, k, recall_ks, None, dcg[b0:], hits[b0:])
+        torch.cuda.synchronize()
+        return metrics_from_counts(dcg.cpu().numpy(), hits.cpu().numpy(), np.diff(np.asarray(te_indptr, dtype=np.int64)), k, recall_ks)
+
+
+def metrics_from_counts(dcg, hits, n_held, k, recall_ks):
+    """Host tail of eval_functions.py: IDCG (29-30), the IDCG!=0 / denom!=0 filters (34-36, 58-60), fp64 like NumPy."""
+    tp = 1.0 / np.log2(np.arange(2, k + 2))
+    csum = np.concatenate([[0.0], np.cumsum(tp)])
+    idcg = csum[np.minimum(n_held, k)]
+    keep = n_held > 0
+    out = {"ndcg@%d" % k: (dcg[keep] / idcg[keep]).tolist()}
+    for j, rk in enumerate(recall_ks):
+        denom = np.minimum(rk, n_held)
+        out["recall@%d" % rk] = (hits[keep, j].astype(np.float32) / denom[keep]).tolist()
+    return out

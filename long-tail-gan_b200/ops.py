@@ -9,7 +9,7 @@ from ._lib import check, ptr
 H = 600
 L = 200
 
-S_KL_SUM, S_NLL_SUM, S_SUM_P, S_SUM_Y, S_CNT, S_D_LOSS, S_DB4 = 0, 1, 2, 3, 4, 5, 6
+S_KL_SUM, S_NLL_SUM, S_SUM_P, S_SUM_Y, S_CNT, S_D_LOSS = 0, 1, 2, 3, 4, 5
 S_LR_T, S_ANNEAL, NSCAL = 8, 9, 16
 
 STREAM_ENC_DROPOUT = 1
@@ -116,19 +116,19 @@ def enc_wgrad(dW, n_items, csc_ptr, csc_row, csc_pos, coef, dh1pre):
 
 
 def sample_pairs(logits, B, n_items, uid0, cand_ptr, cand_items, samp_ptr, pop_ptr, pop_items, item_valid, seed, step, step_dev,
-                 samp_items, samp_partner, samp_valid, scal, max_cand):
+                 samp_items, samp_partner, samp_valid, cnt, max_cand):
     check(lib().ltg_sample_pairs(ptr(logits), logits.stride(0), B, n_items, uid0, ptr(cand_ptr), ptr(cand_items), ptr(samp_ptr),
                                  ptr(pop_ptr), ptr(pop_items), ptr(item_valid), seed, step, ptr(step_dev), ptr(samp_items),
-                                 ptr(samp_partner), ptr(samp_valid), ptr(scal), max_cand, _stream()))
+                                 ptr(samp_partner), ptr(samp_valid), ptr(cnt), max_cand, _stream()))
 
 
 def disc_gather(E_bf16, pop_ids, niche_ids, P, Xp, Xn):
     check(lib().ltg_disc_gather(ptr(E_bf16), ptr(pop_ids), ptr(niche_ids), P, ptr(Xp), ptr(Xn), _stream()))
 
 
-def disc_head(Y3, P, h3, w4, b4, label, keep, y_out, scal, dz3=None, dw4=None, db3=None):
+def disc_head(Y3, P, h3, w4, b4, label, keep, y_out, scal, dz3=None, dw4=None, db3=None, db4=None):
     check(lib().ltg_disc_head(ptr(Y3), Y3.stride(0), P, h3, ptr(w4), ptr(b4), ptr(label), keep, ptr(y_out), ptr(scal), ptr(dz3),
-                              ptr(dw4), ptr(db3), _stream()))
+                              ptr(dw4), ptr(db3), ptr(db4), _stream()))
 
 
 def drop_tanh_bwd(dH, Hact, P, N, keep, dz, dbias):

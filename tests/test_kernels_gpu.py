@@ -287,7 +287,7 @@ def test_adam_matches_tf_formula(ops):
     orc.tf_adam_step(p0, m0, v0, g.cpu(), lr_t)
     assert (p.cpu() - p0).abs().max().item() < 1e-6
     assert (m.cpu() - m0).abs().max().item() < 1e-7
-    assert (v.cpu() - v0).abs().max().item() < 1e-9
+    assert (v.cpu() - v0).abs().max().item() < 1e-8
     assert (sh.float().cpu() - p0).abs().max().item() < 2e-2
     # lr_t from the device step state
     words = torch.zeros(4, dtype=torch.int32, device="cuda"); scal = torch.zeros(16, device="cuda")
@@ -316,7 +316,7 @@ def test_enc_wgrad_and_enc_adam(ops):
     Xc = np.zeros((B, I), dtype=np.float32); Xc[rows, indices] = coef
     want = Xc.T @ dh1
     assert np.abs(dW.cpu().numpy() - want).max() < 1e-4
-    p = torch.randn(I, 600, device="cuda"); m = torch.zeros(I, 600, device="cuda"); v = torch.zeros(I, 600, device="cuda")
+    p = torch.randn(I, 600, device="cuda"); m = torch.zeros(I, 600, device="cuda"); v = torch.rand(I, 600, device="cuda") * 1e-2 + 1e-3
     m += 0.01  # rows without gradient must still move (dense Adam, F7)
     p0, m0, v0 = p.cpu().clone(), m.cpu().clone(), v.cpu().clone()
     p_init = p.cpu().clone()
@@ -360,10 +360,10 @@ def test_sampler_matches_gumbel_topk_oracle_bit_exact(ops):
     K = int(samp_ptr[-1])
     si = torch.full((K,), -7, dtype=torch.int32, device="cuda"); sp = torch.full((K,), -7, dtype=torch.int32, device="cuda")
     sv = torch.full((K,), -7, dtype=torch.int32, device="cuda")
-    scal = torch.zeros(16, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
     seed, step, uid0 = 777, 3, 500
     ops.sample_pairs(lg, B, I, uid0, dev(cand_ptr), dev(np.concatenate(cand)), dev(samp_ptr), dev(pop_ptr), dev(np.concatenate(pops)),
-                     dev(valid), seed, step, None, si, sp, sv, scal, int(max(len(c) for c in cand)))
+                     dev(valid), seed, step, None, si, sp, sv, cnt, int(max(len(c) for c in cand)))
     torch.cuda.synchronize()
     si, sp, sv = si.cpu().numpy(), sp.cpu().numpy(), sv.cpu().numpy()
     lgf = lg.float().cpu().numpy()
@@ -385,9 +385,9 @@ def test_sampler_matches_gumbel_topk_oracle_bit_exact(ops):
         want_p = pops[u][((r.astype(np.uint64) * np.uint64(len(pops[u]))) >> np.uint64(32)).astype(np.int64)]
         assert np.array_equal(sp[s0:s1], want_p)
         want_v = (valid[got] & valid[want_p]).astype(np.int32)
-        assert np.array_equal(sv[s0:s1], want_v)
+        assert np.array_equal(sv[s0:s1], np.where(want_v > 0, 1, -1))
         nvalid += int(want_v.sum())
-    assert scal[ops.S_CNT].item() == nvalid
+    assert cnt.item() == nvalid
 
 
 def test_sampler_distribution_chi_square(ops):
@@ -405,9 +405,9 @@ def test_sampler_distribution_chi_square(ops):
     samp_ptr = (np.arange(R + 1) * n_draw).astype(np.int32)
     pop_ptr = np.arange(R + 1).astype(np.int32)
     si = torch.zeros(R * n_draw, dtype=torch.int32, device="cuda"); sp = torch.zeros_like(si); sv = torch.zeros_like(si)
-    scal = torch.zeros(16, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
     ops.sample_pairs(lg, R, I, 0, dev(cand_ptr), dev(np.tile(cand, R)), dev(samp_ptr), dev(pop_ptr), dev(np.zeros(R, dtype=np.int32)),
-                     dev(np.ones(I, dtype=np.uint8)), 2024, 1, None, si, sp, sv, scal, len(cand))
+                     dev(np.ones(I, dtype=np.uint8)), 2024, 1, None, si, sp, sv, cnt, len(cand))
     torch.cuda.synchronize()
     got = np.bincount(si.cpu().numpy(), minlength=I)[cand]
     p = np.exp(lg[0].float().cpu().numpy()[cand].astype(np.float64)); p /= p.sum()
@@ -476,8 +476,8 @@ def test_disc_gather_head_and_backward(ops):
     label = torch.randint(-1, 2, (P,), dtype=torch.int32, device="cuda")
     y = torch.zeros(P, device="cuda"); scal = torch.zeros(16, device="cuda")
     dz3 = torch.full((P, ld), 7.0, device="cuda", dtype=torch.bfloat16); dz3[:, h3:] = 0
-    dw4 = torch.zeros(h3, device="cuda"); db3 = torch.zeros(h3, device="cuda")
-    ops.disc_head(Y3, P, h3, w4, b4, label, keep, y, scal, dz3, dw4, db3)
+    dw4 = torch.zeros(h3, device="cuda"); db3 = torch.zeros(h3, device="cuda"); db4 = torch.zeros(1, device="cuda")
+    ops.disc_head(Y3, P, h3, w4, b4, label, keep, y, scal, dz3, dw4, db3, db4)
     torch.cuda.synchronize()
     Yf = Y3[:, :h3].float()
     a = Yf.clone().requires_grad_(True); w4r = w4.clone().requires_grad_(True); b4r = b4.clone().requires_grad_(True)
@@ -488,7 +488,8 @@ def test_disc_gather_head_and_backward(ops):
     assert (y - yr).abs().max().item() < 1e-5
     assert abs(scal[ops.S_D_LOSS].item() - loss.item()) < 1e-3 * abs(loss.item())
     assert abs(scal[ops.S_SUM_Y].item() - yr[gen].sum().item()) < 1e-3
-    assert abs(scal[ops.S_DB4].item() - gb.item()) < 1e-3
+    assert abs(db4.item() - gb.item()) < 1e-3
+    assert scal[ops.S_CNT].item() == int(gen.sum().item())
     assert (dw4 - gw).abs().max().item() < 1e-3
     dact = torch.where(Yf != 0, (1 - (Yf * keep) ** 2) / keep, torch.zeros_like(Yf))
     want_dz3 = ga * dact
