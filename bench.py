@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""Headline benchmark: GAN-step users/sec of the Long-Tail-GAN hot path at the ML-20M-shaped configuration
+(136,677 users x 20,108 items, VAE 600-200, batch 500 per GPU), BASELINE.json `configs[1]`.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torch.distributed.run, one rank per GPU)
+  python bench.py --impl reference ...                     (the reference's CPU data flow on the host cores)
+
+One "step" = one GAN step over one batch of B users per GPU: phase A (generator inference + niche sampling + pair
+construction, train.py:192-269) + one discriminator update (train.py:300) + one generator update (train.py:326).
+`value` is users/sec with the inputs resident in HBM; `e2e` is the same step with the batch's inputs copied from pinned
+host memory and the losses read back inside the timed region. Prints ONE JSON line on rank 0.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CONFIG = "ml20m"
+BATCH = 500
+N_BENCH_BATCHES = 8   # distinct user batches cycled through by the timed steps (per GPU)
+H0, H1, H2, H3 = 100, 150, 250, 300   # config.ini h0..h3_size
+LR, LAM = 1e-4, 1.0                    # config.ini LEARNING_RATE, GANLAMBDA
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=48)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-steps", type=int, default=6, help="steps of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            rows = [r.strip().split(",") for r in open(self.path).read().strip().splitlines() if r.strip()]
+            sm = sorted(float(r[0]) for r in rows)
+            if sm:
+                out["sm_mhz"] = sm[len(sm) // 2]
+                out["sm_max_mhz"] = float(rows[0][1])
+                out["samples"] = len(sm)
+                out["power_w_max"] = max(float(r[2]) for r in rows)
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for j, nm in enumerate(names):
+                    if any(r[3 + j].strip().lower().startswith("active") for r in rows):
+                        out["reasons"].append(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return out
+
+
+def cpu_baseline(tabs, n_steps, n_items):
+    """The reference's CPU data flow (oracle/cpu_step.py) on a bounded sample of the same workload."""
+    import torch
+    from oracle.cpu_step import CpuGanStep
+    step = CpuGanStep(n_items, H0, H1, H2, H3, LR, LAM)
+    N = len(tabs["indptr"]) - 1
+    step.step(tabs, 0, min(BATCH, N))  # warm-up (thread pools, allocator)
+    t0 = time.perf_counter()
+    users = 0
+    parts = {"t_a": 0.0, "t_d": 0.0, "t_g": 0.0}
+    for i in range(n_steps):
+        b0 = ((i + 1) * BATCH) % max(BATCH, N - BATCH + 1)
+        r = step.step(tabs, b0, min(N, b0 + BATCH))
+        users += min(N, b0 + BATCH) - b0
+        for k in parts:
+            parts[k] += r[k]
+    dt = time.perf_counter() - t0
+    return dict(value=users / dt, unit="users/s", cores=torch.get_num_threads(), kind="port",
+                sample="%d GAN steps (A+D+G) of %d users at the %s shape, dense fp32 PyTorch-CPU restatement of the TF graph + the "
+                       "reference's host sampling loop; %.2f s/step (A %.2f, D %.2f, G %.2f)"
+                       % (n_steps, BATCH, CONFIG, dt / n_steps, parts["t_a"] / n_steps, parts["t_d"] / n_steps, parts["t_g"] / n_steps),
+                host_cpu_count=os.cpu_count())
+
+
+def workload_config(world):
+    syn = importlib.import_module("long-tail-gan_b200.synthetic")
+    N, I, deg = syn.CONFIGS[CONFIG]
+    return dict(workload="ML-20M-shaped synthetic: %d users x %d items, VAE 600-200, batch %d per GPU, GAN step = A + D + G" % (N, I, BATCH),
+                users=N, items=I, batch_per_gpu=BATCH, global_batch=BATCH * world, parallelism="dp%d" % world,
+                disc="h0..h3 = %d/%d/%d/%d" % (H0, H1, H2, H3), ganlambda=LAM,
+                l2_policy="per-step working set (weights + Adam state, ~0.8 GB touched) exceeds the 126 MB L2; timed steps cycle over "
+                          "%d distinct user batches; no explicit flush" % N_BENCH_BATCHES)
+
+
+def run_reference(args, rank, world):
+    """`--impl reference`: rank 0 times the reference's CPU path (port; TensorFlow is not installable here)."""
+    if rank != 0:
+        return
+    syn = importlib.import_module("long-tail-gan_b200.synthetic")
+    N, I, deg = syn.CONFIGS[CONFIG]
+    n_steps = max(1, min(args.steps, 8))
+    tabs = syn.make_config(CONFIG, n_users=BATCH * (n_steps + 2))
+    cb = cpu_baseline(tabs, n_steps, I)
+    line = dict(impl="reference", metric="gan_step_users_per_sec", value=cb["value"], unit="users/s", n_gpus=world, steps=n_steps,
+                warmup=1, ms_per_step=1e3 * BATCH / cb["value"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="fp32",
+                data="synthetic", config=workload_config(world), cpu_baseline=cb,
+                e2e=dict(value=cb["value"], unit="users/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(0)
+    if args.gpus != world and rank == 0 and world == 1 and args.gpus > 1:
+        print("bench.py: --gpus %d requested but WORLD_SIZE=1; launch with torch.distributed.run" % args.gpus, file=sys.stderr)
+
+    pkg = importlib.import_module("long-tail-gan_b200")
+    pkg._lib.build()
+    syn = importlib.import_module("long-tail-gan_b200.synthetic")
+    gen = importlib.import_module("long-tail-gan_b200.generator")
+    dis = importlib.import_module("long-tail-gan_b200.discriminator")
+    eng = importlib.import_module("long-tail-gan_b200.engine")
+    ops = importlib.import_module("long-tail-gan_b200.ops")
+    ops.init()
+
+    N, I, deg = syn.CONFIGS[CONFIG]
+    nb = N_BENCH_BATCHES
+    # every rank owns its own contiguous slice of users (user-sharded data parallel, weak scaling)
+    tabs = syn.make_config(CONFIG, n_users=BATCH * nb * world)
+    data = eng.TrainData(batch_size=BATCH, first_batch=rank * nb, max_batches=nb, **tabs)
+    vae = gen.MultiVAE([200, 600, I], lam=0.0, random_seed=98765)
+    vae.init_weights(98765)
+    disc = dis.Discriminator(I, I, H0, H1, H2, H3, seed=4242)
+    engine = eng.GanEngine(vae, disc, data.max_B, data.max_P, seed=2026, lr=LR, lam=LAM, use_graphs=not args.no_graphs, world_size=world,
+                           B_global=BATCH * world)
+    eng.pin_host_inputs(data)
+
+    def step(i):
+        bi = i % nb
+        engine.run_phase_a(data, bi)
+        engine.run_d_step(data, bi)
+        engine.run_g_step(data, bi)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # graph capture for every batch that the timed region touches (not counted as warm-up)
+    for i in range(nb):
+        step(i)
+    barrier()
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    k0 = engine.kernels_launched
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = engine.kernels_launched - k0
+
+    # ---- end-to-end: the step's inputs come from pinned host memory, the losses go back to the host, every step ----
+    host_scal = torch.zeros(ops.NSCAL, dtype=torch.float32).pin_memory()
+    h2d = 0
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.steps):
+        bi = i % nb
+        h2d += eng.upload_batch(data.batches[bi])
+        step(i)
+        host_scal.copy_(engine.scal, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller consumes the losses before issuing the next step
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-phase split and the dominant kernel (fused Adam over the [I,600] decoder weight), CUDA events, same stream ----
+    def timed(fn, n):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(n):
+            fn(i)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    n_ph = max(8, min(args.steps, 32))
+    t_a = timed(lambda i: engine.run_phase_a(data, i % nb), n_ph)
+    t_d = timed(lambda i: engine.run_d_step(data, i % nb), n_ph)
+    t_g = timed(lambda i: engine.run_g_step(data, i % nb), n_ph)
+    n_par = I * 600
+    t_adam = timed(lambda i: ops.adam(vae.WdT, vae.WdT_m, vae.WdT_v, engine.dWdT, vae.WdT_b, scal=engine.scal), 50)
+    bt0 = data.batches[0]
+    t_enc_adam = timed(lambda i: ops.enc_adam(vae.W_q0, vae.W_q0_m, vae.W_q0_v, vae.W_q0_b, I, bt0["csc_ptr"], bt0["csc_row"], bt0["csc_pos"],
+                                              data.coef, engine.dh1pre, scal=engine.scal), 50)
+
+    # max over ranks (device time)
+    times = torch.tensor([ms, ms_e2e, t_a, t_d, t_g, t_adam, t_enc_adam], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms, ms_e2e, t_a, t_d, t_g, t_adam, t_enc_adam = [float(x) for x in times.cpu()]
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        users = BATCH * world * args.steps
+        adam_bytes = 30.0 * n_par          # p,m,v read+write (24) + fp32 gradient read (4) + bf16 shadow write (2)
+        enc_bytes = 26.0 * n_par           # same without the gradient read: rebuilt from the batch CSC (L2-resident operands)
+        roof = dict(bound="hbm", kernel="adam_kernel (fused TF-Adam + bf16 shadow over W_dec^T [I,600])",
+                    achieved=adam_bytes / (t_adam * 1e-3) / 1e9, peak=peak, unit="GB/s", frac=adam_bytes / (t_adam * 1e-3) / 1e9 / peak,
+                    traffic=None, peak_source=peak_src, algorithmic_bytes_per_launch=adam_bytes, ms_per_launch=t_adam,
+                    how="CUDA events around 50 back-to-back launches on the launching stream after the timed region; each launch "
+                        "touches 362 MB (> L2)",
+                    second=dict(kernel="enc_adam_kernel (CSC gradient rebuild + TF-Adam over W_q0 [I,600])",
+                                achieved=enc_bytes / (t_enc_adam * 1e-3) / 1e9, frac=enc_bytes / (t_enc_adam * 1e-3) / 1e9 / peak,
+                                algorithmic_bytes_per_launch=enc_bytes, ms_per_launch=t_enc_adam))
+        line = dict(metric="gan_step_users_per_sec", value=users / (ms * 1e-3), unit="users/s", n_gpus=world, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="bf16", data="synthetic", config=workload_config(world),
+                    e2e=dict(value=users / (ms_e2e * 1e-3), unit="users/s", h2d_bytes_per_step=h2d // args.steps,
+                             d2h_bytes_per_step=ops.NSCAL * 4, ms_per_step=ms_e2e / args.steps),
+                    gpu_launches=launches, clocks=clocks, roofline=roof,
+                    phases_ms=dict(A=t_a, D=t_d, G=t_g, epoch_weighted_users_per_sec=BATCH * world / ((t_a + 10 * t_d + 10 * t_g) * 1e-3)),
+                    pairs_per_step=dict(real=int(np.mean([b["Pr"] for b in data.batches])), generated_slots=int(np.mean([b["K"] for b in data.batches]))),
+                    graphs=not args.no_graphs)
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(tabs, args.cpu_steps, I)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

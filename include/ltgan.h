@@ -65,10 +65,13 @@ int ltg_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int 
 
 /* ---- a3: encoder (MultiVAE.py:148-155): l2_normalize + dropout + x*W_q0 + b + tanh, as a CSR gather-sum -----------
  * indptr[B+1] (absolute offsets into indices/values), values may be NULL (all ones). uid0 = global id of row 0 (RNG key).
- * Writes h1 (bf16 [B, ld_h1]) and coef[nnz] = x_ui * rsqrt(max(|x_u|^2,1e-12)) * mask/keep at the same offsets as indices. */
+ * Writes h1 (bf16 [B, ld_h1]) and coef[nnz] = x_ui * rsqrt(max(|x_u|^2,1e-12)) * mask/keep at the same offsets as indices.
+ * Rows longer than 128 nonzeros are split over several CTAs: max_row_nnz bounds the row length of this call, pre_ws
+ * (fp32 [B, H]) and counters (int32 [B]) are zero-initialised workspaces that the kernel leaves zeroed again.               */
 int ltg_enc_gather_fwd(const int32_t* indptr, const int32_t* indices, const float* values, int B, int n_items, int64_t uid0,
                        const void* W_enc_bf16, const float* b_q0, float keep, uint64_t seed, uint32_t step,
-                       const uint32_t* step_dev, void* h1_bf16, int ld_h1, float* coef, void* stream);
+                       const uint32_t* step_dev, void* h1_bf16, int ld_h1, float* coef, int max_row_nnz, float* pre_ws,
+                       int32_t* counters, void* stream);
 
 /* ---- a3/a4: latent head (MultiVAE.py:157-162,178-181): KL, std, reparameterisation ---------------------------------
  * mulv fp32 [B, 2L] = [mu | logvar]. eps may be NULL (Philox Box-Muller keyed by uid). Writes z bf16 [B, ld_z],
@@ -86,7 +89,7 @@ int ltg_tanh_bwd(const float* dy, int ld_dy, const void* y_bf16, int ld_y, int B
 
 /* ---- a5/a6: decoder + catalog softmax (MultiVAE.py:169,108-112,143) -------------------------------------------------
  * logits = h2 * W_dec + b_dec through the tcgen05 GEMM with the softmax-statistics epilogue: bf16 logits stash
- * [B, ld_logits] (NULL = statistics only) and partial (max,sumexp) per 256-column block: partial[nblk(256)][B].       */
+ * [B, ld_logits] (NULL = statistics only) and partial (max,sumexp) pairs: partial[2*ceil(n_items/256)][B] float2.     */
 int ltg_dec_logits_fwd(const void* h2_bf16, int ld_h2, const void* WdT_bf16, const float* b_dec, int B, int n_items,
                        void* logits_bf16, int ld_logits, float* partial, void* stream);
 /* Row pass: lse[B]; nll: scal[NLL_SUM] += -sum_i x_ui (logit_ui - lse_u); sampled-probability sum per user s_u[B] and

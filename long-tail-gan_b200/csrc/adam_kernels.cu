@@ -58,11 +58,25 @@ __device__ __forceinline__ float4 enc_row_grad(int item, int c4, const int32_t* 
                                                const float* __restrict__ dh1, int ld) {
   float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
   const int e0 = __ldg(csc_ptr + item), e1 = __ldg(csc_ptr + item + 1);
-  for (int e = e0; e < e1; ++e) {
-    const float c = __ldg(coef + __ldg(csc_pos + e));
-    if (c != 0.f) {
-      const float4 d = __ldg(reinterpret_cast<const float4*>(dh1 + (size_t)__ldg(csc_row + e) * ld) + c4);
-      g.x = fmaf(c, d.x, g.x); g.y = fmaf(c, d.y, g.y); g.z = fmaf(c, d.z, g.z); g.w = fmaf(c, d.w, g.w);
+  // hot items appear in hundreds of batch rows: keep 4 independent (index -> coef, index -> dh1 row) chains in flight
+  for (int e = e0; e < e1; e += 4) {
+    int pos[4], row[4];
+    float c[4];
+    float4 d[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const bool ok = e + q < e1;
+      pos[q] = ok ? __ldg(csc_pos + e + q) : -1;
+      row[q] = ok ? __ldg(csc_row + e + q) : 0;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      c[q] = pos[q] >= 0 ? __ldg(coef + pos[q]) : 0.f;
+      d[q] = __ldg(reinterpret_cast<const float4*>(dh1 + (size_t)row[q] * ld) + c4);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      g.x = fmaf(c[q], d[q].x, g.x); g.y = fmaf(c[q], d[q].y, g.y); g.z = fmaf(c[q], d[q].z, g.z); g.w = fmaf(c[q], d[q].w, g.w);
     }
   }
   return g;

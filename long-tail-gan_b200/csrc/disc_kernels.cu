@@ -91,14 +91,15 @@ disc_head_kernel(const __nv_bfloat16* __restrict__ Y3, int ld, int P, int h3, co
   }
 }
 
-constexpr int COLSUM_ROWS = 32;
+constexpr int COLSUM_ROWS = 16;
 
 __global__ void drop_tanh_bwd_kernel(const float* __restrict__ dH, int ld_dh, const __nv_bfloat16* __restrict__ Hact, int ld_h, int P, int N,
                                      float keep, __nv_bfloat16* __restrict__ dz, int ld_dz, float* __restrict__ db) {
   const bool drop = keep > 0.f && keep < 1.f;
   const int r0 = blockIdx.x * COLSUM_ROWS;
   const int r1 = min(P, r0 + COLSUM_ROWS);
-  for (int c = threadIdx.x; c < N; c += blockDim.x) {
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c < N) {
     float cs = 0.f;
     for (int r = r0; r < r1; ++r) {
       const float y = __bfloat162float(Hact[(size_t)r * ld_h + c]);
@@ -148,7 +149,7 @@ extern "C" int ltg_drop_tanh_bwd(const float* dH, int ld_dh, const void* Hact_bf
                                  void* dz_bf16, int ld_dz, float* dbias, void* stream) {
   LTG_REQUIRE(dH && Hact_bf16 && dz_bf16);
   if (P <= 0) return LTG_OK;
-  drop_tanh_bwd_kernel<<<(P + COLSUM_ROWS - 1) / COLSUM_ROWS, 256, 0, (cudaStream_t)stream>>>(
+  drop_tanh_bwd_kernel<<<dim3((P + COLSUM_ROWS - 1) / COLSUM_ROWS, (N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
       dH, ld_dh, reinterpret_cast<const __nv_bfloat16*>(Hact_bf16), ld_h, P, N, keep, reinterpret_cast<__nv_bfloat16*>(dz_bf16), ld_dz, dbias);
   LTG_CHECK_LAUNCH();
   return LTG_OK;

@@ -2,13 +2,14 @@
 //
 //   D[M,N] = A[M,K] * B[N,K]^T          (each operand either K-major or MN-major in HBM)
 //
-// One persistent CTA per SM, 192 threads:
+// One persistent CTA per SM, 320 threads:
 //   warp 0      TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx-count)
 //   warp 1      MMA issuer     (one elected lane issues tcgen05.mma 128xBNx16, fp32 accumulators in TMEM,
 //                               tcgen05.commit releases smem slots / publishes the accumulator)
-//   warps 2..5  epilogue       (tcgen05.ld 32x32b: thread == accumulator row; the Epi functor consumes
+//   warps 2..9  epilogue       (tcgen05.ld 32x32b: thread == accumulator row; the Epi functor consumes
 //                               32-column chunks, so row-wise reductions such as the catalog softmax
-//                               statistics are thread-local)
+//                               statistics are thread-local; warps w and w+4 share a TMEM sub-partition and
+//                               take the even / odd chunks -- one warp per scheduler was issue-latency bound)
 // The TMEM accumulator is double buffered (2*BN columns) so the epilogue of tile i overlaps the
 // mainloop of tile i+1. Split-K is supported (tile index carries the split; Epi decides how to merge).
 //
@@ -28,7 +29,8 @@ namespace ltg {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 8;                       // two per TMEM sub-partition, alternating 32-column chunks
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
 // ----------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -181,7 +183,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], GEMM_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -257,8 +259,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else {
-    // ===================== epilogue (4 warps, one TMEM sub-partition each) =====================
+    // ===================== epilogue (8 warps; TMEM sub-partition = warp % 4, chunk parity = half) =====================
     const int sub = warp & 3;  // hardware rule: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+    const int half = (warp - 2) >> 2;
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m_blk = t % shape.m_blocks;
@@ -269,10 +272,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int row = m_blk * GEMM_BM + sub * 32 + lane;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      Epi epi(ep, row, n0, n_blk, split, shape);
+      Epi epi(ep, row, n0, n_blk * 2 + half, split, shape);
       const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = half * 32; c < BN; c += 64) {
         if (n0 + c >= shape.N) break;  // warp-uniform
         float v[32];
         tmem_ld32(taddr + c, v);
@@ -297,6 +300,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ----------------------------------------------------------------------------------------------
 // Epilogues
 // ----------------------------------------------------------------------------------------------
+
+// MUFU.TANH: max abs error ~5e-4, below the bf16 rounding of every tensor the GEMM epilogues write through tanh
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // Generic: out = dropout(act(alpha*acc + bias[col])) -> fp32 and/or bf16, or fp32 atomic accumulate (split-K).
 // A designated column (`aux_col`) can be diverted to `aux_out[row]` (used to get column sums for free
@@ -326,13 +336,26 @@ struct EpiStore {
   __device__ void chunk(int col0, float (&v)[32]) {
     if (row >= M) return;
     const bool drop = p.keep > 0.f && p.keep < 1.f;
+    if (p.bias != nullptr) {
+      if (col0 + 32 <= N && ((reinterpret_cast<uintptr_t>(p.bias + col0) & 15) == 0)) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      float x = v[i] * p.alpha;
-      const int col = col0 + i;
-      if (p.bias != nullptr && col < N) x += __ldg(p.bias + col);
-      if (p.act == 1) x = tanhf(x);
-      v[i] = x;
+        for (int i = 0; i < 8; ++i) {
+          const float4 b = __ldg(b4 + i);
+          v[4 * i] = fmaf(v[4 * i], p.alpha, b.x); v[4 * i + 1] = fmaf(v[4 * i + 1], p.alpha, b.y);
+          v[4 * i + 2] = fmaf(v[4 * i + 2], p.alpha, b.z); v[4 * i + 3] = fmaf(v[4 * i + 3], p.alpha, b.w);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], p.alpha, (col0 + i < N) ? __ldg(p.bias + col0 + i) : 0.f);
+      }
+    } else if (p.alpha != 1.0f) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+    }
+    if (p.act == 1) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = tanh_approx(v[i]);
     }
     if (drop) {
       // rng idx = row*rng_ld + col; col0 % 32 == 0 and rng_ld % 4 == 0, so 4 consecutive cols share one Philox block
@@ -390,14 +413,14 @@ struct EpiStore {
   __device__ void finish() {}
 };
 
-// Decoder forward: logits = acc + b_dec -> bf16 stash, plus per-(n-block,row) softmax partials
+// Decoder forward: logits = acc + b_dec -> bf16 stash, plus per-(n-block,chunk-parity,row) softmax partials
 // (row max, sum exp(x - max)) so the [B, I] logits never exist in fp32 in HBM.
 // Restates MultiVAE.py:169 (matmul + bias) and the reductions inside log_softmax/softmax (108, 143).
 struct EpiLogitsStats {
   struct Params {
     __nv_bfloat16* logits; int ld;   // [M, ld] bf16 (may be null: statistics only)
     const float* bias;               // [N]
-    float2* partial;                 // [n_blocks, M] (max, sumexp)
+    float2* partial;                 // [2*n_blocks, M] (max, sumexp): one entry per (n block, chunk parity)
   };
   const Params& p;
   int row, M, N, n_blk;
@@ -406,19 +429,32 @@ struct EpiLogitsStats {
       : p(p_), row(row_), M(s.M), N(s.N), n_blk(n_blk_), mx(-INFINITY), sum(0.f) {}
   __device__ void chunk(int col0, float (&v)[32]) {
     if (row >= M) return;
-    float cmax = -INFINITY;
+    if (col0 + 32 <= N && ((reinterpret_cast<uintptr_t>(p.bias + col0) & 15) == 0)) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int col = col0 + i;
-      float x = (col < N) ? v[i] + __ldg(p.bias + col) : -INFINITY;
-      v[i] = x;
-      cmax = fmaxf(cmax, x);
+      for (int i = 0; i < 8; ++i) {
+        const float4 b = __ldg(b4 + i);
+        v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = (col0 + i < N) ? v[i] + __ldg(p.bias + col0 + i) : -INFINITY;
     }
-    const float nm = fmaxf(mx, cmax);  // finite: every processed chunk has col0 < N
-    float s = 0.f;
+    // four independent chains for the max and for the sum (one epilogue warp per scheduler pair: latency, not throughput)
+    float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) s += __expf(v[i] - nm);
-    sum = sum * __expf(mx - nm) + s;
+    for (int i = 4; i < 32; i += 4) {
+      m0 = fmaxf(m0, v[i]); m1 = fmaxf(m1, v[i + 1]); m2 = fmaxf(m2, v[i + 2]); m3 = fmaxf(m3, v[i + 3]);
+    }
+    const float nm = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));  // finite: every processed chunk has col0 < N
+    const float nml = nm * 1.4426950408889634f;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      s0 += exp2f(fmaf(v[i], 1.4426950408889634f, -nml)); s1 += exp2f(fmaf(v[i + 1], 1.4426950408889634f, -nml));
+      s2 += exp2f(fmaf(v[i + 2], 1.4426950408889634f, -nml)); s3 += exp2f(fmaf(v[i + 3], 1.4426950408889634f, -nml));
+    }
+    sum = sum * exp2f((mx - nm) * 1.4426950408889634f) + ((s0 + s1) + (s2 + s3));
     mx = nm;
     if (p.logits != nullptr) {
       __nv_bfloat16* o = p.logits + (size_t)row * p.ld + col0;

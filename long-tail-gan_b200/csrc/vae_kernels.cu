@@ -10,28 +10,34 @@ constexpr int L = LTG_L;
 constexpr int HV = H / 8;  // 75 16-byte vectors per bf16 weight row
 
 // ---------------------------------------------------------------------------------------------
-// a3: encoder. One CTA per user; the CTA first turns the CSR row into (item, coef) pairs in shared
-// memory (norm, Philox dropout bit per nonzero), then 75 threads each own one 16-byte column slice
-// of the 1200-byte bf16 W_q0 rows and stream the surviving rows with 4 loads in flight.
+// a3: encoder. CTA (u, c) owns chunk c (ENC_CHUNK nonzeros) of user u's CSR row: it turns the chunk into
+// (item, coef) pairs in shared memory (norm, Philox dropout bit per nonzero), then 75 threads each own
+// one 16-byte column slice of the 1200-byte bf16 W_q0 rows and stream the surviving rows with 4 loads in
+// flight. Users that fit one chunk (the common case) are finished in place; longer rows (heavy users,
+// up to 2000 interactions) are spread over several CTAs that accumulate into an fp32 workspace row, and
+// the last CTA to arrive applies bias + tanh and clears the workspace again (self-cleaning, no memset).
 // Restates MultiVAE.py:148 (l2_normalize), 149 (dropout), 152-155 (matmul + bias + tanh).
 // ---------------------------------------------------------------------------------------------
 constexpr int ENC_THREADS = 96;
-constexpr int ENC_CHUNK = 512;
+constexpr int ENC_CHUNK = 128;
 
 __global__ void __launch_bounds__(ENC_THREADS)
 enc_gather_fwd_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
                       int n_items, int64_t uid0, const uint4* __restrict__ W, const float* __restrict__ bias, float keep,
                       uint64_t seed, uint32_t step, const uint32_t* __restrict__ step_dev, __nv_bfloat16* __restrict__ h1,
-                      int ld_h1, float* __restrict__ coef) {
+                      int ld_h1, float* __restrict__ coef, float* __restrict__ pre_ws, int* __restrict__ counters) {
   __shared__ int s_item[ENC_CHUNK];
   __shared__ float s_coef[ENC_CHUNK];
   __shared__ float s_red[ENC_THREADS / 32];
+  __shared__ int s_last;
   const int u = blockIdx.x;
   const int tid = threadIdx.x;
   const int beg = indptr[u], end = indptr[u + 1];
+  const int nchunks = max(1, (end - beg + ENC_CHUNK - 1) / ENC_CHUNK);
+  if ((int)blockIdx.y >= nchunks) return;
   if (step_dev != nullptr) step += *step_dev;
 
-  // squared norm of the row (values == NULL: binary row)
+  // squared norm of the whole row (values == NULL: binary row)
   float ss = 0.f;
   if (values != nullptr) {
     for (int j = beg + tid; j < end; j += ENC_THREADS) { float v = values[j]; ss += v * v; }
@@ -52,53 +58,70 @@ enc_gather_fwd_kernel(const int32_t* __restrict__ indptr, const int32_t* __restr
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
 
-  for (int c0 = beg; c0 < end; c0 += ENC_CHUNK) {
-    const int cnt = min(ENC_CHUNK, end - c0);
-    for (int j = tid; j < cnt; j += ENC_THREADS) {
-      const int item = indices[c0 + j];
-      const float val = values != nullptr ? values[c0 + j] : 1.0f;
-      float c = val * scale;
-      if (drop) {
-        const uint32_t r = ltg_rand_u32(seed, LTG_STREAM_ENC_DROPOUT, step, (uint64_t)(uid0 + u) * (uint64_t)n_items + (uint64_t)item);
-        if (r >= thr) c = 0.f;
-      }
-      s_item[j] = item;
-      s_coef[j] = c;
-      coef[c0 + j] = c;
+  const int c0 = beg + blockIdx.y * ENC_CHUNK;
+  const int cnt = min(ENC_CHUNK, end - c0);
+  for (int j = tid; j < cnt; j += ENC_THREADS) {
+    const int item = indices[c0 + j];
+    const float val = values != nullptr ? values[c0 + j] : 1.0f;
+    float c = val * scale;
+    if (drop) {
+      const uint32_t r = ltg_rand_u32(seed, LTG_STREAM_ENC_DROPOUT, step, (uint64_t)(uid0 + u) * (uint64_t)n_items + (uint64_t)item);
+      if (r >= thr) c = 0.f;
     }
-    __syncthreads();
+    s_item[j] = item;
+    s_coef[j] = c;
+    coef[c0 + j] = c;
+  }
+  __syncthreads();
+  if (tid < HV) {
+    int j = 0;
+    for (; j + 4 <= cnt; j += 4) {
+      uint4 w[4]; float c[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        c[q] = s_coef[j + q];
+        w[q] = make_uint4(0, 0, 0, 0);
+        if (c[q] != 0.f) w[q] = __ldg(W + (size_t)s_item[j + q] * HV + tid);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float2 a = unpack_bf16x2(w[q].x), b = unpack_bf16x2(w[q].y), d = unpack_bf16x2(w[q].z), e = unpack_bf16x2(w[q].w);
+        acc[0] = fmaf(c[q], a.x, acc[0]); acc[1] = fmaf(c[q], a.y, acc[1]);
+        acc[2] = fmaf(c[q], b.x, acc[2]); acc[3] = fmaf(c[q], b.y, acc[3]);
+        acc[4] = fmaf(c[q], d.x, acc[4]); acc[5] = fmaf(c[q], d.y, acc[5]);
+        acc[6] = fmaf(c[q], e.x, acc[6]); acc[7] = fmaf(c[q], e.y, acc[7]);
+      }
+    }
+    for (; j < cnt; ++j) {
+      const float c = s_coef[j];
+      if (c != 0.f) {
+        const uint4 w = __ldg(W + (size_t)s_item[j] * HV + tid);
+        float2 a = unpack_bf16x2(w.x), b = unpack_bf16x2(w.y), d = unpack_bf16x2(w.z), e = unpack_bf16x2(w.w);
+        acc[0] = fmaf(c, a.x, acc[0]); acc[1] = fmaf(c, a.y, acc[1]);
+        acc[2] = fmaf(c, b.x, acc[2]); acc[3] = fmaf(c, b.y, acc[3]);
+        acc[4] = fmaf(c, d.x, acc[4]); acc[5] = fmaf(c, d.y, acc[5]);
+        acc[6] = fmaf(c, e.x, acc[6]); acc[7] = fmaf(c, e.y, acc[7]);
+      }
+    }
+  }
+  if (nchunks > 1) {
+    // multi-CTA row: accumulate into the fp32 workspace, last arrival finishes
+    float* ws = pre_ws + (size_t)u * H;
     if (tid < HV) {
-      int j = 0;
-      for (; j + 4 <= cnt; j += 4) {
-        uint4 w[4]; float c[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          c[q] = s_coef[j + q];
-          w[q] = make_uint4(0, 0, 0, 0);
-          if (c[q] != 0.f) w[q] = __ldg(W + (size_t)s_item[j + q] * HV + tid);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float2 a = unpack_bf16x2(w[q].x), b = unpack_bf16x2(w[q].y), d = unpack_bf16x2(w[q].z), e = unpack_bf16x2(w[q].w);
-          acc[0] = fmaf(c[q], a.x, acc[0]); acc[1] = fmaf(c[q], a.y, acc[1]);
-          acc[2] = fmaf(c[q], b.x, acc[2]); acc[3] = fmaf(c[q], b.y, acc[3]);
-          acc[4] = fmaf(c[q], d.x, acc[4]); acc[5] = fmaf(c[q], d.y, acc[5]);
-          acc[6] = fmaf(c[q], e.x, acc[6]); acc[7] = fmaf(c[q], e.y, acc[7]);
-        }
-      }
-      for (; j < cnt; ++j) {
-        const float c = s_coef[j];
-        if (c != 0.f) {
-          const uint4 w = __ldg(W + (size_t)s_item[j] * HV + tid);
-          float2 a = unpack_bf16x2(w.x), b = unpack_bf16x2(w.y), d = unpack_bf16x2(w.z), e = unpack_bf16x2(w.w);
-          acc[0] = fmaf(c, a.x, acc[0]); acc[1] = fmaf(c, a.y, acc[1]);
-          acc[2] = fmaf(c, b.x, acc[2]); acc[3] = fmaf(c, b.y, acc[3]);
-          acc[4] = fmaf(c, d.x, acc[4]); acc[5] = fmaf(c, d.y, acc[5]);
-          acc[6] = fmaf(c, e.x, acc[6]); acc[7] = fmaf(c, e.y, acc[7]);
-        }
-      }
+      for (int i = 0; i < 8; ++i) atomicAdd(ws + tid * 8 + i, acc[i]);
     }
+    __threadfence();
     __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(counters + u, 1) == nchunks - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (tid < HV) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { acc[i] = __ldcg(ws + tid * 8 + i); ws[tid * 8 + i] = 0.f; }
+    }
+    if (tid == 0) counters[u] = 0;
   }
   if (tid < HV) {
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias) + tid * 2);
@@ -153,9 +176,9 @@ __global__ void latent_fwd_kernel(const float* __restrict__ mulv, const float* _
   }
 }
 
-// rows are tiled by 32 per block; every thread owns columns (strided) and sums its column over the tile,
-// then issues one atomic per column per block for the bias gradient.
-constexpr int COLSUM_ROWS = 32;
+// 2-D grid: blockIdx.x tiles the rows by COLSUM_ROWS, blockIdx.y tiles the columns by blockDim.x; every thread owns one
+// column, sums it over the row tile (coalesced across the warp) and issues one atomic per column for the bias gradient.
+constexpr int COLSUM_ROWS = 8;
 
 __global__ void latent_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ mulv, const float* __restrict__ zmu, int B,
                                   float inv_bg, float anneal, const float* __restrict__ scal, __nv_bfloat16* __restrict__ dmulv, int ld,
@@ -163,7 +186,8 @@ __global__ void latent_bwd_kernel(const float* __restrict__ dz, const float* __r
   if (anneal < 0.f) anneal = scal[LTG_S_ANNEAL];
   const int r0 = blockIdx.x * COLSUM_ROWS;
   const int r1 = min(B, r0 + COLSUM_ROWS);
-  for (int c = threadIdx.x; c < 2 * L; c += blockDim.x) {
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c < 2 * L) {
     float cs = 0.f;
     const bool is_mu = c < L;
     const int j = is_mu ? c : c - L;
@@ -187,7 +211,8 @@ __global__ void tanh_bwd_kernel(const float* __restrict__ dy, int ld_dy, const _
                                 __nv_bfloat16* __restrict__ dxb, int ld_dxb, float* __restrict__ dxf, int ld_dxf, float* __restrict__ db) {
   const int r0 = blockIdx.x * COLSUM_ROWS;
   const int r1 = min(B, r0 + COLSUM_ROWS);
-  for (int c = threadIdx.x; c < N; c += blockDim.x) {
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c < N) {
     float cs = 0.f;
     for (int r = r0; r < r1; ++r) {
       const float t = __bfloat162float(y[(size_t)r * ld_y + c]);
@@ -282,28 +307,30 @@ __global__ void dlogits_dense_kernel(const uint4* __restrict__ logits, int ld8, 
   dl[(size_t)u * ld8 + v] = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-// sparse fix-ups: -x_ui/Bg at the user's interactions, -lam*Ybar*pi_ui at the sampled (valid) items. One warp per user.
-__global__ void dlogits_sparse_kernel(const __nv_bfloat16* __restrict__ logits, int ld, const float* __restrict__ lse, int B, float inv_bg,
-                                      float lam, const float* __restrict__ scal, const int32_t* __restrict__ indptr,
-                                      const int32_t* __restrict__ indices, const float* __restrict__ values,
-                                      const int32_t* __restrict__ samp_ptr, const int32_t* __restrict__ samp_items,
-                                      const int32_t* __restrict__ samp_valid, __nv_bfloat16* __restrict__ dl) {
-  const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (u >= B) return;
+// sparse fix-ups: -x_ui/Bg at the user's interactions, -lam*Ybar*pi_ui at the sampled (valid) items. One CTA per user
+// (heavy users have up to 2000 interactions; a single warp made the kernel wait for them).
+constexpr int SPARSE_THREADS = 128;
+__global__ void __launch_bounds__(SPARSE_THREADS)
+dlogits_sparse_kernel(const __nv_bfloat16* __restrict__ logits, int ld, const float* __restrict__ lse, int B, float inv_bg,
+                      float lam, const float* __restrict__ scal, const int32_t* __restrict__ indptr,
+                      const int32_t* __restrict__ indices, const float* __restrict__ values,
+                      const int32_t* __restrict__ samp_ptr, const int32_t* __restrict__ samp_items,
+                      const int32_t* __restrict__ samp_valid, __nv_bfloat16* __restrict__ dl) {
+  const int u = blockIdx.x;
+  const int tid = threadIdx.x;
   __nv_bfloat16* drow = dl + (size_t)u * ld;
-  for (int j = indptr[u] + lane; j < indptr[u + 1]; j += 32) {
+  for (int j = indptr[u] + tid; j < indptr[u + 1]; j += SPARSE_THREADS) {
     const int i = indices[j];
     const float v = values != nullptr ? values[j] : 1.0f;
     drow[i] = __float2bfloat16(__bfloat162float(drow[i]) - v * inv_bg);
   }
   if (lam != 0.f && samp_ptr != nullptr) {
-    __syncwarp();
+    __syncthreads();  // a sampled item may also be one of the user's interactions: order the two read-modify-writes
     const float cnt = scal[LTG_S_CNT];
     const float ybar = cnt > 0.f ? scal[LTG_S_SUM_Y] / cnt : 0.f;
     const float l = lse[u];
     const __nv_bfloat16* row = logits + (size_t)u * ld;
-    for (int j = samp_ptr[u] + lane; j < samp_ptr[u + 1]; j += 32) {
+    for (int j = samp_ptr[u] + tid; j < samp_ptr[u + 1]; j += SPARSE_THREADS) {
       if (samp_valid[j] > 0) {
         const int i = samp_items[j];
         const float pi = __expf(__bfloat162float(row[i]) - l);
@@ -320,13 +347,16 @@ __global__ void dlogits_sparse_kernel(const __nv_bfloat16* __restrict__ logits, 
 // =================================================================================================
 extern "C" int ltg_enc_gather_fwd(const int32_t* indptr, const int32_t* indices, const float* values, int B, int n_items, int64_t uid0,
                                   const void* W_enc_bf16, const float* b_q0, float keep, uint64_t seed, uint32_t step,
-                                  const uint32_t* step_dev, void* h1_bf16, int ld_h1, float* coef, void* stream) {
+                                  const uint32_t* step_dev, void* h1_bf16, int ld_h1, float* coef, int max_row_nnz, float* pre_ws,
+                                  int32_t* counters, void* stream) {
   LTG_REQUIRE(indptr && indices && W_enc_bf16 && b_q0 && h1_bf16 && coef);
   LTG_REQUIRE(ld_h1 % 8 == 0 && ld_h1 >= H);
+  LTG_REQUIRE(max_row_nnz <= ENC_CHUNK || (pre_ws != nullptr && counters != nullptr));
   if (B <= 0) return LTG_OK;
-  enc_gather_fwd_kernel<<<B, ENC_THREADS, 0, (cudaStream_t)stream>>>(indptr, indices, values, n_items, uid0,
-                                                                      reinterpret_cast<const uint4*>(W_enc_bf16), b_q0, keep, seed, step, step_dev,
-                                                                      reinterpret_cast<__nv_bfloat16*>(h1_bf16), ld_h1, coef);
+  const int chunks = max_row_nnz <= ENC_CHUNK ? 1 : (max_row_nnz + ENC_CHUNK - 1) / ENC_CHUNK;
+  enc_gather_fwd_kernel<<<dim3(B, chunks), ENC_THREADS, 0, (cudaStream_t)stream>>>(
+      indptr, indices, values, n_items, uid0, reinterpret_cast<const uint4*>(W_enc_bf16), b_q0, keep, seed, step, step_dev,
+      reinterpret_cast<__nv_bfloat16*>(h1_bf16), ld_h1, coef, pre_ws, counters);
   LTG_CHECK_LAUNCH();
   return LTG_OK;
 }
@@ -347,7 +377,7 @@ extern "C" int ltg_latent_bwd(const float* dz, const float* mulv, const float* z
   LTG_REQUIRE(dz && mulv && zmu && dmulv_bf16);
   LTG_REQUIRE(anneal >= 0.f || scal != nullptr);
   if (B <= 0) return LTG_OK;
-  latent_bwd_kernel<<<(B + COLSUM_ROWS - 1) / COLSUM_ROWS, 256, 0, (cudaStream_t)stream>>>(
+  latent_bwd_kernel<<<dim3((B + COLSUM_ROWS - 1) / COLSUM_ROWS, (2 * L + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
       dz, mulv, zmu, B, 1.0f / (float)B_global, anneal, scal, reinterpret_cast<__nv_bfloat16*>(dmulv_bf16), ld, db_q1);
   LTG_CHECK_LAUNCH();
   return LTG_OK;
@@ -357,7 +387,7 @@ extern "C" int ltg_tanh_bwd(const float* dy, int ld_dy, const void* y_bf16, int 
                             float* dx_f32, int ld_dxf, float* dbias, void* stream) {
   LTG_REQUIRE(dy && y_bf16);
   if (B <= 0) return LTG_OK;
-  tanh_bwd_kernel<<<(B + COLSUM_ROWS - 1) / COLSUM_ROWS, 256, 0, (cudaStream_t)stream>>>(
+  tanh_bwd_kernel<<<dim3((B + COLSUM_ROWS - 1) / COLSUM_ROWS, (N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
       dy, ld_dy, reinterpret_cast<const __nv_bfloat16*>(y_bf16), ld_y, B, N, reinterpret_cast<__nv_bfloat16*>(dx_bf16), ld_dxb, dx_f32,
       ld_dxf, dbias);
   LTG_CHECK_LAUNCH();
@@ -403,8 +433,7 @@ extern "C" int ltg_dec_dlogits(const void* logits_bf16, int ld, const float* lse
   dlogits_dense_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(logits_bf16), ld8, lse, xw, s_u, n_items, inv_bg,
                                                                 lam, scal, reinterpret_cast<uint4*>(dl_bf16));
   LTG_CHECK_LAUNCH();
-  const int threads = 128;
-  dlogits_sparse_kernel<<<(B * 32 + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(
+  dlogits_sparse_kernel<<<B, SPARSE_THREADS, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(logits_bf16), ld, lse, B, inv_bg, lam, scal, indptr, indices, values, samp_ptr, samp_items,
       samp_valid, reinterpret_cast<__nv_bfloat16*>(dl_bf16));
   LTG_CHECK_LAUNCH();

@@ -34,7 +34,7 @@ class TrainData(object):
     """
 
     def __init__(self, n_items, indptr, indices, pop_ptr, pop_items, n_niche, cand_ptr, cand_items, real_ptr, real_niche, real_pop,
-                 eligible, item_valid, batch_size, device="cuda", uid_start=0):
+                 eligible, item_valid, batch_size, device="cuda", uid_start=0, first_batch=0, max_batches=None):
         self.n_items = int(n_items)
         self.N = len(indptr) - 1
         self.batch_size = int(batch_size)
@@ -54,7 +54,13 @@ class TrainData(object):
         n_draw = np.minimum(n_draw, cand_len)
         real_ptr = np.asarray(real_ptr, dtype=np.int64)
         self.batches = []
-        for b0 in range(0, self.N, self.batch_size):
+        starts = list(range(0, self.N, self.batch_size))[first_batch:]
+        if max_batches is not None:
+            starts = starts[:max_batches]
+        self._host = dict(cand_ptr=np.asarray(cand_ptr, dtype=np.int32), cand_items=np.asarray(cand_items, dtype=np.int32),
+                          pop_ptr=np.asarray(pop_ptr, dtype=np.int32), pop_items=np.asarray(pop_items, dtype=np.int32),
+                          indptr=np.asarray(indptr, dtype=np.int32))
+        for b0 in starts:
             b1 = min(self.N, b0 + self.batch_size)
             self.batches.append(self._make_batch(b0, b1, n_draw, real_ptr, real_niche, real_pop, cand_len))
         self.max_B = max(bt["B"] for bt in self.batches)
@@ -80,23 +86,70 @@ class TrainData(object):
         label = np.full(max(P, 1), -1, dtype=np.int32)
         pair_pop[:Pr] = real_pop[r0:r1]; pair_niche[:Pr] = real_niche[r0:r1]; label[:Pr] = 0
         t = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(dev)  # noqa: E731
-        return dict(b0=b0, B=B, uid0=self.uid_start + b0, nnz=e1 - e0, Pr=Pr, K=K, P=P,
+        self._last_host = dict(csc_ptr=csc_ptr, csc_row=rows[order], csc_pos=order + e0, samp_ptr=samp_ptr, pair_pop=pair_pop[:max(Pr, 1)],
+                               pair_niche=pair_niche[:max(Pr, 1)], label=label[:max(Pr, 1)])
+        return dict(b0=b0, B=B, uid0=self.uid_start + b0, nnz=e1 - e0, Pr=Pr, K=K, P=P, e0=e0, e1=e1,
+                    host_src={k: np.ascontiguousarray(v, dtype=np.int32) for k, v in self._last_host.items()},
                     csc_ptr=t(csc_ptr), csc_row=t(rows[order]), csc_pos=t(order + e0), samp_ptr=t(samp_ptr),
                     pair_pop=t(pair_pop), pair_niche=t(pair_niche), label=t(label),
                     cnt=torch.zeros(1, dtype=torch.int32, device=dev),
-                    max_cand=int(cand_len[b0:b1].max()) if B > 0 else 0)
+                    max_cand=int(cand_len[b0:b1].max()) if B > 0 else 0,
+                    max_nnz=int(np.diff(self.h_indptr[b0:b1 + 1]).max()) if B > 0 else 0)
+
+
+def pin_host_inputs(data):
+    """Pinned host mirrors of everything one step consumes, per batch (used by the end-to-end path: the step's inputs are
+    copied host->device inside the timed region). Returns total bytes per batch in bt["h2d_bytes"]."""
+    h = data._host
+    for bt in data.batches:
+        b0, B = bt["b0"], bt["B"]
+        c0, c1 = int(h["cand_ptr"][b0]), int(h["cand_ptr"][b0 + B])
+        p0, p1 = int(h["pop_ptr"][b0]), int(h["pop_ptr"][b0 + B])
+        pairs = []
+
+        def add(dst, src):
+            src = torch.as_tensor(np.ascontiguousarray(src, dtype=np.int32))
+            if src.numel() == 0:
+                return
+            pairs.append((dst, src.pin_memory()))
+
+        add(data.indptr[b0: b0 + B + 1], h["indptr"][b0: b0 + B + 1])
+        add(data.indices[bt["e0"]: bt["e1"]], data.h_indices[bt["e0"]: bt["e1"]])
+        add(data.cand_ptr[b0: b0 + B + 1], h["cand_ptr"][b0: b0 + B + 1])
+        add(data.cand_items[c0:c1], h["cand_items"][c0:c1])
+        add(data.pop_ptr[b0: b0 + B + 1], h["pop_ptr"][b0: b0 + B + 1])
+        add(data.pop_items[p0:p1], h["pop_items"][p0:p1])
+        hs = bt["host_src"]
+        Pr = bt["Pr"]
+        for k in ("csc_ptr", "csc_row", "csc_pos", "samp_ptr"):
+            add(bt[k], hs[k])
+        if Pr > 0:
+            for k in ("pair_pop", "pair_niche", "label"):
+                add(bt[k][:Pr], hs[k][:Pr])
+        bt["h2d"] = pairs
+        bt["h2d_bytes"] = int(sum(src.numel() * 4 for _, src in pairs))
+
+
+def upload_batch(bt):
+    """Asynchronous host->device copy of one batch's inputs from pinned memory (current stream)."""
+    for dst, src in bt["h2d"]:
+        dst.copy_(src, non_blocking=True)
+    return bt["h2d_bytes"]
 
 
 class GanEngine(object):
     """Owns the workspaces and runs phase A / D / G / evaluation for one (vae, discriminator) pair."""
 
     def __init__(self, vae, disc, max_B, max_P=1, seed=0, lr=1e-4, lam=1.0, keep_vae=0.75, keep_d=0.7, total_anneal_steps=20000,
-                 anneal_cap=0.2, B_global=None, use_graphs=True):
+                 anneal_cap=0.2, B_global=None, use_graphs=True, world_size=1):
         ops.init()
+        self.world_size = int(world_size)
+        self.kernels_launched = 0
+        self._kcount = {}
         self.vae, self.disc = vae, disc
         self.I = vae.n_items
         self.ld = _pad(self.I, 8)
-        self.nblk = (self.I + 255) // 256
+        self.nblk = 2 * ((self.I + 255) // 256)  # softmax partials per row: (256-column block) x (chunk parity)
         self.seed, self.lr, self.lam = int(seed), float(lr), float(lam)
         self.keep_vae, self.keep_d = float(keep_vae), float(keep_d)
         self.total_anneal_steps, self.anneal_cap = float(total_anneal_steps), float(anneal_cap)
@@ -118,6 +171,8 @@ class GanEngine(object):
         d = self.disc
         # VAE activations
         self.h1 = torch.zeros(B, H, **bf)
+        self.enc_ws = torch.zeros(B, H, **f32)          # split-row accumulator of the encoder gather (self-cleaning)
+        self.enc_cnt = torch.zeros(B, dtype=torch.int32, device=dev)
         self.mulv = torch.zeros(B, 2 * L, **f32)
         self.z = torch.zeros(B, L, **bf)
         self.zmu = torch.zeros(B, L, **f32)
@@ -131,6 +186,7 @@ class GanEngine(object):
         self.dh2pre = torch.zeros(B, H, **bf)
         self.dmulv = torch.zeros(B, 2 * L, **bf)
         self.dh1pre = torch.zeros(B, H, **f32)
+        self.dW_q0 = torch.zeros(I, H, **f32) if self.world_size > 1 else None  # dense encoder gradient, only for the all-reduce
         # fp32 accumulators that must be zero at the start of a G step: one arena, one memset
         self.zero_g = torch.zeros(B * H + B * L + B * H, **f32)
         self.dh2 = self.zero_g[: B * H].view(B, H)
@@ -148,7 +204,7 @@ class GanEngine(object):
     # ------------------------------------------------------------------------------------------------------------
     # building blocks
     # ------------------------------------------------------------------------------------------------------------
-    def _vae_forward(self, data, bt, is_training, keep, stash=True, indptr=None, indices=None, coef=None, uid0=None, B=None):
+    def _vae_forward(self, data, bt, is_training, keep, stash=True, indptr=None, indices=None, coef=None, uid0=None, B=None, max_nnz=None):
         """MultiVAE.forward_pass (MultiVAE.py:175-186) up to the logits and their softmax statistics."""
         v = self.vae
         B = bt["B"] if B is None else B
@@ -156,7 +212,8 @@ class GanEngine(object):
         indices = data.indices if indices is None else indices
         coef = data.coef if coef is None else coef
         uid0 = bt["uid0"] if uid0 is None else uid0
-        ops.enc_gather_fwd(indptr, indices, None, B, self.I, uid0, v.W_q0_b, v.view("b_q0"), keep, self.seed, 0, self.words, self.h1, coef)
+        ops.enc_gather_fwd(indptr, indices, None, B, self.I, uid0, v.W_q0_b, v.view("b_q0"), keep, self.seed, 0, self.words, self.h1, coef,
+                           bt["max_nnz"] if max_nnz is None else max_nnz, self.enc_ws, self.enc_cnt)
         ops.gemm(self.h1, v.view("W_q1", "b"), B, 2 * L, H, b_mn=True, bn=64, out_f32=self.mulv, bias=v.view("b_q1"))
         ops.latent_fwd(self.mulv, self.eps_inject if is_training else None, B, uid0, 1.0 if is_training else 0.0, self.seed, 0,
                        self.words, self.z, self.zmu, self.scal)
@@ -204,6 +261,10 @@ class GanEngine(object):
     # D update: train.py:300
     # ------------------------------------------------------------------------------------------------------------
     def d_step(self, data, bi):
+        self._d_fwd_bwd(data, bi)
+        self._d_update()
+
+    def _d_fwd_bwd(self, data, bi):
         bt = data.batches[bi]
         d = self.disc
         P = bt["P"]
@@ -219,28 +280,47 @@ class GanEngine(object):
         ops.gemm(self.Xp, self.dz12, d.h0, d.h1, P, a_mn=True, b_mn=True, splits=sp, bn=64, out_f32=d.view("W1", "g"), atomic=True)
         ops.gemm(self.Xn, self.dz12[:, d.off2:], d.h0, d.h2, P, a_mn=True, b_mn=True, ldb=d.k3, splits=sp, bn=64,
                  out_f32=d.view("W2", "g"), atomic=True)
+
+    def _d_update(self):
+        d = self.disc
         ops.adam(d.arena, d.arena_m, d.arena_v, d.arena_g, d.arena_b, scal=self.scal)
 
     # ------------------------------------------------------------------------------------------------------------
     # G update: train.py:326
     # ------------------------------------------------------------------------------------------------------------
     def g_step(self, data, bi, update=True):
+        """Single-GPU G update. The data-parallel variant (run_g_step with world_size > 1) runs the same three parts with
+        the two exchange steps in between."""
+        self._g_forward(data, bi)
+        self._g_backward(data, bi)
+        if update:
+            self._g_update(data, bi)
+
+    def _g_forward(self, data, bi):
         bt = data.batches[bi]
         v = self.vae
         B, Pr, K = bt["B"], bt["Pr"], bt["K"]
-        Bg = B if self.B_global is None else self.B_global
         self.scal.zero_()
         self.zero_g.zero_()
         v.small_g.zero_()
         ops.step_advance(self.words, self.scal, 2, self.lr, anneal_cap=self.anneal_cap, total_anneal_steps=self.total_anneal_steps)
         indptr, indices = self._vae_forward(data, bt, True, self.keep_vae)
-        lam = self.lam if K > 0 else 0.0
         samp = (bt["samp_ptr"], bt["pair_niche"][Pr:], bt["label"][Pr:]) if K > 0 else (None, None, None)
         if K > 0:
             # y_generated with fresh dropout masks (keep_prob 0.7 is fed in the G step too, train.py:326)
             self._disc_forward(bt["pair_pop"][Pr:], bt["pair_niche"][Pr:], bt["label"][Pr:], K, False)
         ops.dec_row_stats(self.partial, self.nblk, self.logits, B, indptr, indices, None, samp[0], samp[1], samp[2], self.lse, self.xw,
                           self.su, self.scal)
+
+    def _g_backward(self, data, bi):
+        bt = data.batches[bi]
+        v = self.vae
+        B, Pr, K = bt["B"], bt["Pr"], bt["K"]
+        Bg = (B if self.B_global is None else self.B_global)
+        indptr = data.indptr[bt["b0"]: bt["b0"] + B + 1]
+        indices = data.indices
+        lam = self.lam if (K > 0 or self.world_size > 1) else 0.0
+        samp = (bt["samp_ptr"], bt["pair_niche"][Pr:], bt["label"][Pr:]) if K > 0 else (None, None, None)
         ops.dec_dlogits(self.logits, self.lse, self.xw, self.su, B, self.I, Bg, lam, self.scal, indptr, indices, None, samp[0], samp[1],
                         samp[2], self.dl)
         # decoder backward: dh2 = dl W_p1^T (split-K over the catalog), dW_p1^T = dl^T [h2 | 1]
@@ -254,22 +334,35 @@ class GanEngine(object):
         ops.gemm(self.dmulv, v.view("W_q1", "b"), B, H, 2 * L, bn=64, out_f32=self.dh1)
         ops.gemm(self.h1, self.dmulv, H, 2 * L, B, a_mn=True, b_mn=True, bn=64, out_f32=v.view("W_q1", "g"))
         ops.tanh_bwd(self.dh1, self.h1, B, H, dx_f32=self.dh1pre, dbias=v.view("b_q0", "g"))
-        if update:
+        if self.world_size > 1:
+            ops.enc_wgrad(self.dW_q0, self.I, bt["csc_ptr"], bt["csc_row"], bt["csc_pos"], data.coef, self.dh1pre)
+
+    def _g_update(self, data, bi):
+        bt = data.batches[bi]
+        v = self.vae
+        if self.world_size > 1:
+            ops.adam(v.W_q0, v.W_q0_m, v.W_q0_v, self.dW_q0, v.W_q0_b, scal=self.scal)
+        else:
             ops.enc_adam(v.W_q0, v.W_q0_m, v.W_q0_v, v.W_q0_b, self.I, bt["csc_ptr"], bt["csc_row"], bt["csc_pos"], data.coef,
                          self.dh1pre, scal=self.scal)
-            ops.adam(v.WdT, v.WdT_m, v.WdT_v, self.dWdT, v.WdT_b, scal=self.scal)
-            ops.adam(v.small, v.small_m, v.small_v, v.small_g, v.small_b, scal=self.scal)
+        ops.adam(v.WdT, v.WdT_m, v.WdT_v, self.dWdT, v.WdT_b, scal=self.scal)
+        ops.adam(v.small, v.small_m, v.small_v, v.small_g, v.small_b, scal=self.scal)
 
     # ------------------------------------------------------------------------------------------------------------
     # graph capture / replay
     # ------------------------------------------------------------------------------------------------------------
     def _run(self, key, fn):
         if not self.use_graphs:
+            k0 = ops.kernel_launches
             fn()
+            self.kernels_launched += ops.kernel_launches - k0
             return
         g = self._graphs.get(key)
         if g is None:
+            k0 = ops.kernel_launches
             fn()  # eager warm-up (also opts kernels into their shared-memory sizes outside of capture)
+            self._kcount[key] = ops.kernel_launches - k0
+            self.kernels_launched += self._kcount[key]
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
@@ -277,15 +370,34 @@ class GanEngine(object):
             self._graphs[key] = g
             return
         g.replay()
+        self.kernels_launched += self._kcount[key]
 
     def run_phase_a(self, data, bi):
         self._run(("a", id(data), bi), lambda: self.phase_a(data, bi))
 
     def run_d_step(self, data, bi):
-        self._run(("d", id(data), bi), lambda: self.d_step(data, bi))
+        if self.world_size == 1:
+            self._run(("d", id(data), bi), lambda: self.d_step(data, bi))
+            return
+        import torch.distributed as dist
+        self._run(("d1", id(data), bi), lambda: self._d_fwd_bwd(data, bi))
+        dist.all_reduce(self.disc.arena_g)          # 161 k discriminator gradients: one small bucket
+        self._run(("d2", id(data), bi), self._d_update)
 
     def run_g_step(self, data, bi):
-        self._run(("g", id(data), bi), lambda: self.g_step(data, bi))
+        if self.world_size == 1:
+            self._run(("g", id(data), bi), lambda: self.g_step(data, bi))
+            return
+        import torch.distributed as dist
+        self._run(("g1", id(data), bi), lambda: self._g_forward(data, bi))
+        # F3: the adversarial term needs the GLOBAL sums (sum p, sum y, cnt) before the backward pass starts
+        dist.all_reduce(self.scal[ops.S_SUM_P: ops.S_CNT + 1])
+        self._run(("g2", id(data), bi), lambda: self._g_backward(data, bi))
+        # the one real exchange step of the path: gradient reduction over NVLink
+        dist.all_reduce(self.dW_q0)
+        dist.all_reduce(self.dWdT)
+        dist.all_reduce(self.vae.small_g)
+        self._run(("g3", id(data), bi), lambda: self._g_update(data, bi))
 
     # ------------------------------------------------------------------------------------------------------------
     # losses of the last step (host reads; train.py:303,329 print them once per sub-epoch)
@@ -317,6 +429,7 @@ class GanEngine(object):
         tep = torch.as_tensor(np.ascontiguousarray(te_indptr, dtype=np.int32)).to(dev)
         tei = torch.as_tensor(np.ascontiguousarray(te_indices if len(te_indices) else np.zeros(1), dtype=np.int32)).to(dev)
         coef = torch.zeros(max(1, len(tr_indices)), dtype=torch.float32, device=dev)
+        max_eval_nnz = int(np.diff(np.asarray(tr_indptr, dtype=np.int64)).max()) if N > 0 else 0
         scores = torch.zeros(batch, self.ld, dtype=torch.float32, device=dev)
         dcg = torch.zeros(N, dtype=torch.float64, device=dev)
         hits = torch.zeros(N, len(recall_ks), dtype=torch.int32, device=dev)
@@ -327,7 +440,7 @@ class GanEngine(object):
             ops.step_advance(self.words, self.scal, 0, self.lr)
             ip = trp[b0: b0 + B + 1]
             ops.enc_gather_fwd(ip, tri, None, B, self.I, uid_start + b0, v.W_q0_b, v.view("b_q0"), keep, self.seed, 0, self.words,
-                               self.h1, coef)
+                               self.h1, coef, max_eval_nnz, self.enc_ws, self.enc_cnt)
             ops.gemm(self.h1, v.view("W_q1", "b"), B, 2 * L, H, b_mn=True, bn=64, out_f32=self.mulv, bias=v.view("b_q1"))
             ops.latent_fwd(self.mulv, None, B, uid_start + b0, 0.0, self.seed, 0, self.words, self.z, self.zmu, self.scal)
             ops.gemm(self.z, v.view("W_p0", "b"), B, H, L, b_mn=True, bn=64, out_bf16=self.h2, bias=v.view("b_p0"), act=1)

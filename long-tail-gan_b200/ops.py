@@ -19,6 +19,13 @@ STREAM_SAMPLE = 8
 STREAM_PARTNER = 9
 
 _initialised = False
+# number of CUDA kernels launched through this module (graph capture counts the captured launches once)
+kernel_launches = 0
+
+
+def _count(n=1):
+    global kernel_launches
+    kernel_launches += n
 
 
 def lib():
@@ -40,6 +47,7 @@ def _stream():
 
 
 def step_advance(words, scal, kind, lr, beta1=0.9, beta2=0.999, anneal_cap=0.2, total_anneal_steps=20000.0):
+    _count(1)
     check(lib().ltg_step_advance(ptr(words), ptr(scal), kind, lr, beta1, beta2, anneal_cap, total_anneal_steps, _stream()))
 
 
@@ -47,6 +55,7 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, splits=1,
          act=0, alpha=1.0, atomic=False, keep=1.0, seed=0, rng_stream=0, rng_step=0, rng_step_dev=None, rng_ld=0, aux_col=-1,
          aux_out=None, ld_f32=None, ld_bf16=None):
     """D[M,N] = alpha*A*B^T on the tcgen05 GEMM. A is [M,K] (or stored [K,M] when a_mn), B is [N,K] (or [K,N] when b_mn)."""
+    _count(1)
     lda = A.stride(0) if lda is None else lda
     ldb = B.stride(0) if ldb is None else ldb
     if out_f32 is not None and ld_f32 is None:
@@ -58,85 +67,103 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, splits=1,
                               ptr(rng_step_dev), rng_ld, aux_col, ptr(aux_out), _stream()))
 
 
-def enc_gather_fwd(indptr, indices, values, B, n_items, uid0, W_enc_bf16, b_q0, keep, seed, step, step_dev, h1, coef):
+def enc_gather_fwd(indptr, indices, values, B, n_items, uid0, W_enc_bf16, b_q0, keep, seed, step, step_dev, h1, coef, max_row_nnz=0,
+                   pre_ws=None, counters=None):
+    _count(1)
     check(lib().ltg_enc_gather_fwd(ptr(indptr), ptr(indices), ptr(values), B, n_items, uid0, ptr(W_enc_bf16), ptr(b_q0), keep, seed,
-                                   step, ptr(step_dev), ptr(h1), h1.stride(0), ptr(coef), _stream()))
+                                   step, ptr(step_dev), ptr(h1), h1.stride(0), ptr(coef), max_row_nnz, ptr(pre_ws), ptr(counters),
+                                   _stream()))
 
 
 def latent_fwd(mulv, eps, B, uid0, is_training, seed, step, step_dev, z, zmu, scal):
+    _count(1)
     check(lib().ltg_latent_fwd(ptr(mulv), ptr(eps), B, uid0, float(is_training), seed, step, ptr(step_dev), ptr(z), z.stride(0),
                                ptr(zmu), ptr(scal), _stream()))
 
 
 def latent_bwd(dz, mulv, zmu, B, B_global, anneal, scal, dmulv, db_q1):
+    _count(1)
     check(lib().ltg_latent_bwd(ptr(dz), ptr(mulv), ptr(zmu), B, B_global, anneal, ptr(scal), ptr(dmulv), dmulv.stride(0), ptr(db_q1),
                                _stream()))
 
 
 def tanh_bwd(dy, y_bf16, B, N, dx_bf16=None, dx_f32=None, dbias=None):
+    _count(1)
     check(lib().ltg_tanh_bwd(ptr(dy), dy.stride(0), ptr(y_bf16), y_bf16.stride(0), B, N, ptr(dx_bf16),
                              dx_bf16.stride(0) if dx_bf16 is not None else 0, ptr(dx_f32),
                              dx_f32.stride(0) if dx_f32 is not None else 0, ptr(dbias), _stream()))
 
 
 def dec_logits_fwd(h2, WdT_bf16, b_dec, B, n_items, logits, partial):
+    _count(1)
     check(lib().ltg_dec_logits_fwd(ptr(h2), h2.stride(0), ptr(WdT_bf16), ptr(b_dec), B, n_items, ptr(logits),
                                    logits.stride(0) if logits is not None else 0, ptr(partial), _stream()))
 
 
 def dec_row_stats(partial, n_blocks, logits, B, indptr, indices, values, samp_ptr, samp_items, samp_valid, lse, xw, s_u, scal):
+    _count(1)
     check(lib().ltg_dec_row_stats(ptr(partial), n_blocks, ptr(logits), logits.stride(0) if logits is not None else 0, B, ptr(indptr),
                                   ptr(indices), ptr(values), ptr(samp_ptr), ptr(samp_items), ptr(samp_valid), ptr(lse), ptr(xw),
                                   ptr(s_u), ptr(scal), _stream()))
 
 
 def dec_probs(logits, lse, B, n_items, out):
+    _count(1)
     check(lib().ltg_dec_probs(ptr(logits), logits.stride(0), ptr(lse), B, n_items, ptr(out), out.stride(0), _stream()))
 
 
 def dec_dlogits(logits, lse, xw, s_u, B, n_items, B_global, lam, scal, indptr, indices, values, samp_ptr, samp_items, samp_valid, dl):
+    _count(2)
     check(lib().ltg_dec_dlogits(ptr(logits), logits.stride(0), ptr(lse), ptr(xw), ptr(s_u), B, n_items, B_global, lam, ptr(scal),
                                 ptr(indptr), ptr(indices), ptr(values), ptr(samp_ptr), ptr(samp_items), ptr(samp_valid), ptr(dl),
                                 _stream()))
 
 
 def adam(p, m, v, g, shadow, lr_t=-1.0, scal=None, beta1=0.9, beta2=0.999, eps=1e-8):
+    _count(1)
     check(lib().ltg_adam(ptr(p), ptr(m), ptr(v), ptr(g), ptr(shadow), p.numel(), lr_t, ptr(scal), beta1, beta2, eps, _stream()))
 
 
 def enc_adam(p, m, v, shadow, n_items, csc_ptr, csc_row, csc_pos, coef, dh1pre, lr_t=-1.0, scal=None, beta1=0.9, beta2=0.999,
              eps=1e-8):
+    _count(1)
     check(lib().ltg_enc_adam(ptr(p), ptr(m), ptr(v), ptr(shadow), n_items, ptr(csc_ptr), ptr(csc_row), ptr(csc_pos), ptr(coef),
                              ptr(dh1pre), dh1pre.stride(0), lr_t, ptr(scal), beta1, beta2, eps, _stream()))
 
 
 def enc_wgrad(dW, n_items, csc_ptr, csc_row, csc_pos, coef, dh1pre):
+    _count(1)
     check(lib().ltg_enc_wgrad(ptr(dW), n_items, ptr(csc_ptr), ptr(csc_row), ptr(csc_pos), ptr(coef), ptr(dh1pre), dh1pre.stride(0),
                               _stream()))
 
 
 def sample_pairs(logits, B, n_items, uid0, cand_ptr, cand_items, samp_ptr, pop_ptr, pop_items, item_valid, seed, step, step_dev,
                  samp_items, samp_partner, samp_valid, cnt, max_cand):
+    _count(1)
     check(lib().ltg_sample_pairs(ptr(logits), logits.stride(0), B, n_items, uid0, ptr(cand_ptr), ptr(cand_items), ptr(samp_ptr),
                                  ptr(pop_ptr), ptr(pop_items), ptr(item_valid), seed, step, ptr(step_dev), ptr(samp_items),
                                  ptr(samp_partner), ptr(samp_valid), ptr(cnt), max_cand, _stream()))
 
 
 def disc_gather(E_bf16, pop_ids, niche_ids, P, Xp, Xn):
+    _count(1)
     check(lib().ltg_disc_gather(ptr(E_bf16), ptr(pop_ids), ptr(niche_ids), P, ptr(Xp), ptr(Xn), _stream()))
 
 
 def disc_head(Y3, P, h3, w4, b4, label, keep, y_out, scal, dz3=None, dw4=None, db3=None, db4=None):
+    _count(1)
     check(lib().ltg_disc_head(ptr(Y3), Y3.stride(0), P, h3, ptr(w4), ptr(b4), ptr(label), keep, ptr(y_out), ptr(scal), ptr(dz3),
                               ptr(dw4), ptr(db3), ptr(db4), _stream()))
 
 
 def drop_tanh_bwd(dH, Hact, P, N, keep, dz, dbias):
+    _count(1)
     check(lib().ltg_drop_tanh_bwd(ptr(dH), dH.stride(0), ptr(Hact), Hact.stride(0), P, N, keep, ptr(dz), dz.stride(0), ptr(dbias),
                                   _stream()))
 
 
 def topk_metrics(scores, n_rows, n_items, seen_ptr, seen_items, held_ptr, held_items, k, rks, topk_idx, dcg, hits):
+    _count(1)
     import numpy as np
     rk = np.asarray(list(rks), dtype=np.int32)
     is_bf16 = scores.dtype == torch.bfloat16
@@ -146,5 +173,6 @@ def topk_metrics(scores, n_rows, n_items, seen_ptr, seen_items, held_ptr, held_i
 
 
 def cast_bf16(src, dst, rows, cols):
+    _count(1)
     check(lib().ltg_cast_bf16(ptr(src), src.stride(0) if src.dim() > 1 else cols, ptr(dst), dst.stride(0) if dst.dim() > 1 else cols,
                               rows, cols, _stream()))

@@ -134,7 +134,7 @@ def test_enc_gather_fwd_matches_oracle(ops):
     seed, step, keep, uid0 = 42, 5, 0.75, 1000
     h1 = torch.zeros(B, 600, device="cuda", dtype=torch.bfloat16)
     coef = torch.zeros(len(indices), device="cuda")
-    ops.enc_gather_fwd(dev(indptr), dev(indices), None, B, I, uid0, Wb, dev(b), keep, seed, step, None, h1, coef)
+    ops.enc_gather_fwd(dev(indptr), dev(indices), None, B, I, uid0, Wb, dev(b), keep, seed, step, None, h1, coef, int(np.diff(indptr).max()))
     torch.cuda.synchronize()
     X = np.zeros((B, I), dtype=np.float32)
     rows = np.repeat(np.arange(B), np.diff(indptr))
@@ -165,8 +165,11 @@ def test_enc_gather_long_row_and_values(ops):
     b = np.zeros(600, dtype=np.float32)
     h1 = torch.zeros(3, 600, device="cuda", dtype=torch.bfloat16)
     coef = torch.zeros(n, device="cuda")
-    ops.enc_gather_fwd(dev(indptr), dev(indices), dev(vals), 3, I, 0, Wb, dev(b), 1.0, 1, 0, None, h1, coef)
+    ws = torch.zeros(3, 600, device="cuda"); cn = torch.zeros(3, dtype=torch.int32, device="cuda")
+    for _ in range(2):  # twice: the split-row workspace must come back zeroed
+        ops.enc_gather_fwd(dev(indptr), dev(indices), dev(vals), 3, I, 0, Wb, dev(b), 1.0, 1, 0, None, h1, coef, n, ws, cn)
     torch.cuda.synchronize()
+    assert ws.abs().max().item() == 0.0 and cn.abs().max().item() == 0
     x = np.zeros(I, dtype=np.float32); x[indices] = vals
     want = np.tanh((x / np.sqrt((x * x).sum())) @ Wb.float().cpu().numpy())
     assert np.abs(h1[0].float().cpu().numpy() - want).max() < 1e-2
@@ -220,7 +223,7 @@ def test_decoder_logits_stats_and_dlogits(ops):
     WdT = (torch.randn(I, 600, device="cuda") * 0.08).bfloat16()
     bd = torch.randn(I, device="cuda") * 0.1
     logits = torch.zeros(B, ld, device="cuda", dtype=torch.bfloat16)
-    nblk = (I + 255) // 256
+    nblk = 2 * ((I + 255) // 256)
     partial = torch.zeros(nblk, B, 2, device="cuda")
     ops.dec_logits_fwd(h2, WdT, bd, B, I, logits, partial)
     ref = h2.float() @ WdT.float().t() + bd

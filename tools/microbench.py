@@ -33,7 +33,7 @@ def main():
     WdT = (torch.randn(I, H, device=dev) * 0.05).bfloat16()
     bd = torch.zeros(I, device=dev)
     logits = torch.zeros(B, ld, device=dev, dtype=torch.bfloat16)
-    nblk = (I + 255) // 256
+    nblk = 2 * ((I + 255) // 256)
     partial = torch.zeros(nblk, B, 2, device=dev)
     t = timeit(lambda: ops.dec_logits_fwd(h2, WdT, bd, B, I, logits, partial))
     fl = 2.0 * B * H * I
@@ -63,7 +63,7 @@ def main():
     bq = torch.zeros(H, device=dev)
     h1 = torch.zeros(B, H, device=dev, dtype=torch.bfloat16)
     coef = torch.zeros(B * nnz_per, device=dev)
-    t = timeit(lambda: ops.enc_gather_fwd(indptr, indices, None, B, I, 0, Wenc, bq, 0.75, 1, 0, None, h1, coef))
+    t = timeit(lambda: ops.enc_gather_fwd(indptr, indices, None, B, I, 0, Wenc, bq, 0.75, 1, 0, None, h1, coef, nnz_per))
     print("enc_gather_fwd        %8.1f us  %6.1f GB/s" % (t, B * nnz_per * 0.75 * 1204 / t / 1e3))
     rows = np.repeat(np.arange(B), nnz_per)
     order = np.lexsort((rows, idx_np))
