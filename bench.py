@@ -186,7 +186,7 @@ def main():
     vae.init_weights(98765)
     disc = dis.Discriminator(I, I, H0, H1, H2, H3, seed=4242)
     engine = eng.GanEngine(vae, disc, data.max_B, data.max_P, seed=2026, lr=LR, lam=LAM, use_graphs=not args.no_graphs, world_size=world,
-                           B_global=BATCH * world)
+                           B_global=BATCH * world, max_active=data.max_active)
     eng.pin_host_inputs(data)
 
     def step(i):
@@ -256,8 +256,8 @@ def main():
     n_par = I * 600
     t_adam = timed(lambda i: ops.adam(vae.WdT, vae.WdT_m, vae.WdT_v, engine.dWdT, vae.WdT_b, scal=engine.scal), 50)
     bt0 = data.batches[0]
-    t_enc_adam = timed(lambda i: ops.enc_adam(vae.W_q0, vae.W_q0_m, vae.W_q0_v, vae.W_q0_b, I, bt0["csc_ptr"], bt0["csc_row"], bt0["csc_pos"],
-                                              data.coef, engine.dh1pre, scal=engine.scal), 50)
+    t_enc_adam = timed(lambda i: ops.enc_adam(vae.W_q0, vae.W_q0_m, vae.W_q0_v, vae.W_q0_b, I, bt0["slot_of_item"], engine.G_enc,
+                                              scal=engine.scal), 50)
 
     # max over ranks (device time)
     times = torch.tensor([ms, ms_e2e, t_a, t_d, t_g, t_adam, t_enc_adam], dtype=torch.float64, device="cuda")
@@ -269,13 +269,13 @@ def main():
         peak, peak_src = measured_peaks()
         users = BATCH * world * args.steps
         adam_bytes = 30.0 * n_par          # p,m,v read+write (24) + fp32 gradient read (4) + bf16 shadow write (2)
-        enc_bytes = 26.0 * n_par           # same without the gradient read: rebuilt from the batch CSC (L2-resident operands)
+        enc_bytes = 26.0 * n_par           # same without a dense gradient read: the compact gradient rows are L2-resident
         roof = dict(bound="hbm", kernel="adam_kernel (fused TF-Adam + bf16 shadow over W_dec^T [I,600])",
                     achieved=adam_bytes / (t_adam * 1e-3) / 1e9, peak=peak, unit="GB/s", frac=adam_bytes / (t_adam * 1e-3) / 1e9 / peak,
                     traffic=None, peak_source=peak_src, algorithmic_bytes_per_launch=adam_bytes, ms_per_launch=t_adam,
                     how="CUDA events around 50 back-to-back launches on the launching stream after the timed region; each launch "
                         "touches 362 MB (> L2)",
-                    second=dict(kernel="enc_adam_kernel (CSC gradient rebuild + TF-Adam over W_q0 [I,600])",
+                    second=dict(kernel="enc_adam_kernel (TF-Adam over W_q0 [I,600], gradient rows fetched through slot_of_item)",
                                 achieved=enc_bytes / (t_enc_adam * 1e-3) / 1e9, frac=enc_bytes / (t_enc_adam * 1e-3) / 1e9 / peak,
                                 algorithmic_bytes_per_launch=enc_bytes, ms_per_launch=t_enc_adam))
         line = dict(metric="gan_step_users_per_sec", value=users / (ms * 1e-3), unit="users/s", n_gpus=world, steps=args.steps,

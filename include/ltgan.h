@@ -54,24 +54,29 @@ int ltg_step_advance(uint32_t* words, float* scal, int kind, float lr, float bet
 
 /* ---- generic bf16 tensor-core GEMM (tcgen05/TMA/TMEM) ------------------------------------------------------------
  * D[M,N] = alpha * A * B^T with A given as [M,K] (a_mn=0, pitch lda) or stored transposed [K,M] (a_mn=1), B likewise
- * ([N,K] or [K,N]); epilogue: +bias[N], act (0 none / 1 tanh), dropout(keep) keyed by idx=row*rng_ld+col, outputs fp32
+ * ([N,K] or [K,N]); epilogue: +bias[N], act (0 none / 1 tanh), dropout(keep) from a counter hash of (row*rng_ld+col)/2, outputs fp32
  * and/or bf16, `atomic` = split-K accumulation into a zeroed fp32 buffer; column `aux_col` is diverted to aux_out[row].
- * bn in {64,128,256}. Building block of every dense layer below (tf.matmul sites: MultiVAE.py:152,169;
+ * dact_src (bf16 [M, dact_ld], may be NULL): multiply the result by d/da dropout(tanh(a)) recovered from the stored
+ * post-dropout activation (backward of discriminator.py:25,30,44 fused into the dgrad GEMM).
+ * bn in {64,128,192,256}. Building block of every dense layer below (tf.matmul sites: MultiVAE.py:152,169;
  * discriminator.py:25-55) and their autodiff transposes (train.py:163-164).                                        */
 int ltg_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int N, int K, int splits, int bn,
                   float* out_f32, int ld_f32, void* out_bf16, int ld_bf16, const float* bias, int act, float alpha, int atomic,
                   float keep, uint64_t seed, uint32_t rng_stream, uint32_t rng_step, const uint32_t* rng_step_dev, int rng_ld,
-                  int aux_col, float* aux_out, void* stream);
+                  int aux_col, float* aux_out, const void* dact_src, int dact_ld, float dact_keep, void* stream);
 
 /* ---- a3: encoder (MultiVAE.py:148-155): l2_normalize + dropout + x*W_q0 + b + tanh, as a CSR gather-sum -----------
  * indptr[B+1] (absolute offsets into indices/values), values may be NULL (all ones). uid0 = global id of row 0 (RNG key).
  * Writes h1 (bf16 [B, ld_h1]) and coef[nnz] = x_ui * rsqrt(max(|x_u|^2,1e-12)) * mask/keep at the same offsets as indices.
  * Rows longer than 128 nonzeros are split over several CTAs: max_row_nnz bounds the row length of this call, pre_ws
- * (fp32 [B, H]) and counters (int32 [B]) are zero-initialised workspaces that the kernel leaves zeroed again.               */
+ * (fp32 [B, H]) and counters (int32 [B]) are zero-initialised workspaces that the kernel leaves zeroed again.
+ * Optional (training): xc_bf16 [B, ld_xc] (zeroed by the caller) receives coef at column slot_of_item[item] -- the dense
+ * coefficient matrix over the batch's active items, i.e. the A operand of the encoder weight-gradient GEMM
+ * dW_q0[active] = Xc^T dh1pre (autodiff of MultiVAE.py:152).                                                                  */
 int ltg_enc_gather_fwd(const int32_t* indptr, const int32_t* indices, const float* values, int B, int n_items, int64_t uid0,
                        const void* W_enc_bf16, const float* b_q0, float keep, uint64_t seed, uint32_t step,
                        const uint32_t* step_dev, void* h1_bf16, int ld_h1, float* coef, int max_row_nnz, float* pre_ws,
-                       int32_t* counters, void* stream);
+                       int32_t* counters, const int32_t* slot_of_item, void* xc_bf16, int ld_xc, void* stream);
 
 /* ---- a3/a4: latent head (MultiVAE.py:157-162,178-181): KL, std, reparameterisation ---------------------------------
  * mulv fp32 [B, 2L] = [mu | logvar]. eps may be NULL (Philox Box-Muller keyed by uid). Writes z bf16 [B, ld_z],
@@ -89,7 +94,7 @@ int ltg_tanh_bwd(const float* dy, int ld_dy, const void* y_bf16, int ld_y, int B
 
 /* ---- a5/a6: decoder + catalog softmax (MultiVAE.py:169,108-112,143) -------------------------------------------------
  * logits = h2 * W_dec + b_dec through the tcgen05 GEMM with the softmax-statistics epilogue: bf16 logits stash
- * [B, ld_logits] (NULL = statistics only) and partial (max,sumexp) pairs: partial[2*ceil(n_items/256)][B] float2.     */
+ * [B, ld_logits] (NULL = statistics only) and partial (max,sumexp) pairs: partial[4*ceil(n_items/256)][B] float2.     */
 int ltg_dec_logits_fwd(const void* h2_bf16, int ld_h2, const void* WdT_bf16, const float* b_dec, int B, int n_items,
                        void* logits_bf16, int ld_logits, float* partial, void* stream);
 /* Row pass: lse[B]; nll: scal[NLL_SUM] += -sum_i x_ui (logit_ui - lse_u); sampled-probability sum per user s_u[B] and
@@ -113,14 +118,16 @@ int ltg_dec_dlogits(const void* logits_bf16, int ld, const float* lse, const flo
  * p,m,v fp32 updated in place; g fp32; optional bf16 shadow with the same layout. lr_t < 0: read scal[LTG_S_LR_T].    */
 int ltg_adam(float* p, float* m, float* v, const float* g, void* shadow_bf16, int64_t n, float lr_t, const float* scal,
              float beta1, float beta2, float eps, void* stream);
-/* Encoder weight W_q0 [n_items, H]: gradient is never materialised -- row i is rebuilt from the batch CSC
- * (csc_ptr[n_items+1], csc_row[nnz] = batch row, csc_pos[nnz] = offset into coef) as sum coef*dh1pre[row,:], then Adam. */
-int ltg_enc_adam(float* p, float* m, float* v, void* shadow_bf16, int n_items, const int32_t* csc_ptr, const int32_t* csc_row,
-                 const int32_t* csc_pos, const float* coef, const float* dh1pre, int ld_dh1, float lr_t, const float* scal,
-                 float beta1, float beta2, float eps, void* stream);
-/* Dense gradient of W_q0 (parity checks / data-parallel all-reduce path): dW[i,:] = sum coef*dh1pre[row,:].             */
-int ltg_enc_wgrad(float* dW, int n_items, const int32_t* csc_ptr, const int32_t* csc_row, const int32_t* csc_pos,
-                  const float* coef, const float* dh1pre, int ld_dh1, void* stream);
+/* Encoder weight W_q0 [n_items, H]. Its gradient X^T dh1pre is non-zero only on the batch's ACTIVE items, so it is built
+ * compactly: G[slot, :] = sum over the item's batch entries of coef * dh1pre[row, :], one CTA per active item
+ * (act_ptr[n_active+1] delimits the item's entries in csc_row[] = batch row / csc_pos[] = offset into coef).                */
+int ltg_enc_wgrad_compact(float* G, int n_active, const int32_t* act_ptr, const int32_t* csc_row, const int32_t* csc_pos,
+                          const float* coef, const float* dh1pre, int ld_dh1, void* stream);
+/* Dense TF-Adam sweep over W_q0 (every row moves, F7); row i takes gradient G[slot_of_item[i], :] (slot -1: zero).           */
+int ltg_enc_adam(float* p, float* m, float* v, void* shadow_bf16, int n_items, const int32_t* slot_of_item, const float* G,
+                 float lr_t, const float* scal, float beta1, float beta2, float eps, void* stream);
+/* Dense gradient of W_q0 (parity checks / data-parallel all-reduce path): dW[i, :] = G[slot_of_item[i], :] or 0.             */
+int ltg_enc_wgrad_expand(float* dW, int n_items, const int32_t* slot_of_item, const float* G, void* stream);
 
 /* ---- a9/a10: niche sampling + pair construction (sample.py:40-67, train.py:212-251) --------------------------------
  * Per user u: candidates cand[cand_ptr[u]..), draw n_u = samp_ptr[u+1]-samp_ptr[u] items without replacement with
@@ -139,13 +146,10 @@ int ltg_sample_pairs(const void* logits_bf16, int ld_logits, int B, int n_items,
 int ltg_disc_gather(const void* E_bf16, const int32_t* pop_ids, const int32_t* niche_ids, int P, void* Xp, void* Xn, void* stream);
 /* Head: s = Y3*w4 + b4, y = sigmoid(s); label[row]: 0 real, 1 generated, <0 ignored.
  * Accumulates scal[D_LOSS], scal[SUM_Y] and scal[CNT] (generated rows), and when dz3 != NULL the backward seed:
- * dz3 bf16 [P, ld] = ds*w4*dact(Y3), dw4[h3] += Y3^T ds, *db4 += sum ds, db3[h3] += colsum(dz3).                    */
+ * dz3 bf16 [P, ld] = ds*w4*dact(Y3), dw4[h3] += Y3^T ds, *db4 += sum ds. (The fc1 bias gradient comes out of the
+ * weight-gradient GEMM through the ones column of the hidden activation.)                                              */
 int ltg_disc_head(const void* Y3_bf16, int ld, int P, int h3, const float* w4, const float* b4, const int32_t* label,
-                  float keep, float* y_out, float* scal, void* dz3_bf16, float* dw4, float* db3, float* db4, void* stream);
-/* dz = dH * dact(Hact) for a dropout(tanh) layer stored post-dropout in bf16; column sums -> dbias (atomic).             */
-int ltg_drop_tanh_bwd(const float* dH, int ld_dh, const void* Hact_bf16, int ld_h, int P, int N, float keep,
-                      void* dz_bf16, int ld_dz, float* dbias, void* stream);
-
+                  float keep, float* y_out, float* scal, void* dz3_bf16, float* dw4, float* db4, void* stream);
 /* ---- a16/a17: ranking metrics (eval_functions.py:11-62, train.py:341) -----------------------------------------------
  * Per row: scores (fp32 or bf16, pitch ld) with the row's seen items (seen_ptr/seen_items, may be NULL) forced to -inf,
  * exact top-k (k <= 128; ties: lowest index first) sorted by score descending -> topk_idx [n, k] (may be NULL),

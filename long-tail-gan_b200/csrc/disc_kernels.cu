@@ -1,7 +1,6 @@
 // a11/a12: discriminator pieces that are not GEMMs (discriminator.py:14-55, train.py:142).
 //   - frozen embedding gather (F5)
 //   - head: fc2 (h3 -> 1) + sigmoid + both loss terms + backward seed
-//   - backward through dropout(tanh(.)) layers stored post-dropout in bf16
 // The three dense layers run on the tcgen05 GEMM (gemm_ops.cu) with the bias+tanh+dropout epilogue.
 #include "ltg_common.cuh"
 #include "../../include/ltgan.h"
@@ -28,33 +27,42 @@ __device__ __forceinline__ float dact_drop_tanh(float y, float keep, bool drop) 
   return (1.0f - t * t) / keep;
 }
 
-constexpr int HEAD_ROWS = 32;      // rows per CTA
-constexpr int HEAD_THREADS = 256;  // 8 warps x 4 rows
-constexpr int HEAD_MAXH3 = 512;
+constexpr int HEAD_THREADS = 256;  // 8 warps, each walks rows with a grid stride
+constexpr int HEAD_MAXH3 = 320;    // 10 columns per lane
+constexpr int HEAD_CPL = HEAD_MAXH3 / 32;
 
+// One warp per row: lane l owns columns l, l+32, ... (coalesced 64-byte row segments). The weight gradient
+// dw4 = Y3^T ds is accumulated in registers over all rows a warp visits, then reduced once per CTA in shared memory and
+// once per CTA in global memory (the per-element shared-memory atomics of the first version cost 45 us).
 __global__ void __launch_bounds__(HEAD_THREADS)
 disc_head_kernel(const __nv_bfloat16* __restrict__ Y3, int ld, int P, int h3, const float* __restrict__ w4, const float* __restrict__ b4,
                  const int32_t* __restrict__ label, float keep, float* __restrict__ y_out, float* __restrict__ scal,
-                 __nv_bfloat16* __restrict__ dz3, float* __restrict__ dw4, float* __restrict__ db3, float* __restrict__ db4) {
-  __shared__ float s_w4[HEAD_MAXH3];
+                 __nv_bfloat16* __restrict__ dz3, float* __restrict__ dw4, float* __restrict__ db4) {
   __shared__ float s_dw4[HEAD_MAXH3];
-  __shared__ float s_db3[HEAD_MAXH3];
   __shared__ float s_acc[4];  // d_loss, sum_y, db4, cnt
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool bwd = dz3 != nullptr;
   const bool drop = keep > 0.f && keep < 1.f;
-  for (int j = tid; j < h3; j += HEAD_THREADS) { s_w4[j] = w4[j]; s_dw4[j] = 0.f; s_db3[j] = 0.f; }
+  for (int j = tid; j < HEAD_MAXH3; j += HEAD_THREADS) s_dw4[j] = 0.f;
   if (tid < 4) s_acc[tid] = 0.f;
   __syncthreads();
+  float wv[HEAD_CPL], gw[HEAD_CPL];
+#pragma unroll
+  for (int k = 0; k < HEAD_CPL; ++k) { const int j = lane + 32 * k; wv[k] = j < h3 ? __ldg(w4 + j) : 0.f; gw[k] = 0.f; }
   const float bias = b4[0];
   float loss = 0.f, sumy = 0.f, sds = 0.f, ngen = 0.f;
-  for (int rr = warp; rr < HEAD_ROWS; rr += HEAD_THREADS / 32) {
-    const int row = blockIdx.x * HEAD_ROWS + rr;
-    if (row >= P) break;
+  const int warps_total = gridDim.x * (HEAD_THREADS / 32);
+  for (int row = blockIdx.x * (HEAD_THREADS / 32) + warp; row < P; row += warps_total) {
     const int lab = label[row];
     const __nv_bfloat16* yr = Y3 + (size_t)row * ld;
+    float yv[HEAD_CPL];
     float s = 0.f;
-    for (int j = lane; j < h3; j += 32) s = fmaf(__bfloat162float(yr[j]), s_w4[j], s);
+#pragma unroll
+    for (int k = 0; k < HEAD_CPL; ++k) {
+      const int j = lane + 32 * k;
+      yv[k] = j < h3 ? __bfloat162float(yr[j]) : 0.f;
+      s = fmaf(yv[k], wv[k], s);
+    }
     s = warp_sum(s) + bias;
     const float y = 1.0f / (1.0f + __expf(-s));
     if (lane == 0 && y_out != nullptr) y_out[row] = y;
@@ -66,16 +74,21 @@ disc_head_kernel(const __nv_bfloat16* __restrict__ Y3, int ld, int P, int h3, co
     if (lane == 0) { loss += l; if (lab == 1) { sumy += y; ngen += 1.f; } sds += ds; }
     if (bwd) {
       __nv_bfloat16* dr = dz3 + (size_t)row * ld;
-      for (int j = lane; j < h3; j += 32) {
-        const float yv = __bfloat162float(yr[j]);
-        const float d = ds * s_w4[j] * dact_drop_tanh(yv, keep, drop);
-        dr[j] = __float2bfloat16(d);
-        atomicAdd(&s_dw4[j], yv * ds);
-        atomicAdd(&s_db3[j], d);
+#pragma unroll
+      for (int k = 0; k < HEAD_CPL; ++k) {
+        const int j = lane + 32 * k;
+        if (j < h3) {
+          dr[j] = __float2bfloat16(ds * wv[k] * dact_drop_tanh(yv[k], keep, drop));
+          gw[k] = fmaf(yv[k], ds, gw[k]);
+        }
       }
     }
   }
   if (lane == 0) { atomicAdd(&s_acc[0], loss); atomicAdd(&s_acc[1], sumy); atomicAdd(&s_acc[2], sds); atomicAdd(&s_acc[3], ngen); }
+  if (bwd) {
+#pragma unroll
+    for (int k = 0; k < HEAD_CPL; ++k) atomicAdd(&s_dw4[lane + 32 * k], gw[k]);
+  }
   __syncthreads();
   if (tid == 0) {
     atomicAdd(scal + LTG_S_D_LOSS, s_acc[0]);
@@ -83,32 +96,8 @@ disc_head_kernel(const __nv_bfloat16* __restrict__ Y3, int ld, int P, int h3, co
     atomicAdd(scal + LTG_S_CNT, s_acc[3]);
     if (bwd && db4 != nullptr) atomicAdd(db4, s_acc[2]);
   }
-  if (bwd) {
-    for (int j = tid; j < h3; j += HEAD_THREADS) {
-      if (dw4 != nullptr) atomicAdd(dw4 + j, s_dw4[j]);
-      if (db3 != nullptr) atomicAdd(db3 + j, s_db3[j]);
-    }
-  }
-}
-
-constexpr int COLSUM_ROWS = 16;
-
-__global__ void drop_tanh_bwd_kernel(const float* __restrict__ dH, int ld_dh, const __nv_bfloat16* __restrict__ Hact, int ld_h, int P, int N,
-                                     float keep, __nv_bfloat16* __restrict__ dz, int ld_dz, float* __restrict__ db) {
-  const bool drop = keep > 0.f && keep < 1.f;
-  const int r0 = blockIdx.x * COLSUM_ROWS;
-  const int r1 = min(P, r0 + COLSUM_ROWS);
-  const int c = blockIdx.y * blockDim.x + threadIdx.x;
-  if (c < N) {
-    float cs = 0.f;
-    for (int r = r0; r < r1; ++r) {
-      const float y = __bfloat162float(Hact[(size_t)r * ld_h + c]);
-      const float o = dH[(size_t)r * ld_dh + c] * dact_drop_tanh(y, keep, drop);
-      dz[(size_t)r * ld_dz + c] = __float2bfloat16(o);
-      cs += o;
-    }
-    if (db != nullptr) atomicAdd(db + c, cs);
-  }
+  if (bwd && dw4 != nullptr)
+    for (int j = tid; j < h3; j += HEAD_THREADS) atomicAdd(dw4 + j, s_dw4[j]);
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ src, int64_t ld_src, __nv_bfloat16* __restrict__ dst, int64_t ld_dst,
@@ -134,23 +123,15 @@ extern "C" int ltg_disc_gather(const void* E_bf16, const int32_t* pop_ids, const
 }
 
 extern "C" int ltg_disc_head(const void* Y3_bf16, int ld, int P, int h3, const float* w4, const float* b4, const int32_t* label,
-                             float keep, float* y_out, float* scal, void* dz3_bf16, float* dw4, float* db3, float* db4, void* stream) {
+                             float keep, float* y_out, float* scal, void* dz3_bf16, float* dw4, float* db4, void* stream) {
   LTG_REQUIRE(Y3_bf16 && w4 && b4 && label && scal);
   LTG_REQUIRE(h3 > 0 && h3 <= HEAD_MAXH3 && ld >= h3);
   if (P <= 0) return LTG_OK;
-  disc_head_kernel<<<(P + HEAD_ROWS - 1) / HEAD_ROWS, HEAD_THREADS, 0, (cudaStream_t)stream>>>(
+  int blocks = (P + HEAD_THREADS / 32 - 1) / (HEAD_THREADS / 32);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  disc_head_kernel<<<blocks, HEAD_THREADS, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(Y3_bf16), ld, P, h3, w4, b4, label, keep, y_out, scal, reinterpret_cast<__nv_bfloat16*>(dz3_bf16),
-      dw4, db3, db4);
-  LTG_CHECK_LAUNCH();
-  return LTG_OK;
-}
-
-extern "C" int ltg_drop_tanh_bwd(const float* dH, int ld_dh, const void* Hact_bf16, int ld_h, int P, int N, float keep,
-                                 void* dz_bf16, int ld_dz, float* dbias, void* stream) {
-  LTG_REQUIRE(dH && Hact_bf16 && dz_bf16);
-  if (P <= 0) return LTG_OK;
-  drop_tanh_bwd_kernel<<<dim3((P + COLSUM_ROWS - 1) / COLSUM_ROWS, (N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-      dH, ld_dh, reinterpret_cast<const __nv_bfloat16*>(Hact_bf16), ld_h, P, N, keep, reinterpret_cast<__nv_bfloat16*>(dz_bf16), ld_dz, dbias);
+      dw4, db4);
   LTG_CHECK_LAUNCH();
   return LTG_OK;
 }

@@ -2,14 +2,15 @@
 //
 //   D[M,N] = A[M,K] * B[N,K]^T          (each operand either K-major or MN-major in HBM)
 //
-// One persistent CTA per SM, 320 threads:
+// One persistent CTA per SM, 576 threads:
 //   warp 0      TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx-count)
 //   warp 1      MMA issuer     (one elected lane issues tcgen05.mma 128xBNx16, fp32 accumulators in TMEM,
 //                               tcgen05.commit releases smem slots / publishes the accumulator)
-//   warps 2..9  epilogue       (tcgen05.ld 32x32b: thread == accumulator row; the Epi functor consumes
-//                               32-column chunks, so row-wise reductions such as the catalog softmax
-//                               statistics are thread-local; warps w and w+4 share a TMEM sub-partition and
-//                               take the even / odd chunks -- one warp per scheduler was issue-latency bound)
+//   warps 2..17 epilogue       (tcgen05.ld 32x32b: thread == accumulator row; the Epi functor consumes
+//                               16-column chunks, so row-wise reductions such as the catalog softmax
+//                               statistics are thread-local; the four warps that share a TMEM sub-partition
+//                               take interleaved chunks. ncu showed the epilogue, not the MMA, sets the tile
+//                               time and that it is issue-latency bound: 4 warps per scheduler, <=113 registers)
 // The TMEM accumulator is double buffered (2*BN columns) so the epilogue of tile i overlaps the
 // mainloop of tile i+1. Split-K is supported (tile index carries the split; Epi decides how to merge).
 //
@@ -29,8 +30,9 @@ namespace ltg {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_EPI_WARPS = 8;                       // two per TMEM sub-partition, alternating 32-column chunks
-constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int GEMM_EPI_WARPS = 16;                      // four per TMEM sub-partition, interleaved 16-column chunks
+constexpr int GEMM_CW = 16;                             // epilogue chunk width (columns per tcgen05.ld)
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;   // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
 
 // ----------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -92,21 +94,18 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives row (lane base + t).
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
+// 32 lanes x 16 consecutive fp32 columns: thread t of the warp receives row (lane base + t).
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr) : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -163,7 +162,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr int B_BYTES = BN * GEMM_BK * 2;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   constexpr uint32_t IDESC = umma_idesc(GEMM_BM, BN, A_MN, B_MN);
-  static_assert(BN % 64 == 0 && BN <= 256, "BN must be 64, 128, 192 or 256");
+  static_assert(BN % 64 == 0 && BN <= 256, "BN must be 64, 128, 192 or 256");  // UMMA N: multiple of 16 up to 256; B boxes are 64 wide
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -259,9 +258,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else {
-    // ===================== epilogue (8 warps; TMEM sub-partition = warp % 4, chunk parity = half) =====================
+    // ===================== epilogue (16 warps; TMEM sub-partition = warp % 4, chunk phase = quarter) =====================
     const int sub = warp & 3;  // hardware rule: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)
-    const int half = (warp - 2) >> 2;
+    const int quarter = (warp - 2) >> 2;
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m_blk = t % shape.m_blocks;
@@ -272,13 +271,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int row = m_blk * GEMM_BM + sub * 32 + lane;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      Epi epi(ep, row, n0, n_blk * 2 + half, split, shape);
+      Epi epi(ep, row, n0, n_blk * 4 + quarter, split, shape);
       const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c = half * 32; c < BN; c += 64) {
+      for (int c = quarter * GEMM_CW; c < BN; c += 4 * GEMM_CW) {
         if (n0 + c >= shape.N) break;  // warp-uniform
-        float v[32];
-        tmem_ld32(taddr + c, v);
+        float v[GEMM_CW];
+        tmem_ld16(taddr + c, v);
         epi.chunk(n0 + c, v);
       }
       epi.finish();
@@ -320,59 +319,89 @@ struct EpiStore {
     int atomic;             // 1: red.add into out_f32 (which the caller zeroed)
     float alpha;
     float keep;             // dropout keep prob; >= 1 or <= 0 disables
-    uint64_t seed; uint32_t rng_stream, rng_step; const uint32_t* rng_step_dev; int rng_ld;  // element idx = row*rng_ld + col
+    uint64_t seed; uint32_t rng_stream, rng_step; const uint32_t* rng_step_dev; int rng_ld;  // pair idx = (row*rng_ld + col)/2
     int aux_col; float* aux_out;  // aux_col < 0 disables
+    const __nv_bfloat16* dact_src; int dact_ld; float dact_keep;  // multiply by d/da dropout(tanh(a)) recovered from the stored activation
   };
   const Params& p;
   int row, M, N;
-  uint32_t thr, step;
+  uint32_t thr16, key;
   float inv_keep;
+  bool drop;
   __device__ EpiStore(const Params& p_, int row_, int, int, int, const GemmShape& s) : p(p_), row(row_), M(s.M), N(s.N) {
-    const bool drop = p.keep > 0.f && p.keep < 1.f;
-    step = p.rng_step + ((drop && p.rng_step_dev != nullptr) ? *p.rng_step_dev : 0u);
-    thr = drop ? ltg_keep_threshold(p.keep) : 0xFFFFFFFFu;
+    drop = p.keep > 0.f && p.keep < 1.f;
+    thr16 = drop ? ltg_keep_threshold16(p.keep) : 65536u;
     inv_keep = drop ? 1.0f / p.keep : 1.0f;
+    key = 0;
+    if (drop) key = ltg_hash_key(p.seed, p.rng_stream, p.rng_step + (p.rng_step_dev != nullptr ? *p.rng_step_dev : 0u));
   }
-  __device__ void chunk(int col0, float (&v)[32]) {
+  __device__ void chunk(int col0, float (&v)[GEMM_CW]) {
     if (row >= M) return;
-    const bool drop = p.keep > 0.f && p.keep < 1.f;
+    constexpr int CW = GEMM_CW;
+    const bool full = col0 + CW <= N;
     if (p.bias != nullptr) {
-      if (col0 + 32 <= N && ((reinterpret_cast<uintptr_t>(p.bias + col0) & 15) == 0)) {
+      if (full && ((reinterpret_cast<uintptr_t>(p.bias + col0) & 15) == 0)) {
         const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < CW / 4; ++i) {
           const float4 b = __ldg(b4 + i);
           v[4 * i] = fmaf(v[4 * i], p.alpha, b.x); v[4 * i + 1] = fmaf(v[4 * i + 1], p.alpha, b.y);
           v[4 * i + 2] = fmaf(v[4 * i + 2], p.alpha, b.z); v[4 * i + 3] = fmaf(v[4 * i + 3], p.alpha, b.w);
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], p.alpha, (col0 + i < N) ? __ldg(p.bias + col0 + i) : 0.f);
+        for (int i = 0; i < CW; ++i) v[i] = fmaf(v[i], p.alpha, (col0 + i < N) ? __ldg(p.bias + col0 + i) : 0.f);
       }
     } else if (p.alpha != 1.0f) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+      for (int i = 0; i < CW; ++i) v[i] *= p.alpha;
     }
     if (p.act == 1) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = tanh_approx(v[i]);
+      for (int i = 0; i < CW; ++i) v[i] = tanh_approx(v[i]);
     }
-    if (drop) {
-      // rng idx = row*rng_ld + col; col0 % 32 == 0 and rng_ld % 4 == 0, so 4 consecutive cols share one Philox block
-      const uint64_t base = (uint64_t)row * (uint64_t)p.rng_ld + (uint64_t)col0;
+    if (p.dact_src != nullptr) {
+      // backward through y = dropout(tanh(a)) stored post-dropout: dy/da = mask/keep * (1 - tanh^2) = (1 - (y*keep)^2)/keep where y != 0
+      const __nv_bfloat16* src = p.dact_src + (size_t)row * p.dact_ld + col0;
+      const bool dd = p.dact_keep > 0.f && p.dact_keep < 1.f;
+      const float kk = dd ? p.dact_keep : 1.0f, ik = 1.0f / kk;
+      if (full && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const uint64_t blk = (base >> 2) + q;
-        Philox4 r = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), p.rng_stream, step, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-        v[4 * q + 0] = r.x < thr ? v[4 * q + 0] * inv_keep : 0.f;
-        v[4 * q + 1] = r.y < thr ? v[4 * q + 1] * inv_keep : 0.f;
-        v[4 * q + 2] = r.z < thr ? v[4 * q + 2] * inv_keep : 0.f;
-        v[4 * q + 3] = r.w < thr ? v[4 * q + 3] * inv_keep : 0.f;
+        for (int q = 0; q < CW / 8; ++q) {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(src) + q);
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 y = unpack_bf16x2(w[j]);
+            const float t0 = y.x * kk, t1 = y.y * kk;
+            v[8 * q + 2 * j] *= (dd && y.x == 0.f) ? 0.f : (1.0f - t0 * t0) * ik;
+            v[8 * q + 2 * j + 1] *= (dd && y.y == 0.f) ? 0.f : (1.0f - t1 * t1) * ik;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < CW; ++i) {
+          if (col0 + i < N) {
+            const float y = __bfloat162float(src[i]);
+            const float t = y * kk;
+            v[i] *= (dd && y == 0.f) ? 0.f : (1.0f - t * t) * ik;
+          }
+        }
       }
     }
-    if (p.aux_col >= col0 && p.aux_col < col0 + 32) {
+    if (drop) {
+      // col0 % 16 == 0 and rng_ld % 2 == 0: one hash per pair of adjacent columns
+      const uint64_t pbase = ((uint64_t)row * (uint64_t)p.rng_ld + (uint64_t)col0) >> 1;
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
+      for (int q = 0; q < CW / 2; ++q) {
+        const uint32_t h = ltg_hash_pair(key, pbase + q);
+        v[2 * q] = (h & 0xFFFFu) < thr16 ? v[2 * q] * inv_keep : 0.f;
+        v[2 * q + 1] = (h >> 16) < thr16 ? v[2 * q + 1] * inv_keep : 0.f;
+      }
+    }
+    if (p.aux_col >= col0 && p.aux_col < col0 + CW) {
+#pragma unroll
+      for (int i = 0; i < CW; ++i)
         if (col0 + i == p.aux_col) {
           if (p.atomic) atomicAdd(p.aux_out + row, v[i]); else p.aux_out[row] = v[i];
         }
@@ -382,22 +411,22 @@ struct EpiStore {
       float* o = p.out_f32 + (size_t)row * p.ld_f32 + col0;
       if (p.atomic) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
+        for (int i = 0; i < CW; ++i)
           if (col0 + i < nlim) atomicAdd(o + i, v[i]);
-      } else if (col0 + 32 <= nlim && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+      } else if (col0 + CW <= nlim && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        for (int i = 0; i < CW; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
       } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
+        for (int i = 0; i < CW; ++i)
           if (col0 + i < nlim) o[i] = v[i];
       }
     }
     if (p.out_bf16 != nullptr) {
       __nv_bfloat16* o = p.out_bf16 + (size_t)row * p.ld_bf16 + col0;
-      if (col0 + 32 <= nlim && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+      if (col0 + CW <= nlim && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
+        for (int i = 0; i < CW; i += 8) {
           uint4 u;
           u.x = pack_bf16x2(v[i], v[i + 1]); u.y = pack_bf16x2(v[i + 2], v[i + 3]);
           u.z = pack_bf16x2(v[i + 4], v[i + 5]); u.w = pack_bf16x2(v[i + 6], v[i + 7]);
@@ -405,7 +434,7 @@ struct EpiStore {
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
+        for (int i = 0; i < CW; ++i)
           if (col0 + i < nlim) o[i] = __float2bfloat16(v[i]);
       }
     }
@@ -420,47 +449,49 @@ struct EpiLogitsStats {
   struct Params {
     __nv_bfloat16* logits; int ld;   // [M, ld] bf16 (may be null: statistics only)
     const float* bias;               // [N]
-    float2* partial;                 // [2*n_blocks, M] (max, sumexp): one entry per (n block, chunk parity)
+    float2* partial;                 // [4*n_blocks, M] (max, sumexp): one entry per (n block, chunk phase)
   };
   const Params& p;
-  int row, M, N, n_blk;
+  int row, M, N, slot;
   float mx, sum;
-  __device__ EpiLogitsStats(const Params& p_, int row_, int, int n_blk_, int, const GemmShape& s)
-      : p(p_), row(row_), M(s.M), N(s.N), n_blk(n_blk_), mx(-INFINITY), sum(0.f) {}
-  __device__ void chunk(int col0, float (&v)[32]) {
+  __device__ EpiLogitsStats(const Params& p_, int row_, int, int slot_, int, const GemmShape& s)
+      : p(p_), row(row_), M(s.M), N(s.N), slot(slot_), mx(-INFINITY), sum(0.f) {}
+  __device__ void chunk(int col0, float (&v)[GEMM_CW]) {
     if (row >= M) return;
-    if (col0 + 32 <= N && ((reinterpret_cast<uintptr_t>(p.bias + col0) & 15) == 0)) {
+    constexpr int CW = GEMM_CW;
+    constexpr float LOG2E = 1.4426950408889634f;
+    if (col0 + CW <= N && ((reinterpret_cast<uintptr_t>(p.bias + col0) & 15) == 0)) {
       const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < CW / 4; ++i) {
         const float4 b = __ldg(b4 + i);
         v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = (col0 + i < N) ? v[i] + __ldg(p.bias + col0 + i) : -INFINITY;
+      for (int i = 0; i < CW; ++i) v[i] = (col0 + i < N) ? v[i] + __ldg(p.bias + col0 + i) : -INFINITY;
     }
-    // four independent chains for the max and for the sum (one epilogue warp per scheduler pair: latency, not throughput)
+    // four independent chains for the max and for the sum
     float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
 #pragma unroll
-    for (int i = 4; i < 32; i += 4) {
+    for (int i = 4; i < CW; i += 4) {
       m0 = fmaxf(m0, v[i]); m1 = fmaxf(m1, v[i + 1]); m2 = fmaxf(m2, v[i + 2]); m3 = fmaxf(m3, v[i + 3]);
     }
     const float nm = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));  // finite: every processed chunk has col0 < N
-    const float nml = nm * 1.4426950408889634f;
+    const float nml = nm * LOG2E;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      s0 += exp2f(fmaf(v[i], 1.4426950408889634f, -nml)); s1 += exp2f(fmaf(v[i + 1], 1.4426950408889634f, -nml));
-      s2 += exp2f(fmaf(v[i + 2], 1.4426950408889634f, -nml)); s3 += exp2f(fmaf(v[i + 3], 1.4426950408889634f, -nml));
+    for (int i = 0; i < CW; i += 4) {
+      s0 += exp2f(fmaf(v[i], LOG2E, -nml)); s1 += exp2f(fmaf(v[i + 1], LOG2E, -nml));
+      s2 += exp2f(fmaf(v[i + 2], LOG2E, -nml)); s3 += exp2f(fmaf(v[i + 3], LOG2E, -nml));
     }
-    sum = sum * exp2f((mx - nm) * 1.4426950408889634f) + ((s0 + s1) + (s2 + s3));
+    sum = sum * exp2f((mx - nm) * LOG2E) + ((s0 + s1) + (s2 + s3));
     mx = nm;
     if (p.logits != nullptr) {
       __nv_bfloat16* o = p.logits + (size_t)row * p.ld + col0;
-      if (col0 + 32 <= N && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+      if (col0 + CW <= N && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
+        for (int i = 0; i < CW; i += 8) {
           uint4 u;
           u.x = pack_bf16x2(v[i], v[i + 1]); u.y = pack_bf16x2(v[i + 2], v[i + 3]);
           u.z = pack_bf16x2(v[i + 4], v[i + 5]); u.w = pack_bf16x2(v[i + 6], v[i + 7]);
@@ -468,13 +499,13 @@ struct EpiLogitsStats {
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
+        for (int i = 0; i < CW; ++i)
           if (col0 + i < N) o[i] = __float2bfloat16(v[i]);
       }
     }
   }
   __device__ void finish() {
-    if (row < M) p.partial[(size_t)n_blk * M + row] = make_float2(mx, sum);
+    if (row < M) p.partial[(size_t)slot * M + row] = make_float2(mx, sum);
   }
 };
 

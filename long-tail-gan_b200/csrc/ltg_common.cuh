@@ -87,6 +87,28 @@ __host__ __device__ __forceinline__ uint32_t ltg_keep_threshold(float keep) {
   return (uint32_t)t;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cheap stateless dropout bits for the GEMM epilogues (discriminator.py:25,30,44 dropout layers): one 32-bit
+// integer hash ("lowbias32" finaliser) per PAIR of adjacent columns, 16 bits per keep/drop decision
+// (threshold floor(keep * 65536)). Philox costs ~15 instructions per element inside an epilogue that is
+// issue-latency bound; this costs ~4. oracle/philox.py mirrors it bit for bit.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t ltg_lowbias32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t ltg_hash_key(uint64_t seed, uint32_t stream, uint32_t step) {
+  return ltg_lowbias32((uint32_t)seed ^ ltg_lowbias32((uint32_t)(seed >> 32) ^ ltg_lowbias32(stream * 0x9E3779B9u + step)));
+}
+// pair index p = (row * rng_ld + col) / 2 (col even); low half decides col, high half decides col + 1
+__host__ __device__ __forceinline__ uint32_t ltg_hash_pair(uint32_t key, uint64_t p) {
+  return ltg_lowbias32(((uint32_t)p * 0x9E3779B1u) ^ ((uint32_t)(p >> 32) * 0x85ebca6bu) ^ key);
+}
+__host__ __device__ __forceinline__ uint32_t ltg_keep_threshold16(float keep) {
+  int t = (int)((double)keep * 65536.0);
+  return (uint32_t)(t < 0 ? 0 : (t > 65536 ? 65536 : t));
+}
+
 // uniform strictly inside (0,1): ((u32 >> 8) + 0.5) * 2^-24 (exact in fp32)
 __device__ __forceinline__ float ltg_u01(uint32_t r) { return ((float)(r >> 8) + 0.5f) * (1.0f / 16777216.0f); }
 

@@ -17,7 +17,7 @@
 
 namespace {
 
-constexpr int SAMP_THREADS = 128;
+constexpr int SAMP_THREADS = 512;  // heavy users (thousands of candidates) set the kernel's duration: give each CTA 16 warps
 
 __device__ __forceinline__ uint32_t float_to_ordered(float f) {
   const uint32_t u = __float_as_uint(f);

@@ -25,7 +25,8 @@ __global__ void __launch_bounds__(ENC_THREADS)
 enc_gather_fwd_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
                       int n_items, int64_t uid0, const uint4* __restrict__ W, const float* __restrict__ bias, float keep,
                       uint64_t seed, uint32_t step, const uint32_t* __restrict__ step_dev, __nv_bfloat16* __restrict__ h1,
-                      int ld_h1, float* __restrict__ coef, float* __restrict__ pre_ws, int* __restrict__ counters) {
+                      int ld_h1, float* __restrict__ coef, float* __restrict__ pre_ws, int* __restrict__ counters,
+                      const int32_t* __restrict__ slot_of_item, __nv_bfloat16* __restrict__ xc, int ld_xc) {
   __shared__ int s_item[ENC_CHUNK];
   __shared__ float s_coef[ENC_CHUNK];
   __shared__ float s_red[ENC_THREADS / 32];
@@ -71,6 +72,8 @@ enc_gather_fwd_kernel(const int32_t* __restrict__ indptr, const int32_t* __restr
     s_item[j] = item;
     s_coef[j] = c;
     coef[c0 + j] = c;
+    // dense bf16 coefficient matrix over the batch's active items: the A operand of the encoder weight-gradient GEMM
+    if (xc != nullptr) xc[(size_t)u * ld_xc + slot_of_item[item]] = __float2bfloat16(c);
   }
   __syncthreads();
   if (tid < HV) {
@@ -226,44 +229,62 @@ __global__ void tanh_bwd_kernel(const float* __restrict__ dy, int ld_dy, const _
 }
 
 // ---------------------------------------------------------------------------------------------
-// a6: row statistics of the catalog softmax. One warp per user.
+// a6: row statistics of the catalog softmax. One CTA per user (the interaction list of a heavy user is 20x the mean).
 // ---------------------------------------------------------------------------------------------
-__global__ void dec_row_stats_kernel(const float2* __restrict__ partial, int n_blocks, const __nv_bfloat16* __restrict__ logits, int ld, int B,
-                                     const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
-                                     const int32_t* __restrict__ samp_ptr, const int32_t* __restrict__ samp_items,
-                                     const int32_t* __restrict__ samp_valid, float* __restrict__ lse_out, float* __restrict__ xw_out,
-                                     float* __restrict__ su_out, float* __restrict__ scal) {
-  const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (u >= B) return;
+constexpr int STATS_THREADS = 128;
+
+__device__ __forceinline__ float block_sum_128(float v, float* s_red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return s_red[0] + s_red[1] + s_red[2] + s_red[3];
+}
+__device__ __forceinline__ float block_max_128(float v, float* s_red) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+}
+
+__global__ void __launch_bounds__(STATS_THREADS)
+dec_row_stats_kernel(const float2* __restrict__ partial, int n_blocks, const __nv_bfloat16* __restrict__ logits, int ld, int B,
+                     const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
+                     const int32_t* __restrict__ samp_ptr, const int32_t* __restrict__ samp_items,
+                     const int32_t* __restrict__ samp_valid, float* __restrict__ lse_out, float* __restrict__ xw_out,
+                     float* __restrict__ su_out, float* __restrict__ scal) {
+  __shared__ float s_red[4];
+  const int u = blockIdx.x;
+  const int tid = threadIdx.x;
   float mx = -INFINITY;
-  for (int b = lane; b < n_blocks; b += 32) mx = fmaxf(mx, partial[(size_t)b * B + u].x);
-  mx = warp_max(mx);
+  for (int b = tid; b < n_blocks; b += STATS_THREADS) mx = fmaxf(mx, partial[(size_t)b * B + u].x);
+  mx = block_max_128(mx, s_red);
   float s = 0.f;
-  for (int b = lane; b < n_blocks; b += 32) {
+  for (int b = tid; b < n_blocks; b += STATS_THREADS) {
     const float2 p = partial[(size_t)b * B + u];
     s += p.y * __expf(p.x - mx);
   }
-  s = warp_sum(s);
+  s = block_sum_128(s, s_red);
   const float lse = mx + logf(s);
   const __nv_bfloat16* row = logits + (size_t)u * ld;
   float nll = 0.f, xw = 0.f;
   if (indptr != nullptr) {
-    for (int j = indptr[u] + lane; j < indptr[u + 1]; j += 32) {
+    for (int j = indptr[u] + tid; j < indptr[u + 1]; j += STATS_THREADS) {
       const float v = values != nullptr ? values[j] : 1.0f;
       nll -= v * (__bfloat162float(row[indices[j]]) - lse);
       xw += v;
     }
-    nll = warp_sum(nll);
-    xw = warp_sum(xw);
+    nll = block_sum_128(nll, s_red);
+    xw = block_sum_128(xw, s_red);
   }
   float sp = 0.f;
   if (samp_ptr != nullptr) {
-    for (int j = samp_ptr[u] + lane; j < samp_ptr[u + 1]; j += 32)
+    for (int j = samp_ptr[u] + tid; j < samp_ptr[u + 1]; j += STATS_THREADS)
       if (samp_valid[j] > 0) sp += __expf(__bfloat162float(row[samp_items[j]]) - lse);
-    sp = warp_sum(sp);
+    sp = block_sum_128(sp, s_red);
   }
-  if (lane == 0) {
+  if (tid == 0) {
     lse_out[u] = lse;
     if (xw_out != nullptr) xw_out[u] = xw;
     if (su_out != nullptr) su_out[u] = sp;
@@ -348,15 +369,16 @@ dlogits_sparse_kernel(const __nv_bfloat16* __restrict__ logits, int ld, const fl
 extern "C" int ltg_enc_gather_fwd(const int32_t* indptr, const int32_t* indices, const float* values, int B, int n_items, int64_t uid0,
                                   const void* W_enc_bf16, const float* b_q0, float keep, uint64_t seed, uint32_t step,
                                   const uint32_t* step_dev, void* h1_bf16, int ld_h1, float* coef, int max_row_nnz, float* pre_ws,
-                                  int32_t* counters, void* stream) {
+                                  int32_t* counters, const int32_t* slot_of_item, void* xc_bf16, int ld_xc, void* stream) {
   LTG_REQUIRE(indptr && indices && W_enc_bf16 && b_q0 && h1_bf16 && coef);
   LTG_REQUIRE(ld_h1 % 8 == 0 && ld_h1 >= H);
   LTG_REQUIRE(max_row_nnz <= ENC_CHUNK || (pre_ws != nullptr && counters != nullptr));
+  LTG_REQUIRE(xc_bf16 == nullptr || slot_of_item != nullptr);
   if (B <= 0) return LTG_OK;
   const int chunks = max_row_nnz <= ENC_CHUNK ? 1 : (max_row_nnz + ENC_CHUNK - 1) / ENC_CHUNK;
   enc_gather_fwd_kernel<<<dim3(B, chunks), ENC_THREADS, 0, (cudaStream_t)stream>>>(
       indptr, indices, values, n_items, uid0, reinterpret_cast<const uint4*>(W_enc_bf16), b_q0, keep, seed, step, step_dev,
-      reinterpret_cast<__nv_bfloat16*>(h1_bf16), ld_h1, coef, pre_ws, counters);
+      reinterpret_cast<__nv_bfloat16*>(h1_bf16), ld_h1, coef, pre_ws, counters, slot_of_item, reinterpret_cast<__nv_bfloat16*>(xc_bf16), ld_xc);
   LTG_CHECK_LAUNCH();
   return LTG_OK;
 }
@@ -401,8 +423,7 @@ extern "C" int ltg_dec_row_stats(const float* partial, int n_blocks, const void*
   LTG_REQUIRE(partial && lse && scal);
   LTG_REQUIRE((indptr == nullptr && samp_ptr == nullptr) || logits_bf16 != nullptr);
   if (B <= 0) return LTG_OK;
-  const int threads = 128;
-  dec_row_stats_kernel<<<(B * 32 + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(
+  dec_row_stats_kernel<<<B, STATS_THREADS, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float2*>(partial), n_blocks, reinterpret_cast<const __nv_bfloat16*>(logits_bf16), ld_logits, B, indptr, indices,
       values, samp_ptr, samp_items, samp_valid, lse, xw, s_u, scal);
   LTG_CHECK_LAUNCH();

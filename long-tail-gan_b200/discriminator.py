@@ -4,10 +4,13 @@
 HBM layout: one fp32 arena (master + Adam m, v + gradient + bf16 shadow, identical layouts) so a D update is a single
 fused Adam launch. Matrices are stored with pitches that are multiples of 8 elements (16 B in bf16) so TMA can read
 them, padding is zero and receives zero gradient:
-  W1 [h0, ld1]  W2 [h0, ld2]  W3 [k3, ld3]  w4 [ld3]  b12 [k3]  b3 [ld3]  b4 [4]
-where k3 is the pitch of the concatenated hidden activation [h1 | pad | h2 | pad] (branch 2 starts at a 16-byte aligned
-column), W3 has matching zero rows. The item-embedding table E [n_items, h0] is a frozen random constant (it is not in
-d_params, discriminator.py:14,47 / SURVEY F5): stored once as bf16 [n_items, 128].
+  W1 [h0+1, ld1]  W2 [h0+1, ld2]  W3 [k3, ld3]  w4 [ld3]  b4 [4]
+Biases are the LAST ROW of their weight matrix ("ones-column" form): the gathered embedding rows carry a constant 1 in
+column h0 and the hidden activation [h1 | pad | h2 | 1 | pad] carries a constant 1 in column `one3`, so x*W + b is a
+single GEMM with K+1, and the bias gradient is simply one more row of the weight-gradient GEMM -- no bias vectors, no
+column-sum reductions. k3 is the pitch of the hidden activation (branch 2 starts at a 16-byte aligned column), W3 has
+matching zero rows. The item-embedding table E [n_items, h0] is a frozen random constant (it is not in d_params,
+discriminator.py:14,47 / SURVEY F5): stored once as bf16 [n_items, 128] with column h0 = 1.
 """
 import numpy as np
 import torch
@@ -22,16 +25,16 @@ def _pad(n, q):
 class Discriminator(object):
     def __init__(self, n_items, FEATURE_LEN, h0_size, h1_size, h2_size, h3_size, device=None, seed=None):
         assert FEATURE_LEN == n_items or FEATURE_LEN is None
-        assert h0_size <= 128, "embedding rows are staged as 128-column bf16 rows"
+        assert h0_size < 128, "embedding rows are staged as 128-column bf16 rows (h0 values + the ones column)"
         self.n_items, self.h0, self.h1, self.h2, self.h3 = int(n_items), int(h0_size), int(h1_size), int(h2_size), int(h3_size)
         self.device = torch.device("cuda" if device is None else device)
         self.ld1 = _pad(self.h1, 8)
         self.ld2 = _pad(self.h2, 8)
         self.ld3 = _pad(self.h3, 8)
         self.off2 = _pad(self.h1, 8)                 # column where branch 2 starts inside the hidden activation
-        self.k3 = _pad(self.off2 + self.h2, 8)       # pitch / K of the fc1 input
-        segs = [("W1", self.h0 * self.ld1), ("W2", self.h0 * self.ld2), ("W3", self.k3 * self.ld3), ("w4", self.ld3), ("b12", self.k3),
-                ("b3", self.ld3), ("b4", 4)]
+        self.one3 = self.off2 + self.h2              # column of the constant 1 inside the hidden activation
+        self.k3 = _pad(self.one3 + 1, 8)             # pitch / K of the fc1 input
+        segs = [("W1", (self.h0 + 1) * self.ld1), ("W2", (self.h0 + 1) * self.ld2), ("W3", self.k3 * self.ld3), ("w4", self.ld3), ("b4", 4)]
         self._off = {}
         off = 0
         for name, n in segs:
@@ -59,7 +62,7 @@ class Discriminator(object):
         arena = {"p": self.arena, "m": self.arena_m, "v": self.arena_v, "g": self.arena_g, "b": self.arena_b}[which]
         off, n = self._off[name]
         t = arena[off:off + n]
-        shapes = {"W1": (self.h0, self.ld1), "W2": (self.h0, self.ld2), "W3": (self.k3, self.ld3)}
+        shapes = {"W1": (self.h0 + 1, self.ld1), "W2": (self.h0 + 1, self.ld2), "W3": (self.k3, self.ld3)}
         return t.view(*shapes[name]) if name in shapes else t
 
     # ---- parameters in the reference order d_params = [w1,b1,w2,b2,w3,b3,w4,b4] (discriminator.py:47) ----------------
@@ -67,10 +70,10 @@ class Discriminator(object):
         return torch.cat([torch.arange(0, self.h1), torch.arange(self.off2, self.off2 + self.h2)]).to(self.device)
 
     def get_params(self, which="p"):
-        W3 = self.view("W3", which)[self._rows3()][:, : self.h3]
-        b12 = self.view("b12", which)
-        return [self.view("W1", which)[:, : self.h1].clone(), b12[: self.h1].clone(), self.view("W2", which)[:, : self.h2].clone(),
-                b12[self.off2: self.off2 + self.h2].clone(), W3.clone(), self.view("b3", which)[: self.h3].clone(),
+        W1, W2, W3 = self.view("W1", which), self.view("W2", which), self.view("W3", which)
+        h0 = self.h0
+        return [W1[:h0, : self.h1].clone(), W1[h0, : self.h1].clone(), W2[:h0, : self.h2].clone(), W2[h0, : self.h2].clone(),
+                W3[self._rows3()][:, : self.h3].clone(), W3[self.one3, : self.h3].clone(),
                 self.view("w4", which)[: self.h3].clone().reshape(self.h3, 1), self.view("b4", which)[:1].clone()]
 
     @property
@@ -80,23 +83,25 @@ class Discriminator(object):
     def set_params(self, E, d_params):
         w1, b1, w2, b2, w3, b3, w4, b4 = [torch.as_tensor(p, dtype=torch.float32).to(self.device) for p in d_params]
         self.arena.zero_()
-        self.view("W1")[:, : self.h1] = w1
-        self.view("W2")[:, : self.h2] = w2
-        W3 = self.view("W3")
+        h0 = self.h0
+        W1, W2, W3 = self.view("W1"), self.view("W2"), self.view("W3")
+        W1[:h0, : self.h1] = w1; W1[h0, : self.h1] = b1
+        W2[:h0, : self.h2] = w2; W2[h0, : self.h2] = b2
         W3[: self.h1, : self.h3] = w3[: self.h1]
         W3[self.off2: self.off2 + self.h2, : self.h3] = w3[self.h1:]
+        W3[self.one3, : self.h3] = b3
         self.view("w4")[: self.h3] = w4.reshape(-1)
-        b12 = self.view("b12")
-        b12[: self.h1] = b1
-        b12[self.off2: self.off2 + self.h2] = b2
-        self.view("b3")[: self.h3] = b3
         self.view("b4")[:1] = b4.reshape(-1)
         self.arena_b.copy_(self.arena)
         if E is not None:
             self.E.copy_(torch.as_tensor(E, dtype=torch.float32).to(self.device))
-            self.E_b.zero_()
-            self.E_b[:, : self.h0] = self.E
+            self._refresh_E()
         self.arena_m.zero_(); self.arena_v.zero_()
+
+    def _refresh_E(self):
+        self.E_b.zero_()
+        self.E_b[:, : self.h0] = self.E
+        self.E_b[:, self.h0] = 1.0   # ones column: the bias rows of W1 / W2 ride the same GEMM
 
     def init_weights(self, seed=None):
         """discriminator.py:14-41: truncated_normal(stddev=0.1) matrices (unseeded in the reference), zero biases."""
@@ -119,8 +124,7 @@ class Discriminator(object):
         for k, v in sd.items():
             getattr(self, k).copy_(v.to(self.device))
         self.arena_b.copy_(self.arena)
-        self.E_b.zero_()
-        self.E_b[:, : self.h0] = self.E
+        self._refresh_E()
 
     def __repr__(self):
         return "Discriminator(h0=%d,h1=%d,h2=%d,h3=%d)" % (self.h0, self.h1, self.h2, self.h3)

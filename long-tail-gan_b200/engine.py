@@ -66,6 +66,7 @@ class TrainData(object):
         self.max_B = max(bt["B"] for bt in self.batches)
         self.max_P = max(bt["P"] for bt in self.batches)
         self.max_K = max(bt["K"] for bt in self.batches)
+        self.max_active = max(bt["n_active"] for bt in self.batches)
 
     def _make_batch(self, b0, b1, n_draw, real_ptr, real_niche, real_pop, cand_len):
         B = b1 - b0
@@ -74,9 +75,11 @@ class TrainData(object):
         idx = self.h_indices[e0:e1].astype(np.int64)
         rows = np.repeat(np.arange(B, dtype=np.int64), np.diff(self.h_indptr[b0:b1 + 1]))
         order = np.lexsort((rows, idx))  # item-major, then batch row
-        csc_ptr = np.zeros(self.n_items + 1, dtype=np.int64)
-        np.add.at(csc_ptr, idx + 1, 1)
-        csc_ptr = np.cumsum(csc_ptr)
+        # active items of the batch: compact CSC (act_ptr over the active items) + slot_of_item[I] (-1 = not in the batch)
+        active, counts = np.unique(idx, return_counts=True)
+        act_ptr = np.concatenate([[0], np.cumsum(counts)])
+        slot_of_item = np.full(self.n_items, -1, dtype=np.int64)
+        slot_of_item[active] = np.arange(len(active))
         samp_ptr = np.concatenate([[0], np.cumsum(n_draw[b0:b1])])
         K = int(samp_ptr[-1])
         r0, r1 = int(real_ptr[b0]), int(real_ptr[b1])
@@ -86,11 +89,14 @@ class TrainData(object):
         label = np.full(max(P, 1), -1, dtype=np.int32)
         pair_pop[:Pr] = real_pop[r0:r1]; pair_niche[:Pr] = real_niche[r0:r1]; label[:Pr] = 0
         t = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(dev)  # noqa: E731
-        self._last_host = dict(csc_ptr=csc_ptr, csc_row=rows[order], csc_pos=order + e0, samp_ptr=samp_ptr, pair_pop=pair_pop[:max(Pr, 1)],
+        self._last_host = dict(act_ptr=act_ptr, slot_of_item=slot_of_item, csc_row=rows[order], csc_pos=order + e0, samp_ptr=samp_ptr,
+                               pair_pop=pair_pop[:max(Pr, 1)],
                                pair_niche=pair_niche[:max(Pr, 1)], label=label[:max(Pr, 1)])
         return dict(b0=b0, B=B, uid0=self.uid_start + b0, nnz=e1 - e0, Pr=Pr, K=K, P=P, e0=e0, e1=e1,
                     host_src={k: np.ascontiguousarray(v, dtype=np.int32) for k, v in self._last_host.items()},
-                    csc_ptr=t(csc_ptr), csc_row=t(rows[order]), csc_pos=t(order + e0), samp_ptr=t(samp_ptr),
+                    act_ptr=t(act_ptr), slot_of_item=t(slot_of_item), n_active=int(len(active)),
+                    csc_row=t(rows[order] if len(order) else np.zeros(1)), csc_pos=t(order + e0 if len(order) else np.zeros(1)),
+                    samp_ptr=t(samp_ptr),
                     pair_pop=t(pair_pop), pair_niche=t(pair_niche), label=t(label),
                     cnt=torch.zeros(1, dtype=torch.int32, device=dev),
                     max_cand=int(cand_len[b0:b1].max()) if B > 0 else 0,
@@ -121,7 +127,7 @@ def pin_host_inputs(data):
         add(data.pop_items[p0:p1], h["pop_items"][p0:p1])
         hs = bt["host_src"]
         Pr = bt["Pr"]
-        for k in ("csc_ptr", "csc_row", "csc_pos", "samp_ptr"):
+        for k in ("act_ptr", "slot_of_item", "csc_row", "csc_pos", "samp_ptr"):
             add(bt[k], hs[k])
         if Pr > 0:
             for k in ("pair_pop", "pair_niche", "label"):
@@ -141,7 +147,7 @@ class GanEngine(object):
     """Owns the workspaces and runs phase A / D / G / evaluation for one (vae, discriminator) pair."""
 
     def __init__(self, vae, disc, max_B, max_P=1, seed=0, lr=1e-4, lam=1.0, keep_vae=0.75, keep_d=0.7, total_anneal_steps=20000,
-                 anneal_cap=0.2, B_global=None, use_graphs=True, world_size=1):
+                 anneal_cap=0.2, B_global=None, use_graphs=True, world_size=1, max_active=None):
         ops.init()
         self.world_size = int(world_size)
         self.kernels_launched = 0
@@ -149,7 +155,7 @@ class GanEngine(object):
         self.vae, self.disc = vae, disc
         self.I = vae.n_items
         self.ld = _pad(self.I, 8)
-        self.nblk = 2 * ((self.I + 255) // 256)  # softmax partials per row: (256-column block) x (chunk parity)
+        self.nblk = 4 * ((self.I + 255) // 256)  # softmax partials per row: (256-column block) x (chunk phase)
         self.seed, self.lr, self.lam = int(seed), float(lr), float(lam)
         self.keep_vae, self.keep_d = float(keep_vae), float(keep_d)
         self.total_anneal_steps, self.anneal_cap = float(total_anneal_steps), float(anneal_cap)
@@ -157,6 +163,7 @@ class GanEngine(object):
         self.use_graphs = use_graphs
         self.device = vae.device
         self.max_B, self.max_P = int(max_B), int(max(1, max_P))
+        self.max_active = int(self.I if max_active is None else max(1, max_active))
         self.words = torch.zeros(4, dtype=torch.int32, device=self.device)
         self.scal = torch.zeros(ops.NSCAL, dtype=torch.float32, device=self.device)
         self._graphs = {}
@@ -186,6 +193,10 @@ class GanEngine(object):
         self.dh2pre = torch.zeros(B, H, **bf)
         self.dmulv = torch.zeros(B, 2 * L, **bf)
         self.dh1pre = torch.zeros(B, H, **f32)
+        self.G_enc = torch.zeros(self.max_active, H, **f32)   # compact encoder gradient: one row per active item of the batch
+        self.ld_xc = _pad(self.max_active, 8)
+        self.Xc = torch.zeros(B, self.ld_xc, **bf)            # dense dropout/normalisation coefficients over the active items
+        self.dh1pre_b = torch.zeros(B, H, **bf)
         self.dW_q0 = torch.zeros(I, H, **f32) if self.world_size > 1 else None  # dense encoder gradient, only for the all-reduce
         # fp32 accumulators that must be zero at the start of a G step: one arena, one memset
         self.zero_g = torch.zeros(B * H + B * L + B * H, **f32)
@@ -195,10 +206,10 @@ class GanEngine(object):
         # discriminator
         self.Xp = torch.zeros(P, 128, **bf); self.Xn = torch.zeros(P, 128, **bf)
         self.Hd = torch.zeros(P, d.k3, **bf)
+        self.Hd[:, d.one3] = 1.0   # ones column: row `one3` of W3 is the fc1 bias
         self.Y3 = torch.zeros(P, d.ld3, **bf)
         self.y = torch.zeros(P, **f32)
         self.dz3 = torch.zeros(P, d.ld3, **bf)
-        self.dH = torch.zeros(P, d.k3, **f32)
         self.dz12 = torch.zeros(P, d.k3, **bf)
 
     # ------------------------------------------------------------------------------------------------------------
@@ -212,8 +223,11 @@ class GanEngine(object):
         indices = data.indices if indices is None else indices
         coef = data.coef if coef is None else coef
         uid0 = bt["uid0"] if uid0 is None else uid0
+        if is_training:
+            self.Xc.zero_()
         ops.enc_gather_fwd(indptr, indices, None, B, self.I, uid0, v.W_q0_b, v.view("b_q0"), keep, self.seed, 0, self.words, self.h1, coef,
-                           bt["max_nnz"] if max_nnz is None else max_nnz, self.enc_ws, self.enc_cnt)
+                           bt["max_nnz"] if max_nnz is None else max_nnz, self.enc_ws, self.enc_cnt,
+                           bt["slot_of_item"] if is_training else None, self.Xc if is_training else None)
         ops.gemm(self.h1, v.view("W_q1", "b"), B, 2 * L, H, b_mn=True, bn=64, out_f32=self.mulv, bias=v.view("b_q1"))
         ops.latent_fwd(self.mulv, self.eps_inject if is_training else None, B, uid0, 1.0 if is_training else 0.0, self.seed, 0,
                        self.words, self.z, self.zmu, self.scal)
@@ -227,16 +241,16 @@ class GanEngine(object):
         seed, kd = self.seed, self.keep_d
         st = ops.STREAM_DISC_DROPOUT
         ops.disc_gather(d.E_b, pop, niche, P, self.Xp, self.Xn)
-        b12 = d.view("b12")
-        ops.gemm(self.Xp, d.view("W1", "b"), P, d.h1, d.h0, lda=128, b_mn=True, bn=64, out_bf16=self.Hd, ld_bf16=d.k3, bias=b12, act=1,
-                 keep=kd, seed=seed, rng_stream=st, rng_step_dev=self.words, rng_ld=d.ld1)
-        ops.gemm(self.Xn, d.view("W2", "b"), P, d.h2, d.h0, lda=128, b_mn=True, bn=64, out_bf16=self.Hd[:, d.off2:], ld_bf16=d.k3,
-                 bias=b12[d.off2:], act=1, keep=kd, seed=seed, rng_stream=st + 1, rng_step_dev=self.words, rng_ld=d.ld2)
-        ops.gemm(self.Hd, d.view("W3", "b"), P, d.h3, d.k3, b_mn=True, bn=64, out_bf16=self.Y3, bias=d.view("b3"), act=1, keep=kd, seed=seed,
+        k1 = d.h0 + 1  # embedding columns + the ones column (bias row of W1 / W2)
+        ops.gemm(self.Xp, d.view("W1", "b"), P, d.h1, k1, lda=128, b_mn=True, bn=ops.pick_bn(P, d.h1), out_bf16=self.Hd, ld_bf16=d.k3,
+                 act=1, keep=kd, seed=seed, rng_stream=st, rng_step_dev=self.words, rng_ld=d.ld1)
+        ops.gemm(self.Xn, d.view("W2", "b"), P, d.h2, k1, lda=128, b_mn=True, bn=ops.pick_bn(P, d.h2), out_bf16=self.Hd[:, d.off2:],
+                 ld_bf16=d.k3, act=1, keep=kd, seed=seed, rng_stream=st + 1, rng_step_dev=self.words, rng_ld=d.ld2)
+        ops.gemm(self.Hd, d.view("W3", "b"), P, d.h3, d.k3, b_mn=True, bn=ops.pick_bn(P, d.h3), out_bf16=self.Y3, act=1, keep=kd, seed=seed,
                  rng_stream=st + 2, rng_step_dev=self.words, rng_ld=d.ld3)
         if backward:
             ops.disc_head(self.Y3, P, d.h3, d.view("w4"), d.view("b4"), label, kd, self.y, self.scal, self.dz3, d.view("w4", "g"),
-                          d.view("b3", "g"), d.view("b4", "g"))
+                          d.view("b4", "g"))
         else:
             ops.disc_head(self.Y3, P, d.h3, d.view("w4"), d.view("b4"), label, kd, self.y, self.scal)
 
@@ -272,14 +286,19 @@ class GanEngine(object):
         d.arena_g.zero_()
         ops.step_advance(self.words, self.scal, 1, self.lr, anneal_cap=self.anneal_cap, total_anneal_steps=self.total_anneal_steps)
         self._disc_forward(bt["pair_pop"], bt["pair_niche"], bt["label"], P, True)
-        sp = max(1, min(32, P // 512))
-        # dW3 = Hd^T dz3 ; dH = dz3 W3^T ; dz12 = dH * dact ; dW1 = Xp^T dz1 ; dW2 = Xn^T dz2     (autodiff of discriminator.py:25-55)
-        ops.gemm(self.Hd, self.dz3, d.k3, d.h3, P, a_mn=True, b_mn=True, splits=sp, bn=64, out_f32=d.view("W3", "g"), atomic=True)
-        ops.gemm(self.dz3, d.view("W3", "b"), P, d.k3, d.h3, bn=64, out_f32=self.dH)
-        ops.drop_tanh_bwd(self.dH, self.Hd, P, d.k3, self.keep_d, self.dz12, d.view("b12", "g"))
-        ops.gemm(self.Xp, self.dz12, d.h0, d.h1, P, a_mn=True, b_mn=True, splits=sp, bn=64, out_f32=d.view("W1", "g"), atomic=True)
-        ops.gemm(self.Xn, self.dz12[:, d.off2:], d.h0, d.h2, P, a_mn=True, b_mn=True, ldb=d.k3, splits=sp, bn=64,
-                 out_f32=d.view("W2", "g"), atomic=True)
+        # autodiff of discriminator.py:25-55; every bias gradient is the ones-row of its weight-gradient GEMM
+        k1 = d.h0 + 1
+        bn3 = ops.pick_bn(d.k3, d.h3, True)
+        ops.gemm(self.Hd, self.dz3, d.k3, d.h3, P, a_mn=True, b_mn=True, splits=ops.pick_splits(d.k3, d.h3, P, bn3), bn=bn3,
+                 out_f32=d.view("W3", "g"), atomic=True)                                           # dW3 (+ db3) = Hd^T dz3
+        ops.gemm(self.dz3, d.view("W3", "b"), P, d.k3, d.h3, bn=ops.pick_bn(P, d.k3), out_bf16=self.dz12, dact_src=self.Hd,
+                 dact_keep=self.keep_d)                                                            # dz12 = (dz3 W3^T) * dact(Hd)
+        bn1 = ops.pick_bn(k1, d.h1, True)
+        ops.gemm(self.Xp, self.dz12, k1, d.h1, P, a_mn=True, b_mn=True, splits=ops.pick_splits(k1, d.h1, P, bn1), bn=bn1,
+                 out_f32=d.view("W1", "g"), atomic=True)                                           # dW1 (+ db1) = Xp^T dz1
+        bn2 = ops.pick_bn(k1, d.h2, True)
+        ops.gemm(self.Xn, self.dz12[:, d.off2:], k1, d.h2, P, a_mn=True, b_mn=True, ldb=d.k3, splits=ops.pick_splits(k1, d.h2, P, bn2),
+                 bn=bn2, out_f32=d.view("W2", "g"), atomic=True)                                   # dW2 (+ db2) = Xn^T dz2
 
     def _d_update(self):
         d = self.disc
@@ -333,9 +352,11 @@ class GanEngine(object):
         ops.latent_bwd(self.dz, self.mulv, self.zmu, B, Bg, -1.0, self.scal, self.dmulv, v.view("b_q1", "g"))
         ops.gemm(self.dmulv, v.view("W_q1", "b"), B, H, 2 * L, bn=64, out_f32=self.dh1)
         ops.gemm(self.h1, self.dmulv, H, 2 * L, B, a_mn=True, b_mn=True, bn=64, out_f32=v.view("W_q1", "g"))
-        ops.tanh_bwd(self.dh1, self.h1, B, H, dx_f32=self.dh1pre, dbias=v.view("b_q0", "g"))
+        ops.tanh_bwd(self.dh1, self.h1, B, H, dx_bf16=self.dh1pre_b, dx_f32=self.dh1pre, dbias=v.view("b_q0", "g"))
+        # encoder weight gradient over the batch's active items as a tensor-core GEMM: G = Xc^T dh1pre   [n_active, 600]
+        ops.gemm(self.Xc, self.dh1pre_b, bt["n_active"], H, B, a_mn=True, b_mn=True, bn=ops.pick_bn(bt["n_active"], H), out_f32=self.G_enc)
         if self.world_size > 1:
-            ops.enc_wgrad(self.dW_q0, self.I, bt["csc_ptr"], bt["csc_row"], bt["csc_pos"], data.coef, self.dh1pre)
+            ops.enc_wgrad_expand(self.dW_q0, self.I, bt["slot_of_item"], self.G_enc)
 
     def _g_update(self, data, bi):
         bt = data.batches[bi]
@@ -343,8 +364,7 @@ class GanEngine(object):
         if self.world_size > 1:
             ops.adam(v.W_q0, v.W_q0_m, v.W_q0_v, self.dW_q0, v.W_q0_b, scal=self.scal)
         else:
-            ops.enc_adam(v.W_q0, v.W_q0_m, v.W_q0_v, v.W_q0_b, self.I, bt["csc_ptr"], bt["csc_row"], bt["csc_pos"], data.coef,
-                         self.dh1pre, scal=self.scal)
+            ops.enc_adam(v.W_q0, v.W_q0_m, v.W_q0_v, v.W_q0_b, self.I, bt["slot_of_item"], self.G_enc, scal=self.scal)
         ops.adam(v.WdT, v.WdT_m, v.WdT_v, self.dWdT, v.WdT_b, scal=self.scal)
         ops.adam(v.small, v.small_m, v.small_v, v.small_g, v.small_b, scal=self.scal)
 

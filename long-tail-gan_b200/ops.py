@@ -51,9 +51,40 @@ def step_advance(words, scal, kind, lr, beta1=0.9, beta2=0.999, anneal_cap=0.2, 
     check(lib().ltg_step_advance(ptr(words), ptr(scal), kind, lr, beta1, beta2, anneal_cap, total_anneal_steps, _stream()))
 
 
+def pick_bn(M, N, splits_ok=False):
+    """Tile width for the tcgen05 GEMM. Large-M problems take the widest tile that wastes the fewest padded columns (fewer
+    tiles, A streamed once per n-block); problems with only a handful of 128-row blocks take 64-wide tiles so that the tile
+    count, not the tile efficiency, fills the SMs -- unless split-K provides the parallelism (splits_ok)."""
+    m_blocks = (M + 127) // 128
+    if m_blocks < 37 and not splits_ok:
+        return 64
+    if N <= 64:
+        return 64
+    if N <= 128:
+        return 128
+    if N <= 192:
+        return 192
+    if N <= 256:
+        return 256
+    best = None
+    for bn in (256, 192, 128):
+        padded = (N + bn - 1) // bn * bn
+        if best is None or padded < best[0]:
+            best = (padded, bn)
+    return best[1]
+
+
+def pick_splits(M, N, K, bn, n_sm=148):
+    """Split-K factor that brings the tile count of a skinny (small M*N, long K) GEMM up to about one wave of CTAs."""
+    tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
+    kb = (K + 63) // 64
+    # at most 32 splits: every split adds one fp32 atomic per output element, all landing on the same addresses
+    return max(1, min(kb, n_sm // max(1, tiles), 32))
+
+
 def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, splits=1, bn=128, out_f32=None, out_bf16=None, bias=None,
          act=0, alpha=1.0, atomic=False, keep=1.0, seed=0, rng_stream=0, rng_step=0, rng_step_dev=None, rng_ld=0, aux_col=-1,
-         aux_out=None, ld_f32=None, ld_bf16=None):
+         aux_out=None, ld_f32=None, ld_bf16=None, dact_src=None, dact_keep=1.0):
     """D[M,N] = alpha*A*B^T on the tcgen05 GEMM. A is [M,K] (or stored [K,M] when a_mn), B is [N,K] (or [K,N] when b_mn)."""
     _count(1)
     lda = A.stride(0) if lda is None else lda
@@ -64,15 +95,16 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, splits=1,
         ld_bf16 = out_bf16.stride(0)
     check(lib().ltg_gemm_bf16(ptr(A), lda, int(a_mn), ptr(B), ldb, int(b_mn), M, N, K, splits, bn, ptr(out_f32), ld_f32 or 0,
                               ptr(out_bf16), ld_bf16 or 0, ptr(bias), act, alpha, int(atomic), keep, seed, rng_stream, rng_step,
-                              ptr(rng_step_dev), rng_ld, aux_col, ptr(aux_out), _stream()))
+                              ptr(rng_step_dev), rng_ld, aux_col, ptr(aux_out), ptr(dact_src),
+                              dact_src.stride(0) if dact_src is not None else 0, dact_keep, _stream()))
 
 
 def enc_gather_fwd(indptr, indices, values, B, n_items, uid0, W_enc_bf16, b_q0, keep, seed, step, step_dev, h1, coef, max_row_nnz=0,
-                   pre_ws=None, counters=None):
+                   pre_ws=None, counters=None, slot_of_item=None, xc=None):
     _count(1)
     check(lib().ltg_enc_gather_fwd(ptr(indptr), ptr(indices), ptr(values), B, n_items, uid0, ptr(W_enc_bf16), ptr(b_q0), keep, seed,
                                    step, ptr(step_dev), ptr(h1), h1.stride(0), ptr(coef), max_row_nnz, ptr(pre_ws), ptr(counters),
-                                   _stream()))
+                                   ptr(slot_of_item), ptr(xc), xc.stride(0) if xc is not None else 0, _stream()))
 
 
 def latent_fwd(mulv, eps, B, uid0, is_training, seed, step, step_dev, z, zmu, scal):
@@ -124,17 +156,21 @@ def adam(p, m, v, g, shadow, lr_t=-1.0, scal=None, beta1=0.9, beta2=0.999, eps=1
     check(lib().ltg_adam(ptr(p), ptr(m), ptr(v), ptr(g), ptr(shadow), p.numel(), lr_t, ptr(scal), beta1, beta2, eps, _stream()))
 
 
-def enc_adam(p, m, v, shadow, n_items, csc_ptr, csc_row, csc_pos, coef, dh1pre, lr_t=-1.0, scal=None, beta1=0.9, beta2=0.999,
-             eps=1e-8):
+def enc_wgrad_compact(G, n_active, act_ptr, csc_row, csc_pos, coef, dh1pre):
     _count(1)
-    check(lib().ltg_enc_adam(ptr(p), ptr(m), ptr(v), ptr(shadow), n_items, ptr(csc_ptr), ptr(csc_row), ptr(csc_pos), ptr(coef),
-                             ptr(dh1pre), dh1pre.stride(0), lr_t, ptr(scal), beta1, beta2, eps, _stream()))
+    check(lib().ltg_enc_wgrad_compact(ptr(G), n_active, ptr(act_ptr), ptr(csc_row), ptr(csc_pos), ptr(coef), ptr(dh1pre),
+                                      dh1pre.stride(0), _stream()))
 
 
-def enc_wgrad(dW, n_items, csc_ptr, csc_row, csc_pos, coef, dh1pre):
+def enc_adam(p, m, v, shadow, n_items, slot_of_item, G, lr_t=-1.0, scal=None, beta1=0.9, beta2=0.999, eps=1e-8):
     _count(1)
-    check(lib().ltg_enc_wgrad(ptr(dW), n_items, ptr(csc_ptr), ptr(csc_row), ptr(csc_pos), ptr(coef), ptr(dh1pre), dh1pre.stride(0),
-                              _stream()))
+    check(lib().ltg_enc_adam(ptr(p), ptr(m), ptr(v), ptr(shadow), n_items, ptr(slot_of_item), ptr(G), lr_t, ptr(scal), beta1, beta2,
+                             eps, _stream()))
+
+
+def enc_wgrad_expand(dW, n_items, slot_of_item, G):
+    _count(1)
+    check(lib().ltg_enc_wgrad_expand(ptr(dW), n_items, ptr(slot_of_item), ptr(G), _stream()))
 
 
 def sample_pairs(logits, B, n_items, uid0, cand_ptr, cand_items, samp_ptr, pop_ptr, pop_items, item_valid, seed, step, step_dev,
@@ -150,16 +186,10 @@ def disc_gather(E_bf16, pop_ids, niche_ids, P, Xp, Xn):
     check(lib().ltg_disc_gather(ptr(E_bf16), ptr(pop_ids), ptr(niche_ids), P, ptr(Xp), ptr(Xn), _stream()))
 
 
-def disc_head(Y3, P, h3, w4, b4, label, keep, y_out, scal, dz3=None, dw4=None, db3=None, db4=None):
+def disc_head(Y3, P, h3, w4, b4, label, keep, y_out, scal, dz3=None, dw4=None, db4=None):
     _count(1)
     check(lib().ltg_disc_head(ptr(Y3), Y3.stride(0), P, h3, ptr(w4), ptr(b4), ptr(label), keep, ptr(y_out), ptr(scal), ptr(dz3),
-                              ptr(dw4), ptr(db3), ptr(db4), _stream()))
-
-
-def drop_tanh_bwd(dH, Hact, P, N, keep, dz, dbias):
-    _count(1)
-    check(lib().ltg_drop_tanh_bwd(ptr(dH), dH.stride(0), ptr(Hact), Hact.stride(0), P, N, keep, ptr(dz), dz.stride(0), ptr(dbias),
-                                  _stream()))
+                              ptr(dw4), ptr(db4), _stream()))
 
 
 def topk_metrics(scores, n_rows, n_items, seen_ptr, seen_items, held_ptr, held_items, k, rks, topk_idx, dcg, hits):

@@ -82,3 +82,36 @@ def normal_eps(seed, step, idx):
 def gumbel(seed, step, idx):
     r = rand_u32(seed, STREAM_SAMPLE, step, idx)
     return (-np.log(-np.log(u01(r)))).astype(np.float32)
+
+
+# ---- cheap counter hash used by the GEMM-epilogue dropout (ltg_common.cuh: ltg_lowbias32 / ltg_hash_key / ltg_hash_pair) ----
+def lowbias32(x):
+    x = np.asarray(x, dtype=np.uint64) & _MASK32
+    x ^= x >> np.uint64(16)
+    x = (x * np.uint64(0x7feb352d)) & _MASK32
+    x ^= x >> np.uint64(15)
+    x = (x * np.uint64(0x846ca68b)) & _MASK32
+    x ^= x >> np.uint64(16)
+    return x
+
+
+def hash_key(seed, stream, step):
+    inner = lowbias32((np.uint64(stream) * np.uint64(0x9E3779B9) + np.uint64(step)) & _MASK32)
+    mid = lowbias32(np.uint64((seed >> 32) & 0xFFFFFFFF) ^ inner)
+    return lowbias32(np.uint64(seed & 0xFFFFFFFF) ^ mid)
+
+
+def hash_keep_mask(seed, stream, step, n_rows, n_cols, rng_ld, keep):
+    """Keep-mask [n_rows, n_cols] of the GEMM dropout epilogue: pair p = (row*rng_ld + col) // 2, low 16 bits decide the even
+    column, high 16 bits the odd one, kept iff bits < floor(keep * 65536)."""
+    if not (0.0 < keep < 1.0):
+        return np.ones((n_rows, n_cols), dtype=bool)
+    key = hash_key(seed, stream, step)
+    idx = np.arange(n_rows, dtype=np.uint64)[:, None] * np.uint64(rng_ld) + np.arange(n_cols, dtype=np.uint64)[None, :]
+    p = idx >> np.uint64(1)
+    x = ((p & _MASK32) * np.uint64(0x9E3779B1)) & _MASK32
+    x ^= ((p >> np.uint64(32)) * np.uint64(0x85ebca6b)) & _MASK32
+    h = lowbias32(x ^ key)
+    bits = np.where((idx & np.uint64(1)) == 0, h & np.uint64(0xFFFF), h >> np.uint64(16))
+    thr = int(float(np.float32(keep)) * 65536.0)
+    return bits < np.uint64(thr)

@@ -48,15 +48,14 @@ def setup():
     E, dparams = orc.init_disc_params(I, H0, H1, H2, H3, seed=77)
     disc.set_params(E, dparams)
     data = eng.TrainData(batch_size=BATCH, **tabs)
-    engine = eng.GanEngine(vae, disc, data.max_B, data.max_P, seed=SEED, lr=1e-4, lam=1.0, use_graphs=False)
+    engine = eng.GanEngine(vae, disc, data.max_B, data.max_P, seed=SEED, lr=1e-4, lam=1.0, use_graphs=False, max_active=data.max_active)
     return dict(eng=eng, vae=vae, disc=disc, data=data, engine=engine, tabs=tabs, params=params, E=E, dparams=dparams)
 
 
 def disc_masks(step, n_rows, disc):
     out = []
     for layer, (n, ld) in enumerate(((disc.h1, disc.ld1), (disc.h2, disc.ld2), (disc.h3, disc.ld3))):
-        idx = np.arange(n_rows, dtype=np.uint64)[:, None] * np.uint64(ld) + np.arange(n, dtype=np.uint64)[None, :]
-        out.append(torch.from_numpy(philox.keep_mask(SEED, philox.STREAM_DISC_DROPOUT + layer, step, idx, 0.7)))
+        out.append(torch.from_numpy(philox.hash_keep_mask(SEED, philox.STREAM_DISC_DROPOUT + layer, step, n_rows, n, ld, 0.7)))
     return out
 
 
@@ -174,7 +173,7 @@ def test_g_step_matches_oracle(setup):
     # gradients: [W_q0, W_q1, W_p0, W_p1, b_q0, b_q1, b_p0, b_p1]
     ops = importlib.import_module("long-tail-gan_b200.ops")
     dWq0 = torch.zeros(I, 600, device="cuda")
-    ops.enc_wgrad(dWq0, I, bt["csc_ptr"], bt["csc_row"], bt["csc_pos"], data.coef, engine.dh1pre)
+    ops.enc_wgrad_expand(dWq0, I, bt["slot_of_item"], engine.G_enc)
     torch.cuda.synchronize()
     dev_grads = [dWq0, vae.view("W_q1", "g"), vae.view("W_p0", "g"), engine.dWdT.t(), vae.view("b_q0", "g"), vae.view("b_q1", "g"),
                  vae.view("b_p0", "g"), vae.view("b_p1", "g")]
@@ -196,7 +195,7 @@ def test_graph_replay_equals_eager(setup):
         disc = dis.Discriminator(I, I, H0, H1, H2, H3, seed=1)
         disc.set_params(s["E"], s["dparams"])
         data = eng.TrainData(batch_size=BATCH, **s["tabs"])
-        e = eng.GanEngine(vae, disc, data.max_B, data.max_P, seed=SEED, use_graphs=use_graphs)
+        e = eng.GanEngine(vae, disc, data.max_B, data.max_P, seed=SEED, use_graphs=use_graphs, max_active=data.max_active)
         for _ in range(3):
             for bi in range(2):
                 e.run_phase_a(data, bi)

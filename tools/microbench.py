@@ -33,7 +33,7 @@ def main():
     WdT = (torch.randn(I, H, device=dev) * 0.05).bfloat16()
     bd = torch.zeros(I, device=dev)
     logits = torch.zeros(B, ld, device=dev, dtype=torch.bfloat16)
-    nblk = 2 * ((I + 255) // 256)
+    nblk = 4 * ((I + 255) // 256)
     partial = torch.zeros(nblk, B, 2, device=dev)
     t = timeit(lambda: ops.dec_logits_fwd(h2, WdT, bd, B, I, logits, partial))
     fl = 2.0 * B * H * I
@@ -65,13 +65,6 @@ def main():
     coef = torch.zeros(B * nnz_per, device=dev)
     t = timeit(lambda: ops.enc_gather_fwd(indptr, indices, None, B, I, 0, Wenc, bq, 0.75, 1, 0, None, h1, coef, nnz_per))
     print("enc_gather_fwd        %8.1f us  %6.1f GB/s" % (t, B * nnz_per * 0.75 * 1204 / t / 1e3))
-    rows = np.repeat(np.arange(B), nnz_per)
-    order = np.lexsort((rows, idx_np))
-    csc_ptr = np.zeros(I + 1, dtype=np.int64); np.add.at(csc_ptr, idx_np + 1, 1); csc_ptr = np.cumsum(csc_ptr).astype(np.int32)
-    dh1 = torch.randn(B, H, device=dev)
-    cp, cr, cpos = (torch.from_numpy(x).to(dev) for x in (csc_ptr, rows[order].astype(np.int32), order.astype(np.int32)))
-    t = timeit(lambda: ops.enc_adam(p.view(I, H), m.view(I, H), v.view(I, H), sh.view(I, H), I, cp, cr, cpos, coef, dh1, lr_t=1e-4))
-    print("enc_adam [I,600]      %8.1f us  %6.1f GB/s (26 B/param)" % (t, 26.0 * n / t / 1e3))
     dlo = torch.zeros(B, ld, device=dev, dtype=torch.bfloat16)
     lse = torch.zeros(B, device=dev); xw = torch.ones(B, device=dev) * 73
     t = timeit(lambda: ops.dec_dlogits(logits, lse, xw, None, B, I, B, 0.0, None, indptr, indices, None, None, None, None, dlo))
