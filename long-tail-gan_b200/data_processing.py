@@ -1,0 +1,240 @@
+"""Data layer with the reference's loader names and return conventions (Codes/data_processing.py), rewritten on
+NumPy/SciPy sparse algebra so that it scales past the toy catalog: the O(I^2) Python set intersections of
+`load_overlap_coeff` (data_processing.py:110-167) become one sparse X^T X, and the per-user Python loops of
+`load_items_to_sample` / `load_vectors` (170-271) become row-wise max / arg-max over slices of that matrix.
+
+Every loader returns what the reference returns (dicts keyed by user / item id, scipy CSR matrices) so `train.py` reads
+like the reference; `build_train_tables` converts them to the flat int32 CSR-style arrays the device engine consumes.
+"""
+import codecs
+
+import numpy as np
+import pandas as pd
+from scipy import sparse
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# interaction matrices (data_processing.py:6-37)
+# ---------------------------------------------------------------------------------------------------------------------
+def csr_from_pairs(rows, cols, n_rows, n_cols, dtype):
+    """CSR of a binary interaction list: counting sort by (row, col), duplicates summed -- the arrays scipy's
+    csr_matrix((ones, (rows, cols))) + sort_indices produce (bit-exact, tests/test_data_processing.py)."""
+    rows = np.asarray(rows, dtype=np.int64)
+    cols = np.asarray(cols, dtype=np.int64)
+    key = rows * n_cols + cols
+    uniq, counts = np.unique(key, return_counts=True)
+    r = uniq // n_cols
+    indptr = np.zeros(n_rows + 1, dtype=np.int64)
+    np.add.at(indptr, r + 1, 1)
+    return np.cumsum(indptr).astype(np.int32), (uniq % n_cols).astype(np.int32), counts.astype(dtype)
+
+
+def load_train_data(csv_file, n_items):
+    """data_processing.py:6-17: returns (CSR float32 [uid.max()+1, n_items], uid.min())."""
+    tp = pd.read_csv(csv_file)
+    n_users = int(tp["uid"].max()) + 1
+    indptr, indices, data = csr_from_pairs(tp["uid"].to_numpy(), tp["sid"].to_numpy(), n_users, n_items, np.float32)
+    return sparse.csr_matrix((data, indices, indptr), shape=(n_users, n_items), dtype="float32"), int(tp["uid"].min())
+
+
+def load_tr_te_data(csv_file_tr, csv_file_te, n_items):
+    """data_processing.py:20-37: fold-in / held-out CSR float64 with the uid offset removed."""
+    tp_tr = pd.read_csv(csv_file_tr)
+    tp_te = pd.read_csv(csv_file_te)
+    start_idx = int(min(tp_tr["uid"].min(), tp_te["uid"].min()))
+    end_idx = int(max(tp_tr["uid"].max(), tp_te["uid"].max()))
+    n = end_idx - start_idx + 1
+    out = []
+    for tp in (tp_tr, tp_te):
+        indptr, indices, data = csr_from_pairs(tp["uid"].to_numpy() - start_idx, tp["sid"].to_numpy(), n, n_items, np.float64)
+        out.append(sparse.csr_matrix((data, indices, indptr), shape=(n, n_items), dtype="float64"))
+    return out[0], out[1], start_idx
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GAN side tables (data_processing.py:40-340)
+# ---------------------------------------------------------------------------------------------------------------------
+def _read_show2id(show2id_path):
+    SHOW2ID = {}
+    with codecs.open(show2id_path, "r", "utf-8") as f:
+        for row in f:
+            s = row.strip().split("\t")
+            SHOW2ID[s[0]] = s[1]
+    return SHOW2ID
+
+
+def load_item_one_hot_features(item_list_path, SHOW2ID, n_items):
+    """data_processing.py:40-70. The reference materialises an n_items-long one-hot list per item; only membership
+    (`id in ITEM_FEATURE_DICT`, train.py:240) and FEATURE_LEN are ever used, so the dict maps id -> id and the dense
+    array (fed to a placeholder nobody reads, train.py:300) is not built."""
+    ITEM_OH_DICT = {}
+    FEATURE_LEN = 0
+    with codecs.open(item_list_path, "r", "utf-8") as f:
+        for row in f:
+            s = row.strip()
+            if s in SHOW2ID:
+                ITEM_OH_DICT[int(SHOW2ID[s])] = int(SHOW2ID[s])
+                FEATURE_LEN = n_items
+    return ITEM_OH_DICT, FEATURE_LEN, None
+
+
+def load_user_items(csv_file_path):
+    """data_processing.py:72-96: uid -> list of sids in file order."""
+    tp = pd.read_csv(csv_file_path)
+    u = tp.iloc[:, 0].to_numpy()
+    s = tp.iloc[:, 1].to_numpy()
+    out = {}
+    for uid, sid in zip(u.tolist(), s.tolist()):
+        out.setdefault(uid, []).append(sid)
+    return out
+
+
+class OverlapCoeffs(object):
+    """OVERLAP_COEFFS[a][b] = |U_a & U_b| / min(|U_a|, |U_b|) (data_processing.py:100-107) backed by a dense float64
+    matrix; indexable like the reference's dict of dicts."""
+
+    def __init__(self, matrix, present):
+        self.matrix = matrix
+        self.present = present
+
+    def __getitem__(self, a):
+        return self.matrix[a]
+
+    def __contains__(self, a):
+        return bool(self.present[a])
+
+    def __len__(self):
+        return int(self.present.sum())
+
+
+def load_overlap_coeff(show2id_path, user_tag_matrix_path):
+    """data_processing.py:110-167 as one sparse product: C = X^T X on the binary user x item matrix of item_counts.csv,
+    coefficient = C[a,b] / min(C[a,a], C[b,b]) in float64 (the same division the reference performs)."""
+    SHOW2ID = _read_show2id(show2id_path)
+    tp = pd.read_csv(user_tag_matrix_path, dtype=str)
+    users = tp.iloc[:, 0].to_numpy()
+    tags = tp.iloc[:, 1].to_numpy()
+    keep = np.asarray([t in SHOW2ID for t in tags])
+    users, tags = users[keep], tags[keep]
+    item = np.asarray([int(SHOW2ID[t]) for t in tags], dtype=np.int64)
+    _, uidx = np.unique(users, return_inverse=True)
+    n_items = int(max(int(v) for v in SHOW2ID.values())) + 1
+    X = sparse.csr_matrix((np.ones(len(item), dtype=np.int64), (uidx, item)), shape=(uidx.max() + 1, n_items))
+    X.data[:] = 1  # sets: a (user, item) pair counts once
+    X.sum_duplicates()
+    X.data[:] = 1
+    C = (X.T @ X).toarray().astype(np.float64)
+    deg = np.diag(C).copy()
+    present = deg > 0
+    denom = np.minimum(deg[:, None], deg[None, :])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        M = np.where(denom > 0, C / denom, 0.0)
+    return OverlapCoeffs(M, present)
+
+
+def load_items_to_sample(user_popular_data, user_niche_data, NICHE_TAGS, OVERLAP_COEFFS, N):
+    """data_processing.py:170-224: candidates = the user's niche items + the top max(2n, 10-n) other niche items ranked by
+    their best overlap with any of the user's niche items (stable: ties keep ascending item id, which is the iteration
+    order of the reference's `NICHE_TAGS - curr_niche_tags` set of small ints)."""
+    M = OVERLAP_COEFFS.matrix
+    niche_sorted = np.asarray(sorted(NICHE_TAGS), dtype=np.int64)
+    out = {}
+    for user_idx in range(N):
+        if user_idx not in user_popular_data or user_idx not in user_niche_data:
+            continue
+        cur = np.asarray(user_niche_data[user_idx], dtype=np.int64)
+        n = len(cur)
+        num_sample = max(2 * n, 10 - n)
+        others = niche_sorted[~np.isin(niche_sorted, cur)]
+        best = M[np.ix_(cur, others)].max(axis=0) if len(others) else np.zeros(0)
+        order = np.argsort(-best, kind="stable")[: min(num_sample, len(others))]
+        out[user_idx] = np.sort(np.concatenate([cur, others[order]]))
+    return out
+
+
+def load_vectors(user_popular_data, user_niche_data, OVERLAP_COEFFS, ITEM_FEATURE_DICT, N):
+    """data_processing.py:227-271: for each niche item of the user the popular item of the user with the highest overlap
+    (first maximum in list order), dropped when either id is not in ITEM_FEATURE_DICT."""
+    M = OVERLAP_COEFFS.matrix
+    x_niche, x_pop = {}, {}
+    for user_idx in range(N):
+        if user_idx not in user_popular_data or user_idx not in user_niche_data:
+            continue
+        pops = np.asarray(user_popular_data[user_idx], dtype=np.int64)
+        niches = np.asarray(user_niche_data[user_idx], dtype=np.int64)
+        best = pops[np.argmax(M[np.ix_(niches, pops)], axis=1)]
+        cn, cp = [], []
+        for a, b in zip(niches.tolist(), best.tolist()):
+            if a in ITEM_FEATURE_DICT and b in ITEM_FEATURE_DICT:
+                cn.append(a)
+                cp.append(b)
+        x_niche[user_idx] = cn
+        x_pop[user_idx] = cp
+    return x_niche, x_pop
+
+
+def load_pop_niche_tags(show2id_path, item_list_path, niche_tags_path, n_items):
+    """data_processing.py:275-340."""
+    SHOW2ID = _read_show2id(show2id_path)
+    IDs_present = set()
+    with codecs.open(item_list_path, "r", "utf-8") as f:
+        for row in f:
+            s = row.strip()
+            if s in SHOW2ID:
+                IDs_present.add(SHOW2ID[s])
+    NICHE_TAGS = set()
+    with codecs.open(niche_tags_path, "r", "utf-8") as f:
+        for row in f:
+            s = row.strip()
+            if s in SHOW2ID and SHOW2ID[s] in IDs_present:
+                NICHE_TAGS.add(int(SHOW2ID[s]))
+    ALL_TAGS = list(range(n_items))
+    OTHER_TAGS = np.asarray(sorted(set(ALL_TAGS) - NICHE_TAGS))
+    return SHOW2ID, IDs_present, NICHE_TAGS, ALL_TAGS, OTHER_TAGS
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# flat tables for the device engine
+# ---------------------------------------------------------------------------------------------------------------------
+def _ragged(d, n):
+    ptr = np.zeros(n + 1, dtype=np.int64)
+    chunks = []
+    for u in range(n):
+        v = d.get(u)
+        if v is not None and len(v):
+            chunks.append(np.asarray(v, dtype=np.int64))
+            ptr[u + 1] = len(chunks[-1])
+    items = np.concatenate(chunks) if chunks else np.zeros(0, dtype=np.int64)
+    return np.cumsum(ptr).astype(np.int32), items.astype(np.int32)
+
+
+def build_train_tables(train_data, user_popular_data, user_niche_data, user_x_niche_vectors, user_x_popular_n_vectors,
+                       USER_TAGS_TO_SAMPLE, ITEM_FEATURE_DICT, n_items):
+    """Reference-shaped side tables -> the keyword arguments of engine.TrainData."""
+    N = train_data.shape[0]
+    csr = train_data.tocsr()
+    csr.sort_indices()
+    pop_ptr, pop_items = _ragged(user_popular_data, N)
+    cand_ptr, cand_items = _ragged(USER_TAGS_TO_SAMPLE, N)
+    real_ptr, real_niche = _ragged(user_x_niche_vectors, N)
+    _, real_pop = _ragged(user_x_popular_n_vectors, N)
+    n_niche = np.asarray([len(user_niche_data.get(u, ())) for u in range(N)], dtype=np.int32)
+    eligible = np.asarray([(u in user_popular_data) and (u in user_niche_data) for u in range(N)], dtype=bool)
+    item_valid = np.zeros(n_items, dtype=np.uint8)
+    item_valid[np.asarray(sorted(ITEM_FEATURE_DICT.keys()), dtype=np.int64)] = 1
+    return dict(n_items=n_items, indptr=csr.indptr.astype(np.int32), indices=csr.indices.astype(np.int32), pop_ptr=pop_ptr,
+                pop_items=pop_items, n_niche=n_niche, cand_ptr=cand_ptr, cand_items=cand_items, real_ptr=real_ptr,
+                real_niche=real_niche, real_pop=real_pop, eligible=eligible, item_valid=item_valid)
+
+
+def tables_from_golden(npz):
+    """The same tables from the committed fixture tests/golden/askubuntu_sample.npz (generated by the reference loaders)."""
+    g = npz
+    n_items = int(g["n_items"])
+    item_valid = np.zeros(n_items, dtype=np.uint8)
+    item_valid[g["valid_items"]] = 1
+    n_niche = np.diff(g["niche_ptr"]).astype(np.int32)
+    eligible = np.asarray(g["has_pop"], dtype=bool) & np.asarray(g["has_niche"], dtype=bool)
+    return dict(n_items=n_items, indptr=g["train_indptr"].astype(np.int32), indices=g["train_indices"].astype(np.int32),
+                pop_ptr=g["pop_ptr"], pop_items=g["pop_items"], n_niche=n_niche, cand_ptr=g["cand_ptr"], cand_items=g["cand_items"],
+                real_ptr=g["real_ptr"], real_niche=g["real_niche"], real_pop=g["real_pop"], eligible=eligible, item_valid=item_valid)
