@@ -67,6 +67,21 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// Same load, delivered to the same shared-memory offset (and signalling the mbarrier at the same offset) of every CTA in cta_mask.
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -92,6 +107,12 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 // Arrive on an mbarrier once every previously issued tcgen05.mma of this thread has retired.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Same, arriving on the barrier at this offset in every CTA of cta_mask (slot release for multicast operands).
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
 
 // 32 lanes x 16 consecutive fp32 columns: thread t of the warp receives row (lane base + t).
@@ -153,7 +174,7 @@ __host__ __device__ constexpr size_t gemm_smem_bytes() {
 // The kernel. Epi: struct with `Params`, ctor(const Params&, row, n0, n_blk, split, shape),
 // `chunk(col0, v[32])`, `finish()`.
 // ----------------------------------------------------------------------------------------------
-template <int BN, bool A_MN, bool B_MN, class Epi>
+template <int BN, bool A_MN, bool B_MN, int CM, class Epi>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ GemmShape shape, const __grid_constant__ typename Epi::Params ep) {
@@ -163,6 +184,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   constexpr uint32_t IDESC = umma_idesc(GEMM_BM, BN, A_MN, B_MN);
   static_assert(BN % 64 == 0 && BN <= 256, "BN must be 64, 128, 192 or 256");  // UMMA N: multiple of 16 up to 256; B boxes are 64 wide
+  static_assert(CM == 1 || CM == 2 || CM == 4, "cluster size along M");
+  // CM > 1: the CM CTAs of a cluster work on CM consecutive 128-row blocks of the SAME n-block / k-range. Each loads its own A
+  // tile and 1/CM of the shared B tile, multicast to all of them, so the B operand crosses L2->SM once per cluster instead of
+  // once per CTA. A stage may be refilled only when every CTA of the cluster has consumed it: tcgen05.commit multicasts the
+  // release to all CM empty barriers (init count CM).
+  constexpr uint16_t MC_MASK = (uint16_t)((1u << CM) - 1u);
+  const uint32_t crank = CM > 1 ? cluster_ctarank() : 0u;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -181,30 +209,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CM); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], GEMM_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if constexpr (CM > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_tiles = shape.m_blocks * shape.n_blocks * shape.splits;
+  // cluster tiles: (group of CM row blocks, n block, split); CTA `crank` of the cluster takes row block m_group*CM + crank
+  const int m_groups = (shape.m_blocks + CM - 1) / CM;
+  const int num_tiles = m_groups * shape.n_blocks * shape.splits;
+  const int tile0 = blockIdx.x / CM;
+  const int tile_stride = gridDim.x / CM;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m_blk = t % shape.m_blocks;
-        const int rest = t / shape.m_blocks;
+      for (int t = tile0; t < num_tiles; t += tile_stride) {
+        const int m_blk = (t % m_groups) * CM + (int)crank;
+        const int rest = t / m_groups;
         const int n_blk = rest % shape.n_blocks;
         const int split = rest / shape.n_blocks;
         const int kb0 = split * shape.kb_per_split;
         const int kb1 = min(shape.k_blocks, kb0 + shape.kb_per_split);
-        const int m0 = m_blk * GEMM_BM, n0 = n_blk * BN;
+        const int m0 = m_blk * GEMM_BM, n0 = n_blk * BN;   // m0 may lie beyond M for the padding block of the last group: TMA zero-fills
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
@@ -217,11 +250,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           } else {
             tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);
           }
-          if constexpr (B_MN) {
+          if constexpr (CM == 1) {
+            if constexpr (B_MN) {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, &full_bar[stage], n0 + j * 64, k0);
+              for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, &full_bar[stage], n0 + j * 64, k0);
+            } else {
+              tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);
+            }
+          } else if constexpr (B_MN) {
+            // every 64(n) x 64(k) box is split along k: this CTA fetches k rows [crank*64/CM, +64/CM) of each box for everybody
+            constexpr int KR = 64 / CM;
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d_mc(sb + j * 8192 + crank * (KR * 128), &tmB, &full_bar[stage], n0 + j * 64, k0 + (int)crank * KR, MC_MASK);
           } else {
-            tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);
+            // the BN x 64(k) tile is split along n: this CTA fetches rows [crank*BN/CM, +BN/CM) for everybody
+            constexpr int NR = BN / CM;
+            tma_load_2d_mc(sb + crank * (NR * 128), &tmB, &full_bar[stage], k0, n0 + (int)crank * NR, MC_MASK);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -232,8 +277,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int split = (t / shape.m_blocks) / shape.n_blocks;
+      for (int t = tile0; t < num_tiles; t += tile_stride) {
+        const int split = (t / m_groups) / shape.n_blocks;
         const int kb0 = split * shape.kb_per_split;
         const int kb1 = min(shape.k_blocks, kb0 + shape.kb_per_split);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -250,7 +295,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint64_t db = B_MN ? umma_desc_mn(sb + k * 2048, 8192) : umma_desc_k(sb + k * 32);
             umma_bf16(tmem_d, da, db, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+          if constexpr (CM == 1) umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+          else umma_commit_mc(&empty_bar[stage], MC_MASK);       // ... in every CTA of the cluster
           if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -262,9 +308,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int sub = warp & 3;  // hardware rule: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)
     const int quarter = (warp - 2) >> 2;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m_blk = t % shape.m_blocks;
-      const int rest = t / shape.m_blocks;
+    for (int t = tile0; t < num_tiles; t += tile_stride) {
+      const int m_blk = (t % m_groups) * CM + (int)crank;
+      const int rest = t / m_groups;
       const int n_blk = rest % shape.n_blocks;
       const int split = rest / shape.n_blocks;
       const int n0 = n_blk * BN;
@@ -290,6 +336,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CM > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it or arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -541,19 +588,58 @@ inline int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t inner, ui
 
 int ltg_num_sms();
 
+int ltg_gemm_cluster_override();  // -1: heuristic; 1/2/4 forces the cluster size (env LTG_GEMM_CM, experiments)
+
+template <int BN, bool A_MN, bool B_MN, int CM, class Epi>
+int launch_gemm_cm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, const GemmShape& s, const typename Epi::Params& ep,
+                   cudaStream_t stream) {
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (A_MN) rc = make_tmap_bf16(&tmA, A, (uint64_t)s.M, (uint64_t)s.K, (uint64_t)lda, 64, 64);
+  else rc = make_tmap_bf16(&tmA, A, (uint64_t)s.K, (uint64_t)s.M, (uint64_t)lda, 64, GEMM_BM);
+  if (rc) return rc;
+  if (B_MN) rc = make_tmap_bf16(&tmB, B, (uint64_t)s.N, (uint64_t)s.K, (uint64_t)ldb, 64, 64 / CM);
+  else rc = make_tmap_bf16(&tmB, B, (uint64_t)s.K, (uint64_t)s.N, (uint64_t)ldb, 64, BN / CM);
+  if (rc) return rc;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, CM, Epi>;
+  static int max_clusters = 0;  // per instantiation
+  const size_t smem = gemm_smem_bytes<BN>();
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CM; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (max_clusters == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { ltg_set_last_error(cudaGetErrorString(e), __FILE__, __LINE__); return LTG_ERR_CUDA; }
+    if (CM > 1) {
+      cfg.gridDim = dim3(ltg_num_sms() / CM * CM);
+      int n = 0;
+      e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+      if (e != cudaSuccess || n <= 0) { ltg_set_last_error("cudaOccupancyMaxActiveClusters failed", __FILE__, __LINE__); return LTG_ERR_CUDA; }
+      max_clusters = n;
+    } else {
+      max_clusters = ltg_num_sms();
+    }
+  }
+  const int m_groups = (s.m_blocks + CM - 1) / CM;
+  const int tiles = m_groups * s.n_blocks * s.splits;
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  cfg.gridDim = dim3(clusters * CM);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, s, ep);
+  if (e != cudaSuccess) { ltg_set_last_error(cudaGetErrorString(e), __FILE__, __LINE__); return LTG_ERR_CUDA; }
+  return LTG_OK;
+}
+
 // A: [M,K] (a_mn=false, pitch lda over K) or stored [K,M] (a_mn=true, pitch lda over M). Same for B with N.
 template <int BN, bool A_MN, bool B_MN, class Epi>
 int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, int M, int N, int K, int splits,
                 const typename Epi::Params& ep, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return LTG_OK;
-  CUtensorMap tmA, tmB;
-  int rc;
-  if (A_MN) rc = make_tmap_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, 64);
-  else rc = make_tmap_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, GEMM_BM);
-  if (rc) return rc;
-  if (B_MN) rc = make_tmap_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, 64);
-  else rc = make_tmap_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, BN);
-  if (rc) return rc;
   GemmShape s;
   s.M = M; s.N = N; s.K = K;
   s.m_blocks = (M + GEMM_BM - 1) / GEMM_BM;
@@ -563,19 +649,13 @@ int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb
   if (splits > s.k_blocks) splits = s.k_blocks;
   s.kb_per_split = (s.k_blocks + splits - 1) / splits;
   s.splits = (s.k_blocks + s.kb_per_split - 1) / s.kb_per_split;  // no empty split
-  const int tiles = s.m_blocks * s.n_blocks * s.splits;
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, Epi>;
-  static bool attr_set = false;  // per instantiation
-  const size_t smem = gemm_smem_bytes<BN>();
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { ltg_set_last_error(cudaGetErrorString(e), __FILE__, __LINE__); return LTG_ERR_CUDA; }
-    attr_set = true;
-  }
-  const int grid = tiles < ltg_num_sms() ? tiles : ltg_num_sms();
-  kern<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, s, ep);
-  LTG_CHECK_LAUNCH();
-  return LTG_OK;
+  // cluster along M: row blocks of the same n-block share the B operand (TMA multicast)
+  int cm = s.m_blocks >= 4 ? 4 : (s.m_blocks >= 2 ? 2 : 1);
+  const int ov = ltg_gemm_cluster_override();
+  if (ov == 1 || ov == 2 || ov == 4) cm = ov;
+  if (cm == 4) return launch_gemm_cm<BN, A_MN, B_MN, 4, Epi>(A, lda, B, ldb, s, ep, stream);
+  if (cm == 2) return launch_gemm_cm<BN, A_MN, B_MN, 2, Epi>(A, lda, B, ldb, s, ep, stream);
+  return launch_gemm_cm<BN, A_MN, B_MN, 1, Epi>(A, lda, B, ldb, s, ep, stream);
 }
 
 }  // namespace ltg

@@ -1,6 +1,7 @@
 // Runtime glue of libltgan.so: error reporting, driver entry points, device step state.
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include "gemm_sm100.cuh"
 #include "../../include/ltgan.h"
 
@@ -24,6 +25,15 @@ PFN_encodeTiled ltg_get_encode_tiled() {
   }
   fn = reinterpret_cast<PFN_encodeTiled>(p);
   return fn;
+}
+
+int ltg_gemm_cluster_override() {
+  static int v = -2;
+  if (v == -2) {
+    const char* e = getenv("LTG_GEMM_CM");
+    v = e != nullptr ? atoi(e) : -1;
+  }
+  return v;
 }
 
 int ltg_num_sms() {
