@@ -270,9 +270,17 @@ def main():
         users = BATCH * world * args.steps
         adam_bytes = 30.0 * n_par          # p,m,v read+write (24) + fp32 gradient read (4) + bf16 shadow write (2)
         enc_bytes = 26.0 * n_par           # same without a dense gradient read: the compact gradient rows are L2-resident
+        traffic = None
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full` capture
+            for rec in json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_adam_full.json"))):
+                if "adam_kernel" in rec["kernel"] and "enc_adam" not in rec["kernel"] and int(rec["grid"]) >= 1000:
+                    traffic = rec["dram_total_MB"] * 1e6
+        except Exception:
+            traffic = None
         roof = dict(bound="hbm", kernel="adam_kernel (fused TF-Adam + bf16 shadow over W_dec^T [I,600])",
                     achieved=adam_bytes / (t_adam * 1e-3) / 1e9, peak=peak, unit="GB/s", frac=adam_bytes / (t_adam * 1e-3) / 1e9 / peak,
-                    traffic=None, peak_source=peak_src, algorithmic_bytes_per_launch=adam_bytes, ms_per_launch=t_adam,
+                    traffic=traffic, traffic_source="profiles/r1_ncu_adam_full.json (ncu --set full; writes still resident in L2 at kernel end are not counted)",
+                    peak_source=peak_src, algorithmic_bytes_per_launch=adam_bytes, ms_per_launch=t_adam,
                     how="CUDA events around 50 back-to-back launches on the launching stream after the timed region; each launch "
                         "touches 362 MB (> L2)",
                     second=dict(kernel="enc_adam_kernel (TF-Adam over W_q0 [I,600], gradient rows fetched through slot_of_item)",

@@ -47,7 +47,7 @@ int ltg_init(void);
 
 /* Persistent step state (device): words[0] = rng step, words[1] = Adam step t (shared by D and G updates, F6),
  * words[2] = G-update count (KL anneal, train.py:319-324). ltg_step_advance bumps the counters on the device and
- * writes LTG_S_LR_T / LTG_S_ANNEAL into `scal`, so a captured graph needs no host values.
+ * writes LTG_S_LR_T / LTG_S_ANNEAL into `scal` after zeroing its accumulator slots [0, 8), so a captured graph needs no host values.
  *   kind: 0 = phase-A (rng only), 1 = D update (rng + Adam t), 2 = G update (rng + Adam t + anneal count)      */
 int ltg_step_advance(uint32_t* words, float* scal, int kind, float lr, float beta1, float beta2,
                      float anneal_cap, float total_anneal_steps, void* stream);
@@ -55,7 +55,8 @@ int ltg_step_advance(uint32_t* words, float* scal, int kind, float lr, float bet
 /* ---- generic bf16 tensor-core GEMM (tcgen05/TMA/TMEM) ------------------------------------------------------------
  * D[M,N] = alpha * A * B^T with A given as [M,K] (a_mn=0, pitch lda) or stored transposed [K,M] (a_mn=1), B likewise
  * ([N,K] or [K,N]); epilogue: +bias[N], act (0 none / 1 tanh), dropout(keep) from a counter hash of (row*rng_ld+col)/2, outputs fp32
- * and/or bf16, `atomic` = split-K accumulation into a zeroed fp32 buffer; column `aux_col` is diverted to aux_out[row].
+ * and/or bf16; split-K either accumulates with `atomic` into a zeroed fp32 buffer or (split_stride > 0) stores the partial of
+ * split s at out_f32 + s*split_stride for the consumer to sum; column `aux_col` is diverted to aux_out[row].
  * dact_src (bf16 [M, dact_ld], may be NULL): multiply the result by d/da dropout(tanh(a)) recovered from the stored
  * post-dropout activation (backward of discriminator.py:25,30,44 fused into the dgrad GEMM).
  * bn in {64,128,192,256}. Building block of every dense layer below (tf.matmul sites: MultiVAE.py:152,169;
@@ -63,7 +64,7 @@ int ltg_step_advance(uint32_t* words, float* scal, int kind, float lr, float bet
 int ltg_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int N, int K, int splits, int bn,
                   float* out_f32, int ld_f32, void* out_bf16, int ld_bf16, const float* bias, int act, float alpha, int atomic,
                   float keep, uint64_t seed, uint32_t rng_stream, uint32_t rng_step, const uint32_t* rng_step_dev, int rng_ld,
-                  int aux_col, float* aux_out, const void* dact_src, int dact_ld, float dact_keep, void* stream);
+                  int aux_col, float* aux_out, const void* dact_src, int dact_ld, float dact_keep, int64_t split_stride, void* stream);
 
 /* ---- a3: encoder (MultiVAE.py:148-155): l2_normalize + dropout + x*W_q0 + b + tanh, as a CSR gather-sum -----------
  * indptr[B+1] (absolute offsets into indices/values), values may be NULL (all ones). uid0 = global id of row 0 (RNG key).
@@ -88,9 +89,10 @@ int ltg_latent_fwd(const float* mulv, const float* eps, int B, int64_t uid0, flo
 int ltg_latent_bwd(const float* dz, const float* mulv, const float* zmu, int B, int B_global, float anneal, const float* scal,
                    void* dmulv_bf16, int ld, float* db_q1, void* stream);
 
-/* dx = dy * (1 - y^2) for y = tanh(.) stored as bf16 [B, ld_y]; outputs bf16 and/or fp32; column sums -> dbias (atomic). */
-int ltg_tanh_bwd(const float* dy, int ld_dy, const void* y_bf16, int ld_y, int B, int N, void* dx_bf16, int ld_dxb,
-                 float* dx_f32, int ld_dxf, float* dbias, void* stream);
+/* dx = dy * (1 - y^2) for y = tanh(.) stored as bf16 [B, ld_y]; outputs bf16 and/or fp32; column sums -> dbias (atomic).
+ * dy may be given as n_partials split-K partial buffers (dy + s*partial_stride), which are summed on the fly.             */
+int ltg_tanh_bwd(const float* dy, int ld_dy, int n_partials, int64_t partial_stride, const void* y_bf16, int ld_y, int B, int N,
+                 void* dx_bf16, int ld_dxb, float* dx_f32, int ld_dxf, float* dbias, void* stream);
 
 /* ---- a5/a6: decoder + catalog softmax (MultiVAE.py:169,108-112,143) -------------------------------------------------
  * logits = h2 * W_dec + b_dec through the tcgen05 GEMM with the softmax-statistics epilogue: bf16 logits stash
@@ -115,9 +117,10 @@ int ltg_dec_dlogits(const void* logits_bf16, int ld, const float* lse, const flo
                     void* dl_bf16, void* stream);
 
 /* ---- a13: TF-semantics Adam (train.py:160-164; F6 shared step, F7 dense) ------------------------------------------
- * p,m,v fp32 updated in place; g fp32; optional bf16 shadow with the same layout. lr_t < 0: read scal[LTG_S_LR_T].    */
-int ltg_adam(float* p, float* m, float* v, const float* g, void* shadow_bf16, int64_t n, float lr_t, const float* scal,
-             float beta1, float beta2, float eps, void* stream);
+ * p,m,v fp32 updated in place; g fp32; optional bf16 shadow with the same layout. lr_t < 0: read scal[LTG_S_LR_T].
+ * g may be given as n_partials buffers (g + s*partial_stride: split-K partials of the weight-gradient GEMMs), summed on the fly. */
+int ltg_adam(float* p, float* m, float* v, const float* g, int n_partials, int64_t partial_stride, void* shadow_bf16, int64_t n,
+             float lr_t, const float* scal, float beta1, float beta2, float eps, void* stream);
 /* Encoder weight W_q0 [n_items, H]. Its gradient X^T dh1pre is non-zero only on the batch's ACTIVE items, so it is built
  * compactly: G[slot, :] = sum over the item's batch entries of coef * dh1pre[row, :], one CTA per active item
  * (act_ptr[n_active+1] delimits the item's entries in csc_row[] = batch row / csc_pos[] = offset into coef).                */

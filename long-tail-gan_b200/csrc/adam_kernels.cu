@@ -24,14 +24,19 @@ __device__ __forceinline__ void adam_update4(float4& p, float4& m, float4& v, co
 }
 
 __global__ void __launch_bounds__(256)
-adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g,
-            __nv_bfloat16* __restrict__ shadow, int64_t n, float lr_t, const float* __restrict__ scal, float b1, float b2, float eps) {
+adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g, int n_partials,
+            int64_t partial_stride, __nv_bfloat16* __restrict__ shadow, int64_t n, float lr_t, const float* __restrict__ scal, float b1,
+            float b2, float eps) {
   if (lr_t < 0.f) lr_t = scal[LTG_S_LR_T];
   const int64_t n4 = n >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 pp = ld_stream_f4(p + 4 * i), mm = ld_stream_f4(m + 4 * i), vv = ld_stream_f4(v + 4 * i);
-    const float4 gg = ld_stream_f4(g + 4 * i);
+    float4 gg = ld_stream_f4(g + 4 * i);
+    for (int sp = 1; sp < n_partials; ++sp) {  // split-K partials of the producing GEMM
+      const float4 o = ld_stream_f4(g + (size_t)sp * partial_stride + 4 * i);
+      gg.x += o.x; gg.y += o.y; gg.z += o.z; gg.w += o.w;
+    }
     adam_update4(pp, mm, vv, gg, lr_t, b1, b2, eps);
     st_stream_f4(p + 4 * i, pp); st_stream_f4(m + 4 * i, mm); st_stream_f4(v + 4 * i, vv);
     if (shadow != nullptr) {
@@ -42,7 +47,8 @@ adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
   // tail (n % 4)
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     const int64_t i = (n4 << 2) + threadIdx.x;
-    const float gg = g[i];
+    float gg = g[i];
+    for (int sp = 1; sp < n_partials; ++sp) gg += g[(size_t)sp * partial_stride + i];
     const float mm = b1 * m[i] + (1.f - b1) * gg;
     const float vv = b2 * v[i] + (1.f - b2) * gg * gg;
     const float pp = p[i] - lr_t * mm / (sqrtf(vv) + eps);
@@ -152,16 +158,17 @@ int grid_for(int64_t work_items, int threads, int max_blocks) {
 // 148 SMs x 8 resident 256-thread CTAs: one full wave, grid-stride over the rest
 static const int kStreamBlocks = 148 * 8;
 
-extern "C" int ltg_adam(float* p, float* m, float* v, const float* g, void* shadow_bf16, int64_t n, float lr_t, const float* scal,
-                        float beta1, float beta2, float eps, void* stream) {
-  LTG_REQUIRE(p && m && v && g);
+extern "C" int ltg_adam(float* p, float* m, float* v, const float* g, int n_partials, int64_t partial_stride, void* shadow_bf16, int64_t n,
+                        float lr_t, const float* scal, float beta1, float beta2, float eps, void* stream) {
+  LTG_REQUIRE(p && m && v && g && n_partials >= 1);
+  LTG_REQUIRE(n_partials == 1 || (partial_stride % 4 == 0 && partial_stride >= n));
   LTG_REQUIRE(lr_t >= 0.f || scal != nullptr);
   LTG_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v) |
                 reinterpret_cast<uintptr_t>(g)) & 15) == 0);
   LTG_REQUIRE((reinterpret_cast<uintptr_t>(shadow_bf16) & 7) == 0);
   if (n <= 0) return LTG_OK;
-  adam_kernel<<<grid_for(n >> 2, 256, kStreamBlocks), 256, 0, (cudaStream_t)stream>>>(p, m, v, g, reinterpret_cast<__nv_bfloat16*>(shadow_bf16),
-                                                                                       n, lr_t, scal, beta1, beta2, eps);
+  adam_kernel<<<grid_for(n >> 2, 256, kStreamBlocks), 256, 0, (cudaStream_t)stream>>>(
+      p, m, v, g, n_partials, partial_stride, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n, lr_t, scal, beta1, beta2, eps);
   LTG_CHECK_LAUNCH();
   return LTG_OK;
 }

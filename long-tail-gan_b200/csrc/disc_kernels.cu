@@ -28,12 +28,12 @@ __device__ __forceinline__ float dact_drop_tanh(float y, float keep, bool drop) 
 }
 
 constexpr int HEAD_THREADS = 256;  // 8 warps, each walks rows with a grid stride
-constexpr int HEAD_MAXH3 = 320;    // 10 columns per lane
-constexpr int HEAD_CPL = HEAD_MAXH3 / 32;
+constexpr int HEAD_MAXH3 = 320;    // 5 column pairs per lane
+constexpr int HEAD_PPL = HEAD_MAXH3 / 64;
 
-// One warp per row: lane l owns columns l, l+32, ... (coalesced 64-byte row segments). The weight gradient
-// dw4 = Y3^T ds is accumulated in registers over all rows a warp visits, then reduced once per CTA in shared memory and
-// once per CTA in global memory (the per-element shared-memory atomics of the first version cost 45 us).
+// One warp per row: lane l owns the column pairs (2l, 2l+1) + 64k (128-byte coalesced row segments, bf16x2 loads). The
+// weight gradient dw4 = Y3^T ds is accumulated in registers over all rows a warp visits, then reduced once per CTA in
+// shared memory and once per CTA in global memory (the per-element shared-memory atomics of the first version cost 45 us).
 __global__ void __launch_bounds__(HEAD_THREADS)
 disc_head_kernel(const __nv_bfloat16* __restrict__ Y3, int ld, int P, int h3, const float* __restrict__ w4, const float* __restrict__ b4,
                  const int32_t* __restrict__ label, float keep, float* __restrict__ y_out, float* __restrict__ scal,
@@ -46,22 +46,28 @@ disc_head_kernel(const __nv_bfloat16* __restrict__ Y3, int ld, int P, int h3, co
   for (int j = tid; j < HEAD_MAXH3; j += HEAD_THREADS) s_dw4[j] = 0.f;
   if (tid < 4) s_acc[tid] = 0.f;
   __syncthreads();
-  float wv[HEAD_CPL], gw[HEAD_CPL];
+  float2 wv[HEAD_PPL], gw[HEAD_PPL];
 #pragma unroll
-  for (int k = 0; k < HEAD_CPL; ++k) { const int j = lane + 32 * k; wv[k] = j < h3 ? __ldg(w4 + j) : 0.f; gw[k] = 0.f; }
+  for (int k = 0; k < HEAD_PPL; ++k) {
+    const int j = 2 * lane + 64 * k;
+    wv[k].x = j < h3 ? __ldg(w4 + j) : 0.f;
+    wv[k].y = j + 1 < h3 ? __ldg(w4 + j + 1) : 0.f;
+    gw[k] = make_float2(0.f, 0.f);
+  }
   const float bias = b4[0];
   float loss = 0.f, sumy = 0.f, sds = 0.f, ngen = 0.f;
   const int warps_total = gridDim.x * (HEAD_THREADS / 32);
   for (int row = blockIdx.x * (HEAD_THREADS / 32) + warp; row < P; row += warps_total) {
     const int lab = label[row];
-    const __nv_bfloat16* yr = Y3 + (size_t)row * ld;
-    float yv[HEAD_CPL];
+    const __nv_bfloat16* yr = Y3 + (size_t)row * ld;   // ld is even and >= h3 rounded up to 2: pair loads stay inside the row
+    float2 yv[HEAD_PPL];
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < HEAD_CPL; ++k) {
-      const int j = lane + 32 * k;
-      yv[k] = j < h3 ? __bfloat162float(yr[j]) : 0.f;
-      s = fmaf(yv[k], wv[k], s);
+    for (int k = 0; k < HEAD_PPL; ++k) {
+      const int j = 2 * lane + 64 * k;
+      yv[k] = j < ld ? unpack_bf16x2(*reinterpret_cast<const uint32_t*>(yr + j)) : make_float2(0.f, 0.f);
+      s = fmaf(yv[k].x, wv[k].x, s);
+      s = fmaf(yv[k].y, wv[k].y, s);
     }
     s = warp_sum(s) + bias;
     const float y = 1.0f / (1.0f + __expf(-s));
@@ -75,11 +81,14 @@ disc_head_kernel(const __nv_bfloat16* __restrict__ Y3, int ld, int P, int h3, co
     if (bwd) {
       __nv_bfloat16* dr = dz3 + (size_t)row * ld;
 #pragma unroll
-      for (int k = 0; k < HEAD_CPL; ++k) {
-        const int j = lane + 32 * k;
-        if (j < h3) {
-          dr[j] = __float2bfloat16(ds * wv[k] * dact_drop_tanh(yv[k], keep, drop));
-          gw[k] = fmaf(yv[k], ds, gw[k]);
+      for (int k = 0; k < HEAD_PPL; ++k) {
+        const int j = 2 * lane + 64 * k;
+        if (j < h3) {  // h3 is even in every configuration this kernel accepts
+          const float d0 = ds * wv[k].x * dact_drop_tanh(yv[k].x, keep, drop);
+          const float d1 = ds * wv[k].y * dact_drop_tanh(yv[k].y, keep, drop);
+          *reinterpret_cast<uint32_t*>(dr + j) = pack_bf16x2(d0, d1);
+          gw[k].x = fmaf(yv[k].x, ds, gw[k].x);
+          gw[k].y = fmaf(yv[k].y, ds, gw[k].y);
         }
       }
     }
@@ -87,7 +96,10 @@ disc_head_kernel(const __nv_bfloat16* __restrict__ Y3, int ld, int P, int h3, co
   if (lane == 0) { atomicAdd(&s_acc[0], loss); atomicAdd(&s_acc[1], sumy); atomicAdd(&s_acc[2], sds); atomicAdd(&s_acc[3], ngen); }
   if (bwd) {
 #pragma unroll
-    for (int k = 0; k < HEAD_CPL; ++k) atomicAdd(&s_dw4[lane + 32 * k], gw[k]);
+    for (int k = 0; k < HEAD_PPL; ++k) {
+      atomicAdd(&s_dw4[2 * lane + 64 * k], gw[k].x);
+      atomicAdd(&s_dw4[2 * lane + 64 * k + 1], gw[k].y);
+    }
   }
   __syncthreads();
   if (tid == 0) {
@@ -125,7 +137,7 @@ extern "C" int ltg_disc_gather(const void* E_bf16, const int32_t* pop_ids, const
 extern "C" int ltg_disc_head(const void* Y3_bf16, int ld, int P, int h3, const float* w4, const float* b4, const int32_t* label,
                              float keep, float* y_out, float* scal, void* dz3_bf16, float* dw4, float* db4, void* stream) {
   LTG_REQUIRE(Y3_bf16 && w4 && b4 && label && scal);
-  LTG_REQUIRE(h3 > 0 && h3 <= HEAD_MAXH3 && ld >= h3);
+  LTG_REQUIRE(h3 > 0 && h3 <= HEAD_MAXH3 && h3 % 2 == 0 && ld >= h3 && ld % 2 == 0);
   if (P <= 0) return LTG_OK;
   int blocks = (P + HEAD_THREADS / 32 - 1) / (HEAD_THREADS / 32);
   if (blocks > 148 * 4) blocks = 148 * 4;

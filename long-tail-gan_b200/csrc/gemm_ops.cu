@@ -17,11 +17,11 @@ static int dispatch_major(const __nv_bfloat16* A, int lda, int a_mn, const __nv_
 extern "C" int ltg_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int N, int K, int splits, int bn,
                              float* out_f32, int ld_f32, void* out_bf16, int ld_bf16, const float* bias, int act, float alpha, int atomic,
                              float keep, uint64_t seed, uint32_t rng_stream, uint32_t rng_step, const uint32_t* rng_step_dev, int rng_ld,
-                             int aux_col, float* aux_out, const void* dact_src, int dact_ld, float dact_keep, void* stream) {
+                             int aux_col, float* aux_out, const void* dact_src, int dact_ld, float dact_keep, int64_t split_stride, void* stream) {
   LTG_REQUIRE(A != nullptr && B != nullptr);
   LTG_REQUIRE(out_f32 != nullptr || out_bf16 != nullptr);
   LTG_REQUIRE(!atomic || (out_f32 != nullptr && out_bf16 == nullptr && act == 0 && bias == nullptr));
-  LTG_REQUIRE(splits <= 1 || atomic);
+  LTG_REQUIRE(splits <= 1 || atomic || (split_stride > 0 && out_f32 != nullptr && out_bf16 == nullptr && act == 0 && bias == nullptr));
   LTG_REQUIRE(aux_col < 0 || aux_out != nullptr);
   LTG_REQUIRE(dact_src == nullptr || dact_ld >= N);
   const bool drop = keep > 0.f && keep < 1.f;
@@ -29,7 +29,7 @@ extern "C" int ltg_gemm_bf16(const void* A, int lda, int a_mn, const void* B, in
   EpiStore::Params ep;
   ep.out_f32 = out_f32; ep.ld_f32 = ld_f32;
   ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); ep.ld_bf16 = ld_bf16;
-  ep.bias = bias; ep.act = act; ep.atomic = atomic; ep.alpha = alpha;
+  ep.bias = bias; ep.act = act; ep.atomic = atomic; ep.alpha = alpha; ep.split_stride = splits > 1 ? split_stride : 0;
   ep.keep = keep; ep.seed = seed; ep.rng_stream = rng_stream; ep.rng_step = rng_step; ep.rng_step_dev = rng_step_dev; ep.rng_ld = rng_ld;
   ep.aux_col = aux_col; ep.aux_out = aux_out;
   ep.dact_src = reinterpret_cast<const __nv_bfloat16*>(dact_src); ep.dact_ld = dact_ld; ep.dact_keep = dact_keep;

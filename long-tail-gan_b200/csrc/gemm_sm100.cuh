@@ -364,6 +364,7 @@ struct EpiStore {
     const float* bias;      // [N] or null
     int act;                // 0 none, 1 tanh
     int atomic;             // 1: red.add into out_f32 (which the caller zeroed)
+    int64_t split_stride;   // > 0: split s stores its partial tile at out_f32 + s*split_stride (the consumer sums the partials)
     float alpha;
     float keep;             // dropout keep prob; >= 1 or <= 0 disables
     uint64_t seed; uint32_t rng_stream, rng_step; const uint32_t* rng_step_dev; int rng_ld;  // pair idx = (row*rng_ld + col)/2
@@ -371,11 +372,11 @@ struct EpiStore {
     const __nv_bfloat16* dact_src; int dact_ld; float dact_keep;  // multiply by d/da dropout(tanh(a)) recovered from the stored activation
   };
   const Params& p;
-  int row, M, N;
+  int row, M, N, split;
   uint32_t thr16, key;
   float inv_keep;
   bool drop;
-  __device__ EpiStore(const Params& p_, int row_, int, int, int, const GemmShape& s) : p(p_), row(row_), M(s.M), N(s.N) {
+  __device__ EpiStore(const Params& p_, int row_, int, int, int split_, const GemmShape& s) : p(p_), row(row_), M(s.M), N(s.N), split(split_) {
     drop = p.keep > 0.f && p.keep < 1.f;
     thr16 = drop ? ltg_keep_threshold16(p.keep) : 65536u;
     inv_keep = drop ? 1.0f / p.keep : 1.0f;
@@ -455,7 +456,7 @@ struct EpiStore {
     }
     const int nlim = (p.aux_col >= 0 && p.aux_col < N) ? p.aux_col : N;  // columns >= aux_col are not part of `out`
     if (p.out_f32 != nullptr) {
-      float* o = p.out_f32 + (size_t)row * p.ld_f32 + col0;
+      float* o = p.out_f32 + (size_t)split * (size_t)p.split_stride + (size_t)row * p.ld_f32 + col0;
       if (p.atomic) {
 #pragma unroll
         for (int i = 0; i < CW; ++i)

@@ -65,7 +65,9 @@ extern "C" int ltg_init(void) {
 // words[0] rng step, words[1] Adam t, words[2] G-update count.
 __global__ void step_advance_kernel(uint32_t* words, float* scal, int kind, float lr, double beta1, double beta2,
                                     float anneal_cap, float total_anneal_steps) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (blockIdx.x != 0) return;
+  if (threadIdx.x < 8) scal[threadIdx.x] = 0.f;   // per-step accumulators (KL, NLL, sum p, sum y, cnt, d_loss)
+  if (threadIdx.x != 0) return;
   words[0] += 1;
   if (kind >= 1) {
     const uint32_t t = ++words[1];

@@ -168,7 +168,6 @@ class GanEngine(object):
         self.scal = torch.zeros(ops.NSCAL, dtype=torch.float32, device=self.device)
         self._graphs = {}
         self._alloc()
-        self.dgrad_splits = 8
         self.eps_inject = None  # optional [B, L] fp32 tensor used instead of the Philox normal (parity tests)
 
     def _alloc(self):
@@ -198,11 +197,14 @@ class GanEngine(object):
         self.Xc = torch.zeros(B, self.ld_xc, **bf)            # dense dropout/normalisation coefficients over the active items
         self.dh1pre_b = torch.zeros(B, H, **bf)
         self.dW_q0 = torch.zeros(I, H, **f32) if self.world_size > 1 else None  # dense encoder gradient, only for the all-reduce
-        # fp32 accumulators that must be zero at the start of a G step: one arena, one memset
-        self.zero_g = torch.zeros(B * H + B * L + B * H, **f32)
-        self.dh2 = self.zero_g[: B * H].view(B, H)
-        self.dz = self.zero_g[B * H: B * H + B * L].view(B, L)
-        self.dh1 = self.zero_g[B * H + B * L:].view(B, H)
+        # split-K partials of the decoder dgrad (summed by the tanh-backward kernel that consumes them: no atomics, no memset)
+        self.dgrad_splits = ops.actual_splits(I, ops.pick_splits(B, H, I, 128))
+        self.dh2_part = torch.zeros(self.dgrad_splits, B, H, **f32)
+        self.dz = torch.zeros(B, L, **f32)
+        self.dh1 = torch.zeros(B, H, **f32)
+        # split-K partials of the three discriminator weight-gradient GEMMs (summed by the Adam kernel)
+        self.d_splits_max = 32
+        self.arena_gp = torch.zeros(self.d_splits_max, d.arena_n, **f32) if self.world_size == 1 else None
         # discriminator
         self.Xp = torch.zeros(P, 128, **bf); self.Xn = torch.zeros(P, 128, **bf)
         self.Hd = torch.zeros(P, d.k3, **bf)
@@ -235,7 +237,7 @@ class GanEngine(object):
         ops.dec_logits_fwd(self.h2, v.WdT_b, v.view("b_p1"), B, self.I, self.logits if stash else None, self.partial)
         return indptr, indices
 
-    def _disc_forward(self, pop, niche, label, P, backward):
+    def _disc_forward(self, pop, niche, label, P, backward, g_w4=None, g_b4=None):
         """discriminator.py:16-55 on P pairs (real and generated share the weights, so they run as one batch)."""
         d = self.disc
         seed, kd = self.seed, self.keep_d
@@ -249,8 +251,7 @@ class GanEngine(object):
         ops.gemm(self.Hd, d.view("W3", "b"), P, d.h3, d.k3, b_mn=True, bn=ops.pick_bn(P, d.h3), out_bf16=self.Y3, act=1, keep=kd, seed=seed,
                  rng_stream=st + 2, rng_step_dev=self.words, rng_ld=d.ld3)
         if backward:
-            ops.disc_head(self.Y3, P, d.h3, d.view("w4"), d.view("b4"), label, kd, self.y, self.scal, self.dz3, d.view("w4", "g"),
-                          d.view("b4", "g"))
+            ops.disc_head(self.Y3, P, d.h3, d.view("w4"), d.view("b4"), label, kd, self.y, self.scal, self.dz3, g_w4, g_b4)
         else:
             ops.disc_head(self.Y3, P, d.h3, d.view("w4"), d.view("b4"), label, kd, self.y, self.scal)
 
@@ -260,7 +261,6 @@ class GanEngine(object):
     def phase_a(self, data, bi):
         bt = data.batches[bi]
         B = bt["B"]
-        self.scal.zero_()
         ops.step_advance(self.words, self.scal, 0, self.lr, anneal_cap=self.anneal_cap, total_anneal_steps=self.total_anneal_steps)
         # train.py:200: sess.run(generator_out) with default placeholders: dropout 0.75 (F4), is_training 0
         self._vae_forward(data, bt, False, self.keep_vae)
@@ -282,27 +282,39 @@ class GanEngine(object):
         bt = data.batches[bi]
         d = self.disc
         P = bt["P"]
-        self.scal.zero_()
-        d.arena_g.zero_()
         ops.step_advance(self.words, self.scal, 1, self.lr, anneal_cap=self.anneal_cap, total_anneal_steps=self.total_anneal_steps)
-        self._disc_forward(bt["pair_pop"], bt["pair_niche"], bt["label"], P, True)
-        # autodiff of discriminator.py:25-55; every bias gradient is the ones-row of its weight-gradient GEMM
+        # autodiff of discriminator.py:25-55; every bias gradient is the ones-row of its weight-gradient GEMM.
+        # Single GPU: the split-K partials of the three weight-gradient GEMMs go to arena_gp[s] and the Adam kernel sums them.
+        # Data parallel: atomic accumulation into arena_g (which is what gets all-reduced).
         k1 = d.h0 + 1
+        part = self.world_size == 1
         bn3 = ops.pick_bn(d.k3, d.h3, True)
-        ops.gemm(self.Hd, self.dz3, d.k3, d.h3, P, a_mn=True, b_mn=True, splits=ops.pick_splits(d.k3, d.h3, P, bn3), bn=bn3,
-                 out_f32=d.view("W3", "g"), atomic=True)                                           # dW3 (+ db3) = Hd^T dz3
+        sp = ops.actual_splits(P, min(self.d_splits_max, ops.pick_splits(d.k3, d.h3, P, bn3)))
+        self._d_parts = sp if part else 1
+        if part:
+            gW = lambda name: self.arena_gp[0][d._off[name][0]: d._off[name][0] + d._off[name][1]]  # noqa: E731
+            self.arena_gp[0][d._off["w4"][0]:].zero_()   # w4 / b4 gradients are accumulated by disc_head with atomics
+            kw = dict(split_stride=d.arena_n)
+        else:
+            d.arena_g.zero_()
+            gW = lambda name: d.view(name, "g")  # noqa: E731
+            kw = dict(atomic=True)
+        self._disc_forward(bt["pair_pop"], bt["pair_niche"], bt["label"], P, True, g_w4=gW("w4"), g_b4=gW("b4"))
+        ops.gemm(self.Hd, self.dz3, d.k3, d.h3, P, a_mn=True, b_mn=True, splits=sp, bn=bn3, out_f32=gW("W3"), ld_f32=d.ld3, **kw)   # dW3 (+db3)
         ops.gemm(self.dz3, d.view("W3", "b"), P, d.k3, d.h3, bn=ops.pick_bn(P, d.k3), out_bf16=self.dz12, dact_src=self.Hd,
                  dact_keep=self.keep_d)                                                            # dz12 = (dz3 W3^T) * dact(Hd)
-        bn1 = ops.pick_bn(k1, d.h1, True)
-        ops.gemm(self.Xp, self.dz12, k1, d.h1, P, a_mn=True, b_mn=True, splits=ops.pick_splits(k1, d.h1, P, bn1), bn=bn1,
-                 out_f32=d.view("W1", "g"), atomic=True)                                           # dW1 (+ db1) = Xp^T dz1
-        bn2 = ops.pick_bn(k1, d.h2, True)
-        ops.gemm(self.Xn, self.dz12[:, d.off2:], k1, d.h2, P, a_mn=True, b_mn=True, ldb=d.k3, splits=ops.pick_splits(k1, d.h2, P, bn2),
-                 bn=bn2, out_f32=d.view("W2", "g"), atomic=True)                                   # dW2 (+ db2) = Xn^T dz2
+        ops.gemm(self.Xp, self.dz12, k1, d.h1, P, a_mn=True, b_mn=True, splits=sp, bn=ops.pick_bn(k1, d.h1, True), out_f32=gW("W1"),
+                 ld_f32=d.ld1, **kw)                                                               # dW1 (+db1) = Xp^T dz1
+        ops.gemm(self.Xn, self.dz12[:, d.off2:], k1, d.h2, P, a_mn=True, b_mn=True, ldb=d.k3, splits=sp, bn=ops.pick_bn(k1, d.h2, True),
+                 out_f32=gW("W2"), ld_f32=d.ld2, **kw)                                             # dW2 (+db2) = Xn^T dz2
 
     def _d_update(self):
         d = self.disc
-        ops.adam(d.arena, d.arena_m, d.arena_v, d.arena_g, d.arena_b, scal=self.scal)
+        if self.world_size == 1:
+            ops.adam(d.arena, d.arena_m, d.arena_v, self.arena_gp, d.arena_b, scal=self.scal, n_partials=self._d_parts,
+                     partial_stride=d.arena_n)
+        else:
+            ops.adam(d.arena, d.arena_m, d.arena_v, d.arena_g, d.arena_b, scal=self.scal)
 
     # ------------------------------------------------------------------------------------------------------------
     # G update: train.py:326
@@ -319,8 +331,6 @@ class GanEngine(object):
         bt = data.batches[bi]
         v = self.vae
         B, Pr, K = bt["B"], bt["Pr"], bt["K"]
-        self.scal.zero_()
-        self.zero_g.zero_()
         v.small_g.zero_()
         ops.step_advance(self.words, self.scal, 2, self.lr, anneal_cap=self.anneal_cap, total_anneal_steps=self.total_anneal_steps)
         indptr, indices = self._vae_forward(data, bt, True, self.keep_vae)
@@ -343,10 +353,12 @@ class GanEngine(object):
         ops.dec_dlogits(self.logits, self.lse, self.xw, self.su, B, self.I, Bg, lam, self.scal, indptr, indices, None, samp[0], samp[1],
                         samp[2], self.dl)
         # decoder backward: dh2 = dl W_p1^T (split-K over the catalog), dW_p1^T = dl^T [h2 | 1]
-        ops.gemm(self.dl, v.WdT_b, B, H, self.I, b_mn=True, splits=self.dgrad_splits, bn=128, out_f32=self.dh2, atomic=True)
+        ops.gemm(self.dl, v.WdT_b, B, H, self.I, b_mn=True, splits=self.dgrad_splits, bn=128, out_f32=self.dh2_part, ld_f32=H,
+                 split_stride=self.max_B * H)
         ops.gemm(self.dl, self.h2, self.I, H + 1, B, a_mn=True, b_mn=True, bn=128, out_f32=self.dWdT, ld_f32=H, aux_col=H,
                  aux_out=v.view("b_p1", "g"))
-        ops.tanh_bwd(self.dh2, self.h2, B, H, dx_bf16=self.dh2pre, dbias=v.view("b_p0", "g"))
+        ops.tanh_bwd(self.dh2_part, self.h2, B, H, dx_bf16=self.dh2pre, dbias=v.view("b_p0", "g"), n_partials=self.dgrad_splits,
+                     partial_stride=self.max_B * H, ld_dy=H)
         ops.gemm(self.dh2pre, v.view("W_p0", "b"), B, L, H, bn=64, out_f32=self.dz)
         ops.gemm(self.z, self.dh2pre, L, H, B, a_mn=True, b_mn=True, bn=64, out_f32=v.view("W_p0", "g"))
         ops.latent_bwd(self.dz, self.mulv, self.zmu, B, Bg, -1.0, self.scal, self.dmulv, v.view("b_q1", "g"))
@@ -456,7 +468,6 @@ class GanEngine(object):
         v = self.vae
         for b0 in range(0, N, batch):
             B = min(batch, N - b0)
-            self.scal.zero_()
             ops.step_advance(self.words, self.scal, 0, self.lr)
             ip = trp[b0: b0 + B + 1]
             ops.enc_gather_fwd(ip, tri, None, B, self.I, uid_start + b0, v.W_q0_b, v.view("b_q0"), keep, self.seed, 0, self.words,

@@ -74,17 +74,26 @@ def pick_bn(M, N, splits_ok=False):
     return best[1]
 
 
-def pick_splits(M, N, K, bn, n_sm=148):
-    """Split-K factor that brings the tile count of a skinny (small M*N, long K) GEMM up to about one wave of CTAs."""
+def pick_splits(M, N, K, bn, n_sm=132):
+    """Split-K factor that brings the tile count of a skinny (small M*N, long K) GEMM up to about one wave of CTAs
+    (132 rather than 148: 4-CTA clusters cannot use the SMs of GPCs whose SM count is not a multiple of 4)."""
     tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
     kb = (K + 63) // 64
     # at most 32 splits: every split adds one fp32 atomic per output element, all landing on the same addresses
     return max(1, min(kb, n_sm // max(1, tiles), 32))
 
 
+def actual_splits(K, splits):
+    """Number of splits launch_gemm really uses (no empty split): mirrors gemm_sm100.cuh."""
+    kb = (K + 63) // 64
+    splits = max(1, min(splits, kb))
+    per = (kb + splits - 1) // splits
+    return (kb + per - 1) // per
+
+
 def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, splits=1, bn=128, out_f32=None, out_bf16=None, bias=None,
          act=0, alpha=1.0, atomic=False, keep=1.0, seed=0, rng_stream=0, rng_step=0, rng_step_dev=None, rng_ld=0, aux_col=-1,
-         aux_out=None, ld_f32=None, ld_bf16=None, dact_src=None, dact_keep=1.0):
+         aux_out=None, ld_f32=None, ld_bf16=None, dact_src=None, dact_keep=1.0, split_stride=0):
     """D[M,N] = alpha*A*B^T on the tcgen05 GEMM. A is [M,K] (or stored [K,M] when a_mn), B is [N,K] (or [K,N] when b_mn)."""
     _count(1)
     lda = A.stride(0) if lda is None else lda
@@ -96,7 +105,7 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, splits=1,
     check(lib().ltg_gemm_bf16(ptr(A), lda, int(a_mn), ptr(B), ldb, int(b_mn), M, N, K, splits, bn, ptr(out_f32), ld_f32 or 0,
                               ptr(out_bf16), ld_bf16 or 0, ptr(bias), act, alpha, int(atomic), keep, seed, rng_stream, rng_step,
                               ptr(rng_step_dev), rng_ld, aux_col, ptr(aux_out), ptr(dact_src),
-                              dact_src.stride(0) if dact_src is not None else 0, dact_keep, _stream()))
+                              dact_src.stride(0) if dact_src is not None else 0, dact_keep, split_stride, _stream()))
 
 
 def enc_gather_fwd(indptr, indices, values, B, n_items, uid0, W_enc_bf16, b_q0, keep, seed, step, step_dev, h1, coef, max_row_nnz=0,
@@ -119,9 +128,10 @@ def latent_bwd(dz, mulv, zmu, B, B_global, anneal, scal, dmulv, db_q1):
                                _stream()))
 
 
-def tanh_bwd(dy, y_bf16, B, N, dx_bf16=None, dx_f32=None, dbias=None):
+def tanh_bwd(dy, y_bf16, B, N, dx_bf16=None, dx_f32=None, dbias=None, n_partials=1, partial_stride=0, ld_dy=None):
     _count(1)
-    check(lib().ltg_tanh_bwd(ptr(dy), dy.stride(0), ptr(y_bf16), y_bf16.stride(0), B, N, ptr(dx_bf16),
+    check(lib().ltg_tanh_bwd(ptr(dy), dy.stride(0) if ld_dy is None else ld_dy, n_partials, partial_stride, ptr(y_bf16), y_bf16.stride(0), B, N,
+                             ptr(dx_bf16),
                              dx_bf16.stride(0) if dx_bf16 is not None else 0, ptr(dx_f32),
                              dx_f32.stride(0) if dx_f32 is not None else 0, ptr(dbias), _stream()))
 
@@ -151,9 +161,10 @@ def dec_dlogits(logits, lse, xw, s_u, B, n_items, B_global, lam, scal, indptr, i
                                 _stream()))
 
 
-def adam(p, m, v, g, shadow, lr_t=-1.0, scal=None, beta1=0.9, beta2=0.999, eps=1e-8):
+def adam(p, m, v, g, shadow, lr_t=-1.0, scal=None, beta1=0.9, beta2=0.999, eps=1e-8, n_partials=1, partial_stride=0):
     _count(1)
-    check(lib().ltg_adam(ptr(p), ptr(m), ptr(v), ptr(g), ptr(shadow), p.numel(), lr_t, ptr(scal), beta1, beta2, eps, _stream()))
+    check(lib().ltg_adam(ptr(p), ptr(m), ptr(v), ptr(g), n_partials, partial_stride, ptr(shadow), p.numel(), lr_t, ptr(scal), beta1, beta2,
+                         eps, _stream()))
 
 
 def enc_wgrad_compact(G, n_active, act_ptr, csc_row, csc_pos, coef, dh1pre):

@@ -118,6 +118,8 @@ def test_d_step_matches_oracle(setup):
     loss, grads = orc.d_step(s["E"], ps, dm, dv, pairs, m_real, m_gen, 0.7, orc.tf_adam_lr_t(1e-4, t))
     got = engine.last_losses(bt["B"])
     assert abs(got["d_loss"] - loss) < 1e-3 * abs(loss), (got["d_loss"], loss)
+    gsum = engine.arena_gp[: engine._d_parts].sum(0)          # split-K partials of the weight-gradient GEMMs
+    disc.arena_g.copy_(gsum)
     ggrads = disc.get_params("g")
     for name, g_dev, g_ref in zip("w1 b1 w2 b2 w3 b3 w4 b4".split(), ggrads, grads):
         assert rel(g_dev.reshape(g_ref.shape), g_ref) < 3e-2, (name, rel(g_dev.reshape(g_ref.shape), g_ref))
