@@ -167,6 +167,10 @@ class GanEngine(object):
         self.words = torch.zeros(4, dtype=torch.int32, device=self.device)
         self.scal = torch.zeros(ops.NSCAL, dtype=torch.float32, device=self.device)
         self._graphs = {}
+        # side streams: independent branches of a step (captured as parallel branches of the CUDA graph)
+        self.s1 = torch.cuda.Stream(device=self.device)
+        self.s2 = torch.cuda.Stream(device=self.device)
+        self.overlap = True
         self._alloc()
         self.eps_inject = None  # optional [B, L] fp32 tensor used instead of the Philox normal (parity tests)
 
@@ -217,6 +221,17 @@ class GanEngine(object):
     # ------------------------------------------------------------------------------------------------------------
     # building blocks
     # ------------------------------------------------------------------------------------------------------------
+    def _fork(self, side):
+        """Start a parallel branch on `side` that depends on everything issued so far on the current stream."""
+        if not self.overlap:
+            return torch.cuda.stream(torch.cuda.current_stream())
+        side.wait_stream(torch.cuda.current_stream())
+        return torch.cuda.stream(side)
+
+    def _join(self, side):
+        if self.overlap:
+            torch.cuda.current_stream().wait_stream(side)
+
     def _vae_forward(self, data, bt, is_training, keep, stash=True, indptr=None, indices=None, coef=None, uid0=None, B=None, max_nnz=None):
         """MultiVAE.forward_pass (MultiVAE.py:175-186) up to the logits and their softmax statistics."""
         v = self.vae
@@ -300,13 +315,17 @@ class GanEngine(object):
             gW = lambda name: d.view(name, "g")  # noqa: E731
             kw = dict(atomic=True)
         self._disc_forward(bt["pair_pop"], bt["pair_niche"], bt["label"], P, True, g_w4=gW("w4"), g_b4=gW("b4"))
-        ops.gemm(self.Hd, self.dz3, d.k3, d.h3, P, a_mn=True, b_mn=True, splits=sp, bn=bn3, out_f32=gW("W3"), ld_f32=d.ld3, **kw)   # dW3 (+db3)
+        with self._fork(self.s1):
+            ops.gemm(self.Hd, self.dz3, d.k3, d.h3, P, a_mn=True, b_mn=True, splits=sp, bn=bn3, out_f32=gW("W3"), ld_f32=d.ld3, **kw)  # dW3 (+db3)
         ops.gemm(self.dz3, d.view("W3", "b"), P, d.k3, d.h3, bn=ops.pick_bn(P, d.k3), out_bf16=self.dz12, dact_src=self.Hd,
                  dact_keep=self.keep_d)                                                            # dz12 = (dz3 W3^T) * dact(Hd)
-        ops.gemm(self.Xp, self.dz12, k1, d.h1, P, a_mn=True, b_mn=True, splits=sp, bn=ops.pick_bn(k1, d.h1, True), out_f32=gW("W1"),
-                 ld_f32=d.ld1, **kw)                                                               # dW1 (+db1) = Xp^T dz1
+        with self._fork(self.s2):
+            ops.gemm(self.Xp, self.dz12, k1, d.h1, P, a_mn=True, b_mn=True, splits=sp, bn=ops.pick_bn(k1, d.h1, True), out_f32=gW("W1"),
+                     ld_f32=d.ld1, **kw)                                                           # dW1 (+db1) = Xp^T dz1
         ops.gemm(self.Xn, self.dz12[:, d.off2:], k1, d.h2, P, a_mn=True, b_mn=True, ldb=d.k3, splits=sp, bn=ops.pick_bn(k1, d.h2, True),
                  out_f32=gW("W2"), ld_f32=d.ld2, **kw)                                             # dW2 (+db2) = Xn^T dz2
+        self._join(self.s2)
+        self._join(self.s1)
 
     def _d_update(self):
         d = self.disc
@@ -323,8 +342,10 @@ class GanEngine(object):
         """Single-GPU G update. The data-parallel variant (run_g_step with world_size > 1) runs the same three parts with
         the two exchange steps in between."""
         self._g_forward(data, bi)
+        self._fuse_update = bool(update) and self.world_size == 1
         self._g_backward(data, bi)
-        if update:
+        self._fuse_update = False
+        if update and self.world_size > 1:
             self._g_update(data, bi)
 
     def _g_forward(self, data, bi):
@@ -333,11 +354,15 @@ class GanEngine(object):
         B, Pr, K = bt["B"], bt["Pr"], bt["K"]
         v.small_g.zero_()
         ops.step_advance(self.words, self.scal, 2, self.lr, anneal_cap=self.anneal_cap, total_anneal_steps=self.total_anneal_steps)
+        if K > 0:
+            # y_generated with fresh dropout masks (keep_prob 0.7 is fed in the G step too, train.py:326): independent of the
+            # generator forward, so it runs as a parallel branch
+            with self._fork(self.s1):
+                self._disc_forward(bt["pair_pop"][Pr:], bt["pair_niche"][Pr:], bt["label"][Pr:], K, False)
         indptr, indices = self._vae_forward(data, bt, True, self.keep_vae)
         samp = (bt["samp_ptr"], bt["pair_niche"][Pr:], bt["label"][Pr:]) if K > 0 else (None, None, None)
         if K > 0:
-            # y_generated with fresh dropout masks (keep_prob 0.7 is fed in the G step too, train.py:326)
-            self._disc_forward(bt["pair_pop"][Pr:], bt["pair_niche"][Pr:], bt["label"][Pr:], K, False)
+            self._join(self.s1)
         ops.dec_row_stats(self.partial, self.nblk, self.logits, B, indptr, indices, None, samp[0], samp[1], samp[2], self.lse, self.xw,
                           self.su, self.scal)
 
@@ -352,23 +377,42 @@ class GanEngine(object):
         samp = (bt["samp_ptr"], bt["pair_niche"][Pr:], bt["label"][Pr:]) if K > 0 else (None, None, None)
         ops.dec_dlogits(self.logits, self.lse, self.xw, self.su, B, self.I, Bg, lam, self.scal, indptr, indices, None, samp[0], samp[1],
                         samp[2], self.dl)
-        # decoder backward: dh2 = dl W_p1^T (split-K over the catalog), dW_p1^T = dl^T [h2 | 1]
+        # decoder backward: dh2 = dl W_p1^T (split-K over the catalog), dW_p1^T = dl^T [h2 | 1].
+        # Branch s1: decoder weight gradient (+ its Adam sweep when the update is fused into this graph, single GPU) -- HBM-bound,
+        # runs under the latency-bound chain of small GEMMs of the encoder-side backward on the main stream.
+        fuse_update = self.world_size == 1 and getattr(self, "_fuse_update", False)
+        with self._fork(self.s1):
+            ops.gemm(self.dl, self.h2, self.I, H + 1, B, a_mn=True, b_mn=True, bn=128, out_f32=self.dWdT, ld_f32=H, aux_col=H,
+                     aux_out=v.view("b_p1", "g"))
         ops.gemm(self.dl, v.WdT_b, B, H, self.I, b_mn=True, splits=self.dgrad_splits, bn=128, out_f32=self.dh2_part, ld_f32=H,
                  split_stride=self.max_B * H)
-        ops.gemm(self.dl, self.h2, self.I, H + 1, B, a_mn=True, b_mn=True, bn=128, out_f32=self.dWdT, ld_f32=H, aux_col=H,
-                 aux_out=v.view("b_p1", "g"))
+        if fuse_update:
+            # the Adam sweep rewrites the bf16 decoder weights the dgrad GEMM above reads: order it after dgrad
+            if self.overlap:
+                self.s1.wait_stream(torch.cuda.current_stream())
+            with (torch.cuda.stream(self.s1) if self.overlap else torch.cuda.stream(torch.cuda.current_stream())):
+                ops.adam(v.WdT, v.WdT_m, v.WdT_v, self.dWdT, v.WdT_b, scal=self.scal)
         ops.tanh_bwd(self.dh2_part, self.h2, B, H, dx_bf16=self.dh2pre, dbias=v.view("b_p0", "g"), n_partials=self.dgrad_splits,
                      partial_stride=self.max_B * H, ld_dy=H)
+        with self._fork(self.s2):
+            ops.gemm(self.z, self.dh2pre, L, H, B, a_mn=True, b_mn=True, bn=64, out_f32=v.view("W_p0", "g"))
         ops.gemm(self.dh2pre, v.view("W_p0", "b"), B, L, H, bn=64, out_f32=self.dz)
-        ops.gemm(self.z, self.dh2pre, L, H, B, a_mn=True, b_mn=True, bn=64, out_f32=v.view("W_p0", "g"))
         ops.latent_bwd(self.dz, self.mulv, self.zmu, B, Bg, -1.0, self.scal, self.dmulv, v.view("b_q1", "g"))
+        self._join(self.s2)
+        with self._fork(self.s2):
+            ops.gemm(self.h1, self.dmulv, H, 2 * L, B, a_mn=True, b_mn=True, bn=64, out_f32=v.view("W_q1", "g"))
         ops.gemm(self.dmulv, v.view("W_q1", "b"), B, H, 2 * L, bn=64, out_f32=self.dh1)
-        ops.gemm(self.h1, self.dmulv, H, 2 * L, B, a_mn=True, b_mn=True, bn=64, out_f32=v.view("W_q1", "g"))
         ops.tanh_bwd(self.dh1, self.h1, B, H, dx_bf16=self.dh1pre_b, dx_f32=self.dh1pre, dbias=v.view("b_q0", "g"))
         # encoder weight gradient over the batch's active items as a tensor-core GEMM: G = Xc^T dh1pre   [n_active, 600]
         ops.gemm(self.Xc, self.dh1pre_b, bt["n_active"], H, B, a_mn=True, b_mn=True, bn=ops.pick_bn(bt["n_active"], H), out_f32=self.G_enc)
         if self.world_size > 1:
             ops.enc_wgrad_expand(self.dW_q0, self.I, bt["slot_of_item"], self.G_enc)
+        if fuse_update:
+            ops.enc_adam(v.W_q0, v.W_q0_m, v.W_q0_v, v.W_q0_b, self.I, bt["slot_of_item"], self.G_enc, scal=self.scal)
+        self._join(self.s2)
+        self._join(self.s1)
+        if fuse_update:
+            ops.adam(v.small, v.small_m, v.small_v, v.small_g, v.small_b, scal=self.scal)
 
     def _g_update(self, data, bi):
         bt = data.batches[bi]
