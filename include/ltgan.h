@@ -116,6 +116,13 @@ int ltg_dec_dlogits(const void* logits_bf16, int ld, const float* lse, const flo
                     const int32_t* samp_ptr, const int32_t* samp_items, const int32_t* samp_valid,
                     void* dl_bf16, void* stream);
 
+/* Fused G-step variant of ltg_dec_row_stats + ltg_dec_dlogits: one CTA per user computes lse / NLL / sampled-probability sum and
+ * writes its row of d g_loss / d logits (dense part + sparse fix-ups). scal[SUM_Y], scal[CNT] must be final before the call.     */
+int ltg_dec_row_bwd(const float* partial, int n_blocks, const void* logits_bf16, int ld, int B, int n_items, int B_global, float lam,
+                    const int32_t* indptr, const int32_t* indices, const float* values,
+                    const int32_t* samp_ptr, const int32_t* samp_items, const int32_t* samp_valid,
+                    float* lse, float* scal, void* dl_bf16, void* stream);
+
 /* ---- a13: TF-semantics Adam (train.py:160-164; F6 shared step, F7 dense) ------------------------------------------
  * p,m,v fp32 updated in place; g fp32; optional bf16 shadow with the same layout. lr_t < 0: read scal[LTG_S_LR_T].
  * g may be given as n_partials buffers (g + s*partial_stride: split-K partials of the weight-gradient GEMMs), summed on the fly. */
@@ -137,12 +144,14 @@ int ltg_enc_wgrad_expand(float* dW, int n_items, const int32_t* slot_of_item, co
  * probability proportional to softmax(logits)[u, cand] (Gumbel-top-k == numpy's successive draw in distribution, F9),
  * emit them in ascending item order at slots samp_ptr[u].., each paired with a uniformly drawn popular item of the user
  * (pop_ptr/pop_items), valid[slot] = +1 if both ids are in the item-feature table (item_valid[n_items] bytes, F10), else -1.
- * *cnt (int32, may be NULL) += number of valid pairs.                                                                            */
+ * *cnt (int32, may be NULL) += number of valid pairs. user_order (may be NULL): permutation of the batch rows giving the CTA
+ * launch order (heaviest candidate lists first).                                                                            */
 int ltg_sample_pairs(const void* logits_bf16, int ld_logits, int B, int n_items, int64_t uid0,
                      const int32_t* cand_ptr, const int32_t* cand_items, const int32_t* samp_ptr,
                      const int32_t* pop_ptr, const int32_t* pop_items, const uint8_t* item_valid,
                      uint64_t seed, uint32_t step, const uint32_t* step_dev,
-                     int32_t* samp_items, int32_t* samp_partner, int32_t* samp_valid, int32_t* cnt, int max_cand, void* stream);
+                     int32_t* samp_items, int32_t* samp_partner, int32_t* samp_valid, int32_t* cnt, int max_cand,
+                     const int32_t* user_order, void* stream);
 
 /* ---- a11/a12: discriminator (discriminator.py:14-55, train.py:142) --------------------------------------------------
  * Frozen embedding gather (F5): rows of E_bf16 [n_items, 128] (cols 100.. are zero) -> Xp, Xn bf16 [P, 128].            */

@@ -30,14 +30,15 @@ sample_pairs_kernel(const __nv_bfloat16* __restrict__ logits, int ld, int n_item
                     const int32_t* __restrict__ pop_ptr, const int32_t* __restrict__ pop_items, const uint8_t* __restrict__ item_valid,
                     uint64_t seed, uint32_t step, const uint32_t* __restrict__ step_dev,
                     int32_t* __restrict__ samp_items, int32_t* __restrict__ samp_partner, int32_t* __restrict__ samp_valid,
-                    int32_t* __restrict__ cnt_out) {
+                    int32_t* __restrict__ cnt_out, const int32_t* __restrict__ user_order) {
   extern __shared__ uint32_t s_keys[];  // [max_cand]
   __shared__ uint32_t s_hist[256];
   __shared__ uint32_t s_sel[2];          // digit, remaining-k
   __shared__ int s_warp[SAMP_THREADS / 32 + 1];
   __shared__ int s_base, s_eq_base, s_nvalid;
 
-  const int u = blockIdx.x;
+  // heavy users first (user_order sorts by candidate count, descending): the longest CTAs start at t = 0
+  const int u = user_order != nullptr ? user_order[blockIdx.x] : blockIdx.x;
   const int tid = threadIdx.x;
   const int s0 = samp_ptr[u];
   const int c0 = cand_ptr[u];
@@ -150,7 +151,8 @@ extern "C" int ltg_sample_pairs(const void* logits_bf16, int ld_logits, int B, i
                                 const int32_t* cand_ptr, const int32_t* cand_items, const int32_t* samp_ptr,
                                 const int32_t* pop_ptr, const int32_t* pop_items, const uint8_t* item_valid,
                                 uint64_t seed, uint32_t step, const uint32_t* step_dev,
-                                int32_t* samp_items, int32_t* samp_partner, int32_t* samp_valid, int32_t* cnt, int max_cand, void* stream) {
+                                int32_t* samp_items, int32_t* samp_partner, int32_t* samp_valid, int32_t* cnt, int max_cand, const int32_t* user_order,
+                                void* stream) {
   LTG_REQUIRE(logits_bf16 && cand_ptr && cand_items && samp_ptr && pop_ptr && pop_items && item_valid);
   LTG_REQUIRE(samp_items && samp_partner && samp_valid);
   LTG_REQUIRE(max_cand >= 0 && (size_t)max_cand * 4 <= 200 * 1024);
@@ -164,7 +166,7 @@ extern "C" int ltg_sample_pairs(const void* logits_bf16, int ld_logits, int B, i
   }
   sample_pairs_kernel<<<B, SAMP_THREADS, smem, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(logits_bf16), ld_logits, n_items, uid0, cand_ptr, cand_items, samp_ptr, pop_ptr, pop_items,
-      item_valid, seed, step, step_dev, samp_items, samp_partner, samp_valid, cnt);
+      item_valid, seed, step, step_dev, samp_items, samp_partner, samp_valid, cnt, user_order);
   LTG_CHECK_LAUNCH();
   return LTG_OK;
 }

@@ -78,16 +78,17 @@ enc_gather_fwd_kernel(const int32_t* __restrict__ indptr, const int32_t* __restr
   __syncthreads();
   if (tid < HV) {
     int j = 0;
-    for (; j + 4 <= cnt; j += 4) {
-      uint4 w[4]; float c[4];
+    constexpr int EU = 8;  // 16-byte loads in flight per thread
+    for (; j + EU <= cnt; j += EU) {
+      uint4 w[EU]; float c[EU];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < EU; ++q) {
         c[q] = s_coef[j + q];
         w[q] = make_uint4(0, 0, 0, 0);
         if (c[q] != 0.f) w[q] = __ldg(W + (size_t)s_item[j + q] * HV + tid);
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < EU; ++q) {
         float2 a = unpack_bf16x2(w[q].x), b = unpack_bf16x2(w[q].y), d = unpack_bf16x2(w[q].z), e = unpack_bf16x2(w[q].w);
         acc[0] = fmaf(c[q], a.x, acc[0]); acc[1] = fmaf(c[q], a.y, acc[1]);
         acc[2] = fmaf(c[q], b.x, acc[2]); acc[3] = fmaf(c[q], b.y, acc[3]);
@@ -364,6 +365,124 @@ dlogits_sparse_kernel(const __nv_bfloat16* __restrict__ logits, int ld, const fl
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// a6 + a12 fused for the G step: one CTA per user does (1) the softmax row statistics (lse, NLL, sum of the sampled
+// probabilities), (2) the dense part of d g_loss / d logits for its row, (3) the sparse fix-ups. Everything is row-local
+// (the only cross-row quantity, Ybar = sum y / cnt, comes from the discriminator head that ran before), so the three
+// launches + two grid-wide dependencies of the unfused path collapse into one.
+// ---------------------------------------------------------------------------------------------
+constexpr int ROWBWD_THREADS = 256;
+
+__global__ void __launch_bounds__(ROWBWD_THREADS)
+dec_row_bwd_kernel(const float2* __restrict__ partial, int n_blocks, const __nv_bfloat16* __restrict__ logits, int ld, int B, int n_items,
+                   float inv_bg, float lam, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                   const float* __restrict__ values, const int32_t* __restrict__ samp_ptr, const int32_t* __restrict__ samp_items,
+                   const int32_t* __restrict__ samp_valid, float* __restrict__ lse_out, float* __restrict__ scal,
+                   __nv_bfloat16* __restrict__ dl) {
+  __shared__ float s_red[ROWBWD_THREADS / 32];
+  const int u = blockIdx.x, tid = threadIdx.x;
+  auto bsum = [&](float v) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((tid & 31) == 0) s_red[tid >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < ROWBWD_THREADS / 32; ++w) t += s_red[w];
+    return t;
+  };
+  auto bmax = [&](float v) {
+    v = warp_max(v);
+    __syncthreads();
+    if ((tid & 31) == 0) s_red[tid >> 5] = v;
+    __syncthreads();
+    float t = s_red[0];
+#pragma unroll
+    for (int w = 1; w < ROWBWD_THREADS / 32; ++w) t = fmaxf(t, s_red[w]);
+    return t;
+  };
+  // (1) statistics
+  float mx = -INFINITY;
+  for (int b = tid; b < n_blocks; b += ROWBWD_THREADS) mx = fmaxf(mx, partial[(size_t)b * B + u].x);
+  mx = bmax(mx);
+  float s = 0.f;
+  for (int b = tid; b < n_blocks; b += ROWBWD_THREADS) {
+    const float2 p = partial[(size_t)b * B + u];
+    s += p.y * __expf(p.x - mx);
+  }
+  s = bsum(s);
+  const float lse = mx + logf(s);
+  const __nv_bfloat16* row = logits + (size_t)u * ld;
+  __nv_bfloat16* drow = dl + (size_t)u * ld;
+  float nll = 0.f, xw = 0.f, sp = 0.f;
+  for (int j = indptr[u] + tid; j < indptr[u + 1]; j += ROWBWD_THREADS) {
+    const float v = values != nullptr ? values[j] : 1.0f;
+    nll -= v * (__bfloat162float(row[indices[j]]) - lse);
+    xw += v;
+  }
+  const bool gan = lam != 0.f && samp_ptr != nullptr;
+  if (samp_ptr != nullptr)
+    for (int j = samp_ptr[u] + tid; j < samp_ptr[u + 1]; j += ROWBWD_THREADS)
+      if (samp_valid[j] > 0) sp += __expf(__bfloat162float(row[samp_items[j]]) - lse);
+  nll = bsum(nll); xw = bsum(xw); sp = bsum(sp);
+  float ybar = 0.f;
+  if (gan) {
+    const float cnt = scal[LTG_S_CNT];
+    ybar = cnt > 0.f ? scal[LTG_S_SUM_Y] / cnt : 0.f;
+  }
+  if (tid == 0) {
+    lse_out[u] = lse;
+    atomicAdd(scal + LTG_S_NLL_SUM, nll);
+    if (samp_ptr != nullptr) atomicAdd(scal + LTG_S_SUM_P, sp);
+  }
+  // (2) dense: dl = pi * (xw/Bg + lam*Ybar*s_u)
+  const float a = xw * inv_bg + (gan ? lam * ybar * sp : 0.f);
+  const int ld8 = ld >> 3;
+  const uint4* src = reinterpret_cast<const uint4*>(row);
+  uint4* dst = reinterpret_cast<uint4*>(drow);
+  for (int v0 = tid; v0 < ld8; v0 += 4 * ROWBWD_THREADS) {
+    uint4 x[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int v = v0 + q * ROWBWD_THREADS;
+      x[q] = v < ld8 ? ld_nc_v4(src + v) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int v = v0 + q * ROWBWD_THREADS;
+      if (v >= ld8) continue;
+      const uint32_t xi[4] = {x[q].x, x[q].y, x[q].z, x[q].w};
+      uint32_t o[4];
+      const int c0 = v * 8;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack_bf16x2(xi[k]);
+        const float p0 = (c0 + 2 * k < n_items) ? __expf(f.x - lse) * a : 0.f;
+        const float p1 = (c0 + 2 * k + 1 < n_items) ? __expf(f.y - lse) * a : 0.f;
+        o[k] = pack_bf16x2(p0, p1);
+      }
+      dst[v] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  __syncthreads();
+  // (3) sparse fix-ups
+  for (int j = indptr[u] + tid; j < indptr[u + 1]; j += ROWBWD_THREADS) {
+    const int i = indices[j];
+    const float v = values != nullptr ? values[j] : 1.0f;
+    drow[i] = __float2bfloat16(__bfloat162float(drow[i]) - v * inv_bg);
+  }
+  if (gan) {
+    __syncthreads();
+    for (int j = samp_ptr[u] + tid; j < samp_ptr[u + 1]; j += ROWBWD_THREADS) {
+      if (samp_valid[j] > 0) {
+        const int i = samp_items[j];
+        const float pi = __expf(__bfloat162float(row[i]) - lse);
+        drow[i] = __float2bfloat16(__bfloat162float(drow[i]) - lam * ybar * pi);
+      }
+    }
+  }
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -460,6 +579,20 @@ extern "C" int ltg_dec_dlogits(const void* logits_bf16, int ld, const float* lse
   dlogits_sparse_kernel<<<B, SPARSE_THREADS, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(logits_bf16), ld, lse, B, inv_bg, lam, scal, indptr, indices, values, samp_ptr, samp_items,
       samp_valid, reinterpret_cast<__nv_bfloat16*>(dl_bf16));
+  LTG_CHECK_LAUNCH();
+  return LTG_OK;
+}
+
+extern "C" int ltg_dec_row_bwd(const float* partial, int n_blocks, const void* logits_bf16, int ld, int B, int n_items, int B_global, float lam,
+                               const int32_t* indptr, const int32_t* indices, const float* values,
+                               const int32_t* samp_ptr, const int32_t* samp_items, const int32_t* samp_valid,
+                               float* lse, float* scal, void* dl_bf16, void* stream) {
+  LTG_REQUIRE(partial && logits_bf16 && indptr && indices && lse && scal && dl_bf16);
+  LTG_REQUIRE(ld % 8 == 0 && ld >= n_items);
+  if (B <= 0) return LTG_OK;
+  dec_row_bwd_kernel<<<B, ROWBWD_THREADS, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float2*>(partial), n_blocks, reinterpret_cast<const __nv_bfloat16*>(logits_bf16), ld, B, n_items,
+      1.0f / (float)B_global, lam, indptr, indices, values, samp_ptr, samp_items, samp_valid, lse, scal, reinterpret_cast<__nv_bfloat16*>(dl_bf16));
   LTG_CHECK_LAUNCH();
   return LTG_OK;
 }

@@ -100,6 +100,7 @@ class TrainData(object):
                     pair_pop=t(pair_pop), pair_niche=t(pair_niche), label=t(label),
                     cnt=torch.zeros(1, dtype=torch.int32, device=dev),
                     max_cand=int(cand_len[b0:b1].max()) if B > 0 else 0,
+                    samp_order=t(np.argsort(-cand_len[b0:b1], kind="stable")),
                     max_nnz=int(np.diff(self.h_indptr[b0:b1 + 1]).max()) if B > 0 else 0)
 
 
@@ -284,7 +285,7 @@ class GanEngine(object):
             Pr = bt["Pr"]
             ops.sample_pairs(self.logits, B, self.I, bt["uid0"], data.cand_ptr[bt["b0"]: bt["b0"] + B + 1], data.cand_items, bt["samp_ptr"],
                              data.pop_ptr[bt["b0"]: bt["b0"] + B + 1], data.pop_items, data.item_valid, self.seed, 0, self.words,
-                             bt["pair_niche"][Pr:], bt["pair_pop"][Pr:], bt["label"][Pr:], bt["cnt"], bt["max_cand"])
+                             bt["pair_niche"][Pr:], bt["pair_pop"][Pr:], bt["label"][Pr:], bt["cnt"], bt["max_cand"], bt["samp_order"])
 
     # ------------------------------------------------------------------------------------------------------------
     # D update: train.py:300
@@ -363,8 +364,9 @@ class GanEngine(object):
         samp = (bt["samp_ptr"], bt["pair_niche"][Pr:], bt["label"][Pr:]) if K > 0 else (None, None, None)
         if K > 0:
             self._join(self.s1)
-        ops.dec_row_stats(self.partial, self.nblk, self.logits, B, indptr, indices, None, samp[0], samp[1], samp[2], self.lse, self.xw,
-                          self.su, self.scal)
+        if self.world_size > 1:   # DP: the statistics are all-reduced before the backward; single GPU fuses them into the backward
+            ops.dec_row_stats(self.partial, self.nblk, self.logits, B, indptr, indices, None, samp[0], samp[1], samp[2], self.lse, self.xw,
+                              self.su, self.scal)
 
     def _g_backward(self, data, bi):
         bt = data.batches[bi]
@@ -375,8 +377,12 @@ class GanEngine(object):
         indices = data.indices
         lam = self.lam if (K > 0 or self.world_size > 1) else 0.0
         samp = (bt["samp_ptr"], bt["pair_niche"][Pr:], bt["label"][Pr:]) if K > 0 else (None, None, None)
-        ops.dec_dlogits(self.logits, self.lse, self.xw, self.su, B, self.I, Bg, lam, self.scal, indptr, indices, None, samp[0], samp[1],
-                        samp[2], self.dl)
+        if self.world_size > 1:
+            ops.dec_dlogits(self.logits, self.lse, self.xw, self.su, B, self.I, Bg, lam, self.scal, indptr, indices, None, samp[0], samp[1],
+                            samp[2], self.dl)
+        else:
+            ops.dec_row_bwd(self.partial, self.nblk, self.logits, B, self.I, Bg, lam, indptr, indices, None, samp[0], samp[1], samp[2],
+                            self.lse, self.scal, self.dl)
         # decoder backward: dh2 = dl W_p1^T (split-K over the catalog), dW_p1^T = dl^T [h2 | 1].
         # Branch s1: decoder weight gradient (+ its Adam sweep when the update is fused into this graph, single GPU) -- HBM-bound,
         # runs under the latency-bound chain of small GEMMs of the encoder-side backward on the main stream.

@@ -161,6 +161,12 @@ def dec_dlogits(logits, lse, xw, s_u, B, n_items, B_global, lam, scal, indptr, i
                                 _stream()))
 
 
+def dec_row_bwd(partial, n_blocks, logits, B, n_items, B_global, lam, indptr, indices, values, samp_ptr, samp_items, samp_valid, lse, scal, dl):
+    _count(1)
+    check(lib().ltg_dec_row_bwd(ptr(partial), n_blocks, ptr(logits), logits.stride(0), B, n_items, B_global, lam, ptr(indptr), ptr(indices),
+                                ptr(values), ptr(samp_ptr), ptr(samp_items), ptr(samp_valid), ptr(lse), ptr(scal), ptr(dl), _stream()))
+
+
 def adam(p, m, v, g, shadow, lr_t=-1.0, scal=None, beta1=0.9, beta2=0.999, eps=1e-8, n_partials=1, partial_stride=0):
     _count(1)
     check(lib().ltg_adam(ptr(p), ptr(m), ptr(v), ptr(g), n_partials, partial_stride, ptr(shadow), p.numel(), lr_t, ptr(scal), beta1, beta2,
@@ -185,11 +191,11 @@ def enc_wgrad_expand(dW, n_items, slot_of_item, G):
 
 
 def sample_pairs(logits, B, n_items, uid0, cand_ptr, cand_items, samp_ptr, pop_ptr, pop_items, item_valid, seed, step, step_dev,
-                 samp_items, samp_partner, samp_valid, cnt, max_cand):
+                 samp_items, samp_partner, samp_valid, cnt, max_cand, user_order=None):
     _count(1)
     check(lib().ltg_sample_pairs(ptr(logits), logits.stride(0), B, n_items, uid0, ptr(cand_ptr), ptr(cand_items), ptr(samp_ptr),
                                  ptr(pop_ptr), ptr(pop_items), ptr(item_valid), seed, step, ptr(step_dev), ptr(samp_items),
-                                 ptr(samp_partner), ptr(samp_valid), ptr(cnt), max_cand, _stream()))
+                                 ptr(samp_partner), ptr(samp_valid), ptr(cnt), max_cand, ptr(user_order), _stream()))
 
 
 def disc_gather(E_bf16, pop_ids, niche_ids, P, Xp, Xn):

@@ -267,6 +267,17 @@ def test_decoder_logits_stats_and_dlogits(ops):
     err = (dl[:, :I].float().cpu() - g).abs().max().item()
     assert err < 1e-2 * g.abs().max().item() + 1e-6, err
     assert (dl[:, I:] == 0).all()
+    # fused per-user kernel (G step): same statistics and the same dlogits in one launch
+    scal2 = torch.zeros(16, device="cuda"); scal2[ops.S_SUM_Y] = 3.3; scal2[ops.S_CNT] = 7.0
+    lse2 = torch.zeros(B, device="cuda"); dl2 = torch.full((B, ld), 9.0, device="cuda", dtype=torch.bfloat16)
+    ops.dec_row_bwd(partial, nblk, logits, B, I, B, lam, dev(indptr), dev(indices), None, dev(samp_ptr), dev(samp_items), dev(samp_valid),
+                    lse2, scal2, dl2)
+    torch.cuda.synchronize()
+    assert (lse2 - lse).abs().max().item() < 1e-5
+    assert abs(scal2[ops.S_NLL_SUM].item() - want_nll) < 1e-3 * abs(want_nll)
+    assert abs(scal2[ops.S_SUM_P].item() - want_sp) < 2e-3 * abs(want_sp) + 1e-6
+    assert (dl2.float() - dl.float()).abs().max().item() <= 2e-2 * g.abs().max().item()
+    assert (dl2[:, :I].float().cpu() - g).abs().max().item() < 1e-2 * g.abs().max().item() + 1e-6
     # probabilities (compat path)
     out = torch.zeros(B, I, device="cuda")
     ops.dec_probs(logits, lse, B, I, out)
@@ -371,7 +382,8 @@ def test_sampler_matches_gumbel_topk_oracle_bit_exact(ops):
     cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
     seed, step, uid0 = 777, 3, 500
     ops.sample_pairs(lg, B, I, uid0, dev(cand_ptr), dev(np.concatenate(cand)), dev(samp_ptr), dev(pop_ptr), dev(np.concatenate(pops)),
-                     dev(valid), seed, step, None, si, sp, sv, cnt, int(max(len(c) for c in cand)))
+                     dev(valid), seed, step, None, si, sp, sv, cnt, int(max(len(c) for c in cand)),
+                     dev(np.argsort(-np.diff(cand_ptr)).astype(np.int32)))
     torch.cuda.synchronize()
     si, sp, sv = si.cpu().numpy(), sp.cpu().numpy(), sv.cpu().numpy()
     lgf = lg.float().cpu().numpy()
