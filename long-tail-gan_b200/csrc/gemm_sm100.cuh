@@ -283,6 +283,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int kb1 = min(shape.k_blocks, kb0 + shape.kb_per_split);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
+        if (kb0 >= kb1) umma_commit(&tfull_bar[acc]);  // empty split (fixed split count, short K): the epilogue stores zeros
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
@@ -323,7 +324,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int c = quarter * GEMM_CW; c < BN; c += 4 * GEMM_CW) {
         if (n0 + c >= shape.N) break;  // warp-uniform
         float v[GEMM_CW];
-        tmem_ld16(taddr + c, v);
+        if (split * shape.kb_per_split < shape.k_blocks) {
+          tmem_ld16(taddr + c, v);
+        } else {
+#pragma unroll
+          for (int i = 0; i < GEMM_CW; ++i) v[i] = 0.f;  // empty split: nothing was accumulated
+        }
         epi.chunk(n0 + c, v);
       }
       epi.finish();
@@ -647,9 +653,8 @@ int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb
   s.n_blocks = (N + BN - 1) / BN;
   s.k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
   if (splits < 1) splits = 1;
-  if (splits > s.k_blocks) splits = s.k_blocks;
   s.kb_per_split = (s.k_blocks + splits - 1) / splits;
-  s.splits = (s.k_blocks + s.kb_per_split - 1) / s.kb_per_split;  // no empty split
+  s.splits = splits;  // trailing splits may be empty (kb0 >= k_blocks): they store zeros, so a consumer can rely on a fixed count
   // cluster along M: row blocks of the same n-block share the B operand (TMA multicast)
   int cm = s.m_blocks >= 4 ? 4 : (s.m_blocks >= 2 ? 2 : 1);
   const int ov = ltg_gemm_cluster_override();

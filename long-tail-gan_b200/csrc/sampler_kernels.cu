@@ -24,6 +24,29 @@ __device__ __forceinline__ uint32_t float_to_ordered(float f) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+// exclusive prefix sum of one int per thread over the CTA; *total receives the CTA-wide sum. Two barriers.
+__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();  // protects s_warp against the previous use
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  int base = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < SAMP_THREADS / 32; ++w) {
+    const int c = s_warp[w];
+    if (w < warp) base += c;
+    tot += c;
+  }
+  *total = tot;
+  return base + inc - v;
+}
+
 __global__ void __launch_bounds__(SAMP_THREADS)
 sample_pairs_kernel(const __nv_bfloat16* __restrict__ logits, int ld, int n_items, int64_t uid0,
                     const int32_t* __restrict__ cand_ptr, const int32_t* __restrict__ cand_items, const int32_t* __restrict__ samp_ptr,
@@ -34,12 +57,13 @@ sample_pairs_kernel(const __nv_bfloat16* __restrict__ logits, int ld, int n_item
   extern __shared__ uint32_t s_keys[];  // [max_cand]
   __shared__ uint32_t s_hist[256];
   __shared__ uint32_t s_sel[2];          // digit, remaining-k
-  __shared__ int s_warp[SAMP_THREADS / 32 + 1];
-  __shared__ int s_base, s_eq_base, s_nvalid;
+  __shared__ int s_warp[SAMP_THREADS / 32];
+  __shared__ int s_nvalid;
 
   // heavy users first (user_order sorts by candidate count, descending): the longest CTAs start at t = 0
   const int u = user_order != nullptr ? user_order[blockIdx.x] : blockIdx.x;
   const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
   const int s0 = samp_ptr[u];
   const int c0 = cand_ptr[u];
   const int C = cand_ptr[u + 1] - c0;
@@ -58,90 +82,99 @@ sample_pairs_kernel(const __nv_bfloat16* __restrict__ logits, int ld, int n_item
     const float g = -__logf(-__logf(ltg_u01(r)));
     s_keys[c] = float_to_ordered(__bfloat162float(row[item]) + g);
   }
-  if (tid == 0) { s_nvalid = 0; }
+  if (tid == 0) s_nvalid = 0;
   __syncthreads();
 
-  // radix select: the n-th largest key
+  // radix select: the n-th largest key (8 bits per pass; the digit search over the 256 bins is done by warp 0)
   uint32_t prefix = 0, pmask = 0;
   uint32_t k = (uint32_t)n;  // 1-based rank among keys matching the prefix, counted from the top
   for (int shift = 24; shift >= 0; shift -= 8) {
-    for (int i = tid; i < 256; i += SAMP_THREADS) s_hist[i] = 0;
+    if (tid < 256) s_hist[tid] = 0;
     __syncthreads();
     for (int c = tid; c < C; c += SAMP_THREADS) {
       const uint32_t key = s_keys[c];
       if ((key & pmask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
     }
     __syncthreads();
-    if (tid == 0) {
-      uint32_t acc = 0; int d = 255;
-      for (; d > 0; --d) {
-        if (acc + s_hist[d] >= k) break;
-        acc += s_hist[d];
+    if (warp == 0) {
+      // lane l owns bins [8l, 8l+8); suffix sums over lanes give the count of keys in higher bins
+      uint32_t h[8], mine = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { h[q] = s_hist[8 * lane + q]; mine += h[q]; }
+      uint32_t above = 0;  // keys in bins owned by higher lanes
+      uint32_t run = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_down_sync(0xffffffffu, run, o);
+        if (lane + o < 32) run += t;
       }
-      s_sel[0] = (uint32_t)d;
-      s_sel[1] = k - acc;
+      above = run - mine;
+      // the digit lies in this lane's bins iff above < k <= above + mine
+      if (above < k && k <= above + mine) {
+        uint32_t acc = above;
+        int d = 7;
+        for (; d > 0; --d) {
+          if (acc + h[d] >= k) break;
+          acc += h[d];
+        }
+        s_sel[0] = (uint32_t)(8 * lane + d);
+        s_sel[1] = k - acc;
+      }
     }
     __syncthreads();
     prefix |= s_sel[0] << shift;
     pmask |= 255u << shift;
     k = s_sel[1];
-    __syncthreads();
   }
   const uint32_t T = prefix;   // threshold key; `k` of the keys equal to T are taken (first in candidate order)
   const int need_eq = (int)k;
 
-  // ordered compaction
-  if (tid == 0) { s_base = 0; s_eq_base = 0; }
-  __syncthreads();
-  const int lane = tid & 31, warp = tid >> 5;
-  for (int cb = 0; cb < C; cb += SAMP_THREADS) {
-    const int c = cb + tid;
-    const uint32_t key = c < C ? s_keys[c] : 0u;
-    const bool gt = c < C && key > T;
-    const bool eq = c < C && key == T;
-    // rank of this thread's equal-key among equals (block order)
-    const uint32_t eq_ballot = __ballot_sync(0xffffffffu, eq);
-    const int eq_before_w = __popc(eq_ballot & ((1u << lane) - 1));
-    if (lane == 0) s_warp[warp] = __popc(eq_ballot);
-    __syncthreads();
-    int eq_off = s_eq_base;
-    for (int w = 0; w < warp; ++w) eq_off += s_warp[w];
-    const bool take = gt || (eq && (eq_off + eq_before_w) < need_eq);
-    int eq_total = 0;
-    for (int w = 0; w < SAMP_THREADS / 32; ++w) eq_total += s_warp[w];
-    __syncthreads();
-    const uint32_t tk_ballot = __ballot_sync(0xffffffffu, take);
-    const int tk_before_w = __popc(tk_ballot & ((1u << lane) - 1));
-    if (lane == 0) s_warp[warp] = __popc(tk_ballot);
-    __syncthreads();
-    int off = s_base;
-    for (int w = 0; w < warp; ++w) off += s_warp[w];
-    int tk_total = 0;
-    for (int w = 0; w < SAMP_THREADS / 32; ++w) tk_total += s_warp[w];
-    if (take) {
-      const int slot = s0 + off + tk_before_w;
-      const int item = cand_items[c0 + c];
-      const int p0 = pop_ptr[u];
-      const int np = pop_ptr[u + 1] - p0;
-      int partner = -1;
-      if (np > 0) {
-        const uint32_t r = ltg_rand_u32(seed, LTG_STREAM_PARTNER, step, ubase + (uint64_t)item);
-        partner = pop_items[p0 + (int)(((uint64_t)r * (uint64_t)np) >> 32)];  // train.py:236-238
-      }
-      const int ok = (partner >= 0 && item_valid[item] && item_valid[partner]) ? 1 : 0;  // train.py:240-243
-      samp_items[slot] = item;
-      samp_partner[slot] = partner >= 0 ? partner : 0;
-      samp_valid[slot] = ok ? 1 : -1;
-      if (ok) atomicAdd(&s_nvalid, 1);
+  // ordered compaction: every thread owns a contiguous segment of the candidate list
+  const int seg = (C + SAMP_THREADS - 1) / SAMP_THREADS;
+  const int a0 = min(C, tid * seg), a1 = min(C, a0 + seg);
+  int n_eq = 0;
+  for (int c = a0; c < a1; ++c) n_eq += (s_keys[c] == T) ? 1 : 0;
+  int tot_eq;
+  int eq_rank = block_exclusive_scan(n_eq, s_warp, &tot_eq);
+  int n_take = 0;
+  {
+    int er = eq_rank;
+    for (int c = a0; c < a1; ++c) {
+      const uint32_t key = s_keys[c];
+      if (key > T) ++n_take;
+      else if (key == T) { if (er < need_eq) ++n_take; ++er; }
     }
-    __syncthreads();
-    if (tid == 0) { s_base += tk_total; s_eq_base += eq_total; }
-    __syncthreads();
   }
+  int tot_take;
+  int off = block_exclusive_scan(n_take, s_warp, &tot_take);
+  const int p0 = pop_ptr[u];
+  const int np = pop_ptr[u + 1] - p0;
+  int nvalid = 0;
+  for (int c = a0; c < a1; ++c) {
+    const uint32_t key = s_keys[c];
+    bool take = key > T;
+    if (key == T) { take = eq_rank < need_eq; ++eq_rank; }
+    if (!take) continue;
+    const int slot = s0 + off++;
+    const int item = cand_items[c0 + c];
+    int partner = -1;
+    if (np > 0) {
+      const uint32_t r = ltg_rand_u32(seed, LTG_STREAM_PARTNER, step, ubase + (uint64_t)item);
+      partner = pop_items[p0 + (int)(((uint64_t)r * (uint64_t)np) >> 32)];  // train.py:236-238
+    }
+    const int ok = (partner >= 0 && item_valid[item] && item_valid[partner]) ? 1 : 0;  // train.py:240-243
+    samp_items[slot] = item;
+    samp_partner[slot] = partner >= 0 ? partner : 0;
+    samp_valid[slot] = ok ? 1 : -1;
+    nvalid += ok;
+  }
+  nvalid = (int)warp_sum((float)nvalid);
+  if (lane == 0 && nvalid > 0) atomicAdd(&s_nvalid, nvalid);
   // slots that could not be filled (n < nslots)
   for (int j = n + tid; j < nslots; j += SAMP_THREADS) {
     samp_items[s0 + j] = 0; samp_partner[s0 + j] = 0; samp_valid[s0 + j] = -1;
   }
+  __syncthreads();
   if (tid == 0 && s_nvalid > 0 && cnt_out != nullptr) atomicAdd(cnt_out, s_nvalid);
 }
 

@@ -305,8 +305,10 @@ class GanEngine(object):
         k1 = d.h0 + 1
         part = self.world_size == 1
         bn3 = ops.pick_bn(d.k3, d.h3, True)
-        sp = ops.actual_splits(P, min(self.d_splits_max, ops.pick_splits(d.k3, d.h3, P, bn3)))
-        self._d_parts = sp if part else 1
+        # fixed split counts (empty splits store zeros): dW3 has 8 output tiles -> 16 splits fill the machine; dW1/dW2 have one tile
+        sp3 = 16 if part else ops.pick_splits(d.k3, d.h3, P, bn3)
+        sp = self.d_splits_max if part else ops.pick_splits(k1, d.h2, P, 256)
+        self._d_parts = self.d_splits_max if part else 1
         if part:
             gW = lambda name: self.arena_gp[0][d._off[name][0]: d._off[name][0] + d._off[name][1]]  # noqa: E731
             self.arena_gp[0][d._off["w4"][0]:].zero_()   # w4 / b4 gradients are accumulated by disc_head with atomics
@@ -317,7 +319,7 @@ class GanEngine(object):
             kw = dict(atomic=True)
         self._disc_forward(bt["pair_pop"], bt["pair_niche"], bt["label"], P, True, g_w4=gW("w4"), g_b4=gW("b4"))
         with self._fork(self.s1):
-            ops.gemm(self.Hd, self.dz3, d.k3, d.h3, P, a_mn=True, b_mn=True, splits=sp, bn=bn3, out_f32=gW("W3"), ld_f32=d.ld3, **kw)  # dW3 (+db3)
+            ops.gemm(self.Hd, self.dz3, d.k3, d.h3, P, a_mn=True, b_mn=True, splits=sp3, bn=bn3, out_f32=gW("W3"), ld_f32=d.ld3, **kw)  # dW3 (+db3)
         ops.gemm(self.dz3, d.view("W3", "b"), P, d.k3, d.h3, bn=ops.pick_bn(P, d.k3), out_bf16=self.dz12, dact_src=self.Hd,
                  dact_keep=self.keep_d)                                                            # dz12 = (dz3 W3^T) * dact(Hd)
         with self._fork(self.s2):

@@ -84,11 +84,9 @@ def pick_splits(M, N, K, bn, n_sm=132):
 
 
 def actual_splits(K, splits):
-    """Number of splits launch_gemm really uses (no empty split): mirrors gemm_sm100.cuh."""
-    kb = (K + 63) // 64
-    splits = max(1, min(splits, kb))
-    per = (kb + splits - 1) // splits
-    return (kb + per - 1) // per
+    """Number of split-K partials launch_gemm writes: exactly the requested count (trailing splits that receive no k-block
+    store zeros), so consumers can sum a fixed number of partial buffers."""
+    return max(1, splits)
 
 
 def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, splits=1, bn=128, out_f32=None, out_bf16=None, bias=None,
