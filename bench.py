@@ -160,6 +160,7 @@ def main():
     import torch
     import torch.distributed as dist
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -186,7 +187,7 @@ def main():
     vae.init_weights(98765)
     disc = dis.Discriminator(I, I, H0, H1, H2, H3, seed=4242)
     engine = eng.GanEngine(vae, disc, data.max_B, data.max_P, seed=2026, lr=LR, lam=LAM, use_graphs=not args.no_graphs, world_size=world,
-                           B_global=BATCH * world, max_active=data.max_active)
+                           B_global=BATCH * world, max_active=data.max_active, rank=rank)
     eng.pin_host_inputs(data)
 
     def step(i):
@@ -297,9 +298,14 @@ def main():
                     graphs=not args.no_graphs)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(tabs, args.cpu_steps, I)
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # NCCL collectives live inside captured CUDA graphs; tearing the process group down under them can block, and
+        # there is nothing left to flush: synchronise, meet at a barrier and leave.
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -148,9 +148,10 @@ class GanEngine(object):
     """Owns the workspaces and runs phase A / D / G / evaluation for one (vae, discriminator) pair."""
 
     def __init__(self, vae, disc, max_B, max_P=1, seed=0, lr=1e-4, lam=1.0, keep_vae=0.75, keep_d=0.7, total_anneal_steps=20000,
-                 anneal_cap=0.2, B_global=None, use_graphs=True, world_size=1, max_active=None):
+                 anneal_cap=0.2, B_global=None, use_graphs=True, world_size=1, max_active=None, rank=0):
         ops.init()
         self.world_size = int(world_size)
+        self.rank = int(rank)
         self.kernels_launched = 0
         self._kcount = {}
         self.vae, self.disc = vae, disc
@@ -193,7 +194,7 @@ class GanEngine(object):
         self.dl = torch.zeros(B, ld, **bf)
         self.partial = torch.zeros(self.nblk, B, 2, **f32)
         self.lse = torch.zeros(B, **f32); self.xw = torch.zeros(B, **f32); self.su = torch.zeros(B, **f32)
-        self.dWdT = torch.zeros(I, H, **f32)
+        self.dWdT = None  # set below (a view of the padded all-gather/reduce-scatter buffer under data parallelism)
         self.dh2pre = torch.zeros(B, H, **bf)
         self.dmulv = torch.zeros(B, 2 * L, **bf)
         self.dh1pre = torch.zeros(B, H, **f32)
@@ -201,7 +202,30 @@ class GanEngine(object):
         self.ld_xc = _pad(self.max_active, 8)
         self.Xc = torch.zeros(B, self.ld_xc, **bf)            # dense dropout/normalisation coefficients over the active items
         self.dh1pre_b = torch.zeros(B, H, **bf)
-        self.dW_q0 = torch.zeros(I, H, **f32) if self.world_size > 1 else None  # dense encoder gradient, only for the all-reduce
+        if self.world_size > 1:
+            # Sharded optimizer (data parallel): the two [I,600] matrices are row-sharded over the ranks. Gradients are
+            # reduce-scattered, every rank runs Adam on its R rows only (Adam HBM traffic / N) and the bf16 shadows are
+            # all-gathered (2 B/param on the wire instead of 4). Buffers are padded to I_pad = R * world rows.
+            N = self.world_size
+            self.R = (I + N - 1) // N
+            self.I_pad = self.R * N
+            self.row0 = self.rank * self.R
+            self.nrows = max(0, min(I, self.row0 + self.R) - self.row0)
+            self.dWdT_full = torch.zeros(self.I_pad, H, **f32)
+            self.dWq0_full = torch.zeros(self.I_pad, H, **f32)
+            self.dW_q0 = self.dWq0_full[:I]
+            self.g_dec_shard = torch.zeros(self.R, H, **f32)
+            self.g_enc_shard = torch.zeros(self.R, H, **f32)
+            self.WdT_b_full = torch.zeros(self.I_pad, H, **bf); self.WdT_b_shard = torch.zeros(self.R, H, **bf)
+            self.Wq0_b_full = torch.zeros(self.I_pad, H, **bf); self.Wq0_b_shard = torch.zeros(self.R, H, **bf)
+            self.WdT_b_full[:I].copy_(self.vae.WdT_b); self.Wq0_b_full[:I].copy_(self.vae.W_q0_b)
+            self.vae.WdT_b = self.WdT_b_full[:I]      # the compute path reads the all-gathered shadows
+            self.vae.W_q0_b = self.Wq0_b_full[:I]
+            r0, nr = self.row0, self.nrows
+            self.WdT_b_shard[:nr].copy_(self.WdT_b_full[r0:r0 + nr]); self.Wq0_b_shard[:nr].copy_(self.Wq0_b_full[r0:r0 + nr])
+        else:
+            self.dW_q0 = None
+        self.dWdT = self.dWdT_full[:I] if self.world_size > 1 else torch.zeros(I, H, **f32)
         # split-K partials of the decoder dgrad (summed by the tanh-backward kernel that consumes them: no atomics, no memset)
         self.dgrad_splits = ops.actual_splits(I, ops.pick_splits(B, H, I, 128))
         self.dh2_part = torch.zeros(self.dgrad_splits, B, H, **f32)
@@ -366,9 +390,7 @@ class GanEngine(object):
         samp = (bt["samp_ptr"], bt["pair_niche"][Pr:], bt["label"][Pr:]) if K > 0 else (None, None, None)
         if K > 0:
             self._join(self.s1)
-        if self.world_size > 1:   # DP: the statistics are all-reduced before the backward; single GPU fuses them into the backward
-            ops.dec_row_stats(self.partial, self.nblk, self.logits, B, indptr, indices, None, samp[0], samp[1], samp[2], self.lse, self.xw,
-                              self.su, self.scal)
+        # the softmax statistics are fused into the backward's per-user kernel (ltg_dec_row_bwd)
 
     def _g_backward(self, data, bi):
         bt = data.batches[bi]
@@ -379,21 +401,36 @@ class GanEngine(object):
         indices = data.indices
         lam = self.lam if (K > 0 or self.world_size > 1) else 0.0
         samp = (bt["samp_ptr"], bt["pair_niche"][Pr:], bt["label"][Pr:]) if K > 0 else (None, None, None)
-        if self.world_size > 1:
-            ops.dec_dlogits(self.logits, self.lse, self.xw, self.su, B, self.I, Bg, lam, self.scal, indptr, indices, None, samp[0], samp[1],
-                            samp[2], self.dl)
-        else:
-            ops.dec_row_bwd(self.partial, self.nblk, self.logits, B, self.I, Bg, lam, indptr, indices, None, samp[0], samp[1], samp[2],
-                            self.lse, self.scal, self.dl)
+        ops.dec_row_bwd(self.partial, self.nblk, self.logits, B, self.I, Bg, lam, indptr, indices, None, samp[0], samp[1], samp[2],
+                        self.lse, self.scal, self.dl)
         # decoder backward: dh2 = dl W_p1^T (split-K over the catalog), dW_p1^T = dl^T [h2 | 1].
         # Branch s1: decoder weight gradient (+ its Adam sweep when the update is fused into this graph, single GPU) -- HBM-bound,
         # runs under the latency-bound chain of small GEMMs of the encoder-side backward on the main stream.
         fuse_update = self.world_size == 1 and getattr(self, "_fuse_update", False)
+        dp_comm = self.world_size > 1 and getattr(self, "_dp_comm", False)
         with self._fork(self.s1):
             ops.gemm(self.dl, self.h2, self.I, H + 1, B, a_mn=True, b_mn=True, bn=128, out_f32=self.dWdT, ld_f32=H, aux_col=H,
                      aux_out=v.view("b_p1", "g"))
+            if dp_comm:
+                import torch.distributed as dist
+                dist.reduce_scatter_tensor(self.g_dec_shard, self.dWdT_full)
         ops.gemm(self.dl, v.WdT_b, B, H, self.I, b_mn=True, splits=self.dgrad_splits, bn=128, out_f32=self.dh2_part, ld_f32=H,
                  split_stride=self.max_B * H)
+        if dp_comm and self.nrows > 0:
+            # Adam on this rank's decoder rows: after the reduce-scatter (same branch) and after dgrad (it reads the bf16 weights;
+            # the shard Adam only writes the shard staging buffer, the full shadow is replaced by the all-gather at the end)
+            if self.overlap:
+                self.s1.wait_stream(torch.cuda.current_stream())
+            with (torch.cuda.stream(self.s1) if self.overlap else torch.cuda.stream(torch.cuda.current_stream())):
+                r0, nr = self.row0, self.nrows
+                ops.adam(v.WdT[r0:r0 + nr], v.WdT_m[r0:r0 + nr], v.WdT_v[r0:r0 + nr], self.g_dec_shard, self.WdT_b_shard, scal=self.scal)
+        if dp_comm:
+            # every rank (also one whose shard is empty) joins the all-gather; issued here so it overlaps the encoder-side backward
+            if self.overlap:
+                self.s1.wait_stream(torch.cuda.current_stream())
+            with (torch.cuda.stream(self.s1) if self.overlap else torch.cuda.stream(torch.cuda.current_stream())):
+                import torch.distributed as dist
+                dist.all_gather_into_tensor(self.WdT_b_full, self.WdT_b_shard)
         if fuse_update:
             # the Adam sweep rewrites the bf16 decoder weights the dgrad GEMM above reads: order it after dgrad
             if self.overlap:
@@ -415,6 +452,12 @@ class GanEngine(object):
         ops.gemm(self.Xc, self.dh1pre_b, bt["n_active"], H, B, a_mn=True, b_mn=True, bn=ops.pick_bn(bt["n_active"], H), out_f32=self.G_enc)
         if self.world_size > 1:
             ops.enc_wgrad_expand(self.dW_q0, self.I, bt["slot_of_item"], self.G_enc)
+        if dp_comm:
+            import torch.distributed as dist
+            dist.reduce_scatter_tensor(self.g_enc_shard, self.dWq0_full)
+            if self.nrows > 0:
+                r0, nr = self.row0, self.nrows
+                ops.adam(v.W_q0[r0:r0 + nr], v.W_q0_m[r0:r0 + nr], v.W_q0_v[r0:r0 + nr], self.g_enc_shard, self.Wq0_b_shard, scal=self.scal)
         if fuse_update:
             ops.enc_adam(v.W_q0, v.W_q0_m, v.W_q0_v, v.W_q0_b, self.I, bt["slot_of_item"], self.G_enc, scal=self.scal)
         self._join(self.s2)
@@ -426,10 +469,13 @@ class GanEngine(object):
         bt = data.batches[bi]
         v = self.vae
         if self.world_size > 1:
-            ops.adam(v.W_q0, v.W_q0_m, v.W_q0_v, self.dW_q0, v.W_q0_b, scal=self.scal)
+            r0, nr = self.row0, self.nrows
+            if nr > 0:   # this rank's row shard of the two big matrices; gradients arrive reduce-scattered
+                ops.adam(v.W_q0[r0:r0 + nr], v.W_q0_m[r0:r0 + nr], v.W_q0_v[r0:r0 + nr], self.g_enc_shard, self.Wq0_b_shard, scal=self.scal)
+                ops.adam(v.WdT[r0:r0 + nr], v.WdT_m[r0:r0 + nr], v.WdT_v[r0:r0 + nr], self.g_dec_shard, self.WdT_b_shard, scal=self.scal)
         else:
             ops.enc_adam(v.W_q0, v.W_q0_m, v.W_q0_v, v.W_q0_b, self.I, bt["slot_of_item"], self.G_enc, scal=self.scal)
-        ops.adam(v.WdT, v.WdT_m, v.WdT_v, self.dWdT, v.WdT_b, scal=self.scal)
+            ops.adam(v.WdT, v.WdT_m, v.WdT_v, self.dWdT, v.WdT_b, scal=self.scal)
         ops.adam(v.small, v.small_m, v.small_v, v.small_g, v.small_b, scal=self.scal)
 
     # ------------------------------------------------------------------------------------------------------------
@@ -463,25 +509,52 @@ class GanEngine(object):
         if self.world_size == 1:
             self._run(("d", id(data), bi), lambda: self.d_step(data, bi))
             return
+        self._run(("ddp", id(data), bi), lambda: self._d_step_dp(data, bi))
+
+    def _d_step_dp(self, data, bi):
         import torch.distributed as dist
-        self._run(("d1", id(data), bi), lambda: self._d_fwd_bwd(data, bi))
+        self._d_fwd_bwd(data, bi)
         dist.all_reduce(self.disc.arena_g)          # 161 k discriminator gradients: one small bucket
-        self._run(("d2", id(data), bi), self._d_update)
+        self._d_update()
 
     def run_g_step(self, data, bi):
         if self.world_size == 1:
             self._run(("g", id(data), bi), lambda: self.g_step(data, bi))
             return
+        # data parallel: the whole step, collectives included, is ONE captured graph (NCCL ops are capturable), so there is no
+        # host round trip between the forward, the exchange step and the update
+        self._run(("gdp", id(data), bi), lambda: self._g_step_dp(data, bi))
+
+    def _g_step_dp(self, data, bi):
+        """G update under user-sharded data parallelism with a row-sharded optimizer.
+        Collectives, in issue order (identical on every rank): all-reduce(sum y, cnt) -> reduce-scatter(dW_dec) ->
+        all-gather(bf16 W_dec) -> reduce-scatter(dW_enc) -> all-reduce(small grads) -> all-gather(bf16 W_enc).
+        The decoder reduce-scatter is issued from a side branch right after the weight-gradient GEMM, so it travels over NVLink
+        while the encoder-side backward is still computing."""
         import torch.distributed as dist
-        self._run(("g1", id(data), bi), lambda: self._g_forward(data, bi))
-        # F3: the adversarial term needs the GLOBAL sums (sum p, sum y, cnt) before the backward pass starts
-        dist.all_reduce(self.scal[ops.S_SUM_P: ops.S_CNT + 1])
-        self._run(("g2", id(data), bi), lambda: self._g_backward(data, bi))
-        # the one real exchange step of the path: gradient reduction over NVLink
-        dist.all_reduce(self.dW_q0)
-        dist.all_reduce(self.dWdT)
-        dist.all_reduce(self.vae.small_g)
-        self._run(("g3", id(data), bi), lambda: self._g_update(data, bi))
+        v = self.vae
+        self._g_forward(data, bi)
+        # F3: the adversarial term multiplies GLOBAL sums; Ybar = sum y / cnt must be global before the backward pass starts
+        dist.all_reduce(self.scal[ops.S_SUM_Y: ops.S_CNT + 1])
+        self._dp_comm = True
+        self._g_backward(data, bi)
+        self._dp_comm = False
+        r0, nr = self.row0, self.nrows
+        dist.all_reduce(v.small_g)
+        ops.adam(v.small, v.small_m, v.small_v, v.small_g, v.small_b, scal=self.scal)
+        dist.all_gather_into_tensor(self.Wq0_b_full, self.Wq0_b_shard)
+
+    def gather_master(self):
+        """Data parallel only: all-gather the fp32 master rows of the two sharded matrices (checkpointing / checks)."""
+        if self.world_size == 1:
+            return
+        import torch.distributed as dist
+        for t in (self.vae.W_q0, self.vae.WdT, self.vae.W_q0_m, self.vae.WdT_m, self.vae.W_q0_v, self.vae.WdT_v):
+            full = torch.zeros(self.I_pad, H, dtype=torch.float32, device=self.device)
+            shard = torch.zeros(self.R, H, dtype=torch.float32, device=self.device)
+            shard[: self.nrows].copy_(t[self.row0: self.row0 + self.nrows])
+            dist.all_gather_into_tensor(full, shard)
+            t.copy_(full[: self.I])
 
     # ------------------------------------------------------------------------------------------------------------
     # losses of the last step (host reads; train.py:303,329 print them once per sub-epoch)

@@ -34,13 +34,14 @@ def main():
         disc = dis.Discriminator(I, I, 100, 150, 250, 300, seed=1); disc.set_params(E, dparams)
         data = eng.TrainData(batch_size=batch, first_batch=first, max_batches=1, **tabs)
         e = eng.GanEngine(vae, disc, data.max_B, data.max_P, seed=11, lr=1e-3, lam=1.0, keep_d=1.0, use_graphs=False, world_size=world_size,
-                          B_global=B, max_active=data.max_active)
+                          B_global=B, max_active=data.max_active, rank=(rank if world_size > 1 else 0))
         return vae, disc, data, e
 
     vae, disc, data, e = build(world, B // world, rank)
     for _ in range(2):
         e.run_phase_a(data, 0); e.run_d_step(data, 0); e.run_g_step(data, 0)
     torch.cuda.synchronize()
+    e.gather_master()
     dist.barrier()
     if rank == 0:
         vae1, disc1, data1, e1 = build(1, B, 0)
@@ -58,7 +59,8 @@ def main():
         assert r1 < 0.05 and r2 < 0.05 and r3 < 0.05
         print("dp_check ok")
     dist.barrier()
-    dist.destroy_process_group()
+    sys.stdout.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":
