@@ -189,6 +189,8 @@ def main():
     engine = eng.GanEngine(vae, disc, data.max_B, data.max_P, seed=2026, lr=LR, lam=LAM, use_graphs=not args.no_graphs, world_size=world,
                            B_global=BATCH * world, max_active=data.max_active, rank=rank)
     eng.pin_host_inputs(data)
+    if world > 1:
+        engine.attach_dp_tables(eng.build_dp_shard_tables(data, tabs["indptr"], tabs["indices"], world, rank, nb, engine.R))
 
     def step(i):
         bi = i % nb

@@ -79,6 +79,13 @@ int ltg_enc_gather_fwd(const int32_t* indptr, const int32_t* indices, const floa
                        const uint32_t* step_dev, void* h1_bf16, int ld_h1, float* coef, int max_row_nnz, float* pre_ws,
                        int32_t* counters, const int32_t* slot_of_item, void* xc_bf16, int ld_xc, void* stream);
 
+/* Data-parallel encoder gradient: rebuilds the forward coefficients of the GLOBAL batch's interactions that fall into this
+ * rank's item shard (entry e: global batch row e_row[e], item e_item[e], shard slot e_slot[e]; row_uid / row_rnorm per global
+ * row) and scatters them into xc_bf16[row, slot] (zeroed by the caller). The dropout bits are recomputed, not communicated.  */
+int ltg_enc_coef_scatter(const int32_t* e_row, const int32_t* e_item, const int32_t* e_slot, const int64_t* row_uid,
+                         const float* row_rnorm, int n_entries, int n_items, float keep, uint64_t seed, uint32_t step,
+                         const uint32_t* step_dev, void* xc_bf16, int ld_xc, void* stream);
+
 /* ---- a3/a4: latent head (MultiVAE.py:157-162,178-181): KL, std, reparameterisation ---------------------------------
  * mulv fp32 [B, 2L] = [mu | logvar]. eps may be NULL (Philox Box-Muller keyed by uid). Writes z bf16 [B, ld_z],
  * zmu fp32 [B, L] = z - mu, adds sum_u KL_u to scal[LTG_S_KL_SUM].                                                    */

@@ -483,6 +483,30 @@ dec_row_bwd_kernel(const float2* __restrict__ partial, int n_blocks, const __nv_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Data parallel encoder gradient. Rank r owns the item shard [row0, row0+R). For every interaction (u, i) of the GLOBAL
+// batch whose item lies in the shard it rebuilds the forward's coefficient x_ui * rsqrt(|x_u|^2) * mask/keep -- the dropout
+// bit is a stateless function of (seed, step, global uid, item), so no other rank has to send it -- and scatters it into the
+// dense bf16 matrix Xc_glob[g_row, slot] that the shard's weight-gradient GEMM consumes. Only dh1pre travels (all-gather).
+// ---------------------------------------------------------------------------------------------
+__global__ void enc_coef_scatter_kernel(const int32_t* __restrict__ e_row, const int32_t* __restrict__ e_item, const int32_t* __restrict__ e_slot,
+                                        const int64_t* __restrict__ row_uid, const float* __restrict__ row_rnorm, int n_entries, int n_items,
+                                        float keep, uint64_t seed, uint32_t step, const uint32_t* __restrict__ step_dev,
+                                        __nv_bfloat16* __restrict__ xc, int ld_xc) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_entries) return;
+  if (step_dev != nullptr) step += *step_dev;
+  const int r = e_row[e];
+  const int item = e_item[e];
+  const bool drop = keep > 0.f && keep < 1.f;
+  float c = row_rnorm[r];
+  if (drop) {
+    const uint32_t rnd = ltg_rand_u32(seed, LTG_STREAM_ENC_DROPOUT, step, (uint64_t)row_uid[r] * (uint64_t)n_items + (uint64_t)item);
+    c = rnd < ltg_keep_threshold(keep) ? c / keep : 0.f;
+  }
+  xc[(size_t)r * ld_xc + e_slot[e]] = __float2bfloat16(c);
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -593,6 +617,17 @@ extern "C" int ltg_dec_row_bwd(const float* partial, int n_blocks, const void* l
   dec_row_bwd_kernel<<<B, ROWBWD_THREADS, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float2*>(partial), n_blocks, reinterpret_cast<const __nv_bfloat16*>(logits_bf16), ld, B, n_items,
       1.0f / (float)B_global, lam, indptr, indices, values, samp_ptr, samp_items, samp_valid, lse, scal, reinterpret_cast<__nv_bfloat16*>(dl_bf16));
+  LTG_CHECK_LAUNCH();
+  return LTG_OK;
+}
+
+extern "C" int ltg_enc_coef_scatter(const int32_t* e_row, const int32_t* e_item, const int32_t* e_slot, const int64_t* row_uid,
+                                    const float* row_rnorm, int n_entries, int n_items, float keep, uint64_t seed, uint32_t step,
+                                    const uint32_t* step_dev, void* xc_bf16, int ld_xc, void* stream) {
+  LTG_REQUIRE(e_row && e_item && e_slot && row_uid && row_rnorm && xc_bf16);
+  if (n_entries <= 0) return LTG_OK;
+  enc_coef_scatter_kernel<<<(n_entries + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      e_row, e_item, e_slot, row_uid, row_rnorm, n_entries, n_items, keep, seed, step, step_dev, reinterpret_cast<__nv_bfloat16*>(xc_bf16), ld_xc);
   LTG_CHECK_LAUNCH();
   return LTG_OK;
 }

@@ -104,6 +104,44 @@ class TrainData(object):
                     max_nnz=int(np.diff(self.h_indptr[b0:b1 + 1]).max()) if B > 0 else 0)
 
 
+def build_dp_shard_tables(data, tabs_indptr, tabs_indices, world, rank, nb_per_rank, R):
+    """Data parallel: for every local batch index bi, the interactions of the GLOBAL batch (batch rank_q*nb + bi of every rank q,
+    concatenated in rank order) whose item lies in this rank's shard [rank*R, rank*R + R): entry arrays for
+    ltg_enc_coef_scatter, per-row uid / 1/sqrt(nnz), and the shard-local slot map for ltg_enc_adam."""
+    dev = data.device
+    I = data.n_items
+    B = data.batch_size
+    row0 = rank * R
+    nr = max(0, min(I, row0 + R) - row0)
+    indptr = np.asarray(tabs_indptr, dtype=np.int64)
+    indices = np.asarray(tabs_indices, dtype=np.int64)
+    t32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(dev)  # noqa: E731
+    out = []
+    for bi in range(len(data.batches)):
+        rows, items, uids, rnorm = [], [], [], []
+        for q in range(world):
+            u0 = (q * nb_per_rank + bi) * B
+            u1 = min(len(indptr) - 1, u0 + B)
+            deg = np.diff(indptr[u0:u1 + 1])
+            e0, e1 = indptr[u0], indptr[u1]
+            rows.append(np.repeat(np.arange(q * B, q * B + (u1 - u0)), deg))
+            items.append(indices[e0:e1])
+            uu = np.zeros(B, dtype=np.int64); uu[: u1 - u0] = data.uid_start + np.arange(u0, u1)
+            rn = np.zeros(B, dtype=np.float32); rn[: u1 - u0] = 1.0 / np.sqrt(np.maximum(deg, 1e-12)).astype(np.float32)
+            uids.append(uu); rnorm.append(rn)
+        rows = np.concatenate(rows); items = np.concatenate(items)
+        sel = (items >= row0) & (items < row0 + nr)
+        rows, items = rows[sel], items[sel]
+        active = np.unique(items)
+        slot_local = np.full(max(nr, 1), -1, dtype=np.int64)
+        slot_local[active - row0] = np.arange(len(active))
+        out.append(dict(e_row=t32(rows if len(rows) else np.zeros(1)), e_item=t32(items if len(items) else np.zeros(1)),
+                        e_slot=t32(slot_local[items - row0] if len(items) else np.zeros(1)), n_entries=int(len(rows)),
+                        row_uid=torch.as_tensor(np.concatenate(uids)).to(dev), row_rnorm=torch.as_tensor(np.concatenate(rnorm)).to(dev),
+                        slot_local=t32(slot_local), n_active=int(len(active))))
+    return out
+
+
 def pin_host_inputs(data):
     """Pinned host mirrors of everything one step consumes, per batch (used by the end-to-end path: the step's inputs are
     copied host->device inside the timed region). Returns total bytes per batch in bt["h2d_bytes"]."""
@@ -223,6 +261,12 @@ class GanEngine(object):
             self.vae.W_q0_b = self.Wq0_b_full[:I]
             r0, nr = self.row0, self.nrows
             self.WdT_b_shard[:nr].copy_(self.WdT_b_full[r0:r0 + nr]); self.Wq0_b_shard[:nr].copy_(self.Wq0_b_full[r0:r0 + nr])
+            # encoder gradient by activation exchange (see _g_backward): all-gathered dh1pre + locally rebuilt coefficients
+            self.dp_tables = None                      # set by attach_dp_tables()
+            self.dh1_glob = torch.zeros(N * B, H, **bf)
+            self.ld_xcg = _pad(max(1, min(self.R, self.max_active * N)), 8)
+            self.Xc_glob = torch.zeros(N * B, self.ld_xcg, **bf)
+            self.G_shard = torch.zeros(max(1, min(self.R, self.max_active * N)), H, **f32)
         else:
             self.dW_q0 = None
         self.dWdT = self.dWdT_full[:I] if self.world_size > 1 else torch.zeros(I, H, **f32)
@@ -449,10 +493,27 @@ class GanEngine(object):
         ops.gemm(self.dmulv, v.view("W_q1", "b"), B, H, 2 * L, bn=64, out_f32=self.dh1)
         ops.tanh_bwd(self.dh1, self.h1, B, H, dx_bf16=self.dh1pre_b, dx_f32=self.dh1pre, dbias=v.view("b_q0", "g"))
         # encoder weight gradient over the batch's active items as a tensor-core GEMM: G = Xc^T dh1pre   [n_active, 600]
-        ops.gemm(self.Xc, self.dh1pre_b, bt["n_active"], H, B, a_mn=True, b_mn=True, bn=ops.pick_bn(bt["n_active"], H), out_f32=self.G_enc)
-        if self.world_size > 1:
+        if not (self.world_size > 1 and getattr(self, "_dp_comm", False) and self.dp_tables is not None):
+            ops.gemm(self.Xc, self.dh1pre_b, bt["n_active"], H, B, a_mn=True, b_mn=True, bn=ops.pick_bn(bt["n_active"], H), out_f32=self.G_enc)
+        act_exchange = dp_comm and self.dp_tables is not None
+        if self.world_size > 1 and not act_exchange:
             ops.enc_wgrad_expand(self.dW_q0, self.I, bt["slot_of_item"], self.G_enc)
-        if dp_comm:
+        if act_exchange:
+            # encoder gradient of THIS rank's item shard over the GLOBAL batch: only dh1pre (bf16 [B,600] per rank) is exchanged
+            import torch.distributed as dist
+            tb = self.dp_tables[bi]
+            self.Xc_glob.zero_()
+            ops.enc_coef_scatter(tb["e_row"], tb["e_item"], tb["e_slot"], tb["row_uid"], tb["row_rnorm"], tb["n_entries"], self.I,
+                                 self.keep_vae, self.seed, 0, self.words, self.Xc_glob)
+            dist.all_gather_into_tensor(self.dh1_glob, self.dh1pre_b)   # rows beyond B meet all-zero Xc rows
+            if tb["n_active"] > 0:
+                ops.gemm(self.Xc_glob, self.dh1_glob, tb["n_active"], H, self.world_size * self.max_B, a_mn=True, b_mn=True,
+                         bn=ops.pick_bn(tb["n_active"], H), out_f32=self.G_shard)
+            if self.nrows > 0:
+                r0, nr = self.row0, self.nrows
+                ops.enc_adam(v.W_q0[r0:r0 + nr], v.W_q0_m[r0:r0 + nr], v.W_q0_v[r0:r0 + nr], self.Wq0_b_shard, nr, tb["slot_local"],
+                             self.G_shard, scal=self.scal)
+        elif dp_comm:
             import torch.distributed as dist
             dist.reduce_scatter_tensor(self.g_enc_shard, self.dWq0_full)
             if self.nrows > 0:
@@ -543,6 +604,11 @@ class GanEngine(object):
         dist.all_reduce(v.small_g)
         ops.adam(v.small, v.small_m, v.small_v, v.small_g, v.small_b, scal=self.scal)
         dist.all_gather_into_tensor(self.Wq0_b_full, self.Wq0_b_shard)
+
+    def attach_dp_tables(self, tables):
+        """tables = build_dp_shard_tables(...): switches the encoder-gradient exchange from a 48 MB reduce-scatter of dW_q0 to a
+        0.6 MB-per-rank all-gather of dh1pre (the dropout coefficients of the other ranks' users are recomputed locally)."""
+        self.dp_tables = tables
 
     def gather_master(self):
         """Data parallel only: all-gather the fp32 master rows of the two sharded matrices (checkpointing / checks)."""

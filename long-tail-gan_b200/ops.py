@@ -114,6 +114,12 @@ def enc_gather_fwd(indptr, indices, values, B, n_items, uid0, W_enc_bf16, b_q0, 
                                    ptr(slot_of_item), ptr(xc), xc.stride(0) if xc is not None else 0, _stream()))
 
 
+def enc_coef_scatter(e_row, e_item, e_slot, row_uid, row_rnorm, n_entries, n_items, keep, seed, step, step_dev, xc):
+    _count(1)
+    check(lib().ltg_enc_coef_scatter(ptr(e_row), ptr(e_item), ptr(e_slot), ptr(row_uid), ptr(row_rnorm), n_entries, n_items, keep, seed,
+                                     step, ptr(step_dev), ptr(xc), xc.stride(0), _stream()))
+
+
 def latent_fwd(mulv, eps, B, uid0, is_training, seed, step, step_dev, z, zmu, scal):
     _count(1)
     check(lib().ltg_latent_fwd(ptr(mulv), ptr(eps), B, uid0, float(is_training), seed, step, ptr(step_dev), ptr(z), z.stride(0),

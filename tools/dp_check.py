@@ -35,6 +35,8 @@ def main():
         data = eng.TrainData(batch_size=batch, first_batch=first, max_batches=1, **tabs)
         e = eng.GanEngine(vae, disc, data.max_B, data.max_P, seed=11, lr=1e-3, lam=1.0, keep_d=1.0, use_graphs=False, world_size=world_size,
                           B_global=B, max_active=data.max_active, rank=(rank if world_size > 1 else 0))
+        if world_size > 1:
+            e.attach_dp_tables(eng.build_dp_shard_tables(data, tabs["indptr"], tabs["indices"], world_size, rank, 1, e.R))
         return vae, disc, data, e
 
     vae, disc, data, e = build(world, B // world, rank)
