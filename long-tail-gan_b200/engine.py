@@ -277,7 +277,7 @@ class GanEngine(object):
         self.dh1 = torch.zeros(B, H, **f32)
         # split-K partials of the three discriminator weight-gradient GEMMs (summed by the Adam kernel)
         self.d_splits_max = 32
-        self.arena_gp = torch.zeros(self.d_splits_max, d.arena_n, **f32) if self.world_size == 1 else None
+        self.arena_gp = torch.zeros(self.d_splits_max, d.arena_n, **f32)
         # discriminator
         self.Xp = torch.zeros(P, 128, **bf); self.Xn = torch.zeros(P, 128, **bf)
         self.Hd = torch.zeros(P, d.k3, **bf)
@@ -371,7 +371,7 @@ class GanEngine(object):
         # Single GPU: the split-K partials of the three weight-gradient GEMMs go to arena_gp[s] and the Adam kernel sums them.
         # Data parallel: atomic accumulation into arena_g (which is what gets all-reduced).
         k1 = d.h0 + 1
-        part = self.world_size == 1
+        part = True   # data parallel sums the partials into arena_g before the all-reduce (see _d_step_dp)
         bn3 = ops.pick_bn(d.k3, d.h3, True)
         # fixed split counts (empty splits store zeros): dW3 has 8 output tiles -> 16 splits fill the machine; dW1/dW2 have one tile
         sp3 = 16 if part else ops.pick_splits(d.k3, d.h3, P, bn3)
@@ -575,7 +575,8 @@ class GanEngine(object):
     def _d_step_dp(self, data, bi):
         import torch.distributed as dist
         self._d_fwd_bwd(data, bi)
-        dist.all_reduce(self.disc.arena_g)          # 161 k discriminator gradients: one small bucket
+        torch.sum(self.arena_gp, dim=0, out=self.disc.arena_g)   # split-K partials -> one gradient arena
+        dist.all_reduce(self.disc.arena_g)                       # 161 k discriminator gradients: one small bucket
         self._d_update()
 
     def run_g_step(self, data, bi):
