@@ -57,38 +57,50 @@ disc_head_kernel(const __nv_bfloat16* __restrict__ Y3, int ld, int P, int h3, co
   const float bias = b4[0];
   float loss = 0.f, sumy = 0.f, sds = 0.f, ngen = 0.f;
   const int warps_total = gridDim.x * (HEAD_THREADS / 32);
-  for (int row = blockIdx.x * (HEAD_THREADS / 32) + warp; row < P; row += warps_total) {
-    const int lab = label[row];
-    const __nv_bfloat16* yr = Y3 + (size_t)row * ld;   // ld is even and >= h3 rounded up to 2: pair loads stay inside the row
-    float2 yv[HEAD_PPL];
-    float s = 0.f;
+  // two rows per iteration: the loads of both rows are issued before either row's reduction (the kernel is latency-bound)
+  for (int row0 = blockIdx.x * (HEAD_THREADS / 32) + warp; row0 < P; row0 += 2 * warps_total) {
+    const int rows[2] = {row0, row0 + warps_total};
+    float2 yv[2][HEAD_PPL];
+    int lab[2];
 #pragma unroll
-    for (int k = 0; k < HEAD_PPL; ++k) {
-      const int j = 2 * lane + 64 * k;
-      yv[k] = j < ld ? unpack_bf16x2(*reinterpret_cast<const uint32_t*>(yr + j)) : make_float2(0.f, 0.f);
-      s = fmaf(yv[k].x, wv[k].x, s);
-      s = fmaf(yv[k].y, wv[k].y, s);
-    }
-    s = warp_sum(s) + bias;
-    const float y = 1.0f / (1.0f + __expf(-s));
-    if (lane == 0 && y_out != nullptr) y_out[row] = y;
-    // -log(sigmoid(s)) = softplus(-s) ; -log(1 - sigmoid(s)) = softplus(s)     train.py:142
-    // label < 0 (pair dropped by the validity filter, train.py:240-243): no loss, zero gradient row
-    const float sp = (lab == 0) ? -s : s;
-    const float l = lab < 0 ? 0.f : fmaxf(sp, 0.f) + log1pf(__expf(-fabsf(sp)));
-    const float ds = lab < 0 ? 0.f : ((lab == 0) ? (y - 1.0f) : y);
-    if (lane == 0) { loss += l; if (lab == 1) { sumy += y; ngen += 1.f; } sds += ds; }
-    if (bwd) {
-      __nv_bfloat16* dr = dz3 + (size_t)row * ld;
+    for (int q = 0; q < 2; ++q) {
+      const bool ok = rows[q] < P;
+      lab[q] = ok ? label[rows[q]] : -1;
+      const __nv_bfloat16* yr = Y3 + (size_t)(ok ? rows[q] : row0) * ld;   // ld is even and >= h3: pair loads stay inside the row
 #pragma unroll
       for (int k = 0; k < HEAD_PPL; ++k) {
         const int j = 2 * lane + 64 * k;
-        if (j < h3) {  // h3 is even in every configuration this kernel accepts
-          const float d0 = ds * wv[k].x * dact_drop_tanh(yv[k].x, keep, drop);
-          const float d1 = ds * wv[k].y * dact_drop_tanh(yv[k].y, keep, drop);
-          *reinterpret_cast<uint32_t*>(dr + j) = pack_bf16x2(d0, d1);
-          gw[k].x = fmaf(yv[k].x, ds, gw[k].x);
-          gw[k].y = fmaf(yv[k].y, ds, gw[k].y);
+        yv[q][k] = j < ld ? unpack_bf16x2(*reinterpret_cast<const uint32_t*>(yr + j)) : make_float2(0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int row = rows[q];
+      if (row >= P) break;
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < HEAD_PPL; ++k) { s = fmaf(yv[q][k].x, wv[k].x, s); s = fmaf(yv[q][k].y, wv[k].y, s); }
+      s = warp_sum(s) + bias;
+      const float y = 1.0f / (1.0f + __expf(-s));
+      if (lane == 0 && y_out != nullptr) y_out[row] = y;
+      // -log(sigmoid(s)) = softplus(-s) ; -log(1 - sigmoid(s)) = softplus(s)     train.py:142
+      // label < 0 (pair dropped by the validity filter, train.py:240-243): no loss, zero gradient row
+      const float sp = (lab[q] == 0) ? -s : s;
+      const float l = lab[q] < 0 ? 0.f : fmaxf(sp, 0.f) + log1pf(__expf(-fabsf(sp)));
+      const float ds = lab[q] < 0 ? 0.f : ((lab[q] == 0) ? (y - 1.0f) : y);
+      if (lane == 0) { loss += l; if (lab[q] == 1) { sumy += y; ngen += 1.f; } sds += ds; }
+      if (bwd) {
+        __nv_bfloat16* dr = dz3 + (size_t)row * ld;
+#pragma unroll
+        for (int k = 0; k < HEAD_PPL; ++k) {
+          const int j = 2 * lane + 64 * k;
+          if (j < h3) {  // h3 is even in every configuration this kernel accepts
+            const float d0 = ds * wv[k].x * dact_drop_tanh(yv[q][k].x, keep, drop);
+            const float d1 = ds * wv[k].y * dact_drop_tanh(yv[q][k].y, keep, drop);
+            *reinterpret_cast<uint32_t*>(dr + j) = pack_bf16x2(d0, d1);
+            gw[k].x = fmaf(yv[q][k].x, ds, gw[k].x);
+            gw[k].y = fmaf(yv[q][k].y, ds, gw[k].y);
+          }
         }
       }
     }

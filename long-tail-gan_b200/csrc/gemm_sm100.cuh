@@ -655,8 +655,10 @@ int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb
   if (splits < 1) splits = 1;
   s.kb_per_split = (s.k_blocks + splits - 1) / splits;
   s.splits = splits;  // trailing splits may be empty (kb0 >= k_blocks): they store zeros, so a consumer can rely on a fixed count
-  // cluster along M: row blocks of the same n-block share the B operand (TMA multicast)
-  int cm = s.m_blocks >= 4 ? 4 : (s.m_blocks >= 2 ? 2 : 1);
+  // cluster along M: row blocks of the same n-block share the B operand (TMA multicast). 4-CTA clusters can only be
+  // placed on 132 of the 148 SMs (GPCs with 18 SMs strand two), so they are used when the problem has exactly one group of
+  // 3-4 row blocks (batch 500: the whole M extent shares every B tile); longer M runs as CTA pairs on all 148 SMs.
+  int cm = (s.m_blocks == 3 || s.m_blocks == 4) ? 4 : (s.m_blocks >= 2 ? 2 : 1);
   const int ov = ltg_gemm_cluster_override();
   if (ov == 1 || ov == 2 || ov == 4) cm = ov;
   if (cm == 4) return launch_gemm_cm<BN, A_MN, B_MN, 4, Epi>(A, lda, B, ldb, s, ep, stream);

@@ -214,15 +214,22 @@ __global__ void latent_bwd_kernel(const float* __restrict__ dz, const float* __r
 __global__ void tanh_bwd_kernel(const float* __restrict__ dy, int ld_dy, int n_partials, int64_t partial_stride,
                                 const __nv_bfloat16* __restrict__ y, int ld_y, int B, int N,
                                 __nv_bfloat16* __restrict__ dxb, int ld_dxb, float* __restrict__ dxf, int ld_dxf, float* __restrict__ db) {
-  const int r0 = blockIdx.x * COLSUM_ROWS;
-  const int r1 = min(B, r0 + COLSUM_ROWS);
+  constexpr int ROWS = 4;   // small row tile: this kernel sits on the critical path of the backward chain, parallelism first
+  const int r0 = blockIdx.x * ROWS;
+  const int r1 = min(B, r0 + ROWS);
   const int c = blockIdx.y * blockDim.x + threadIdx.x;
   if (c < N) {
     float cs = 0.f;
     for (int r = r0; r < r1; ++r) {
       const float t = __bfloat162float(y[(size_t)r * ld_y + c]);
-      float d = dy[(size_t)r * ld_dy + c];
-      for (int sp = 1; sp < n_partials; ++sp) d += dy[(size_t)sp * partial_stride + (size_t)r * ld_dy + c];  // split-K partials
+      const float* src = dy + (size_t)r * ld_dy + c;
+      float d0 = src[0], d1 = 0.f, d2 = 0.f, d3 = 0.f;   // split-K partials: four independent load chains
+      int sp = 1;
+      for (; sp + 3 <= n_partials; sp += 3) {
+        d1 += src[(size_t)sp * partial_stride]; d2 += src[(size_t)(sp + 1) * partial_stride]; d3 += src[(size_t)(sp + 2) * partial_stride];
+      }
+      for (; sp < n_partials; ++sp) d1 += src[(size_t)sp * partial_stride];
+      const float d = (d0 + d1) + (d2 + d3);
       const float o = d * (1.0f - t * t);
       if (dxb != nullptr) dxb[(size_t)r * ld_dxb + c] = __float2bfloat16(o);
       if (dxf != nullptr) dxf[(size_t)r * ld_dxf + c] = o;
@@ -555,7 +562,7 @@ extern "C" int ltg_tanh_bwd(const float* dy, int ld_dy, int n_partials, int64_t 
                             void* dx_bf16, int ld_dxb, float* dx_f32, int ld_dxf, float* dbias, void* stream) {
   LTG_REQUIRE(dy && y_bf16 && n_partials >= 1);
   if (B <= 0) return LTG_OK;
-  tanh_bwd_kernel<<<dim3((B + COLSUM_ROWS - 1) / COLSUM_ROWS, (N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+  tanh_bwd_kernel<<<dim3((B + 3) / 4, (N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
       dy, ld_dy, n_partials, partial_stride, reinterpret_cast<const __nv_bfloat16*>(y_bf16), ld_y, B, N, reinterpret_cast<__nv_bfloat16*>(dx_bf16), ld_dxb, dx_f32,
       ld_dxf, dbias);
   LTG_CHECK_LAUNCH();
