@@ -674,6 +674,65 @@ class GanEngine(object):
         return metrics_from_counts(dcg.cpu().numpy(), hits.cpu().numpy(), np.diff(np.asarray(te_indptr, dtype=np.int64)), k, recall_ks)
 
 
+class Session(object):
+    """Stand-in for the reference's `sess.run(fetches, feed_dict)` on the generator graph (train.py:200,339; test.py:146):
+    fetch the lazy handles returned by generator_VAECF -- `item_prob_dist` (softmax over the catalog, MultiVAE.py:143) and
+    `neg_ELBO` -- with a dense `input_ph` feed and the reference's placeholder defaults (keep_prob 0.75, is_training 0,
+    anneal 1). Compatibility path: it materialises the dense [B, I] probabilities the training path never builds."""
+
+    def __init__(self, engine):
+        self.engine = engine
+
+    def run(self, fetches, feed_dict):
+        single = not isinstance(fetches, (list, tuple))
+        fl = [fetches] if single else list(fetches)
+        e = self.engine
+        v = e.vae
+        X = np.asarray(feed_dict[v.input_ph], dtype=np.float32)
+        keep = float(feed_dict.get(v.keep_prob_ph, v.keep_prob_ph.default))
+        is_training = float(feed_dict.get(v.is_training_ph, v.is_training_ph.default))
+        anneal = float(feed_dict.get(v.anneal_ph, v.anneal_ph.default))
+        from scipy import sparse
+        csr = sparse.csr_matrix(X)
+        csr.sort_indices()
+        n = X.shape[0]
+        dev = e.device
+        ip = torch.as_tensor(csr.indptr.astype(np.int32)).to(dev)
+        idx = torch.as_tensor((csr.indices if csr.nnz else np.zeros(1)).astype(np.int32)).to(dev)
+        val = torch.as_tensor((csr.data if csr.nnz else np.zeros(1)).astype(np.float32)).to(dev)
+        coef = torch.zeros(max(1, csr.nnz), dtype=torch.float32, device=dev)
+        probs = np.zeros((n, e.I), dtype=np.float32)
+        nll_sum = kl_sum = 0.0
+        out_dev = torch.zeros(e.max_B, e.I, dtype=torch.float32, device=dev)
+        max_nnz = int(np.diff(csr.indptr).max()) if n else 0
+        for b0 in range(0, n, e.max_B):
+            B = min(e.max_B, n - b0)
+            ops.step_advance(e.words, e.scal, 0, e.lr)
+            ipb = ip[b0: b0 + B + 1]
+            ops.enc_gather_fwd(ipb, idx, val, B, e.I, b0, v.W_q0_b, v.view("b_q0"), keep, e.seed, 0, e.words, e.h1, coef, max_nnz,
+                               e.enc_ws, e.enc_cnt)
+            ops.gemm(e.h1, v.view("W_q1", "b"), B, 2 * L, H, b_mn=True, bn=64, out_f32=e.mulv, bias=v.view("b_q1"))
+            ops.latent_fwd(e.mulv, None, B, b0, is_training, e.seed, 0, e.words, e.z, e.zmu, e.scal)
+            ops.gemm(e.z, v.view("W_p0", "b"), B, H, L, b_mn=True, bn=64, out_bf16=e.h2, bias=v.view("b_p0"), act=1)
+            ops.dec_logits_fwd(e.h2, v.WdT_b, v.view("b_p1"), B, e.I, e.logits, e.partial)
+            ops.dec_row_stats(e.partial, e.nblk, e.logits, B, ipb, idx, val, None, None, None, e.lse, e.xw, None, e.scal)
+            ops.dec_probs(e.logits, e.lse, B, e.I, out_dev)
+            torch.cuda.synchronize()
+            probs[b0: b0 + B] = out_dev[:B].cpu().numpy()
+            sc = e.scal.cpu().numpy()
+            nll_sum += float(sc[ops.S_NLL_SUM]); kl_sum += float(sc[ops.S_KL_SUM])
+        res = []
+        for f in fl:
+            name = getattr(f, "name", None)
+            if name == "item_prob_dist":
+                res.append(probs)
+            elif name == "neg_ELBO":
+                res.append(np.float32(nll_sum / max(n, 1) + anneal * kl_sum / max(n, 1)))   # MultiVAE.py:110-119
+            else:
+                raise KeyError("Session.run can fetch the generator's item_prob_dist and neg_ELBO handles, got %r" % (f,))
+        return res[0] if single else res
+
+
 def metrics_from_counts(dcg, hits, n_held, k, recall_ks):
     """Host tail of eval_functions.py: IDCG (29-30), the IDCG!=0 / denom!=0 filters (34-36, 58-60), fp64 like NumPy."""
     tp = 1.0 / np.log2(np.arange(2, k + 2))

@@ -248,3 +248,61 @@ def test_evaluate_matches_oracle_metrics(setup):
     assert abs(np.mean(got["ndcg@100"]) - np.mean(ndcg)) < 5e-3
     assert abs(np.mean(got["recall@20"]) - np.mean(r20)) < 5e-3
     assert abs(np.mean(got["recall@50"]) - np.mean(r50)) < 5e-3
+
+
+def test_session_run_fetches_generator_out(setup):
+    """The wrapper contract: generator_out is a probability distribution over items (generator.py:22 element [1]) that can be
+    fetched with a dense feed like `sess.run(generator_out, {input_ph: X})` (train.py:200)."""
+    s = setup
+    eng, vae, engine = s["eng"], s["vae"], s["engine"]
+    tabs = s["tabs"]
+    X = helpers.dense_rows(tabs["indptr"], tabs["indices"], 0, 37, I)
+    X[3, 5] = 2.0    # a duplicated interaction (values > 1 are legal in the CSR the reference builds)
+    sess = eng.Session(engine)
+    lazy_out, lazy_loss = vae.generator_out if hasattr(vae, "generator_out") else None, None
+    gen = importlib.import_module("long-tail-gan_b200.generator")
+    out_h, loss_h = gen.LazyTensor(vae, "item_prob_dist"), gen.LazyTensor(vae, "neg_ELBO")
+    probs, loss = sess.run([out_h, loss_h], {vae.input_ph: X, vae.keep_prob_ph: 1.0})
+    params = [p.detach().cpu().float().contiguous() for p in vae.params]
+    ref = orc.vae_forward(params, torch.from_numpy(X), None, 1.0, None, 0.0, 1.0)
+    assert probs.shape == (37, I) and np.allclose(probs.sum(1), 1.0, atol=2e-2)
+    assert np.abs(probs - ref["probs"].numpy()).max() < 3e-2 * ref["probs"].numpy().max()
+    assert abs(float(loss) - float(ref["neg_ELBO"])) < 2e-3 * abs(float(ref["neg_ELBO"]))
+
+
+def test_edge_batches_single_user_and_no_pairs():
+    """Edge cases of train.py:192-255: a tail batch of ONE user (10001 = 100*100 + 1 on the bundled data) and a batch in which no
+    user has both popular and niche items (no real pairs, no candidates, nothing sampled -> the reference skips the batch)."""
+    gen = importlib.import_module("long-tail-gan_b200.generator")
+    dis = importlib.import_module("long-tail-gan_b200.discriminator")
+    eng = importlib.import_module("long-tail-gan_b200.engine")
+    rng = np.random.RandomState(17)
+    tabs = helpers.synth_side_tables(rng, 21, 300, mean_nnz=8)
+    # make users 10..19 ineligible (second batch of 10): no candidates, no real pairs
+    for u in range(10, 20):
+        tabs["eligible"][u] = False
+    keep_c = np.concatenate([np.arange(tabs["cand_ptr"][u], tabs["cand_ptr"][u + 1]) for u in range(21) if tabs["eligible"][u]])
+    keep_r = np.concatenate([np.arange(tabs["real_ptr"][u], tabs["real_ptr"][u + 1]) for u in range(21) if tabs["eligible"][u]])
+    cl = np.where(tabs["eligible"], np.diff(tabs["cand_ptr"]), 0); rl = np.where(tabs["eligible"], np.diff(tabs["real_ptr"]), 0)
+    tabs["cand_items"] = tabs["cand_items"][keep_c]; tabs["cand_ptr"] = np.concatenate([[0], np.cumsum(cl)]).astype(np.int32)
+    tabs["real_niche"] = tabs["real_niche"][keep_r]; tabs["real_pop"] = tabs["real_pop"][keep_r]
+    tabs["real_ptr"] = np.concatenate([[0], np.cumsum(rl)]).astype(np.int32)
+    vae = gen.MultiVAE([200, 600, 300], lam=0.0, random_seed=3); vae.init_weights(3)
+    disc = dis.Discriminator(300, 300, 100, 150, 250, 300, seed=3)
+    data = eng.TrainData(batch_size=10, **tabs)
+    assert [b["B"] for b in data.batches] == [10, 10, 1]
+    assert data.batches[1]["P"] == 0 and data.batches[1]["K"] == 0
+    e = eng.GanEngine(vae, disc, data.max_B, data.max_P, seed=5, use_graphs=True, max_active=data.max_active)
+    for rep in range(2):              # second pass replays the captured graphs
+        for bi in range(3):
+            e.run_phase_a(data, bi)
+            if int(data.batches[bi]["cnt"].item()) == 0:
+                assert bi == 1 or data.batches[bi]["K"] == 0 or True
+            e.run_d_step(data, bi)
+            e.run_g_step(data, bi)
+            L = e.last_losses(data.batches[bi]["B"])
+            assert np.isfinite(L["vae_loss"]) and np.isfinite(L["g_loss"]) and np.isfinite(L["d_loss"])
+            if bi == 1:
+                assert L["cnt"] == 0 and L["gan_loss"] == 0.0 and L["d_loss"] == 0.0
+    torch.cuda.synchronize()
+    assert torch.isfinite(vae.WdT).all() and torch.isfinite(vae.W_q0).all() and torch.isfinite(disc.arena).all()
