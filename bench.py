@@ -225,20 +225,43 @@ def main():
     launches = engine.kernels_launched - k0
 
     # ---- end-to-end: the step's inputs come from pinned host memory, the losses go back to the host, every step ----
-    host_scal = torch.zeros(ops.NSCAL, dtype=torch.float32).pin_memory()
+    # Software-pipelined like a real input pipeline: while step i computes, the inputs of step i+1 travel host->device on a
+    # copy stream (into that batch's own device buffers), and the loss scalars of step i are read back asynchronously and
+    # consumed by the host one step later. Every step's H2D and D2H traffic is inside the timed region.
+    host_scal = [torch.zeros(ops.NSCAL, dtype=torch.float32).pin_memory() for _ in range(2)]
+    copy_stream = torch.cuda.Stream()
+    comp = torch.cuda.current_stream()
+    up_done = [torch.cuda.Event() for _ in range(nb)]
+    step_done = [torch.cuda.Event() for _ in range(2)]
     h2d = 0
+    losses_seen = 0
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
+    with torch.cuda.stream(copy_stream):
+        h2d += eng.upload_batch(data.batches[0])
+        up_done[0].record(copy_stream)
     for i in range(args.steps):
         bi = i % nb
-        h2d += eng.upload_batch(data.batches[bi])
+        if i + 1 < args.steps:
+            nxt = (i + 1) % nb
+            copy_stream.wait_event(step_done[(i + 1) % 2]) if i >= 1 else None   # the previous user of those buffers is long done
+            with torch.cuda.stream(copy_stream):
+                h2d += eng.upload_batch(data.batches[nxt])
+                up_done[nxt].record(copy_stream)
+        comp.wait_event(up_done[bi])
         step(i)
-        host_scal.copy_(engine.scal, non_blocking=True)
-        torch.cuda.current_stream().synchronize()   # the caller consumes the losses before issuing the next step
+        host_scal[i % 2].copy_(engine.scal, non_blocking=True)
+        step_done[i % 2].record(comp)
+        if i >= 1:
+            step_done[(i - 1) % 2].synchronize()          # the host consumes the losses of the previous step
+            losses_seen += int(np.isfinite(host_scal[(i - 1) % 2][ops.S_NLL_SUM].item()))
+    step_done[(args.steps - 1) % 2].synchronize()
+    losses_seen += int(np.isfinite(host_scal[(args.steps - 1) % 2][ops.S_NLL_SUM].item()))
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
+    assert losses_seen == args.steps, "every step's loss must have been read back"
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-phase split and the dominant kernel (fused Adam over the [I,600] decoder weight), CUDA events, same stream ----

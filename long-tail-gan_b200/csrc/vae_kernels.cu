@@ -19,7 +19,7 @@ constexpr int HV = H / 8;  // 75 16-byte vectors per bf16 weight row
 // Restates MultiVAE.py:148 (l2_normalize), 149 (dropout), 152-155 (matmul + bias + tanh).
 // ---------------------------------------------------------------------------------------------
 constexpr int ENC_THREADS = 96;
-constexpr int ENC_CHUNK = 128;
+constexpr int ENC_CHUNK = 128;  // nonzeros per CTA (64 was tried: more atomics, no gain)
 
 __global__ void __launch_bounds__(ENC_THREADS)
 enc_gather_fwd_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,

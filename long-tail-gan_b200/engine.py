@@ -309,8 +309,7 @@ class GanEngine(object):
         indices = data.indices if indices is None else indices
         coef = data.coef if coef is None else coef
         uid0 = bt["uid0"] if uid0 is None else uid0
-        if is_training:
-            self.Xc.zero_()
+        # Xc (dense coefficient matrix, G step only) is all-zero here: the G backward clears it again right after its consumer
         ops.enc_gather_fwd(indptr, indices, None, B, self.I, uid0, v.W_q0_b, v.view("b_q0"), keep, self.seed, 0, self.words, self.h1, coef,
                            bt["max_nnz"] if max_nnz is None else max_nnz, self.enc_ws, self.enc_cnt,
                            bt["slot_of_item"] if is_training else None, self.Xc if is_training else None)
@@ -495,6 +494,8 @@ class GanEngine(object):
         # encoder weight gradient over the batch's active items as a tensor-core GEMM: G = Xc^T dh1pre   [n_active, 600]
         if not (self.world_size > 1 and getattr(self, "_dp_comm", False) and self.dp_tables is not None):
             ops.gemm(self.Xc, self.dh1pre_b, bt["n_active"], H, B, a_mn=True, b_mn=True, bn=ops.pick_bn(bt["n_active"], H), out_f32=self.G_enc)
+        with self._fork(self.s2):
+            self.Xc.zero_()   # self-cleaning, off the critical path: the next G forward scatters into an all-zero matrix
         act_exchange = dp_comm and self.dp_tables is not None
         if self.world_size > 1 and not act_exchange:
             ops.enc_wgrad_expand(self.dW_q0, self.I, bt["slot_of_item"], self.G_enc)
