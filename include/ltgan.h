@@ -96,6 +96,22 @@ int ltg_latent_fwd(const float* mulv, const float* eps, int B, int64_t uid0, flo
 int ltg_latent_bwd(const float* dz, const float* mulv, const float* zmu, int B, int B_global, float anneal, const float* scal,
                    void* dmulv_bf16, int ld, float* db_q1, void* stream);
 
+/* Fused middle of the generator (MultiVAE.py:151-162,178-181,168-172), forward: kernel A = [mu|logvar] = h1 W_q1 + b_q1, KL and
+ * the reparameterisation; kernel B = h2 = tanh(z W_p0 + b_p0). 16 batch rows x one fifth of the columns per CTA (160 CTAs at
+ * B = 500), mma.sync m16n8k16, weights streamed from L2. W_q1 bf16 [600,400], W_p0 bf16 [200,600] row-major. Outputs as
+ * ltg_latent_fwd plus h2 (bf16 [B, ld_h2], columns < 600 written). ld_h1 and ld_z multiples of 8.                              */
+int ltg_vae_mid_fwd(const void* h1_bf16, int ld_h1, const void* Wq1_bf16, const float* b_q1, const void* Wp0_bf16,
+                    const float* b_p0, const float* eps, int B, int64_t uid0, float is_training, uint64_t seed, uint32_t step,
+                    const uint32_t* step_dev, float* mulv, void* z_bf16, int ld_z, float* zmu, void* h2_bf16, int ld_h2,
+                    float* scal, void* stream);
+/* Its backward (autodiff of the same lines) from dh2pre bf16 [B,600] (ltg_tanh_bwd's output): kernel A = dz = dh2pre W_p0^T and
+ * the latent backward -> dmulv bf16 [B,400], db_q1[400]; kernel B = dh1 = dmulv W_q1^T, dh1pre = dh1 (1 - h1^2) as fp32 + bf16
+ * [B,600], db_q0[600]. Bias gradients are accumulated atomically (zeroed by the caller). The weight gradients (contractions
+ * over the batch) stay on ltg_gemm_bf16.                                                                                      */
+int ltg_vae_mid_bwd(const void* dh2pre_bf16, const void* Wp0_bf16, const void* Wq1_bf16, const float* mulv, const float* zmu,
+                    const void* h1_bf16, int ld_h1, int B, int B_global, float anneal, const float* scal, void* dmulv_bf16,
+                    float* dh1pre, void* dh1pre_bf16, float* db_q1, float* db_q0, void* stream);
+
 /* dx = dy * (1 - y^2) for y = tanh(.) stored as bf16 [B, ld_y]; outputs bf16 and/or fp32; column sums -> dbias (atomic).
  * dy may be given as n_partials split-K partial buffers (dy + s*partial_stride), which are summed on the fly.             */
 int ltg_tanh_bwd(const float* dy, int ld_dy, int n_partials, int64_t partial_stride, const void* y_bf16, int ld_y, int B, int N,

@@ -211,6 +211,7 @@ class GanEngine(object):
         self.s1 = torch.cuda.Stream(device=self.device)
         self.s2 = torch.cuda.Stream(device=self.device)
         self.overlap = True
+        self.fused_mid = True   # fused 600->400->200->600 middle (mid_kernels.cu) instead of two GEMMs + element-wise launches
         self._alloc()
         self.eps_inject = None  # optional [B, L] fp32 tensor used instead of the Philox normal (parity tests)
 
@@ -313,10 +314,15 @@ class GanEngine(object):
         ops.enc_gather_fwd(indptr, indices, None, B, self.I, uid0, v.W_q0_b, v.view("b_q0"), keep, self.seed, 0, self.words, self.h1, coef,
                            bt["max_nnz"] if max_nnz is None else max_nnz, self.enc_ws, self.enc_cnt,
                            bt["slot_of_item"] if is_training else None, self.Xc if is_training else None)
-        ops.gemm(self.h1, v.view("W_q1", "b"), B, 2 * L, H, b_mn=True, bn=64, out_f32=self.mulv, bias=v.view("b_q1"))
-        ops.latent_fwd(self.mulv, self.eps_inject if is_training else None, B, uid0, 1.0 if is_training else 0.0, self.seed, 0,
-                       self.words, self.z, self.zmu, self.scal)
-        ops.gemm(self.z, v.view("W_p0", "b"), B, H, L, b_mn=True, bn=64, out_bf16=self.h2, bias=v.view("b_p0"), act=1)
+        if self.fused_mid:
+            ops.vae_mid_fwd(self.h1, v.view("W_q1", "b"), v.view("b_q1"), v.view("W_p0", "b"), v.view("b_p0"),
+                            self.eps_inject if is_training else None, B, uid0, 1.0 if is_training else 0.0, self.seed, 0, self.words,
+                            self.mulv, self.z, self.zmu, self.h2, self.scal)
+        else:
+            ops.gemm(self.h1, v.view("W_q1", "b"), B, 2 * L, H, b_mn=True, bn=64, out_f32=self.mulv, bias=v.view("b_q1"))
+            ops.latent_fwd(self.mulv, self.eps_inject if is_training else None, B, uid0, 1.0 if is_training else 0.0, self.seed, 0,
+                           self.words, self.z, self.zmu, self.scal)
+            ops.gemm(self.z, v.view("W_p0", "b"), B, H, L, b_mn=True, bn=64, out_bf16=self.h2, bias=v.view("b_p0"), act=1)
         ops.dec_logits_fwd(self.h2, v.WdT_b, v.view("b_p1"), B, self.I, self.logits if stash else None, self.partial)
         return indptr, indices
 
@@ -480,17 +486,30 @@ class GanEngine(object):
                 self.s1.wait_stream(torch.cuda.current_stream())
             with (torch.cuda.stream(self.s1) if self.overlap else torch.cuda.stream(torch.cuda.current_stream())):
                 ops.adam(v.WdT, v.WdT_m, v.WdT_v, self.dWdT, v.WdT_b, scal=self.scal)
-        ops.tanh_bwd(self.dh2_part, self.h2, B, H, dx_bf16=self.dh2pre, dbias=v.view("b_p0", "g"), n_partials=self.dgrad_splits,
-                     partial_stride=self.max_B * H, ld_dy=H)
-        with self._fork(self.s2):
-            ops.gemm(self.z, self.dh2pre, L, H, B, a_mn=True, b_mn=True, bn=64, out_f32=v.view("W_p0", "g"))
-        ops.gemm(self.dh2pre, v.view("W_p0", "b"), B, L, H, bn=64, out_f32=self.dz)
-        ops.latent_bwd(self.dz, self.mulv, self.zmu, B, Bg, -1.0, self.scal, self.dmulv, v.view("b_q1", "g"))
-        self._join(self.s2)
-        with self._fork(self.s2):
-            ops.gemm(self.h1, self.dmulv, H, 2 * L, B, a_mn=True, b_mn=True, bn=64, out_f32=v.view("W_q1", "g"))
-        ops.gemm(self.dmulv, v.view("W_q1", "b"), B, H, 2 * L, bn=64, out_f32=self.dh1)
-        ops.tanh_bwd(self.dh1, self.h1, B, H, dx_bf16=self.dh1pre_b, dx_f32=self.dh1pre, dbias=v.view("b_q0", "g"))
+        if self.fused_mid:
+            # split-K sum + tanh' with full-machine parallelism, then two fused kernels (dz + latent backward; dh1 + tanh' + db_q0);
+            # the two weight-gradient GEMMs (contractions over the batch) run on side branches
+            ops.tanh_bwd(self.dh2_part, self.h2, B, H, dx_bf16=self.dh2pre, dbias=v.view("b_p0", "g"), n_partials=self.dgrad_splits,
+                         partial_stride=self.max_B * H, ld_dy=H)
+            with self._fork(self.s2):
+                ops.gemm(self.z, self.dh2pre, L, H, B, a_mn=True, b_mn=True, bn=64, out_f32=v.view("W_p0", "g"))
+            ops.vae_mid_bwd(self.dh2pre, v.view("W_p0", "b"), v.view("W_q1", "b"), self.mulv, self.zmu, self.h1, B, Bg, -1.0, self.scal,
+                            self.dmulv, self.dh1pre, self.dh1pre_b, v.view("b_q1", "g"), v.view("b_q0", "g"))
+            self._join(self.s2)
+            with self._fork(self.s2):
+                ops.gemm(self.h1, self.dmulv, H, 2 * L, B, a_mn=True, b_mn=True, bn=64, out_f32=v.view("W_q1", "g"))
+        else:
+            ops.tanh_bwd(self.dh2_part, self.h2, B, H, dx_bf16=self.dh2pre, dbias=v.view("b_p0", "g"), n_partials=self.dgrad_splits,
+                         partial_stride=self.max_B * H, ld_dy=H)
+            with self._fork(self.s2):
+                ops.gemm(self.z, self.dh2pre, L, H, B, a_mn=True, b_mn=True, bn=64, out_f32=v.view("W_p0", "g"))
+            ops.gemm(self.dh2pre, v.view("W_p0", "b"), B, L, H, bn=64, out_f32=self.dz)
+            ops.latent_bwd(self.dz, self.mulv, self.zmu, B, Bg, -1.0, self.scal, self.dmulv, v.view("b_q1", "g"))
+            self._join(self.s2)
+            with self._fork(self.s2):
+                ops.gemm(self.h1, self.dmulv, H, 2 * L, B, a_mn=True, b_mn=True, bn=64, out_f32=v.view("W_q1", "g"))
+            ops.gemm(self.dmulv, v.view("W_q1", "b"), B, H, 2 * L, bn=64, out_f32=self.dh1)
+            ops.tanh_bwd(self.dh1, self.h1, B, H, dx_bf16=self.dh1pre_b, dx_f32=self.dh1pre, dbias=v.view("b_q0", "g"))
         # encoder weight gradient over the batch's active items as a tensor-core GEMM: G = Xc^T dh1pre   [n_active, 600]
         if not (self.world_size > 1 and getattr(self, "_dp_comm", False) and self.dp_tables is not None):
             ops.gemm(self.Xc, self.dh1pre_b, bt["n_active"], H, B, a_mn=True, b_mn=True, bn=ops.pick_bn(bt["n_active"], H), out_f32=self.G_enc)

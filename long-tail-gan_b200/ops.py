@@ -132,6 +132,19 @@ def latent_bwd(dz, mulv, zmu, B, B_global, anneal, scal, dmulv, db_q1):
                                _stream()))
 
 
+def vae_mid_fwd(h1, Wq1_b, b_q1, Wp0_b, b_p0, eps, B, uid0, is_training, seed, step, step_dev, mulv, z, zmu, h2, scal):
+    _count(2)
+    check(lib().ltg_vae_mid_fwd(ptr(h1), h1.stride(0), ptr(Wq1_b), ptr(b_q1), ptr(Wp0_b), ptr(b_p0), ptr(eps), B, uid0, float(is_training),
+                                seed, step, ptr(step_dev), ptr(mulv), ptr(z), z.stride(0), ptr(zmu), ptr(h2), h2.stride(0), ptr(scal),
+                                _stream()))
+
+
+def vae_mid_bwd(dh2pre, Wp0_b, Wq1_b, mulv, zmu, h1, B, B_global, anneal, scal, dmulv, dh1pre, dh1pre_b, db_q1, db_q0):
+    _count(2)
+    check(lib().ltg_vae_mid_bwd(ptr(dh2pre), ptr(Wp0_b), ptr(Wq1_b), ptr(mulv), ptr(zmu), ptr(h1), h1.stride(0), B, B_global, anneal,
+                                ptr(scal), ptr(dmulv), ptr(dh1pre), ptr(dh1pre_b), ptr(db_q1), ptr(db_q0), _stream()))
+
+
 def tanh_bwd(dy, y_bf16, B, N, dx_bf16=None, dx_f32=None, dbias=None, n_partials=1, partial_stride=0, ld_dy=None):
     _count(1)
     check(lib().ltg_tanh_bwd(ptr(dy), dy.stride(0) if ld_dy is None else ld_dy, n_partials, partial_stride, ptr(y_bf16), y_bf16.stride(0), B, N,
