@@ -211,6 +211,7 @@ class GanEngine(object):
         self.s1 = torch.cuda.Stream(device=self.device)
         self.s2 = torch.cuda.Stream(device=self.device)
         self.overlap = True
+        self.fused_disc = ops.disc_fused_supported(self.disc)   # one tcgen05 kernel for the discriminator forward (disc_fused.cu)
         self.fused_mid = True   # fused 600->400->200->600 middle (mid_kernels.cu) instead of two GEMMs + element-wise launches
         self._alloc()
         self.eps_inject = None  # optional [B, L] fp32 tensor used instead of the Philox normal (parity tests)
@@ -332,6 +333,10 @@ class GanEngine(object):
         seed, kd = self.seed, self.keep_d
         st = ops.STREAM_DISC_DROPOUT
         ops.disc_gather(d.E_b, pop, niche, P, self.Xp, self.Xn)
+        if self.fused_disc:
+            ops.disc_fwd_fused(self.Xp, self.Xn, P, d, label, kd, seed, st, self.words, self.Hd, self.y, self.scal,
+                               self.dz3 if backward else None, g_w4 if backward else None, g_b4 if backward else None)
+            return
         k1 = d.h0 + 1  # embedding columns + the ones column (bias row of W1 / W2)
         ops.gemm(self.Xp, d.view("W1", "b"), P, d.h1, k1, lda=128, b_mn=True, bn=ops.pick_bn(P, d.h1), out_bf16=self.Hd, ld_bf16=d.k3,
                  act=1, keep=kd, seed=seed, rng_stream=st, rng_step_dev=self.words, rng_ld=d.ld1)

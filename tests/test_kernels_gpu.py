@@ -528,3 +528,74 @@ def test_disc_gather_head_and_backward(ops):
     dact2 = torch.where(Hf != 0, (1 - (Hf * keep) ** 2) / keep, torch.zeros_like(Hf))
     want = (dz3[:, :h3].float() @ W[:, :h3].float().t()) * dact2
     assert (dz.float() - want).abs().max().item() < 2e-2 * want.abs().max().item() + 1e-6
+
+
+@pytest.mark.parametrize("P,backward,sizes", [(333, True, (100, 150, 250, 300)), (1000, False, (100, 150, 250, 300)), (128, True, (100, 150, 250, 300)),
+                                              (260, True, (40, 24, 56, 64))])
+def test_disc_fused_forward_matches_unfused_chain(ops, P, backward, sizes):
+    """disc_fused.cu (one tcgen05 kernel: branch layers -> fc1 -> head through TMEM / shared memory) against the chain of
+    ltg_gemm_bf16 + ltg_disc_head launches it replaces. The dropout masks are the same counter hash, so the hidden activation
+    must agree to bf16 rounding of tanh.approx inputs (accumulation order differs inside the tensor core only by k-block order:
+    identical here), y / loss / gradients within 1e-3."""
+    disc_mod = importlib.import_module("long-tail-gan_b200.discriminator")
+    h0, h1, h2, h3 = sizes
+    I = 700
+    d = disc_mod.Discriminator(I, I, h0, h1, h2, h3, device="cuda", seed=5)
+    assert ops.disc_fused_supported(d)
+    with torch.no_grad():   # make the head weights and biases non-trivial
+        prm = d.get_params()
+        g = torch.Generator(device="cuda").manual_seed(3)
+        prm = [p + 0.05 * torch.randn(p.shape, device="cuda", generator=g) for p in prm]
+        d.set_params(d.E, prm)
+    pop = torch.randint(0, I, (P,), dtype=torch.int32, device="cuda"); niche = torch.randint(0, I, (P,), dtype=torch.int32, device="cuda")
+    label = torch.randint(-1, 2, (P,), dtype=torch.int32, device="cuda")
+    bf = dict(device="cuda", dtype=torch.bfloat16)
+    Xp = torch.zeros(P, 128, **bf); Xn = torch.zeros(P, 128, **bf)
+    ops.disc_gather(d.E_b, pop, niche, P, Xp, Xn)
+    words = torch.tensor([7, 0, 0, 0], dtype=torch.int32, device="cuda")
+    keep, seed, st = 0.7, 1234, ops.STREAM_DISC_DROPOUT
+    k1 = d.h0 + 1
+
+    def run(fused):
+        Hd = torch.zeros(P, d.k3, **bf); Hd[:, d.one3] = 1.0
+        y = torch.zeros(P, device="cuda"); scal = torch.zeros(16, device="cuda")
+        dz3 = torch.zeros(P, d.ld3, **bf) if backward else None
+        dw4 = torch.zeros(d.ld3, device="cuda") if backward else None
+        db4 = torch.zeros(4, device="cuda") if backward else None
+        if fused:
+            ops.disc_fwd_fused(Xp, Xn, P, d, label, keep, seed, st, words, Hd, y, scal, dz3, dw4, db4)
+        else:
+            Y3 = torch.zeros(P, d.ld3, **bf)
+            ops.gemm(Xp, d.view("W1", "b"), P, d.h1, k1, lda=128, b_mn=True, bn=ops.pick_bn(P, d.h1), out_bf16=Hd, ld_bf16=d.k3, act=1,
+                     keep=keep, seed=seed, rng_stream=st, rng_step_dev=words, rng_ld=d.ld1)
+            ops.gemm(Xn, d.view("W2", "b"), P, d.h2, k1, lda=128, b_mn=True, bn=ops.pick_bn(P, d.h2), out_bf16=Hd[:, d.off2:], ld_bf16=d.k3,
+                     act=1, keep=keep, seed=seed, rng_stream=st + 1, rng_step_dev=words, rng_ld=d.ld2)
+            ops.gemm(Hd, d.view("W3", "b"), P, d.h3, d.k3, b_mn=True, bn=ops.pick_bn(P, d.h3), out_bf16=Y3, act=1, keep=keep, seed=seed,
+                     rng_stream=st + 2, rng_step_dev=words, rng_ld=d.ld3)
+            ops.disc_head(Y3, P, d.h3, d.view("w4"), d.view("b4"), label, keep, y, scal, dz3, dw4, db4)
+        torch.cuda.synchronize()
+        return Hd, y, scal, dz3, dw4, db4
+
+    Hu, yu, su, dzu, dwu, dbu = run(False)
+    Hf, yf, sf, dzf, dwf, dbf = run(True)
+    # same dropout pattern and the ones column / padding layout
+    assert torch.equal(Hu == 0, Hf == 0)
+    assert (Hf[:, d.one3] == 1).all() and (Hf[:, d.one3 + 1:] == 0).all() and (Hf[:, d.h1:d.off2] == 0).all()
+    assert (Hu.float() - Hf.float()).abs().max().item() <= 2e-2     # one bf16 ulp at |x| <= 1.43 (= 1/keep)
+    assert (Hu.float() - Hf.float()).abs().mean().item() < 1e-4
+    assert (yu - yf).abs().max().item() < 2e-3
+    for slot in (ops.S_D_LOSS, ops.S_SUM_Y):
+        assert abs(su[slot].item() - sf[slot].item()) < 1e-3 * max(1.0, abs(su[slot].item()))
+    assert su[ops.S_CNT].item() == sf[ops.S_CNT].item() == int((label == 1).sum().item())
+    if backward:
+        scale = dzu.float().abs().max().item() + 1e-9
+        assert (dzu.float() - dzf.float()).abs().max().item() < 3e-2 * scale
+        assert (dzf[label.long() < 0] == 0).all()
+        assert (dwu - dwf).abs().max().item() < 2e-3 * max(1.0, dwu.abs().max().item())
+        assert abs(dbu[0].item() - dbf[0].item()) < 1e-3 * max(1.0, abs(dbu[0].item()))
+    # independent fp32 restatement of the head on the fused kernel's own hidden activation
+    W3 = d.view("W3", "b").float()[:, : d.h3]
+    a3 = torch.tanh(Hf.float() @ W3)
+    y3 = torch.where(torch.from_numpy(philox.hash_keep_mask(seed, st + 2, 7, P, d.h3, d.ld3, keep)).cuda(), a3 / keep, torch.zeros_like(a3))
+    yr = torch.sigmoid(y3.bfloat16().float() @ d.view("w4")[: d.h3] + d.view("b4")[0])
+    assert (yr - yf).abs().max().item() < 5e-3
