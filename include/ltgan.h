@@ -151,6 +151,27 @@ int ltg_dec_row_bwd(const float* partial, int n_blocks, const void* logits_bf16,
  * g may be given as n_partials buffers (g + s*partial_stride: split-K partials of the weight-gradient GEMMs), summed on the fly. */
 int ltg_adam(float* p, float* m, float* v, const float* g, int n_partials, int64_t partial_stride, void* shadow_bf16, int64_t n,
              float lr_t, const float* scal, float beta1, float beta2, float eps, void* stream);
+/* ---- e: data-parallel exchange over NVLink peer memory (one node) ------------------------------------------
+ * Every table argument is a HOST array of `world` (<= 8) device pointers, entry r = rank r's instance of a peer-mapped buffer
+ * (CUDA VMM / symmetric memory set up by the caller; entry `rank` is the local one). `pads` = peer-mapped uint32
+ * [LTG_PEER_SLOTS][8] signal words, zero-initialised; `epochs` = local device uint32[LTG_PEER_SLOTS], zero-initialised.
+ * All ranks must issue the same sequence of barrier-carrying calls per slot; one slot per stream that issues them.      */
+#define LTG_PEER_SLOTS 4
+/* every rank has executed all work ordered before this call on its stream (and its peer writes are visible) */
+int ltg_peer_barrier(void* const* pads, int rank, int world, int slot, uint32_t* epochs, void* stream);
+/* in-place all-reduce (sum, rank order) of floats [offset, offset+count), count <= 1024, in one single-CTA kernel */
+int ltg_peer_allreduce_small(void* const* bufs, int64_t offset, int count, void* const* pads, int rank, int world, int slot,
+                             uint32_t* epochs, void* stream);
+/* out[i] = sum_r bufs[r][offset + i], i < n; `out` must not be one of the peer-visible buffers; caller orders it with barriers */
+int ltg_peer_reduce(void* const* bufs, int64_t offset, int64_t n, int world, float* out, void* stream);
+/* copy `bytes` from src to byte offset dst_offset_bytes of every rank's dst buffer (all-gather by pushing; 16-byte granularity) */
+int ltg_peer_push(const void* src, int64_t bytes, void* const* dst, int64_t dst_offset_bytes, int world, void* stream);
+/* ltg_adam over this rank's shard p/m/v[n] = elements [offset, offset+n) of the full tensor, with the reduce-scatter and the
+ * all-gather fused in: g = sum_r grads[r][offset+i] (fp32, read from every rank), bf16(p) stored to shadows_bf16[r][offset+i]
+ * of every rank. offset and n multiples of 4.                                                                            */
+int ltg_adam_peer(float* p, float* m, float* v, void* const* grads, void* const* shadows_bf16, int64_t offset, int64_t n, int world,
+                  float lr_t, const float* scal, float beta1, float beta2, float eps, void* stream);
+
 /* Encoder weight W_q0 [n_items, H]. Its gradient X^T dh1pre is non-zero only on the batch's ACTIVE items, so it is built
  * compactly: G[slot, :] = sum over the item's batch entries of coef * dh1pre[row, :], one CTA per active item
  * (act_ptr[n_active+1] delimits the item's entries in csc_row[] = batch row / csc_pos[] = offset into coef).                */

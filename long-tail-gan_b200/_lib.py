@@ -16,7 +16,7 @@ _INCLUDE = os.path.join(_ROOT, "include")
 LIB_PATH = os.path.join(_HERE, "libltgan.so")
 
 SOURCES = ["runtime.cu", "gemm_ops.cu", "vae_kernels.cu", "adam_kernels.cu", "sampler_kernels.cu", "disc_kernels.cu",
-           "topk_kernels.cu", "mid_kernels.cu", "disc_fused.cu"]
+           "topk_kernels.cu", "mid_kernels.cu", "disc_fused.cu", "peer_kernels.cu"]
 HEADERS = ["ltg_common.cuh", "gemm_sm100.cuh"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
@@ -100,6 +100,11 @@ SIGNATURES = {
     "ltg_enc_wgrad_expand": (_I, [_P, _I, _P, _P, _P]),
     "ltg_sample_pairs": (_I, [_P, _I, _I, _I, _I64, _P, _P, _P, _P, _P, _P, _U64, _U32, _P, _P, _P, _P, _P, _I, _P, _P]),
     "ltg_dec_row_bwd": (_I, [_P, _I, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ltg_peer_barrier": (_I, [_P, _I, _I, _I, _P, _P]),
+    "ltg_peer_allreduce_small": (_I, [_P, _I64, _I, _P, _I, _I, _I, _P, _P]),
+    "ltg_peer_reduce": (_I, [_P, _I64, _I64, _I, _P, _P]),
+    "ltg_peer_push": (_I, [_P, _I64, _P, _I64, _I, _P]),
+    "ltg_adam_peer": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _I, _F, _P, _F, _F, _F, _P]),
     "ltg_disc_gather": (_I, [_P, _P, _P, _I, _P, _P, _P]),
     "ltg_disc_fused_supported": (_I, [_I, _I, _I, _I, _I, _I, _I, _I]),
     "ltg_disc_fwd_fused": (_I, [_P, _P, _I, _I, _P, _I, _P, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P, _F, _U64, _U32, _U32, _P, _P, _P, _P, _P, _P, _P, _P]),

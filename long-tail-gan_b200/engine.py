@@ -269,8 +269,11 @@ class GanEngine(object):
             self.ld_xcg = _pad(max(1, min(self.R, self.max_active * N)), 8)
             self.Xc_glob = torch.zeros(N * B, self.ld_xcg, **bf)
             self.G_shard = torch.zeros(max(1, min(self.R, self.max_active * N)), H, **f32)
+            self.peer = None
+            self._setup_peer()
         else:
             self.dW_q0 = None
+            self.peer = None
         self.dWdT = self.dWdT_full[:I] if self.world_size > 1 else torch.zeros(I, H, **f32)
         # split-K partials of the decoder dgrad (summed by the tanh-backward kernel that consumes them: no atomics, no memset)
         self.dgrad_splits = ops.actual_splits(I, ops.pick_splits(B, H, I, 128))
@@ -465,12 +468,24 @@ class GanEngine(object):
         with self._fork(self.s1):
             ops.gemm(self.dl, self.h2, self.I, H + 1, B, a_mn=True, b_mn=True, bn=128, out_f32=self.dWdT, ld_f32=H, aux_col=H,
                      aux_out=v.view("b_p1", "g"))
-            if dp_comm:
+            if dp_comm and self.peer is None:
                 import torch.distributed as dist
                 dist.reduce_scatter_tensor(self.g_dec_shard, self.dWdT_full)
         ops.gemm(self.dl, v.WdT_b, B, H, self.I, b_mn=True, splits=self.dgrad_splits, bn=128, out_f32=self.dh2_part, ld_f32=H,
                  split_stride=self.max_B * H)
-        if dp_comm and self.nrows > 0:
+        if dp_comm and self.peer is not None:
+            # peer-memory path: once every rank has finished its weight-gradient GEMM and its dgrad GEMM (which reads the bf16
+            # weights), ONE kernel sums this rank's rows of all ranks' gradient buffers, runs Adam on them and stores the bf16
+            # result into every rank's weight shadow: reduce-scatter + update + all-gather without a collective launch
+            if self.overlap:
+                self.s1.wait_stream(torch.cuda.current_stream())
+            with (torch.cuda.stream(self.s1) if self.overlap else torch.cuda.stream(torch.cuda.current_stream())):
+                self._pbar(1)
+                if self.nrows > 0:
+                    r0, nr = self.row0, self.nrows
+                    ops.adam_peer(v.WdT[r0:r0 + nr], v.WdT_m[r0:r0 + nr], v.WdT_v[r0:r0 + nr], self.peer["dWdT"], self.peer["WdT_b"], r0 * H,
+                                  self.world_size, scal=self.scal)
+        if dp_comm and self.peer is None and self.nrows > 0:
             # Adam on this rank's decoder rows: after the reduce-scatter (same branch) and after dgrad (it reads the bf16 weights;
             # the shard Adam only writes the shard staging buffer, the full shadow is replaced by the all-gather at the end)
             if self.overlap:
@@ -478,7 +493,7 @@ class GanEngine(object):
             with (torch.cuda.stream(self.s1) if self.overlap else torch.cuda.stream(torch.cuda.current_stream())):
                 r0, nr = self.row0, self.nrows
                 ops.adam(v.WdT[r0:r0 + nr], v.WdT_m[r0:r0 + nr], v.WdT_v[r0:r0 + nr], self.g_dec_shard, self.WdT_b_shard, scal=self.scal)
-        if dp_comm:
+        if dp_comm and self.peer is None:
             # every rank (also one whose shard is empty) joins the all-gather; issued here so it overlaps the encoder-side backward
             if self.overlap:
                 self.s1.wait_stream(torch.cuda.current_stream())
@@ -530,7 +545,12 @@ class GanEngine(object):
             self.Xc_glob.zero_()
             ops.enc_coef_scatter(tb["e_row"], tb["e_item"], tb["e_slot"], tb["row_uid"], tb["row_rnorm"], tb["n_entries"], self.I,
                                  self.keep_vae, self.seed, 0, self.words, self.Xc_glob)
-            dist.all_gather_into_tensor(self.dh1_glob, self.dh1pre_b)   # rows beyond B meet all-zero Xc rows
+            if self.peer is not None:
+                nb_ = self.dh1pre_b.numel() * 2
+                ops.peer_push(self.dh1pre_b, nb_, self.peer["dh1"], self.rank * nb_, self.world_size)
+                self._pbar(0)
+            else:
+                dist.all_gather_into_tensor(self.dh1_glob, self.dh1pre_b)   # rows beyond B meet all-zero Xc rows
             if tb["n_active"] > 0:
                 ops.gemm(self.Xc_glob, self.dh1_glob, tb["n_active"], H, self.world_size * self.max_B, a_mn=True, b_mn=True,
                          bn=ops.pick_bn(tb["n_active"], H), out_f32=self.G_shard)
@@ -601,6 +621,12 @@ class GanEngine(object):
         import torch.distributed as dist
         self._d_fwd_bwd(data, bi)
         torch.sum(self.arena_gp, dim=0, out=self.disc.arena_g)   # split-K partials -> one gradient arena
+        if self.peer is not None:
+            d = self.disc
+            self._pbar(0)
+            ops.peer_reduce(self.peer["arena_g"], 0, d.arena_g.numel(), self.world_size, self.arena_gsum)
+            ops.adam(d.arena, d.arena_m, d.arena_v, self.arena_gsum, d.arena_b, scal=self.scal)
+            return
         dist.all_reduce(self.disc.arena_g)                       # 161 k discriminator gradients: one small bucket
         self._d_update()
 
@@ -622,6 +648,21 @@ class GanEngine(object):
         v = self.vae
         self._g_forward(data, bi)
         # F3: the adversarial term multiplies GLOBAL sums; Ybar = sum y / cnt must be global before the backward pass starts
+        if self.peer is not None:
+            pr = self.peer
+            N = self.world_size
+            ops.peer_allreduce_small(pr["scal"], ops.S_SUM_Y, 2, pr["pads"], self.rank, N, 0, self.peer_epochs)
+            self._dp_comm = True
+            self._g_backward(data, bi)
+            self._dp_comm = False
+            r0, nr = self.row0, self.nrows
+            if nr > 0:   # the encoder rows this rank just updated, into every rank's bf16 shadow
+                ops.peer_push(self.Wq0_b_shard, nr * H * 2, pr["Wq0_b"], r0 * H * 2, N)
+            self._pbar(0)   # every rank's small gradients are final
+            ops.peer_reduce(pr["small_g"], 0, v.small_g.numel(), N, self.small_gsum)
+            ops.adam(v.small, v.small_m, v.small_v, self.small_gsum, v.small_b, scal=self.scal)
+            self._pbar(0)   # end of step: all pushes have landed, nobody still reads this step's gradient buffers
+            return
         dist.all_reduce(self.scal[ops.S_SUM_Y: ops.S_CNT + 1])
         self._dp_comm = True
         self._g_backward(data, bi)
@@ -630,6 +671,53 @@ class GanEngine(object):
         dist.all_reduce(v.small_g)
         ops.adam(v.small, v.small_m, v.small_v, v.small_g, v.small_b, scal=self.scal)
         dist.all_gather_into_tensor(self.Wq0_b_full, self.Wq0_b_shard)
+
+    def _setup_peer(self):
+        """Data parallel on one NVLink node: map every exchanged buffer into all ranks (torch symmetric memory = CUDA VMM handles
+        exchanged through the process group) so the exchange steps run inside our own kernels (peer_kernels.cu) instead of NCCL
+        collectives. LTG_DP_PEER=0, a non-NCCL process group or a failed rendezvous keep the NCCL-collective path."""
+        import os
+        import torch.distributed as dist
+        if os.environ.get("LTG_DP_PEER", "1") == "0" or not dist.is_initialized() or dist.get_backend() != "nccl" or self.world_size > 8:
+            return
+        try:
+            import torch.distributed._symmetric_memory as symm
+            handles = []
+
+            def sym(like):
+                t = symm.empty(*like.shape, dtype=like.dtype, device=self.device)
+                t.copy_(like)
+                h = symm.rendezvous(t, dist.group.WORLD)
+                handles.append(h)
+                return t, ops.peer_table(h.buffer_ptrs)
+
+            peer = {}
+            self.dWdT_full, peer["dWdT"] = sym(self.dWdT_full)
+            self.WdT_b_full, peer["WdT_b"] = sym(self.WdT_b_full)
+            self.Wq0_b_full, peer["Wq0_b"] = sym(self.Wq0_b_full)
+            self.dh1_glob, peer["dh1"] = sym(self.dh1_glob)
+            self.scal, peer["scal"] = sym(self.scal)
+            self.disc.arena_g, peer["arena_g"] = sym(self.disc.arena_g)
+            self.vae.small_g, peer["small_g"] = sym(self.vae.small_g)
+            pads = torch.zeros(ops.PEER_SLOTS * 8, dtype=torch.int32, device=self.device)
+            self._peer_pads, peer["pads"] = sym(pads)
+        except Exception as e:  # noqa: BLE001  -- no peer mapping on this system: NCCL collectives do the same exchange
+            if self.rank == 0:
+                print("long-tail-gan_b200: peer-memory exchange unavailable (%s); using NCCL collectives" % (e,))
+            return
+        I = self.I
+        self.vae.WdT_b = self.WdT_b_full[:I]
+        self.vae.W_q0_b = self.Wq0_b_full[:I]
+        self.peer_epochs = torch.zeros(ops.PEER_SLOTS, dtype=torch.int32, device=self.device)
+        self.arena_gsum = torch.zeros_like(self.disc.arena_g)
+        self.small_gsum = torch.zeros_like(self.vae.small_g)
+        self._peer_handles = handles
+        torch.cuda.synchronize()
+        dist.barrier()
+        self.peer = peer
+
+    def _pbar(self, slot=0):
+        ops.peer_barrier(self.peer["pads"], self.rank, self.world_size, slot, self.peer_epochs)
 
     def attach_dp_tables(self, tables):
         """tables = build_dp_shard_tables(...): switches the encoder-gradient exchange from a 48 MB reduce-scatter of dW_q0 to a

@@ -190,6 +190,40 @@ def adam(p, m, v, g, shadow, lr_t=-1.0, scal=None, beta1=0.9, beta2=0.999, eps=1
                          eps, _stream()))
 
 
+# ---- data-parallel exchange over peer memory (peer_kernels.cu). A "table" is a ctypes array of one device pointer per rank.
+PEER_SLOTS = 4   # LTG_PEER_SLOTS
+
+
+def peer_table(ptrs):
+    import ctypes
+    return (ctypes.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+
+
+def peer_barrier(pads, rank, world, slot, epochs):
+    _count(1)
+    check(lib().ltg_peer_barrier(pads, rank, world, slot, ptr(epochs), _stream()))
+
+
+def peer_allreduce_small(bufs, offset, count, pads, rank, world, slot, epochs):
+    _count(1)
+    check(lib().ltg_peer_allreduce_small(bufs, offset, count, pads, rank, world, slot, ptr(epochs), _stream()))
+
+
+def peer_reduce(bufs, offset, n, world, out):
+    _count(1)
+    check(lib().ltg_peer_reduce(bufs, offset, n, world, ptr(out), _stream()))
+
+
+def peer_push(src, nbytes, dst, dst_offset_bytes, world):
+    _count(1)
+    check(lib().ltg_peer_push(ptr(src), nbytes, dst, dst_offset_bytes, world, _stream()))
+
+
+def adam_peer(p, m, v, grads, shadows, offset, world, lr_t=-1.0, scal=None, beta1=0.9, beta2=0.999, eps=1e-8):
+    _count(1)
+    check(lib().ltg_adam_peer(ptr(p), ptr(m), ptr(v), grads, shadows, offset, p.numel(), world, lr_t, ptr(scal), beta1, beta2, eps, _stream()))
+
+
 def enc_wgrad_compact(G, n_active, act_ptr, csc_row, csc_pos, coef, dh1pre):
     _count(1)
     check(lib().ltg_enc_wgrad_compact(ptr(G), n_active, ptr(act_ptr), ptr(csc_row), ptr(csc_pos), ptr(coef), ptr(dh1pre),

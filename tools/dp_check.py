@@ -44,6 +44,11 @@ def main():
         e.run_phase_a(data, 0); e.run_d_step(data, 0); e.run_g_step(data, 0)
     torch.cuda.synchronize()
     e.gather_master()
+    # every rank's bf16 shadows (what its next forward reads) must be the rounding of the gathered fp32 masters
+    ok_b = bool(torch.equal(vae.WdT_b, vae.WdT.bfloat16())) and bool(torch.equal(vae.W_q0_b, vae.W_q0.bfloat16()))
+    print("rank %d: exchange path = %s, bf16 shadows consistent = %s" % (rank, "peer memory" if e.peer is not None else "NCCL collectives", ok_b),
+          flush=True)
+    assert ok_b
     dist.barrier()
     if rank == 0:
         vae1, disc1, data1, e1 = build(1, B, 0)
