@@ -172,6 +172,11 @@ int ltg_peer_push(const void* src, int64_t bytes, void* const* dst, int64_t dst_
 int ltg_adam_peer(float* p, float* m, float* v, void* const* grads, void* const* shadows_bf16, int64_t offset, int64_t n, int world,
                   float lr_t, const float* scal, float beta1, float beta2, float eps, void* stream);
 
+/* ltg_enc_adam over this rank's item rows (p/m/v = shard base, slot_of_item = shard-local table) with the all-gather fused in:
+ * the updated bf16 row is stored at element offset `offset` + local index of every rank's encoder shadow.                   */
+int ltg_enc_adam_peer(float* p, float* m, float* v, void* const* shadows_bf16, int64_t offset, int n_items, const int32_t* slot_of_item,
+                      const float* G, int world, float lr_t, const float* scal, float beta1, float beta2, float eps, void* stream);
+
 /* Encoder weight W_q0 [n_items, H]. Its gradient X^T dh1pre is non-zero only on the batch's ACTIVE items, so it is built
  * compactly: G[slot, :] = sum over the item's batch entries of coef * dh1pre[row, :], one CTA per active item
  * (act_ptr[n_active+1] delimits the item's entries in csc_row[] = batch row / csc_pos[] = offset into coef).                */

@@ -138,6 +138,37 @@ adam_peer_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict
   }
 }
 
+// enc_adam_kernel (adam_kernels.cu) over this rank's item rows [item0, item0 + n_items): the compact gradient G already holds the
+// global batch (activation exchange), so only the all-gather is fused in: the bf16 row goes to every rank's encoder shadow.
+__global__ void __launch_bounds__(256)
+enc_adam_peer_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, PeerPtrs shadows, int64_t offset, int n_items,
+                     const int32_t* __restrict__ slot_of_item, const float* __restrict__ G, int world, float lr_t,
+                     const float* __restrict__ scal, float b1, float b2, float eps) {
+  constexpr int H4 = LTG_H / 4;
+  if (lr_t < 0.f) lr_t = scal[LTG_S_LR_T];
+  const int64_t n4 = (int64_t)n_items * H4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const int item = (int)(i / H4);
+    const int c4 = (int)(i - (int64_t)item * H4);
+    float4 pp = ld_stream_f4(p + 4 * i), mm = ld_stream_f4(m + 4 * i), vv = ld_stream_f4(v + 4 * i);
+    const int slot = __ldg(slot_of_item + item);
+    float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (slot >= 0) gg = __ldg(reinterpret_cast<const float4*>(G + (size_t)slot * LTG_H) + c4);
+    mm.x = b1 * mm.x + (1.f - b1) * gg.x; mm.y = b1 * mm.y + (1.f - b1) * gg.y;
+    mm.z = b1 * mm.z + (1.f - b1) * gg.z; mm.w = b1 * mm.w + (1.f - b1) * gg.w;
+    vv.x = b2 * vv.x + (1.f - b2) * gg.x * gg.x; vv.y = b2 * vv.y + (1.f - b2) * gg.y * gg.y;
+    vv.z = b2 * vv.z + (1.f - b2) * gg.z * gg.z; vv.w = b2 * vv.w + (1.f - b2) * gg.w * gg.w;
+    pp.x -= lr_t * mm.x / (sqrtf(vv.x) + eps); pp.y -= lr_t * mm.y / (sqrtf(vv.y) + eps);
+    pp.z -= lr_t * mm.z / (sqrtf(vv.z) + eps); pp.w -= lr_t * mm.w / (sqrtf(vv.w) + eps);
+    st_stream_f4(p + 4 * i, pp); st_stream_f4(m + 4 * i, mm); st_stream_f4(v + 4 * i, vv);
+    uint2 s; s.x = pack_bf16x2(pp.x, pp.y); s.y = pack_bf16x2(pp.z, pp.w);
+#pragma unroll
+    for (int r = 0; r < PEER_MAX; ++r)
+      if (r < world) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(shadows.p[r]) + offset + 4 * i) = s;
+  }
+}
+
 int load_ptrs(PeerPtrs* dst, void* const* src, int world) {
   if (src == nullptr || world < 1 || world > PEER_MAX) { ltg_set_last_error("peer table: 1 <= world <= 8 pointers required", __FILE__, __LINE__); return LTG_ERR_ARG; }
   for (int r = 0; r < PEER_MAX; ++r) dst->p[r] = r < world ? src[r] : nullptr;
@@ -219,6 +250,22 @@ extern "C" int ltg_adam_peer(float* p, float* m, float* v, void* const* grads, v
     LTG_REQUIRE((reinterpret_cast<uintptr_t>(grads[r]) & 15) == 0 && (reinterpret_cast<uintptr_t>(shadows_bf16[r]) & 7) == 0);
   if (n <= 0) return LTG_OK;
   adam_peer_kernel<<<stream_grid(n >> 2), 256, 0, (cudaStream_t)stream>>>(p, m, v, pg, ps, offset, n, world, lr_t, scal, beta1, beta2, eps);
+  LTG_CHECK_LAUNCH();
+  return LTG_OK;
+}
+
+extern "C" int ltg_enc_adam_peer(float* p, float* m, float* v, void* const* shadows_bf16, int64_t offset, int n_items,
+                                 const int32_t* slot_of_item, const float* G, int world, float lr_t, const float* scal, float beta1,
+                                 float beta2, float eps, void* stream) {
+  PeerPtrs ps;
+  int rc = load_ptrs(&ps, shadows_bf16, world);
+  if (rc) return rc;
+  LTG_REQUIRE(p && m && v && slot_of_item && G && offset >= 0 && offset % 4 == 0);
+  LTG_REQUIRE(lr_t >= 0.f || scal != nullptr);
+  for (int r = 0; r < world; ++r) LTG_REQUIRE((reinterpret_cast<uintptr_t>(shadows_bf16[r]) & 7) == 0);
+  if (n_items <= 0) return LTG_OK;
+  enc_adam_peer_kernel<<<stream_grid((int64_t)n_items * (LTG_H / 4)), 256, 0, (cudaStream_t)stream>>>(
+      p, m, v, ps, offset, n_items, slot_of_item, G, world, lr_t, scal, beta1, beta2, eps);
   LTG_CHECK_LAUNCH();
   return LTG_OK;
 }

@@ -556,8 +556,12 @@ class GanEngine(object):
                          bn=ops.pick_bn(tb["n_active"], H), out_f32=self.G_shard)
             if self.nrows > 0:
                 r0, nr = self.row0, self.nrows
-                ops.enc_adam(v.W_q0[r0:r0 + nr], v.W_q0_m[r0:r0 + nr], v.W_q0_v[r0:r0 + nr], self.Wq0_b_shard, nr, tb["slot_local"],
-                             self.G_shard, scal=self.scal)
+                if self.peer is not None:   # Adam on the shard rows, bf16 rows stored straight into every rank's encoder shadow
+                    ops.enc_adam_peer(v.W_q0[r0:r0 + nr], v.W_q0_m[r0:r0 + nr], v.W_q0_v[r0:r0 + nr], self.peer["Wq0_b"], r0 * H, nr,
+                                      tb["slot_local"], self.G_shard, self.world_size, scal=self.scal)
+                else:
+                    ops.enc_adam(v.W_q0[r0:r0 + nr], v.W_q0_m[r0:r0 + nr], v.W_q0_v[r0:r0 + nr], self.Wq0_b_shard, nr, tb["slot_local"],
+                                 self.G_shard, scal=self.scal)
         elif dp_comm:
             import torch.distributed as dist
             dist.reduce_scatter_tensor(self.g_enc_shard, self.dWq0_full)
@@ -656,7 +660,7 @@ class GanEngine(object):
             self._g_backward(data, bi)
             self._dp_comm = False
             r0, nr = self.row0, self.nrows
-            if nr > 0:   # the encoder rows this rank just updated, into every rank's bf16 shadow
+            if nr > 0 and self.dp_tables is None:   # (with the activation exchange, enc_adam_peer has already stored them)
                 ops.peer_push(self.Wq0_b_shard, nr * H * 2, pr["Wq0_b"], r0 * H * 2, N)
             self._pbar(0)   # every rank's small gradients are final
             ops.peer_reduce(pr["small_g"], 0, v.small_g.numel(), N, self.small_gsum)

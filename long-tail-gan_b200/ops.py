@@ -224,6 +224,12 @@ def adam_peer(p, m, v, grads, shadows, offset, world, lr_t=-1.0, scal=None, beta
     check(lib().ltg_adam_peer(ptr(p), ptr(m), ptr(v), grads, shadows, offset, p.numel(), world, lr_t, ptr(scal), beta1, beta2, eps, _stream()))
 
 
+def enc_adam_peer(p, m, v, shadows, offset, n_items, slot_of_item, G, world, lr_t=-1.0, scal=None, beta1=0.9, beta2=0.999, eps=1e-8):
+    _count(1)
+    check(lib().ltg_enc_adam_peer(ptr(p), ptr(m), ptr(v), shadows, offset, n_items, ptr(slot_of_item), ptr(G), world, lr_t, ptr(scal), beta1,
+                                  beta2, eps, _stream()))
+
+
 def enc_wgrad_compact(G, n_active, act_ptr, csc_row, csc_pos, coef, dh1pre):
     _count(1)
     check(lib().ltg_enc_wgrad_compact(ptr(G), n_active, ptr(act_ptr), ptr(csc_row), ptr(csc_pos), ptr(coef), ptr(dh1pre),

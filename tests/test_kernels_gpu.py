@@ -599,3 +599,55 @@ def test_disc_fused_forward_matches_unfused_chain(ops, P, backward, sizes):
     y3 = torch.where(torch.from_numpy(philox.hash_keep_mask(seed, st + 2, 7, P, d.h3, d.ld3, keep)).cuda(), a3 / keep, torch.zeros_like(a3))
     yr = torch.sigmoid(y3.bfloat16().float() @ d.view("w4")[: d.h3] + d.view("b4")[0])
     assert (yr - yf).abs().max().item() < 5e-3
+
+
+def test_peer_exchange_kernels_on_one_device(ops):
+    """peer_kernels.cu with pointer tables whose entries all live on this GPU (a table entry is just an address, so two "ranks"
+    can be two local buffers): the pull-sum, the push, the Adam with fused reduce-scatter / all-gather, and the flag barrier with
+    world = 1. The real 2-GPU check over NVLink is tools/dp_check.py."""
+    torch.manual_seed(3)
+    n = 600 * 37
+    off = 600 * 5
+    g0 = torch.randn(off + n + 8, device="cuda"); g1 = torch.randn(off + n + 8, device="cuda")
+    tab_g = ops.peer_table([g0.data_ptr(), g1.data_ptr()])
+    out = torch.zeros(n + 3, device="cuda")
+    ops.peer_reduce(tab_g, off, n + 3, 2, out)
+    torch.cuda.synchronize()
+    assert torch.equal(out, g0[off: off + n + 3] + g1[off: off + n + 3])
+    # Adam over the shard [off, off+n): gradient = g0 + g1 rows, bf16 result into both "ranks'" shadows; equals ltg_adam on the sum
+    p = torch.randn(n, device="cuda"); m = torch.randn(n, device="cuda") * 0.01; v = torch.rand(n, device="cuda") * 1e-3
+    p2, m2, v2 = p.clone(), m.clone(), v.clone()
+    sh0 = torch.zeros(off + n, device="cuda", dtype=torch.bfloat16); sh1 = torch.zeros_like(sh0)
+    ref_sh = torch.zeros(n, device="cuda", dtype=torch.bfloat16)
+    scal = torch.zeros(16, device="cuda")
+    ops.adam_peer(p, m, v, tab_g, ops.peer_table([sh0.data_ptr(), sh1.data_ptr()]), off, 2, lr_t=1e-3, scal=scal)
+    ops.adam(p2, m2, v2, (g0 + g1)[off: off + n].contiguous(), ref_sh, lr_t=1e-3, scal=scal)
+    torch.cuda.synchronize()
+    assert torch.equal(p, p2) and torch.equal(m, m2) and torch.equal(v, v2)
+    assert torch.equal(sh0[off:], ref_sh) and torch.equal(sh1[off:], ref_sh) and (sh0[:off] == 0).all()
+    # encoder variant: compact gradient rows through slot_of_item, bf16 rows into both shadows
+    items, H = 37, 600
+    slot = torch.full((items,), -1, dtype=torch.int32, device="cuda"); slot[::3] = torch.arange(len(slot[::3]), dtype=torch.int32, device="cuda")
+    G = torch.randn(int((slot >= 0).sum()), H, device="cuda")
+    p = torch.randn(items, H, device="cuda"); m = torch.zeros_like(p); v = torch.zeros_like(p)
+    p2, m2, v2 = p.clone(), m.clone(), v.clone()
+    sh0.zero_(); sh1.zero_(); ref2 = torch.zeros(items, H, device="cuda", dtype=torch.bfloat16)
+    ops.enc_adam_peer(p, m, v, ops.peer_table([sh0.data_ptr(), sh1.data_ptr()]), off, items, slot, G, 2, lr_t=1e-3, scal=scal)
+    ops.enc_adam(p2, m2, v2, ref2, items, slot, G, lr_t=1e-3, scal=scal)
+    torch.cuda.synchronize()
+    assert torch.equal(p, p2) and torch.equal(sh0[off: off + items * H].view(items, H), ref2) and torch.equal(sh0, sh1)
+    # push: one source block into slot 1 of two destination buffers
+    src = torch.randn(256, device="cuda")
+    d0 = torch.zeros(3, 256, device="cuda"); d1 = torch.zeros(3, 256, device="cuda")
+    ops.peer_push(src, 1024, ops.peer_table([d0.data_ptr(), d1.data_ptr()]), 1024, 2)
+    torch.cuda.synchronize()
+    assert torch.equal(d0[1], src) and torch.equal(d1[1], src) and (d0[0] == 0).all() and (d0[2] == 0).all()
+    # barrier / small all-reduce with a single rank: must not hang, must leave the values alone, must advance the epochs
+    pads = torch.zeros(ops.PEER_SLOTS * 8, dtype=torch.int32, device="cuda"); epochs = torch.zeros(ops.PEER_SLOTS, dtype=torch.int32, device="cuda")
+    tab_p = ops.peer_table([pads.data_ptr()])
+    vals = torch.arange(16, dtype=torch.float32, device="cuda")
+    ops.peer_barrier(tab_p, 0, 1, 2, epochs)
+    ops.peer_allreduce_small(ops.peer_table([vals.data_ptr()]), 3, 2, tab_p, 0, 1, 0, epochs)
+    torch.cuda.synchronize()
+    assert torch.equal(vals, torch.arange(16, dtype=torch.float32, device="cuda"))
+    assert epochs.tolist() == [2, 0, 1, 0]
