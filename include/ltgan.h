@@ -155,7 +155,9 @@ int ltg_adam(float* p, float* m, float* v, const float* g, int n_partials, int64
  * Every table argument is a HOST array of `world` (<= 8) device pointers, entry r = rank r's instance of a peer-mapped buffer
  * (CUDA VMM / symmetric memory set up by the caller; entry `rank` is the local one). `pads` = peer-mapped uint32
  * [LTG_PEER_SLOTS][8] signal words, zero-initialised; `epochs` = local device uint32[LTG_PEER_SLOTS], zero-initialised.
- * All ranks must issue the same sequence of barrier-carrying calls per slot; one slot per stream that issues them.      */
+ * All ranks must issue the same sequence of barrier-carrying calls per slot; one slot per stream that issues them.
+ * `*_mc` arguments: the NVLS multicast address of the same buffer (NULL = unicast loads/stores to every table entry): stores
+ * are replicated and gradient loads are summed inside the NVSwitch (multimem.st / multimem.ld_reduce).                     */
 #define LTG_PEER_SLOTS 4
 /* every rank has executed all work ordered before this call on its stream (and its peer writes are visible) */
 int ltg_peer_barrier(void* const* pads, int rank, int world, int slot, uint32_t* epochs, void* stream);
@@ -165,16 +167,17 @@ int ltg_peer_allreduce_small(void* const* bufs, int64_t offset, int count, void*
 /* out[i] = sum_r bufs[r][offset + i], i < n; `out` must not be one of the peer-visible buffers; caller orders it with barriers */
 int ltg_peer_reduce(void* const* bufs, int64_t offset, int64_t n, int world, float* out, void* stream);
 /* copy `bytes` from src to byte offset dst_offset_bytes of every rank's dst buffer (all-gather by pushing; 16-byte granularity) */
-int ltg_peer_push(const void* src, int64_t bytes, void* const* dst, int64_t dst_offset_bytes, int world, void* stream);
+int ltg_peer_push(const void* src, int64_t bytes, void* const* dst, void* dst_mc, int64_t dst_offset_bytes, int world, void* stream);
 /* ltg_adam over this rank's shard p/m/v[n] = elements [offset, offset+n) of the full tensor, with the reduce-scatter and the
  * all-gather fused in: g = sum_r grads[r][offset+i] (fp32, read from every rank), bf16(p) stored to shadows_bf16[r][offset+i]
  * of every rank. offset and n multiples of 4.                                                                            */
-int ltg_adam_peer(float* p, float* m, float* v, void* const* grads, void* const* shadows_bf16, int64_t offset, int64_t n, int world,
-                  float lr_t, const float* scal, float beta1, float beta2, float eps, void* stream);
+int ltg_adam_peer(float* p, float* m, float* v, void* const* grads, const float* grads_mc, void* const* shadows_bf16, void* shadows_mc,
+                  int64_t offset, int64_t n, int world, float lr_t, const float* scal, float beta1, float beta2, float eps, void* stream);
 
 /* ltg_enc_adam over this rank's item rows (p/m/v = shard base, slot_of_item = shard-local table) with the all-gather fused in:
  * the updated bf16 row is stored at element offset `offset` + local index of every rank's encoder shadow.                   */
-int ltg_enc_adam_peer(float* p, float* m, float* v, void* const* shadows_bf16, int64_t offset, int n_items, const int32_t* slot_of_item,
+int ltg_enc_adam_peer(float* p, float* m, float* v, void* const* shadows_bf16, void* shadows_mc, int64_t offset, int n_items,
+                      const int32_t* slot_of_item,
                       const float* G, int world, float lr_t, const float* scal, float beta1, float beta2, float eps, void* stream);
 
 /* Encoder weight W_q0 [n_items, H]. Its gradient X^T dh1pre is non-zero only on the batch's ACTIVE items, so it is built

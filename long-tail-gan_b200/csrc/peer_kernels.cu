@@ -42,6 +42,22 @@ __device__ __forceinline__ float ld_peer_f(const float* p) {
   return v;
 }
 
+// NVLS multicast (NVSwitch): one store to the multicast address lands in every rank's buffer (egress 1x instead of world-1 x),
+// one ld_reduce returns the sum of every rank's value, added inside the switch (ingress 1x).
+__device__ __forceinline__ float4 mm_ld_reduce_f4(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void mm_st_b64(void* mc, uint2 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1,%2};" ::"l"(mc), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)) : "memory");
+}
+__device__ __forceinline__ void mm_st_b128(void* mc, uint4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)),
+               "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w)) : "memory");
+}
+
 // Executed by the first warp of ONE CTA. `e` is the barrier number (the same on every rank).
 __device__ __forceinline__ void peer_barrier_warp(const PeerPtrs& pads, int rank, int world, int slot, uint32_t e) {
   const int lane = threadIdx.x & 31;
@@ -99,31 +115,41 @@ peer_reduce_kernel(PeerPtrs bufs, int64_t offset, int64_t n, int world, float* _
 }
 
 __global__ void __launch_bounds__(256)
-peer_push_kernel(const uint4* __restrict__ src, int64_t n16, PeerPtrs dst, int64_t dst_off16, int world) {
+peer_push_kernel(const uint4* __restrict__ src, int64_t n16, PeerPtrs dst, uint4* dst_mc, int64_t dst_off16, int world) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
     const uint4 v = __ldg(src + i);
-    for (int r = 0; r < world; ++r) reinterpret_cast<uint4*>(dst.p[r])[dst_off16 + i] = v;
+    if (dst_mc != nullptr) {
+      mm_st_b128(dst_mc + dst_off16 + i, v);
+    } else {
+      for (int r = 0; r < world; ++r) reinterpret_cast<uint4*>(dst.p[r])[dst_off16 + i] = v;
+    }
   }
 }
 
 // Same update as adam_kernel (adam_kernels.cu); g = sum over ranks of their gradient rows, bf16 result stored to every rank.
 __global__ void __launch_bounds__(256)
-adam_peer_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, PeerPtrs grads, PeerPtrs shadows, int64_t offset,
-                 int64_t n, int world, float lr_t, const float* __restrict__ scal, float b1, float b2, float eps) {
+adam_peer_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, PeerPtrs grads, const float* grads_mc, PeerPtrs shadows,
+                 __nv_bfloat16* shadows_mc, int64_t offset, int64_t n, int world, float lr_t, const float* __restrict__ scal, float b1,
+                 float b2, float eps) {
   if (lr_t < 0.f) lr_t = scal[LTG_S_LR_T];
   const int64_t n4 = n >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 pp = ld_stream_f4(p + 4 * i), mm = ld_stream_f4(m + 4 * i), vv = ld_stream_f4(v + 4 * i);
-    float4 g[PEER_MAX];
+    float4 gg;
+    if (grads_mc != nullptr) {
+      gg = mm_ld_reduce_f4(grads_mc + offset + 4 * i);   // summed inside the NVSwitch; each element is reduced by its owner only
+    } else {
+      float4 g[PEER_MAX];
 #pragma unroll
-    for (int r = 0; r < PEER_MAX; ++r)
-      if (r < world) g[r] = ld_peer_f4(reinterpret_cast<const float*>(grads.p[r]) + offset + 4 * i);
-    float4 gg = g[0];
+      for (int r = 0; r < PEER_MAX; ++r)
+        if (r < world) g[r] = ld_peer_f4(reinterpret_cast<const float*>(grads.p[r]) + offset + 4 * i);
+      gg = g[0];
 #pragma unroll
-    for (int r = 1; r < PEER_MAX; ++r)
-      if (r < world) { gg.x += g[r].x; gg.y += g[r].y; gg.z += g[r].z; gg.w += g[r].w; }   // rank order on every rank
+      for (int r = 1; r < PEER_MAX; ++r)
+        if (r < world) { gg.x += g[r].x; gg.y += g[r].y; gg.z += g[r].z; gg.w += g[r].w; }   // rank order on every rank
+    }
     mm.x = b1 * mm.x + (1.f - b1) * gg.x; mm.y = b1 * mm.y + (1.f - b1) * gg.y;
     mm.z = b1 * mm.z + (1.f - b1) * gg.z; mm.w = b1 * mm.w + (1.f - b1) * gg.w;
     vv.x = b2 * vv.x + (1.f - b2) * gg.x * gg.x; vv.y = b2 * vv.y + (1.f - b2) * gg.y * gg.y;
@@ -132,16 +158,21 @@ adam_peer_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict
     pp.z -= lr_t * mm.z / (sqrtf(vv.z) + eps); pp.w -= lr_t * mm.w / (sqrtf(vv.w) + eps);
     st_stream_f4(p + 4 * i, pp); st_stream_f4(m + 4 * i, mm); st_stream_f4(v + 4 * i, vv);
     uint2 s; s.x = pack_bf16x2(pp.x, pp.y); s.y = pack_bf16x2(pp.z, pp.w);
+    if (shadows_mc != nullptr) {
+      mm_st_b64(shadows_mc + offset + 4 * i, s);
+    } else {
 #pragma unroll
-    for (int r = 0; r < PEER_MAX; ++r)
-      if (r < world) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(shadows.p[r]) + offset + 4 * i) = s;
+      for (int r = 0; r < PEER_MAX; ++r)
+        if (r < world) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(shadows.p[r]) + offset + 4 * i) = s;
+    }
   }
 }
 
 // enc_adam_kernel (adam_kernels.cu) over this rank's item rows [item0, item0 + n_items): the compact gradient G already holds the
 // global batch (activation exchange), so only the all-gather is fused in: the bf16 row goes to every rank's encoder shadow.
 __global__ void __launch_bounds__(256)
-enc_adam_peer_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, PeerPtrs shadows, int64_t offset, int n_items,
+enc_adam_peer_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, PeerPtrs shadows, __nv_bfloat16* shadows_mc,
+                     int64_t offset, int n_items,
                      const int32_t* __restrict__ slot_of_item, const float* __restrict__ G, int world, float lr_t,
                      const float* __restrict__ scal, float b1, float b2, float eps) {
   constexpr int H4 = LTG_H / 4;
@@ -163,9 +194,13 @@ enc_adam_peer_kernel(float* __restrict__ p, float* __restrict__ m, float* __rest
     pp.z -= lr_t * mm.z / (sqrtf(vv.z) + eps); pp.w -= lr_t * mm.w / (sqrtf(vv.w) + eps);
     st_stream_f4(p + 4 * i, pp); st_stream_f4(m + 4 * i, mm); st_stream_f4(v + 4 * i, vv);
     uint2 s; s.x = pack_bf16x2(pp.x, pp.y); s.y = pack_bf16x2(pp.z, pp.w);
+    if (shadows_mc != nullptr) {
+      mm_st_b64(shadows_mc + offset + 4 * i, s);
+    } else {
 #pragma unroll
-    for (int r = 0; r < PEER_MAX; ++r)
-      if (r < world) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(shadows.p[r]) + offset + 4 * i) = s;
+      for (int r = 0; r < PEER_MAX; ++r)
+        if (r < world) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(shadows.p[r]) + offset + 4 * i) = s;
+    }
   }
 }
 
@@ -222,22 +257,23 @@ extern "C" int ltg_peer_reduce(void* const* bufs, int64_t offset, int64_t n, int
   return LTG_OK;
 }
 
-extern "C" int ltg_peer_push(const void* src, int64_t bytes, void* const* dst, int64_t dst_offset_bytes, int world, void* stream) {
+extern "C" int ltg_peer_push(const void* src, int64_t bytes, void* const* dst, void* dst_mc, int64_t dst_offset_bytes, int world, void* stream) {
   PeerPtrs pd;
   int rc = load_ptrs(&pd, dst, world);
   if (rc) return rc;
   LTG_REQUIRE(src != nullptr && bytes >= 0 && bytes % 16 == 0 && dst_offset_bytes >= 0 && dst_offset_bytes % 16 == 0);
-  LTG_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  LTG_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst_mc) & 15) == 0);
   for (int r = 0; r < world; ++r) LTG_REQUIRE((reinterpret_cast<uintptr_t>(dst[r]) & 15) == 0);
   if (bytes == 0) return LTG_OK;
   peer_push_kernel<<<stream_grid(bytes >> 4), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(src), bytes >> 4, pd,
-                                                                              dst_offset_bytes >> 4, world);
+                                                                              reinterpret_cast<uint4*>(dst_mc), dst_offset_bytes >> 4, world);
   LTG_CHECK_LAUNCH();
   return LTG_OK;
 }
 
-extern "C" int ltg_adam_peer(float* p, float* m, float* v, void* const* grads, void* const* shadows_bf16, int64_t offset, int64_t n,
-                             int world, float lr_t, const float* scal, float beta1, float beta2, float eps, void* stream) {
+extern "C" int ltg_adam_peer(float* p, float* m, float* v, void* const* grads, const float* grads_mc, void* const* shadows_bf16,
+                             void* shadows_mc, int64_t offset, int64_t n, int world, float lr_t, const float* scal, float beta1,
+                             float beta2, float eps, void* stream) {
   PeerPtrs pg, ps;
   int rc = load_ptrs(&pg, grads, world);
   if (rc) return rc;
@@ -249,12 +285,14 @@ extern "C" int ltg_adam_peer(float* p, float* m, float* v, void* const* grads, v
   for (int r = 0; r < world; ++r)
     LTG_REQUIRE((reinterpret_cast<uintptr_t>(grads[r]) & 15) == 0 && (reinterpret_cast<uintptr_t>(shadows_bf16[r]) & 7) == 0);
   if (n <= 0) return LTG_OK;
-  adam_peer_kernel<<<stream_grid(n >> 2), 256, 0, (cudaStream_t)stream>>>(p, m, v, pg, ps, offset, n, world, lr_t, scal, beta1, beta2, eps);
+  LTG_REQUIRE((reinterpret_cast<uintptr_t>(grads_mc) & 15) == 0 && (reinterpret_cast<uintptr_t>(shadows_mc) & 7) == 0);
+  adam_peer_kernel<<<stream_grid(n >> 2), 256, 0, (cudaStream_t)stream>>>(p, m, v, pg, grads_mc, ps, reinterpret_cast<__nv_bfloat16*>(shadows_mc), offset, n,
+                                                                          world, lr_t, scal, beta1, beta2, eps);
   LTG_CHECK_LAUNCH();
   return LTG_OK;
 }
 
-extern "C" int ltg_enc_adam_peer(float* p, float* m, float* v, void* const* shadows_bf16, int64_t offset, int n_items,
+extern "C" int ltg_enc_adam_peer(float* p, float* m, float* v, void* const* shadows_bf16, void* shadows_mc, int64_t offset, int n_items,
                                  const int32_t* slot_of_item, const float* G, int world, float lr_t, const float* scal, float beta1,
                                  float beta2, float eps, void* stream) {
   PeerPtrs ps;
@@ -265,7 +303,7 @@ extern "C" int ltg_enc_adam_peer(float* p, float* m, float* v, void* const* shad
   for (int r = 0; r < world; ++r) LTG_REQUIRE((reinterpret_cast<uintptr_t>(shadows_bf16[r]) & 7) == 0);
   if (n_items <= 0) return LTG_OK;
   enc_adam_peer_kernel<<<stream_grid((int64_t)n_items * (LTG_H / 4)), 256, 0, (cudaStream_t)stream>>>(
-      p, m, v, ps, offset, n_items, slot_of_item, G, world, lr_t, scal, beta1, beta2, eps);
+      p, m, v, ps, reinterpret_cast<__nv_bfloat16*>(shadows_mc), offset, n_items, slot_of_item, G, world, lr_t, scal, beta1, beta2, eps);
   LTG_CHECK_LAUNCH();
   return LTG_OK;
 }

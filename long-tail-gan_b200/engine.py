@@ -484,7 +484,7 @@ class GanEngine(object):
                 if self.nrows > 0:
                     r0, nr = self.row0, self.nrows
                     ops.adam_peer(v.WdT[r0:r0 + nr], v.WdT_m[r0:r0 + nr], v.WdT_v[r0:r0 + nr], self.peer["dWdT"], self.peer["WdT_b"], r0 * H,
-                                  self.world_size, scal=self.scal)
+                                  self.world_size, scal=self.scal, grads_mc=self.peer["dWdT_mc"], shadows_mc=self.peer["WdT_b_mc"])
         if dp_comm and self.peer is None and self.nrows > 0:
             # Adam on this rank's decoder rows: after the reduce-scatter (same branch) and after dgrad (it reads the bf16 weights;
             # the shard Adam only writes the shard staging buffer, the full shadow is replaced by the all-gather at the end)
@@ -547,7 +547,7 @@ class GanEngine(object):
                                  self.keep_vae, self.seed, 0, self.words, self.Xc_glob)
             if self.peer is not None:
                 nb_ = self.dh1pre_b.numel() * 2
-                ops.peer_push(self.dh1pre_b, nb_, self.peer["dh1"], self.rank * nb_, self.world_size)
+                ops.peer_push(self.dh1pre_b, nb_, self.peer["dh1"], self.rank * nb_, self.world_size, dst_mc=self.peer["dh1_mc"])
                 self._pbar(0)
             else:
                 dist.all_gather_into_tensor(self.dh1_glob, self.dh1pre_b)   # rows beyond B meet all-zero Xc rows
@@ -558,7 +558,7 @@ class GanEngine(object):
                 r0, nr = self.row0, self.nrows
                 if self.peer is not None:   # Adam on the shard rows, bf16 rows stored straight into every rank's encoder shadow
                     ops.enc_adam_peer(v.W_q0[r0:r0 + nr], v.W_q0_m[r0:r0 + nr], v.W_q0_v[r0:r0 + nr], self.peer["Wq0_b"], r0 * H, nr,
-                                      tb["slot_local"], self.G_shard, self.world_size, scal=self.scal)
+                                      tb["slot_local"], self.G_shard, self.world_size, scal=self.scal, shadows_mc=self.peer["Wq0_b_mc"])
                 else:
                     ops.enc_adam(v.W_q0[r0:r0 + nr], v.W_q0_m[r0:r0 + nr], v.W_q0_v[r0:r0 + nr], self.Wq0_b_shard, nr, tb["slot_local"],
                                  self.G_shard, scal=self.scal)
@@ -661,7 +661,7 @@ class GanEngine(object):
             self._dp_comm = False
             r0, nr = self.row0, self.nrows
             if nr > 0 and self.dp_tables is None:   # (with the activation exchange, enc_adam_peer has already stored them)
-                ops.peer_push(self.Wq0_b_shard, nr * H * 2, pr["Wq0_b"], r0 * H * 2, N)
+                ops.peer_push(self.Wq0_b_shard, nr * H * 2, pr["Wq0_b"], r0 * H * 2, N, dst_mc=pr["Wq0_b_mc"])
             self._pbar(0)   # every rank's small gradients are final
             ops.peer_reduce(pr["small_g"], 0, v.small_g.numel(), N, self.small_gsum)
             ops.adam(v.small, v.small_m, v.small_v, self.small_gsum, v.small_b, scal=self.scal)
@@ -687,19 +687,25 @@ class GanEngine(object):
         try:
             import torch.distributed._symmetric_memory as symm
             handles = []
+            mc = {}
+            # NVLS multicast stores / in-switch reduction (multimem.*): measured on B200 x8 5.11 M vs 4.87 M users/s with unicast
+            # peer accesses, but slower at 2 ranks (1.38 M vs 1.48 M), where a unicast access already moves every byte once
+            mc_env = os.environ.get("LTG_DP_MULTICAST", "")
+            use_mc = (self.world_size >= 4) if mc_env == "" else (mc_env != "0")
 
             def sym(like):
                 t = symm.empty(*like.shape, dtype=like.dtype, device=self.device)
                 t.copy_(like)
                 h = symm.rendezvous(t, dist.group.WORLD)
                 handles.append(h)
+                mc[len(handles) - 1] = int(h.multicast_ptr) if use_mc else 0
                 return t, ops.peer_table(h.buffer_ptrs)
 
             peer = {}
-            self.dWdT_full, peer["dWdT"] = sym(self.dWdT_full)
-            self.WdT_b_full, peer["WdT_b"] = sym(self.WdT_b_full)
-            self.Wq0_b_full, peer["Wq0_b"] = sym(self.Wq0_b_full)
-            self.dh1_glob, peer["dh1"] = sym(self.dh1_glob)
+            self.dWdT_full, peer["dWdT"] = sym(self.dWdT_full); peer["dWdT_mc"] = mc[0]
+            self.WdT_b_full, peer["WdT_b"] = sym(self.WdT_b_full); peer["WdT_b_mc"] = mc[1]
+            self.Wq0_b_full, peer["Wq0_b"] = sym(self.Wq0_b_full); peer["Wq0_b_mc"] = mc[2]
+            self.dh1_glob, peer["dh1"] = sym(self.dh1_glob); peer["dh1_mc"] = mc[3]
             self.scal, peer["scal"] = sym(self.scal)
             self.disc.arena_g, peer["arena_g"] = sym(self.disc.arena_g)
             self.vae.small_g, peer["small_g"] = sym(self.vae.small_g)

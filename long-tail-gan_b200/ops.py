@@ -214,20 +214,22 @@ def peer_reduce(bufs, offset, n, world, out):
     check(lib().ltg_peer_reduce(bufs, offset, n, world, ptr(out), _stream()))
 
 
-def peer_push(src, nbytes, dst, dst_offset_bytes, world):
+def peer_push(src, nbytes, dst, dst_offset_bytes, world, dst_mc=None):
     _count(1)
-    check(lib().ltg_peer_push(ptr(src), nbytes, dst, dst_offset_bytes, world, _stream()))
+    check(lib().ltg_peer_push(ptr(src), nbytes, dst, dst_mc or None, dst_offset_bytes, world, _stream()))
 
 
-def adam_peer(p, m, v, grads, shadows, offset, world, lr_t=-1.0, scal=None, beta1=0.9, beta2=0.999, eps=1e-8):
+def adam_peer(p, m, v, grads, shadows, offset, world, lr_t=-1.0, scal=None, beta1=0.9, beta2=0.999, eps=1e-8, grads_mc=None, shadows_mc=None):
     _count(1)
-    check(lib().ltg_adam_peer(ptr(p), ptr(m), ptr(v), grads, shadows, offset, p.numel(), world, lr_t, ptr(scal), beta1, beta2, eps, _stream()))
+    check(lib().ltg_adam_peer(ptr(p), ptr(m), ptr(v), grads, grads_mc or None, shadows, shadows_mc or None, offset, p.numel(), world, lr_t,
+                              ptr(scal), beta1, beta2, eps, _stream()))
 
 
-def enc_adam_peer(p, m, v, shadows, offset, n_items, slot_of_item, G, world, lr_t=-1.0, scal=None, beta1=0.9, beta2=0.999, eps=1e-8):
+def enc_adam_peer(p, m, v, shadows, offset, n_items, slot_of_item, G, world, lr_t=-1.0, scal=None, beta1=0.9, beta2=0.999, eps=1e-8,
+                  shadows_mc=None):
     _count(1)
-    check(lib().ltg_enc_adam_peer(ptr(p), ptr(m), ptr(v), shadows, offset, n_items, ptr(slot_of_item), ptr(G), world, lr_t, ptr(scal), beta1,
-                                  beta2, eps, _stream()))
+    check(lib().ltg_enc_adam_peer(ptr(p), ptr(m), ptr(v), shadows, shadows_mc or None, offset, n_items, ptr(slot_of_item), ptr(G), world, lr_t,
+                                  ptr(scal), beta1, beta2, eps, _stream()))
 
 
 def enc_wgrad_compact(G, n_active, act_ptr, csc_row, csc_pos, coef, dh1pre):

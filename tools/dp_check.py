@@ -46,7 +46,7 @@ def main():
     e.gather_master()
     # every rank's bf16 shadows (what its next forward reads) must be the rounding of the gathered fp32 masters
     ok_b = bool(torch.equal(vae.WdT_b, vae.WdT.bfloat16())) and bool(torch.equal(vae.W_q0_b, vae.W_q0.bfloat16()))
-    print("rank %d: exchange path = %s, bf16 shadows consistent = %s" % (rank, "peer memory" if e.peer is not None else "NCCL collectives", ok_b),
+    print("rank %d: exchange path = %s, bf16 shadows consistent = %s" % (rank, ("peer memory, multicast %s" % ("on" if e.peer["dWdT_mc"] else "off")) if e.peer is not None else "NCCL collectives", ok_b),
           flush=True)
     assert ok_b
     dist.barrier()
