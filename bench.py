@@ -43,12 +43,14 @@ def parse():
     return ap.parse_args()
 
 
-def measured_peaks():
+def measured_peaks(key="hbm_gbs"):
+    """HBM GB/s or dense bf16 TFLOP/s (burst figure: the kernels are timed alone, back to back) from the driver-written file."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         d = json.load(open(path))
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        if key in d:
+            return float(d[key]), "measured (MEASURED_PEAKS.json %s)" % key
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}[key], "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler(object):
@@ -285,11 +287,24 @@ def main():
     t_enc_adam = timed(lambda i: ops.enc_adam(vae.W_q0, vae.W_q0_m, vae.W_q0_v, vae.W_q0_b, I, bt0["slot_of_item"], engine.G_enc,
                                               scal=engine.scal), 50)
 
+    # the fused discriminator forward: its two launches per step (D: real + generated pairs with the head's backward; G: generated
+    # pairs, forward only) on the pair tables of batch 0
+    dsc = engine.disc
+    t_df_d = t_df_g = 0.0
+    if engine.fused_disc:
+        st_d = ops.STREAM_DISC_DROPOUT
+        gw4 = engine.arena_gp[0][dsc._off["w4"][0]: dsc._off["w4"][0] + dsc._off["w4"][1]]
+        gb4 = engine.arena_gp[0][dsc._off["b4"][0]: dsc._off["b4"][0] + dsc._off["b4"][1]]
+        t_df_d = timed(lambda i: ops.disc_fwd_fused(engine.Xp, engine.Xn, bt0["P"], dsc, bt0["label"], engine.keep_d, engine.seed, st_d,
+                                                    engine.words, engine.Hd, engine.y, engine.scal, engine.dz3, gw4, gb4), 30)
+        t_df_g = timed(lambda i: ops.disc_fwd_fused(engine.Xp, engine.Xn, bt0["K"], dsc, bt0["label"][bt0["Pr"]:], engine.keep_d, engine.seed,
+                                                    st_d, engine.words, engine.Hd, engine.y, engine.scal), 30)
+
     # max over ranks (device time)
-    times = torch.tensor([ms, ms_e2e, t_a, t_d, t_g, t_adam, t_enc_adam], dtype=torch.float64, device="cuda")
+    times = torch.tensor([ms, ms_e2e, t_a, t_d, t_g, t_adam, t_enc_adam, t_df_d, t_df_g], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, t_a, t_d, t_g, t_adam, t_enc_adam = [float(x) for x in times.cpu()]
+    ms, ms_e2e, t_a, t_d, t_g, t_adam, t_enc_adam, t_df_d, t_df_g = [float(x) for x in times.cpu()]
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -303,15 +318,47 @@ def main():
                     traffic = rec["dram_total_MB"] * 1e6
         except Exception:
             traffic = None
-        roof = dict(bound="hbm", kernel="adam_kernel (fused TF-Adam + bf16 shadow over W_dec^T [I,600])",
-                    achieved=adam_bytes / (t_adam * 1e-3) / 1e9, peak=peak, unit="GB/s", frac=adam_bytes / (t_adam * 1e-3) / 1e9 / peak,
-                    traffic=traffic, traffic_source="profiles/r1_ncu_adam_full.json (ncu --set full; writes still resident in L2 at kernel end are not counted)",
-                    peak_source=peak_src, algorithmic_bytes_per_launch=adam_bytes, ms_per_launch=t_adam,
-                    how="CUDA events around 50 back-to-back launches on the launching stream after the timed region; each launch "
-                        "touches 362 MB (> L2)",
-                    second=dict(kernel="enc_adam_kernel (TF-Adam over W_q0 [I,600], gradient rows fetched through slot_of_item)",
-                                achieved=enc_bytes / (t_enc_adam * 1e-3) / 1e9, frac=enc_bytes / (t_enc_adam * 1e-3) / 1e9 / peak,
-                                algorithmic_bytes_per_launch=enc_bytes, ms_per_launch=t_enc_adam))
+        adam_roof = dict(bound="hbm", kernel="adam_kernel (fused TF-Adam + bf16 shadow over W_dec^T [I,600])",
+                         achieved=adam_bytes / (t_adam * 1e-3) / 1e9, peak=peak, unit="GB/s", frac=adam_bytes / (t_adam * 1e-3) / 1e9 / peak,
+                         traffic=traffic, traffic_source="profiles/r1_ncu_adam_full.json (ncu --set full; writes still resident in L2 at kernel end are not counted)",
+                         peak_source=peak_src, algorithmic_bytes_per_launch=adam_bytes, ms_per_launch=t_adam, us_per_step=t_adam * 1e3,
+                         how="CUDA events around 50 back-to-back launches on the launching stream after the timed region; each launch "
+                             "touches 362 MB (> L2)")
+        enc_roof = dict(bound="hbm", kernel="enc_adam_kernel (TF-Adam over W_q0 [I,600], gradient rows fetched through slot_of_item)",
+                        achieved=enc_bytes / (t_enc_adam * 1e-3) / 1e9, peak=peak, unit="GB/s", frac=enc_bytes / (t_enc_adam * 1e-3) / 1e9 / peak,
+                        algorithmic_bytes_per_launch=enc_bytes, ms_per_launch=t_enc_adam, us_per_step=t_enc_adam * 1e3)
+        roof = adam_roof
+        roof["others"] = [enc_roof]
+        if engine.fused_disc and (t_df_d + t_df_g) > t_adam:
+            # By kernel name the fused discriminator forward (two launches per step) now takes the largest share of the step
+            # (profiles/r1_launches_summary_v6.txt), so it is the kernel the roofline line is about. It is GEMM-shaped work (three
+            # chained tcgen05 MMAs per 128 pairs), so it is rated against the tensor roof -- knowing that with K = 128 / 128 / 408 the
+            # MMAs need ~3% of its time and the tanh + counter-hash dropout epilogue (ncu: 21 instructions per activation, IPC 1.5)
+            # is what binds. The two HBM-bound Adam sweeps (the floor of a dense-Adam step) follow in `others`.
+            tpeak, tsrc = measured_peaks("bf16_tflops")
+            fl_pair = 2.0 * ((H0 + 1) * H1 + (H0 + 1) * H2 + (H1 + H2 + 1) * H3) + 2.0 * H3
+            n_d, n_g = int(bt0["P"]), int(bt0["K"])
+            flops = 0.5 * fl_pair * (n_d + n_g)                      # per launch, averaged over the step's two launches
+            t_avg = 0.5 * (t_df_d + t_df_g)
+            by_pair = 2 * 128 * 2 + dsc.k3 * 2                       # gathered rows in, hidden activation out
+            bytes_avg = 0.5 * (n_d * (by_pair + dsc.ld3 * 2) + n_g * by_pair)
+            tr = None
+            try:
+                tr = 0.5 * sum(float(x) for x in json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_disc_fused.json")))["dram_bytes_per_launch"])
+            except Exception:
+                tr = None
+            roof = dict(bound="tensor", kernel="disc_fused_kernel (discriminator forward: 3 chained tcgen05 MMAs + tanh/dropout epilogues + head per 128 pairs)",
+                        achieved=flops / (t_avg * 1e-3) / 1e12, peak=tpeak, unit="TFLOP/s", frac=flops / (t_avg * 1e-3) / 1e12 / tpeak,
+                        traffic=tr, traffic_source="profiles/r1_ncu_disc_fused.json (ncu --set full, mean of the D and the G launch)",
+                        peak_source=tsrc, algorithmic_flops_per_launch=flops, algorithmic_bytes_per_launch=bytes_avg,
+                        ms_per_launch=t_avg, us_per_step=(t_df_d + t_df_g) * 1e3,
+                        launches=dict(D=dict(pairs=n_d, ms=t_df_d), G=dict(pairs=n_g, ms=t_df_g)),
+                        hbm_view=dict(achieved=bytes_avg / (t_avg * 1e-3) / 1e9, peak=peak, unit="GB/s", frac=bytes_avg / (t_avg * 1e-3) / 1e9 / peak),
+                        binding_limit="epilogue instruction issue (SFU tanh + integer hash dropout), not the tensor pipe or HBM: "
+                                      "profiles/r1_ncu_disc_fused.txt",
+                        how="CUDA events around 30 back-to-back launches of each of the step's two configurations on the launching stream",
+                        others=[adam_roof, enc_roof])
+            adam_roof.pop("others", None)
         line = dict(metric="gan_step_users_per_sec", value=users / (ms * 1e-3), unit="users/s", n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="bf16", data="synthetic", config=workload_config(world),

@@ -151,6 +151,14 @@ int ltg_dec_row_bwd(const float* partial, int n_blocks, const void* logits_bf16,
  * g may be given as n_partials buffers (g + s*partial_stride: split-K partials of the weight-gradient GEMMs), summed on the fly. */
 int ltg_adam(float* p, float* m, float* v, const float* g, int n_partials, int64_t partial_stride, void* shadow_bf16, int64_t n,
              float lr_t, const float* scal, float beta1, float beta2, float eps, void* stream);
+/* Weight-gradient GEMM with the optimizer step as its epilogue (decoder W_p1^T, single GPU): G[M,N] = A^T B with A bf16 stored
+ * [K, lda >= M] and B bf16 stored [K, ldb >= N] (for the decoder: A = dlogits [B, I], B = [h2 | 1] [B, 601]); for columns
+ * < n_cols the accumulator is the complete gradient and ltg_adam's update is applied to p/m/v fp32 [M, ld] and the bf16 shadow
+ * in place, so the fp32 gradient matrix is never written; column aux_col (bias gradient) goes to aux_out[M]. train.py:163-164. */
+int ltg_wgrad_adam(const void* A, int lda, const void* B, int ldb, int M, int N, int K, float* p, float* m, float* v, void* shadow_bf16,
+                   int ld, int n_cols, int aux_col, float* aux_out, float lr_t, const float* scal, float beta1, float beta2, float eps,
+                   void* stream);
+
 /* ---- e: data-parallel exchange over NVLink peer memory (one node) ------------------------------------------
  * Every table argument is a HOST array of `world` (<= 8) device pointers, entry r = rank r's instance of a peer-mapped buffer
  * (CUDA VMM / symmetric memory set up by the caller; entry `rank` is the local one). `pads` = peer-mapped uint32

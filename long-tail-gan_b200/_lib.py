@@ -100,6 +100,7 @@ SIGNATURES = {
     "ltg_enc_wgrad_expand": (_I, [_P, _I, _P, _P, _P]),
     "ltg_sample_pairs": (_I, [_P, _I, _I, _I, _I64, _P, _P, _P, _P, _P, _P, _U64, _U32, _P, _P, _P, _P, _P, _I, _P, _P]),
     "ltg_dec_row_bwd": (_I, [_P, _I, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ltg_wgrad_adam": (_I, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _P, _F, _P, _F, _F, _F, _P]),
     "ltg_peer_barrier": (_I, [_P, _I, _I, _I, _P, _P]),
     "ltg_peer_allreduce_small": (_I, [_P, _I64, _I, _P, _I, _I, _I, _P, _P]),
     "ltg_peer_reduce": (_I, [_P, _I64, _I64, _I, _P, _P]),

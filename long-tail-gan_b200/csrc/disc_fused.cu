@@ -46,11 +46,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volati
 // v <- dropout(v) with one hash per pair of adjacent columns (same indices as EpiStore::chunk)
 __device__ __forceinline__ void drop16(float (&v)[16], uint32_t key, uint32_t thr16, float inv_keep, int row, int rng_ld, int col0) {
   const uint64_t pbase = ((uint64_t)row * (uint64_t)rng_ld + (uint64_t)col0) >> 1;
+  const uint32_t thr_hi = thr16 << 16;
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const uint32_t h = ltg_hash_pair(key, pbase + q);
     v[2 * q] = (h & 0xFFFFu) < thr16 ? v[2 * q] * inv_keep : 0.f;
-    v[2 * q + 1] = (h >> 16) < thr16 ? v[2 * q + 1] * inv_keep : 0.f;
+    v[2 * q + 1] = h < thr_hi ? v[2 * q + 1] * inv_keep : 0.f;     // (h >> 16) < thr16 without the shift (thr16 <= 65535 here)
   }
 }
 
@@ -58,6 +59,20 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
   uint4 u;
   u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]); u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
   return u;
+}
+
+// w4[c .. c+16) (zero beyond n); c is a multiple of 16 and w4 is 16-byte aligned
+__device__ __forceinline__ void load_w16(float (&w)[16], const float* __restrict__ w4, int c, int n) {
+  if (c + 16 <= n) {   // warp-uniform
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(w4 + c) + i);
+      w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w[i] = c + i < n ? __ldg(w4 + c + i) : 0.f;
+  }
 }
 
 // 16-byte piece (8 columns starting at g0, a multiple of 8) of row r of the K-major, 128B-swizzled activation tile
@@ -211,10 +226,12 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmXp, const __grid_constan
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = tanh_approx(v[i]);
         if (drop) drop16(v, key, thr16, inv_keep, row, p.ld2, c);
+        if (c + 16 > p.h2) {                     // warp-uniform: only the last chunk(s) hold the ones column / padding
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int g = p.off2 + c + i;
-          if (g >= p.off2 + p.h2) v[i] = (g == p.one3) ? 1.0f : 0.f;
+          for (int i = 0; i < 16; ++i) {
+            const int g = p.off2 + c + i;
+            if (g >= p.off2 + p.h2) v[i] = (g == p.one3) ? 1.0f : 0.f;
+          }
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -251,14 +268,15 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmXp, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = tanh_approx(v[i]);
           if (drop) drop16(v, key, thr16, inv_keep, row, p.ld3, c);
+          float w[16];
+          load_w16(w, p.w4, c, p.ld3);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const uint32_t u = pack_bf16x2(v[2 * i], v[2 * i + 1]);
             yq[j][i] = u;
             const float2 f = unpack_bf16x2(u);   // the head sees the bf16-rounded activation, like the unfused path
-            const int col = c + 2 * i;
-            s = fmaf(f.x, col < p.ld3 ? __ldg(p.w4 + col) : 0.f, s);
-            s = fmaf(f.y, col + 1 < p.ld3 ? __ldg(p.w4 + col + 1) : 0.f, s);
+            s = fmaf(f.x, w[2 * i], s);
+            s = fmaf(f.y, w[2 * i + 1], s);
           }
         } else {
 #pragma unroll
@@ -286,12 +304,12 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmXp, const __grid_constan
         for (int j = 0; j < DF_CH3; ++j) {
           const int c = quarter * 16 + 64 * j;
           if (c < p.ld3) {                       // warp-uniform
-            float d[16], gw[16];
+            float d[16], gw[16], w[16];
+            load_w16(w, p.w4, c, p.ld3);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float2 f = unpack_bf16x2(yq[j][i]);
-              const int col = c + 2 * i;
-              const float w0 = col < p.ld3 ? __ldg(p.w4 + col) : 0.f, w1 = col + 1 < p.ld3 ? __ldg(p.w4 + col + 1) : 0.f;
+              const float w0 = w[2 * i], w1 = w[2 * i + 1];
               float a0, a1;
               if (drop) {
                 const float t0 = f.x * p.keep, t1 = f.y * p.keep;
@@ -375,6 +393,7 @@ extern "C" int ltg_disc_fwd_fused(const void* Xp_bf16, const void* Xn_bf16, int 
                                   const uint32_t* rng_step_dev, void* Hd_bf16, float* y, float* scal, void* dz3_bf16, float* dw4, float* db4,
                                   void* stream) {
   LTG_REQUIRE(Xp_bf16 && Xn_bf16 && W1_bf16 && W2_bf16 && W3_bf16 && w4 && b4 && label && Hd_bf16 && scal);
+  LTG_REQUIRE((reinterpret_cast<uintptr_t>(w4) & 15) == 0);
   LTG_REQUIRE(ltg_disc_fused_supported(k1, ld1, ld2, ld3, off2, one3, h2, k3));
   if (P <= 0) return LTG_OK;
   CUtensorMap tmXp, tmXn, tmW1, tmW2, tmW3;

@@ -60,3 +60,19 @@ extern "C" int ltg_dec_logits_fwd(const void* h2_bf16, int ld_h2, const void* Wd
                                                         reinterpret_cast<const __nv_bfloat16*>(WdT_bf16), LTG_H, B, n_items, LTG_H, 1,
                                                         ep, (cudaStream_t)stream);
 }
+
+// dW = A^T-layout GEMM (A stored [K][M], B stored [K][N]) with the Adam step fused into the epilogue; see EpiAdam.
+extern "C" int ltg_wgrad_adam(const void* A, int lda, const void* B, int ldb, int M, int N, int K, float* p, float* m, float* v,
+                              void* shadow_bf16, int ld, int n_cols, int aux_col, float* aux_out, float lr_t, const float* scal,
+                              float beta1, float beta2, float eps, void* stream) {
+  LTG_REQUIRE(A && B && p && m && v && shadow_bf16);
+  LTG_REQUIRE(ld % 4 == 0 && n_cols % 4 == 0 && n_cols <= ld && n_cols <= N && (aux_col < 0 || aux_out != nullptr));
+  LTG_REQUIRE(lr_t >= 0.f || scal != nullptr);
+  LTG_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(shadow_bf16) & 7) == 0);
+  EpiAdam::Params ep;
+  ep.p = p; ep.m = m; ep.v = v; ep.shadow = reinterpret_cast<__nv_bfloat16*>(shadow_bf16); ep.ld = ld; ep.n_cols = n_cols;
+  ep.aux_col = aux_col; ep.aux_out = aux_out; ep.lr_t = lr_t; ep.scal = scal; ep.b1 = beta1; ep.b2 = beta2; ep.eps = eps;
+  return launch_gemm<128, true, true, EpiAdam>(reinterpret_cast<const __nv_bfloat16*>(A), lda, reinterpret_cast<const __nv_bfloat16*>(B), ldb,
+                                               M, N, K, 1, ep, (cudaStream_t)stream);
+}

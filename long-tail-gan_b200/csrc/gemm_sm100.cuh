@@ -25,6 +25,7 @@
 #pragma once
 #include <cuda.h>
 #include "ltg_common.cuh"
+#include "../../include/ltgan.h"
 
 namespace ltg {
 
@@ -158,16 +159,17 @@ struct GemmShape {
   int splits, kb_per_split;          // split-K: split s covers k blocks [s*kb_per_split, ...)
 };
 
-template <int BN>
+// EPI_SMEM: per-CTA scratch an epilogue asks for (Epi::kSmem); it comes out of the pipeline's stage budget
+template <int BN, int EPI_SMEM = 0>
 __host__ __device__ constexpr int gemm_stages() {
   constexpr int per_stage = GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2;
-  constexpr int s = 196608 / per_stage;
+  constexpr int s = (196608 - EPI_SMEM) / per_stage;
   return s > 8 ? 8 : s;
 }
 
-template <int BN>
+template <int BN, int EPI_SMEM = 0>
 __host__ __device__ constexpr size_t gemm_smem_bytes() {
-  return (size_t)gemm_stages<BN>() * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 1024 /*align slack*/ + 256 /*barriers*/;
+  return (size_t)gemm_stages<BN, EPI_SMEM>() * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_SMEM;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -178,7 +180,7 @@ template <int BN, bool A_MN, bool B_MN, int CM, class Epi>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ GemmShape shape, const __grid_constant__ typename Epi::Params ep) {
-  constexpr int STAGES = gemm_stages<BN>();
+  constexpr int STAGES = gemm_stages<BN, Epi::kSmem>();
   constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   constexpr int B_BYTES = BN * GEMM_BK * 2;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
@@ -202,6 +204,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tfull_bar = bars + 2 * STAGES;    // [2]
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint8_t* epi_scratch = smem + STAGES * (A_BYTES + B_BYTES) + 256;   // Epi::kSmem bytes behind the barrier block
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -318,7 +321,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int row = m_blk * GEMM_BM + sub * 32 + lane;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      Epi epi(ep, row, n0, n_blk * 4 + quarter, split, shape);
+      Epi epi(ep, row, n0, n_blk * 4 + quarter, split, shape, epi_scratch);
       const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
       for (int c = quarter * GEMM_CW; c < BN; c += 4 * GEMM_CW) {
@@ -382,7 +385,8 @@ struct EpiStore {
   uint32_t thr16, key;
   float inv_keep;
   bool drop;
-  __device__ EpiStore(const Params& p_, int row_, int, int, int split_, const GemmShape& s) : p(p_), row(row_), M(s.M), N(s.N), split(split_) {
+  static constexpr int kSmem = 0;
+  __device__ EpiStore(const Params& p_, int row_, int, int, int split_, const GemmShape& s, uint8_t*) : p(p_), row(row_), M(s.M), N(s.N), split(split_) {
     drop = p.keep > 0.f && p.keep < 1.f;
     thr16 = drop ? ltg_keep_threshold16(p.keep) : 65536u;
     inv_keep = drop ? 1.0f / p.keep : 1.0f;
@@ -496,6 +500,100 @@ struct EpiStore {
   __device__ void finish() {}
 };
 
+// Weight-gradient GEMM whose epilogue IS the optimizer step (decoder W_p1^T [I,600], single GPU): the accumulator of output
+// element (item, col) is the complete gradient (K = batch, no split), so TF-Adam (adam_kernels.cu: same formula, same operation
+// order) is applied in place: p, m, v fp32 [M, H] read and written once, bf16 shadow written, and the [I,600] fp32 gradient never
+// exists in HBM (-8 B/param of the 30 B/param the separate gradient store + Adam sweep moved; one 60 us kernel less per step).
+// Thread == row, 16 consecutive columns == 64 contiguous bytes per array. Column `aux_col` (the ones column of the B operand)
+// carries the bias gradient and goes to aux_out[row].
+struct EpiAdam {
+  struct Params {
+    float* p; float* m; float* v; __nv_bfloat16* shadow; int ld;   // [M, ld], ld % 4 == 0
+    int n_cols;                                                    // columns < n_cols are parameters (n_cols % 4 == 0)
+    int aux_col; float* aux_out;
+    float lr_t; const float* scal; float b1, b2, eps;
+  };
+  static constexpr int kSmem = GEMM_EPI_WARPS * 32 * 17 * 4;   // per-warp 32 x 16 fp32 transpose tile (pitch 17: conflict-free)
+  const Params& p;
+  int row, M;
+  float lr_t;
+  float* sw;
+  int n_end;
+  __device__ EpiAdam(const Params& p_, int row_, int n0, int, int, const GemmShape& s, uint8_t* scratch) : p(p_), row(row_), M(s.M) {
+    lr_t = p.lr_t < 0.f ? p.scal[LTG_S_LR_T] : p.lr_t;
+    sw = reinterpret_cast<float*>(scratch) + ((threadIdx.x >> 5) - 2) * (32 * 17);
+    n_end = n0 + 128;                                            // launched with BN = 128 only
+    const int quarter = ((threadIdx.x >> 5) - 2) >> 2;
+    prefetch_chunk(n0 + quarter * GEMM_CW);                      // this warp's first chunk of the tile
+  }
+  // L2 prefetch of the p/m/v pieces this lane will load for the chunk at col0. ncu on the first version: 2.9 TB/s, IPC 0.85 --
+  // every warp walked load -> wait ~1 us -> update -> store chunk after chunk; with the next chunk already on its way to L2 the
+  // loads cost an L2 hit.
+  __device__ __forceinline__ void prefetch_chunk(int col0) const {
+    const int lane = threadIdx.x & 31;
+    const int c4 = (lane & 3) * 4;
+    if (col0 + c4 + 4 > p.n_cols) return;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = row - lane + (lane >> 2) + 8 * j;
+      if (r < M) {
+        const size_t off = (size_t)r * p.ld + col0 + c4;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.p + off));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.m + off));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.v + off));
+      }
+    }
+  }
+  // The accumulator arrives with thread == row (64 B per thread per array, 2400 B apart: 32 half-used sectors per request, measured
+  // 3x slower than the separate Adam sweep). The warp therefore transposes its 32 x 16 chunk through shared memory so that four
+  // lanes cover the 64 contiguous bytes of a row and a request touches 8 rows x 64 B = 16 full sectors.
+  __device__ void chunk(int col0, float (&g)[GEMM_CW]) {
+    const int lane = threadIdx.x & 31;
+    if (row < M && p.aux_col >= col0 && p.aux_col < col0 + GEMM_CW) {
+#pragma unroll
+      for (int i = 0; i < GEMM_CW; ++i)
+        if (col0 + i == p.aux_col) p.aux_out[row] = g[i];
+    }
+    if (col0 + 4 * GEMM_CW < n_end) prefetch_chunk(col0 + 4 * GEMM_CW);   // the chunk this warp handles next (quarters interleave)
+#pragma unroll
+    for (int i = 0; i < GEMM_CW; ++i) sw[lane * 17 + i] = g[i];
+    __syncwarp();
+    const int row_base = row - lane;
+    const int c4 = (lane & 3) * 4;
+    const bool col_ok = col0 + c4 + 4 <= p.n_cols;
+    float4 pp[4], mm[4], vv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {                                // all loads first: 12 independent 16-byte requests per thread
+      const int r = row_base + (lane >> 2) + 8 * j;
+      if (col_ok && r < M) {
+        const size_t off = (size_t)r * p.ld + col0 + c4;
+        pp[j] = ld_stream_f4(p.p + off); mm[j] = ld_stream_f4(p.m + off); vv[j] = ld_stream_f4(p.v + off);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int rl = (lane >> 2) + 8 * j;
+      const int r = row_base + rl;
+      if (col_ok && r < M) {
+        const float gx = sw[rl * 17 + c4], gy = sw[rl * 17 + c4 + 1], gz = sw[rl * 17 + c4 + 2], gw = sw[rl * 17 + c4 + 3];
+        float4 m4 = mm[j], v4 = vv[j], p4 = pp[j];
+        m4.x = p.b1 * m4.x + (1.f - p.b1) * gx; m4.y = p.b1 * m4.y + (1.f - p.b1) * gy;
+        m4.z = p.b1 * m4.z + (1.f - p.b1) * gz; m4.w = p.b1 * m4.w + (1.f - p.b1) * gw;
+        v4.x = p.b2 * v4.x + (1.f - p.b2) * gx * gx; v4.y = p.b2 * v4.y + (1.f - p.b2) * gy * gy;
+        v4.z = p.b2 * v4.z + (1.f - p.b2) * gz * gz; v4.w = p.b2 * v4.w + (1.f - p.b2) * gw * gw;
+        p4.x -= lr_t * m4.x / (sqrtf(v4.x) + p.eps); p4.y -= lr_t * m4.y / (sqrtf(v4.y) + p.eps);
+        p4.z -= lr_t * m4.z / (sqrtf(v4.z) + p.eps); p4.w -= lr_t * m4.w / (sqrtf(v4.w) + p.eps);
+        const size_t off = (size_t)r * p.ld + col0 + c4;
+        st_stream_f4(p.p + off, p4); st_stream_f4(p.m + off, m4); st_stream_f4(p.v + off, v4);
+        uint2 sh; sh.x = pack_bf16x2(p4.x, p4.y); sh.y = pack_bf16x2(p4.z, p4.w);
+        *reinterpret_cast<uint2*>(p.shadow + off) = sh;
+      }
+    }
+    __syncwarp();
+  }
+  __device__ void finish() {}
+};
+
 // Decoder forward: logits = acc + b_dec -> bf16 stash, plus per-(n-block,chunk-parity,row) softmax partials
 // (row max, sum exp(x - max)) so the [B, I] logits never exist in fp32 in HBM.
 // Restates MultiVAE.py:169 (matmul + bias) and the reductions inside log_softmax/softmax (108, 143).
@@ -508,7 +606,8 @@ struct EpiLogitsStats {
   const Params& p;
   int row, M, N, slot;
   float mx, sum;
-  __device__ EpiLogitsStats(const Params& p_, int row_, int, int slot_, int, const GemmShape& s)
+  static constexpr int kSmem = 0;
+  __device__ EpiLogitsStats(const Params& p_, int row_, int, int slot_, int, const GemmShape& s, uint8_t*)
       : p(p_), row(row_), M(s.M), N(s.N), slot(slot_), mx(-INFINITY), sum(0.f) {}
   __device__ void chunk(int col0, float (&v)[GEMM_CW]) {
     if (row >= M) return;
@@ -610,7 +709,7 @@ int launch_gemm_cm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int 
   if (rc) return rc;
   auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, CM, Epi>;
   static int max_clusters = 0;  // per instantiation
-  const size_t smem = gemm_smem_bytes<BN>();
+  const size_t smem = gemm_smem_bytes<BN, Epi::kSmem>();
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;

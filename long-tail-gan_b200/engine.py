@@ -211,6 +211,11 @@ class GanEngine(object):
         self.s1 = torch.cuda.Stream(device=self.device)
         self.s2 = torch.cuda.Stream(device=self.device)
         self.overlap = True
+        # Decoder wgrad GEMM with the Adam step as its epilogue (EpiAdam, ltg_wgrad_adam): correct (tests) and 96 MB/step less HBM
+        # traffic, but measured SLOWER than wgrad GEMM (38 us) + streaming Adam (58 us): 112 us, 2.9 TB/s -- the 16 epilogue warps
+        # walk load -> update -> store chunk by chunk and cannot keep enough HBM requests in flight. Kept off until the epilogue is
+        # restructured (TMA-staged p/m/v tiles).
+        self.fused_wgrad_adam = False
         self.fused_disc = ops.disc_fused_supported(self.disc)   # one tcgen05 kernel for the discriminator forward (disc_fused.cu)
         self.fused_mid = True   # fused 600->400->200->600 middle (mid_kernels.cu) instead of two GEMMs + element-wise launches
         self._alloc()
@@ -465,14 +470,23 @@ class GanEngine(object):
         # runs under the latency-bound chain of small GEMMs of the encoder-side backward on the main stream.
         fuse_update = self.world_size == 1 and getattr(self, "_fuse_update", False)
         dp_comm = self.world_size > 1 and getattr(self, "_dp_comm", False)
-        with self._fork(self.s1):
-            ops.gemm(self.dl, self.h2, self.I, H + 1, B, a_mn=True, b_mn=True, bn=128, out_f32=self.dWdT, ld_f32=H, aux_col=H,
-                     aux_out=v.view("b_p1", "g"))
-            if dp_comm and self.peer is None:
-                import torch.distributed as dist
-                dist.reduce_scatter_tensor(self.g_dec_shard, self.dWdT_full)
+        fused_wa = fuse_update and self.fused_wgrad_adam
+        if not fused_wa:
+            with self._fork(self.s1):
+                ops.gemm(self.dl, self.h2, self.I, H + 1, B, a_mn=True, b_mn=True, bn=128, out_f32=self.dWdT, ld_f32=H, aux_col=H,
+                         aux_out=v.view("b_p1", "g"))
+                if dp_comm and self.peer is None:
+                    import torch.distributed as dist
+                    dist.reduce_scatter_tensor(self.g_dec_shard, self.dWdT_full)
         ops.gemm(self.dl, v.WdT_b, B, H, self.I, b_mn=True, splits=self.dgrad_splits, bn=128, out_f32=self.dh2_part, ld_f32=H,
                  split_stride=self.max_B * H)
+        if fused_wa:
+            # single GPU: the decoder weight-gradient GEMM applies Adam in its epilogue (the [I,600] fp32 gradient never reaches
+            # HBM). It rewrites the bf16 weights the dgrad GEMM above reads, hence the fork AFTER dgrad; it then runs beside the
+            # encoder-side backward chain of the main stream.
+            with self._fork(self.s1):
+                ops.wgrad_adam(self.dl, self.h2, self.I, H + 1, B, v.WdT, v.WdT_m, v.WdT_v, v.WdT_b, H, aux_col=H, aux_out=v.view("b_p1", "g"),
+                               scal=self.scal)
         if dp_comm and self.peer is not None:
             # peer-memory path: once every rank has finished its weight-gradient GEMM and its dgrad GEMM (which reads the bf16
             # weights), ONE kernel sums this rank's rows of all ranks' gradient buffers, runs Adam on them and stores the bf16
@@ -500,7 +514,7 @@ class GanEngine(object):
             with (torch.cuda.stream(self.s1) if self.overlap else torch.cuda.stream(torch.cuda.current_stream())):
                 import torch.distributed as dist
                 dist.all_gather_into_tensor(self.WdT_b_full, self.WdT_b_shard)
-        if fuse_update:
+        if fuse_update and not fused_wa:
             # the Adam sweep rewrites the bf16 decoder weights the dgrad GEMM above reads: order it after dgrad
             if self.overlap:
                 self.s1.wait_stream(torch.cuda.current_stream())

@@ -225,6 +225,13 @@ def adam_peer(p, m, v, grads, shadows, offset, world, lr_t=-1.0, scal=None, beta
                               ptr(scal), beta1, beta2, eps, _stream()))
 
 
+def wgrad_adam(A, B, M, N, K, p, m, v, shadow, n_cols, aux_col=-1, aux_out=None, lr_t=-1.0, scal=None, beta1=0.9, beta2=0.999, eps=1e-8):
+    """dW = A^T B (A stored [K, M], B stored [K, N]) with TF-Adam on p/m/v [M, ld] + bf16 shadow as the GEMM epilogue."""
+    _count(1)
+    check(lib().ltg_wgrad_adam(ptr(A), A.stride(0), ptr(B), B.stride(0), M, N, K, ptr(p), ptr(m), ptr(v), ptr(shadow), p.stride(0), n_cols,
+                               aux_col, ptr(aux_out), lr_t, ptr(scal), beta1, beta2, eps, _stream()))
+
+
 def enc_adam_peer(p, m, v, shadows, offset, n_items, slot_of_item, G, world, lr_t=-1.0, scal=None, beta1=0.9, beta2=0.999, eps=1e-8,
                   shadows_mc=None):
     _count(1)

@@ -651,3 +651,29 @@ def test_peer_exchange_kernels_on_one_device(ops):
     torch.cuda.synchronize()
     assert torch.equal(vals, torch.arange(16, dtype=torch.float32, device="cuda"))
     assert epochs.tolist() == [2, 0, 1, 0]
+
+
+def test_wgrad_adam_epilogue_matches_gemm_then_adam(ops):
+    """EpiAdam (decoder weight-gradient GEMM whose epilogue applies TF-Adam) against the two kernels it replaces: the same GEMM
+    storing the fp32 gradient, then ltg_adam. Same accumulators, same formula: equal up to FMA contraction (1e-6)."""
+    torch.manual_seed(21)
+    K, M, H = 500, 1300, 600
+    A = (torch.randn(K, M + 4, device="cuda") * 0.05).bfloat16()            # stored [K, lda]: dlogits-like
+    Bm = torch.zeros(K, 608, device="cuda", dtype=torch.bfloat16)
+    Bm[:, :H] = torch.tanh(torch.randn(K, H, device="cuda")).bfloat16(); Bm[:, H] = 1.0
+    p = torch.randn(M, H, device="cuda") * 0.1; m = torch.randn(M, H, device="cuda") * 1e-3; v = torch.rand(M, H, device="cuda") * 1e-4
+    p2, m2, v2 = p.clone(), m.clone(), v.clone()
+    sh = torch.zeros(M, H, device="cuda", dtype=torch.bfloat16); sh2 = torch.zeros_like(sh)
+    aux = torch.zeros(M, device="cuda"); aux2 = torch.zeros(M, device="cuda")
+    scal = torch.zeros(16, device="cuda"); scal[ops.S_LR_T] = 3e-4
+    ops.wgrad_adam(A, Bm, M, H + 1, K, p, m, v, sh, H, aux_col=H, aux_out=aux, scal=scal)
+    G = torch.zeros(M, H, device="cuda")
+    ops.gemm(A, Bm, M, H + 1, K, a_mn=True, b_mn=True, bn=128, out_f32=G, ld_f32=H, aux_col=H, aux_out=aux2)
+    ops.adam(p2, m2, v2, G, sh2, scal=scal)
+    torch.cuda.synchronize()
+    assert torch.equal(aux, aux2)
+    want = A[:, :M].float().t() @ Bm[:, :H].float()
+    assert (G - want).abs().max().item() < 2e-2 * want.abs().max().item()
+    for a, b in ((p, p2), (m, m2), (v, v2)):
+        assert (a - b).abs().max().item() <= 1e-6 * max(1.0, b.abs().max().item())
+    assert (sh.float() - sh2.float()).abs().max().item() <= 1e-2 * 0.5 and (sh != sh2).float().mean().item() < 1e-3
