@@ -210,6 +210,10 @@ class GanEngine(object):
         # side streams: independent branches of a step (captured as parallel branches of the CUDA graph)
         self.s1 = torch.cuda.Stream(device=self.device)
         self.s2 = torch.cuda.Stream(device=self.device)
+        # graphs are captured on a high-priority stream: kernel nodes inherit it, so the critical chain (main) wins SMs over the
+        # HBM-bound sweeps and weight-gradient GEMMs of the side branches when both have CTAs ready (LTG_GRAPH_PRIORITY=0: off)
+        import os
+        self._cap_stream = torch.cuda.Stream(device=self.device, priority=-1) if os.environ.get("LTG_GRAPH_PRIORITY", "1") != "0" else None
         self.overlap = True
         # Decoder wgrad GEMM with the Adam step as its epilogue (EpiAdam, ltg_wgrad_adam): correct (tests) and 96 MB/step less HBM
         # traffic, but measured SLOWER than wgrad GEMM (38 us) + streaming Adam (58 us): 112 us, 2.9 TB/s -- the 16 epilogue warps
@@ -619,7 +623,7 @@ class GanEngine(object):
             self.kernels_launched += self._kcount[key]
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with (torch.cuda.graph(g, stream=self._cap_stream) if self._cap_stream is not None else torch.cuda.graph(g)):
                 fn()  # capture only: the eager call above already performed this step
             self._graphs[key] = g
             return
