@@ -54,7 +54,8 @@ def measured_peaks(key="hbm_gbs"):
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    """SM clock / throttle reasons sampled WHILE the timed regions run: an NVML polling thread (5 ms period -- the default timed
+    region is only tens of milliseconds long, too short for `nvidia-smi -lms`), with nvidia-smi as the fallback."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -63,8 +64,40 @@ class ClockSampler(object):
         self.index = index
         self.proc = None
         self.path = None
+        self.thread = None
+        self.rows = []
+        self._stop = False
+        self.max_mhz = None
+
+    def _poll(self, nv, h):
+        reasons = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                   "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                   "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                   "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                self.rows.append((float(mhz), pw, [k for k, b in reasons.items() if mask & b]))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(visible.split(",")[self.index]) if visible and all(x.strip().isdigit() for x in visible.split(",")) else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
@@ -75,6 +108,14 @@ class ClockSampler(object):
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.thread is not None:
+            self._stop = True
+            self.thread.join(timeout=2)
+            if self.rows:
+                sm = sorted(r[0] for r in self.rows)
+                out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=self.max_mhz, samples=len(sm), power_w_max=max(r[1] for r in self.rows),
+                           reasons=sorted({k for r in self.rows for k in r[2]}), source="NVML, 5 ms period over the timed regions")
+            return out
         if self.proc is None:
             return out
         try:
@@ -94,6 +135,7 @@ class ClockSampler(object):
                 for j, nm in enumerate(names):
                     if any(r[3 + j].strip().lower().startswith("active") for r in rows):
                         out["reasons"].append(nm)
+                out["source"] = "nvidia-smi -lms 100"
             os.unlink(self.path)
         except Exception:
             pass
