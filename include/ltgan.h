@@ -48,9 +48,11 @@ int ltg_init(void);
 /* Persistent step state (device): words[0] = rng step, words[1] = Adam step t (shared by D and G updates, F6),
  * words[2] = G-update count (KL anneal, train.py:319-324). ltg_step_advance bumps the counters on the device and
  * writes LTG_S_LR_T / LTG_S_ANNEAL into `scal` after zeroing its accumulator slots [0, 8), so a captured graph needs no host values.
- *   kind: 0 = phase-A (rng only), 1 = D update (rng + Adam t), 2 = G update (rng + Adam t + anneal count)      */
+ *   kind: 0 = phase-A (rng only), 1 = D update (rng + Adam t), 2 = G update (rng + Adam t + anneal count)
+ * zero_buf / zero_words: optional 4-byte-aligned buffer cleared by the same launch (the phase's atomically accumulated
+ * gradients or counters), so no separate memset sits at the head of the phase.                                  */
 int ltg_step_advance(uint32_t* words, float* scal, int kind, float lr, float beta1, float beta2,
-                     float anneal_cap, float total_anneal_steps, void* stream);
+                     float anneal_cap, float total_anneal_steps, void* zero_buf, int64_t zero_words, void* stream);
 
 /* ---- generic bf16 tensor-core GEMM (tcgen05/TMA/TMEM) ------------------------------------------------------------
  * D[M,N] = alpha * A * B^T with A given as [M,K] (a_mn=0, pitch lda) or stored transposed [K,M] (a_mn=1), B likewise

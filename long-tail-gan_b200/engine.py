@@ -367,10 +367,10 @@ class GanEngine(object):
     def phase_a(self, data, bi):
         bt = data.batches[bi]
         B = bt["B"]
-        ops.step_advance(self.words, self.scal, 0, self.lr, anneal_cap=self.anneal_cap, total_anneal_steps=self.total_anneal_steps)
+        ops.step_advance(self.words, self.scal, 0, self.lr, anneal_cap=self.anneal_cap, total_anneal_steps=self.total_anneal_steps,
+                         zero=bt["cnt"])   # the sampler's per-user counters are cleared by the same launch
         # train.py:200: sess.run(generator_out) with default placeholders: dropout 0.75 (F4), is_training 0
         self._vae_forward(data, bt, False, self.keep_vae)
-        bt["cnt"].zero_()
         if bt["K"] > 0:
             Pr = bt["Pr"]
             ops.sample_pairs(self.logits, B, self.I, bt["uid0"], data.cand_ptr[bt["b0"]: bt["b0"] + B + 1], data.cand_items, bt["samp_ptr"],
@@ -388,7 +388,9 @@ class GanEngine(object):
         bt = data.batches[bi]
         d = self.disc
         P = bt["P"]
-        ops.step_advance(self.words, self.scal, 1, self.lr, anneal_cap=self.anneal_cap, total_anneal_steps=self.total_anneal_steps)
+        # (the w4 / b4 gradient slots of partial 0, accumulated by the head with atomics, are cleared by the same launch)
+        ops.step_advance(self.words, self.scal, 1, self.lr, anneal_cap=self.anneal_cap, total_anneal_steps=self.total_anneal_steps,
+                         zero=self.arena_gp[0][d._off["w4"][0]:])
         # autodiff of discriminator.py:25-55; every bias gradient is the ones-row of its weight-gradient GEMM.
         # Single GPU: the split-K partials of the three weight-gradient GEMMs go to arena_gp[s] and the Adam kernel sums them.
         # Data parallel: atomic accumulation into arena_g (which is what gets all-reduced).
@@ -401,7 +403,6 @@ class GanEngine(object):
         self._d_parts = self.d_splits_max if part else 1
         if part:
             gW = lambda name: self.arena_gp[0][d._off[name][0]: d._off[name][0] + d._off[name][1]]  # noqa: E731
-            self.arena_gp[0][d._off["w4"][0]:].zero_()   # w4 / b4 gradients are accumulated by disc_head with atomics
             kw = dict(split_stride=d.arena_n)
         else:
             d.arena_g.zero_()
@@ -445,8 +446,8 @@ class GanEngine(object):
         bt = data.batches[bi]
         v = self.vae
         B, Pr, K = bt["B"], bt["Pr"], bt["K"]
-        v.small_g.zero_()
-        ops.step_advance(self.words, self.scal, 2, self.lr, anneal_cap=self.anneal_cap, total_anneal_steps=self.total_anneal_steps)
+        ops.step_advance(self.words, self.scal, 2, self.lr, anneal_cap=self.anneal_cap, total_anneal_steps=self.total_anneal_steps,
+                         zero=v.small_g)   # bias gradients are accumulated atomically: cleared by the same launch
         if K > 0:
             # y_generated with fresh dropout masks (keep_prob 0.7 is fed in the G step too, train.py:326): independent of the
             # generator forward, so it runs as a parallel branch

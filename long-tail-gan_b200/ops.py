@@ -46,9 +46,13 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def step_advance(words, scal, kind, lr, beta1=0.9, beta2=0.999, anneal_cap=0.2, total_anneal_steps=20000.0):
+def step_advance(words, scal, kind, lr, beta1=0.9, beta2=0.999, anneal_cap=0.2, total_anneal_steps=20000.0, zero=None):
     _count(1)
-    check(lib().ltg_step_advance(ptr(words), ptr(scal), kind, lr, beta1, beta2, anneal_cap, total_anneal_steps, _stream()))
+    zw = 0
+    if zero is not None:
+        assert zero.is_contiguous() and zero.element_size() == 4
+        zw = zero.numel()
+    check(lib().ltg_step_advance(ptr(words), ptr(scal), kind, lr, beta1, beta2, anneal_cap, total_anneal_steps, ptr(zero), zw, _stream()))
 
 
 def pick_bn(M, N, splits_ok=False):
