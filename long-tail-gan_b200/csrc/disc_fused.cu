@@ -43,15 +43,17 @@ struct DiscFusedParams {
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
-// v <- dropout(v) with one hash per pair of adjacent columns (same indices as EpiStore::chunk)
+// v <- dropout(v) with one 64-bit hash per four adjacent columns (same indices and bits as EpiStore::chunk)
 __device__ __forceinline__ void drop16(float (&v)[16], uint32_t key, uint32_t thr16, float inv_keep, int row, int rng_ld, int col0) {
-  const uint64_t pbase = ((uint64_t)row * (uint64_t)rng_ld + (uint64_t)col0) >> 1;
-  const uint32_t thr_hi = thr16 << 16;
+  const uint64_t gbase = ((uint64_t)row * (uint64_t)rng_ld + (uint64_t)col0) >> 2;
+  const uint32_t thr_hi = thr16 << 16;   // thr16 <= 65535 whenever dropout is on
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const uint32_t h = ltg_hash_pair(key, pbase + q);
-    v[2 * q] = (h & 0xFFFFu) < thr16 ? v[2 * q] * inv_keep : 0.f;
-    v[2 * q + 1] = h < thr_hi ? v[2 * q + 1] * inv_keep : 0.f;     // (h >> 16) < thr16 without the shift (thr16 <= 65535 here)
+  for (int q = 0; q < 4; ++q) {
+    const uint2 h = ltg_hash_quad(key, gbase + q);
+    v[4 * q] = (h.x & 0xFFFFu) < thr16 ? v[4 * q] * inv_keep : 0.f;
+    v[4 * q + 1] = h.x < thr_hi ? v[4 * q + 1] * inv_keep : 0.f;
+    v[4 * q + 2] = (h.y & 0xFFFFu) < thr16 ? v[4 * q + 2] * inv_keep : 0.f;
+    v[4 * q + 3] = h.y < thr_hi ? v[4 * q + 3] * inv_keep : 0.f;
   }
 }
 

@@ -25,7 +25,7 @@ extern "C" int ltg_gemm_bf16(const void* A, int lda, int a_mn, const void* B, in
   LTG_REQUIRE(aux_col < 0 || aux_out != nullptr);
   LTG_REQUIRE(dact_src == nullptr || dact_ld >= N);
   const bool drop = keep > 0.f && keep < 1.f;
-  LTG_REQUIRE(!drop || (rng_ld % 2 == 0 && rng_ld >= N));
+  LTG_REQUIRE(!drop || (rng_ld % 4 == 0 && rng_ld >= N));
   EpiStore::Params ep;
   ep.out_f32 = out_f32; ep.ld_f32 = ld_f32;
   ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); ep.ld_bf16 = ld_bf16;

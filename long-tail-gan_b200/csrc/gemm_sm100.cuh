@@ -376,7 +376,7 @@ struct EpiStore {
     int64_t split_stride;   // > 0: split s stores its partial tile at out_f32 + s*split_stride (the consumer sums the partials)
     float alpha;
     float keep;             // dropout keep prob; >= 1 or <= 0 disables
-    uint64_t seed; uint32_t rng_stream, rng_step; const uint32_t* rng_step_dev; int rng_ld;  // pair idx = (row*rng_ld + col)/2
+    uint64_t seed; uint32_t rng_stream, rng_step; const uint32_t* rng_step_dev; int rng_ld;  // group idx = (row*rng_ld + col)/4
     int aux_col; float* aux_out;  // aux_col < 0 disables
     const __nv_bfloat16* dact_src; int dact_ld; float dact_keep;  // multiply by d/da dropout(tanh(a)) recovered from the stored activation
   };
@@ -448,13 +448,16 @@ struct EpiStore {
       }
     }
     if (drop) {
-      // col0 % 16 == 0 and rng_ld % 2 == 0: one hash per pair of adjacent columns
-      const uint64_t pbase = ((uint64_t)row * (uint64_t)p.rng_ld + (uint64_t)col0) >> 1;
+      // col0 % 16 == 0 and rng_ld % 4 == 0: one 64-bit hash per group of four adjacent columns
+      const uint64_t gbase = ((uint64_t)row * (uint64_t)p.rng_ld + (uint64_t)col0) >> 2;
+      const uint32_t thr_hi = thr16 << 16;   // (h >> 16) < thr16  <=>  h < thr16 << 16   (thr16 <= 65535 when drop)
 #pragma unroll
-      for (int q = 0; q < CW / 2; ++q) {
-        const uint32_t h = ltg_hash_pair(key, pbase + q);
-        v[2 * q] = (h & 0xFFFFu) < thr16 ? v[2 * q] * inv_keep : 0.f;
-        v[2 * q + 1] = (h >> 16) < thr16 ? v[2 * q + 1] * inv_keep : 0.f;
+      for (int q = 0; q < CW / 4; ++q) {
+        const uint2 h = ltg_hash_quad(key, gbase + q);
+        v[4 * q] = (h.x & 0xFFFFu) < thr16 ? v[4 * q] * inv_keep : 0.f;
+        v[4 * q + 1] = h.x < thr_hi ? v[4 * q + 1] * inv_keep : 0.f;
+        v[4 * q + 2] = (h.y & 0xFFFFu) < thr16 ? v[4 * q + 2] * inv_keep : 0.f;
+        v[4 * q + 3] = h.y < thr_hi ? v[4 * q + 3] * inv_keep : 0.f;
       }
     }
     if (p.aux_col >= col0 && p.aux_col < col0 + CW) {

@@ -89,7 +89,7 @@ __host__ __device__ __forceinline__ uint32_t ltg_keep_threshold(float keep) {
 
 // ---------------------------------------------------------------------------------------------
 // Cheap stateless dropout bits for the GEMM epilogues (discriminator.py:25,30,44 dropout layers): one 32-bit
-// integer hash ("lowbias32" finaliser) per PAIR of adjacent columns, 16 bits per keep/drop decision
+// integer hash ("lowbias32" finaliser): key derivation for the dropout masks (and, historically, one hash per PAIR of columns), 16 bits per keep/drop decision
 // (threshold floor(keep * 65536)). Philox costs ~15 instructions per element inside an epilogue that is
 // issue-latency bound; this costs ~4. oracle/philox.py mirrors it bit for bit.
 // ---------------------------------------------------------------------------------------------
@@ -103,6 +103,24 @@ __host__ __device__ __forceinline__ uint32_t ltg_hash_key(uint64_t seed, uint32_
 // pair index p = (row * rng_ld + col) / 2 (col even); low half decides col, high half decides col + 1
 __host__ __device__ __forceinline__ uint32_t ltg_hash_pair(uint32_t key, uint64_t p) {
   return ltg_lowbias32(((uint32_t)p * 0x9E3779B1u) ^ ((uint32_t)(p >> 32) * 0x85ebca6bu) ^ key);
+}
+// 64 decision bits for FOUR adjacent columns at once: group index g = (row * rng_ld + col) / 4 (col % 4 == 0), a Philox2x32
+// with 5 rounds keyed by the hashed (seed, stream, step) key: one 32x32->64 multiply + one 3-input xor per round, i.e. ~3
+// instructions per activation instead of ~6.5 for one lowbias32 per pair (ncu: the hash was half of the 21 instructions per
+// activation in the discriminator epilogues). Column 4g+0 / +1 use the low / high half of .x, +2 / +3 those of .y.
+// 5 rounds: keep-rate, row/column/lag-4/adjacent-key correlations of the masks are at the sampling-noise level
+// (tests/test_oracle_cpu.py); 3 rounds are visibly correlated. oracle/philox.py mirrors it bit for bit.
+__host__ __device__ __forceinline__ uint2 ltg_hash_quad(uint32_t key, uint64_t g) {
+  uint32_t L = (uint32_t)g, R = (uint32_t)(g >> 32), k = key;
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+    const uint64_t p = (uint64_t)L * 0xD256D193ull;
+    L = (uint32_t)(p >> 32) ^ k ^ R;
+    R = (uint32_t)p;
+    k += 0x9E3779B9u;
+  }
+  uint2 o; o.x = L; o.y = R;
+  return o;
 }
 __host__ __device__ __forceinline__ uint32_t ltg_keep_threshold16(float keep) {
   int t = (int)((double)keep * 65536.0);

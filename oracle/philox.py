@@ -101,17 +101,31 @@ def hash_key(seed, stream, step):
     return lowbias32(np.uint64(seed & 0xFFFFFFFF) ^ mid)
 
 
+def hash_quad(key, g):
+    """ltg_hash_quad (ltg_common.cuh): Philox2x32, 5 rounds, multiplier 0xD256D193, round keys key + r * 0x9E3779B9, counter
+    (lo32(g), hi32(g)). Returns the two 32-bit output words as uint64 arrays."""
+    g = np.asarray(g, dtype=np.uint64)
+    L = g & _MASK32
+    R = (g >> np.uint64(32)) & _MASK32
+    k = np.uint64(int(key) & 0xFFFFFFFF)
+    for _ in range(5):
+        p = L * np.uint64(0xD256D193)
+        L = ((p >> np.uint64(32)) ^ k ^ R) & _MASK32
+        R = p & _MASK32
+        k = (k + np.uint64(0x9E3779B9)) & _MASK32
+    return L, R
+
+
 def hash_keep_mask(seed, stream, step, n_rows, n_cols, rng_ld, keep):
-    """Keep-mask [n_rows, n_cols] of the GEMM dropout epilogue: pair p = (row*rng_ld + col) // 2, low 16 bits decide the even
-    column, high 16 bits the odd one, kept iff bits < floor(keep * 65536)."""
+    """Keep-mask [n_rows, n_cols] of the GEMM dropout epilogues: group g = (row*rng_ld + col) // 4 -> 64 bits; column 4g+0 / +1
+    take the low / high 16 bits of the first word, +2 / +3 those of the second; kept iff bits < floor(keep * 65536)."""
     if not (0.0 < keep < 1.0):
         return np.ones((n_rows, n_cols), dtype=bool)
     key = hash_key(seed, stream, step)
     idx = np.arange(n_rows, dtype=np.uint64)[:, None] * np.uint64(rng_ld) + np.arange(n_cols, dtype=np.uint64)[None, :]
-    p = idx >> np.uint64(1)
-    x = ((p & _MASK32) * np.uint64(0x9E3779B1)) & _MASK32
-    x ^= ((p >> np.uint64(32)) * np.uint64(0x85ebca6b)) & _MASK32
-    h = lowbias32(x ^ key)
-    bits = np.where((idx & np.uint64(1)) == 0, h & np.uint64(0xFFFF), h >> np.uint64(16))
+    L, R = hash_quad(key, idx >> np.uint64(2))
+    f = idx & np.uint64(3)
+    w = np.where(f < np.uint64(2), L, R)
+    bits = np.where((f & np.uint64(1)) == 0, w & np.uint64(0xFFFF), w >> np.uint64(16))
     thr = int(float(np.float32(keep)) * 65536.0)
     return bits < np.uint64(thr)
