@@ -410,6 +410,10 @@ def main():
                     phases_ms=dict(A=t_a, D=t_d, G=t_g, epoch_weighted_users_per_sec=BATCH * world / ((t_a + 10 * t_d + 10 * t_g) * 1e-3)),
                     pairs_per_step=dict(real=int(np.mean([b["Pr"] for b in data.batches])), generated_slots=int(np.mean([b["K"] for b in data.batches]))),
                     graphs=not args.no_graphs)
+        if world > 1:
+            line["config"]["exchange"] = ("our kernels over NVLink peer memory (%s), flag barriers; no NCCL collective in the step"
+                                          % ("NVLS multicast stores + in-switch reduction" if engine.peer["dWdT_mc"] else "unicast peer loads/stores")
+                                          if engine.peer is not None else "NCCL collectives captured in the step graphs")
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(tabs, args.cpu_steps, I)
         print(json.dumps(line), flush=True)

@@ -732,7 +732,8 @@ class GanEngine(object):
             self._peer_pads, peer["pads"] = sym(pads)
         except Exception as e:  # noqa: BLE001  -- no peer mapping on this system: NCCL collectives do the same exchange
             if self.rank == 0:
-                print("long-tail-gan_b200: peer-memory exchange unavailable (%s); using NCCL collectives" % (e,))
+                import sys
+                print("long-tail-gan_b200: peer-memory exchange unavailable (%s); using NCCL collectives" % (e,), file=sys.stderr)
             return
         I = self.I
         self.vae.WdT_b = self.WdT_b_full[:I]
