@@ -175,7 +175,7 @@ int ltg_peer_barrier(void* const* pads, int rank, int world, int slot, uint32_t*
 int ltg_peer_allreduce_small(void* const* bufs, int64_t offset, int count, void* const* pads, int rank, int world, int slot,
                              uint32_t* epochs, void* stream);
 /* out[i] = sum_r bufs[r][offset + i], i < n; `out` must not be one of the peer-visible buffers; caller orders it with barriers */
-int ltg_peer_reduce(void* const* bufs, int64_t offset, int64_t n, int world, float* out, void* stream);
+int ltg_peer_reduce(void* const* bufs, const float* bufs_mc, int64_t offset, int64_t n, int world, float* out, void* stream);
 /* copy `bytes` from src to byte offset dst_offset_bytes of every rank's dst buffer (all-gather by pushing; 16-byte granularity) */
 int ltg_peer_push(const void* src, int64_t bytes, void* const* dst, void* dst_mc, int64_t dst_offset_bytes, int world, void* stream);
 /* ltg_adam over this rank's shard p/m/v[n] = elements [offset, offset+n) of the full tensor, with the reduce-scatter and the

@@ -103,7 +103,7 @@ SIGNATURES = {
     "ltg_wgrad_adam": (_I, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _P, _F, _P, _F, _F, _F, _P]),
     "ltg_peer_barrier": (_I, [_P, _I, _I, _I, _P, _P]),
     "ltg_peer_allreduce_small": (_I, [_P, _I64, _I, _P, _I, _I, _I, _P, _P]),
-    "ltg_peer_reduce": (_I, [_P, _I64, _I64, _I, _P, _P]),
+    "ltg_peer_reduce": (_I, [_P, _P, _I64, _I64, _I, _P, _P]),
     "ltg_peer_push": (_I, [_P, _I64, _P, _P, _I64, _I, _P]),
     "ltg_adam_peer": (_I, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I, _F, _P, _F, _F, _F, _P]),
     "ltg_enc_adam_peer": (_I, [_P, _P, _P, _P, _P, _I64, _I, _P, _P, _I, _F, _P, _F, _F, _F, _P]),

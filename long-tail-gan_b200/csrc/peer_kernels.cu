@@ -95,14 +95,18 @@ peer_allreduce_small_kernel(PeerPtrs bufs, int64_t offset, int count, PeerPtrs p
 }
 
 __global__ void __launch_bounds__(256)
-peer_reduce_kernel(PeerPtrs bufs, int64_t offset, int64_t n, int world, float* __restrict__ out) {
+peer_reduce_kernel(PeerPtrs bufs, const float* bufs_mc, int64_t offset, int64_t n, int world, float* __restrict__ out) {
   const int64_t n4 = n >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < world; ++r) {
-      const float4 o = ld_peer_f4(reinterpret_cast<const float*>(bufs.p[r]) + offset + 4 * i);
-      s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+    if (bufs_mc != nullptr) {
+      s = mm_ld_reduce_f4(bufs_mc + offset + 4 * i);   // one load, summed inside the NVSwitch
+    } else {
+      for (int r = 0; r < world; ++r) {
+        const float4 o = ld_peer_f4(reinterpret_cast<const float*>(bufs.p[r]) + offset + 4 * i);
+        s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+      }
     }
     *reinterpret_cast<float4*>(out + 4 * i) = s;
   }
@@ -245,14 +249,15 @@ extern "C" int ltg_peer_allreduce_small(void* const* bufs, int64_t offset, int c
   return LTG_OK;
 }
 
-extern "C" int ltg_peer_reduce(void* const* bufs, int64_t offset, int64_t n, int world, float* out, void* stream) {
+extern "C" int ltg_peer_reduce(void* const* bufs, const float* bufs_mc, int64_t offset, int64_t n, int world, float* out, void* stream) {
   PeerPtrs pb;
   int rc = load_ptrs(&pb, bufs, world);
   if (rc) return rc;
   LTG_REQUIRE(out != nullptr && offset >= 0 && offset % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
   for (int r = 0; r < world; ++r) LTG_REQUIRE((reinterpret_cast<uintptr_t>(bufs[r]) & 15) == 0);
   if (n <= 0) return LTG_OK;
-  peer_reduce_kernel<<<stream_grid(n >> 2), 256, 0, (cudaStream_t)stream>>>(pb, offset, n, world, out);
+  LTG_REQUIRE((reinterpret_cast<uintptr_t>(bufs_mc) & 15) == 0);
+  peer_reduce_kernel<<<stream_grid(n >> 2), 256, 0, (cudaStream_t)stream>>>(pb, bufs_mc, offset, n, world, out);
   LTG_CHECK_LAUNCH();
   return LTG_OK;
 }

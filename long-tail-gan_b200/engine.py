@@ -483,6 +483,9 @@ class GanEngine(object):
                 if dp_comm and self.peer is None:
                     import torch.distributed as dist
                     dist.reduce_scatter_tensor(self.g_dec_shard, self.dWdT_full)
+                if dp_comm and self.peer is not None:
+                    self._ev_wgrad = torch.cuda.Event()
+                    self._ev_wgrad.record()
         ops.gemm(self.dl, v.WdT_b, B, H, self.I, b_mn=True, splits=self.dgrad_splits, bn=128, out_f32=self.dh2_part, ld_f32=H,
                  split_stride=self.max_B * H)
         if fused_wa:
@@ -537,6 +540,12 @@ class GanEngine(object):
             self._join(self.s2)
             with self._fork(self.s2):
                 ops.gemm(self.h1, self.dmulv, H, 2 * L, B, a_mn=True, b_mn=True, bn=64, out_f32=v.view("W_q1", "g"))
+                if dp_comm and self.peer is not None:
+                    # every small gradient of this rank is final here (the last one, db_p1, comes from the decoder weight-gradient
+                    # GEMM on branch s1): exchange + update of the small arena run on this branch, beside the encoder chain
+                    torch.cuda.current_stream().wait_event(self._ev_wgrad)
+                    self._small_exchange(2)
+                    self._small_done = True
         else:
             ops.tanh_bwd(self.dh2_part, self.h2, B, H, dx_bf16=self.dh2pre, dbias=v.view("b_p0", "g"), n_partials=self.dgrad_splits,
                          partial_stride=self.max_B * H, ld_dy=H)
@@ -647,7 +656,7 @@ class GanEngine(object):
         if self.peer is not None:
             d = self.disc
             self._pbar(0)
-            ops.peer_reduce(self.peer["arena_g"], 0, d.arena_g.numel(), self.world_size, self.arena_gsum)
+            ops.peer_reduce(self.peer["arena_g"], 0, d.arena_g.numel(), self.world_size, self.arena_gsum, bufs_mc=self.peer["arena_g_mc"])
             ops.adam(d.arena, d.arena_m, d.arena_v, self.arena_gsum, d.arena_b, scal=self.scal)
             return
         dist.all_reduce(self.disc.arena_g)                       # 161 k discriminator gradients: one small bucket
@@ -676,14 +685,14 @@ class GanEngine(object):
             N = self.world_size
             ops.peer_allreduce_small(pr["scal"], ops.S_SUM_Y, 2, pr["pads"], self.rank, N, 0, self.peer_epochs)
             self._dp_comm = True
+            self._small_done = False
             self._g_backward(data, bi)
             self._dp_comm = False
             r0, nr = self.row0, self.nrows
             if nr > 0 and self.dp_tables is None:   # (with the activation exchange, enc_adam_peer has already stored them)
                 ops.peer_push(self.Wq0_b_shard, nr * H * 2, pr["Wq0_b"], r0 * H * 2, N, dst_mc=pr["Wq0_b_mc"])
-            self._pbar(0)   # every rank's small gradients are final
-            ops.peer_reduce(pr["small_g"], 0, v.small_g.numel(), N, self.small_gsum)
-            ops.adam(v.small, v.small_m, v.small_v, self.small_gsum, v.small_b, scal=self.scal)
+            if not self._small_done:
+                self._small_exchange(0)
             self._pbar(0)   # end of step: all pushes have landed, nobody still reads this step's gradient buffers
             return
         dist.all_reduce(self.scal[ops.S_SUM_Y: ops.S_CNT + 1])
@@ -726,8 +735,8 @@ class GanEngine(object):
             self.Wq0_b_full, peer["Wq0_b"] = sym(self.Wq0_b_full); peer["Wq0_b_mc"] = mc[2]
             self.dh1_glob, peer["dh1"] = sym(self.dh1_glob); peer["dh1_mc"] = mc[3]
             self.scal, peer["scal"] = sym(self.scal)
-            self.disc.arena_g, peer["arena_g"] = sym(self.disc.arena_g)
-            self.vae.small_g, peer["small_g"] = sym(self.vae.small_g)
+            self.disc.arena_g, peer["arena_g"] = sym(self.disc.arena_g); peer["arena_g_mc"] = mc[5]
+            self.vae.small_g, peer["small_g"] = sym(self.vae.small_g); peer["small_g_mc"] = mc[6]
             pads = torch.zeros(ops.PEER_SLOTS * 8, dtype=torch.int32, device=self.device)
             self._peer_pads, peer["pads"] = sym(pads)
         except Exception as e:  # noqa: BLE001  -- no peer mapping on this system: NCCL collectives do the same exchange
@@ -745,6 +754,13 @@ class GanEngine(object):
         torch.cuda.synchronize()
         dist.barrier()
         self.peer = peer
+
+    def _small_exchange(self, slot):
+        """barrier (every rank's small gradients are final) -> sum of all ranks' small gradients -> Adam on the replicated small arena"""
+        v = self.vae
+        self._pbar(slot)
+        ops.peer_reduce(self.peer["small_g"], 0, v.small_g.numel(), self.world_size, self.small_gsum, bufs_mc=self.peer["small_g_mc"])
+        ops.adam(v.small, v.small_m, v.small_v, self.small_gsum, v.small_b, scal=self.scal)
 
     def _pbar(self, slot=0):
         ops.peer_barrier(self.peer["pads"], self.rank, self.world_size, slot, self.peer_epochs)

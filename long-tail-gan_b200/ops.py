@@ -213,9 +213,9 @@ def peer_allreduce_small(bufs, offset, count, pads, rank, world, slot, epochs):
     check(lib().ltg_peer_allreduce_small(bufs, offset, count, pads, rank, world, slot, ptr(epochs), _stream()))
 
 
-def peer_reduce(bufs, offset, n, world, out):
+def peer_reduce(bufs, offset, n, world, out, bufs_mc=None):
     _count(1)
-    check(lib().ltg_peer_reduce(bufs, offset, n, world, ptr(out), _stream()))
+    check(lib().ltg_peer_reduce(bufs, bufs_mc or None, offset, n, world, ptr(out), _stream()))
 
 
 def peer_push(src, nbytes, dst, dst_offset_bytes, world, dst_mc=None):
