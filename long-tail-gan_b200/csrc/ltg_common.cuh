@@ -88,10 +88,10 @@ __host__ __device__ __forceinline__ uint32_t ltg_keep_threshold(float keep) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Cheap stateless dropout bits for the GEMM epilogues (discriminator.py:25,30,44 dropout layers): one 32-bit
-// integer hash ("lowbias32" finaliser): key derivation for the dropout masks (and, historically, one hash per PAIR of columns), 16 bits per keep/drop decision
-// (threshold floor(keep * 65536)). Philox costs ~15 instructions per element inside an epilogue that is
-// issue-latency bound; this costs ~4. oracle/philox.py mirrors it bit for bit.
+// Cheap stateless dropout bits for the GEMM epilogues (discriminator.py:25,30,44 dropout layers), 16 bits per keep/drop
+// decision (threshold floor(keep * 65536)). The key of a mask is a "lowbias32" hash of (seed, stream, step); the bits come from
+// ltg_hash_quad below. Philox4x32-10 per element costs ~15 instructions inside an epilogue that is issue bound; this costs ~3.
+// oracle/philox.py mirrors both functions bit for bit.
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ uint32_t ltg_lowbias32(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
@@ -99,10 +99,6 @@ __host__ __device__ __forceinline__ uint32_t ltg_lowbias32(uint32_t x) {
 }
 __host__ __device__ __forceinline__ uint32_t ltg_hash_key(uint64_t seed, uint32_t stream, uint32_t step) {
   return ltg_lowbias32((uint32_t)seed ^ ltg_lowbias32((uint32_t)(seed >> 32) ^ ltg_lowbias32(stream * 0x9E3779B9u + step)));
-}
-// pair index p = (row * rng_ld + col) / 2 (col even); low half decides col, high half decides col + 1
-__host__ __device__ __forceinline__ uint32_t ltg_hash_pair(uint32_t key, uint64_t p) {
-  return ltg_lowbias32(((uint32_t)p * 0x9E3779B1u) ^ ((uint32_t)(p >> 32) * 0x85ebca6bu) ^ key);
 }
 // 64 decision bits for FOUR adjacent columns at once: group index g = (row * rng_ld + col) / 4 (col % 4 == 0), a Philox2x32
 // with 5 rounds keyed by the hashed (seed, stream, step) key: one 32x32->64 multiply + one 3-input xor per round, i.e. ~3
