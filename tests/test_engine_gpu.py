@@ -217,6 +217,39 @@ def test_graph_replay_equals_eager(setup):
     assert (a[2] - b[2]).abs().max().item() < 1e-3
 
 
+def test_run_step_single_graph_equals_three_phases(setup):
+    """engine.run_step (phase A + D + G of one batch captured as ONE graph, what bench.py times) against the three per-phase calls
+    run eagerly on a twin engine: same RNG counters, weights equal up to float-atomic summation order."""
+    s = setup
+    eng = s["eng"]
+    gen = importlib.import_module("long-tail-gan_b200.generator")
+    dis = importlib.import_module("long-tail-gan_b200.discriminator")
+
+    def run(fused):
+        vae = gen.MultiVAE([200, 600, I], lam=0.0, random_seed=98765)
+        vae.set_params(s["params"]); vae.reset_optimizer()
+        disc = dis.Discriminator(I, I, H0, H1, H2, H3, seed=1)
+        disc.set_params(s["E"], s["dparams"])
+        data = eng.TrainData(batch_size=BATCH, **s["tabs"])
+        e = eng.GanEngine(vae, disc, data.max_B, data.max_P, seed=SEED, use_graphs=fused, max_active=data.max_active)
+        for _ in range(3):          # first pass captures, later passes replay
+            for bi in range(2):
+                if fused:
+                    e.run_step(data, bi)
+                else:
+                    e.run_phase_a(data, bi); e.run_d_step(data, bi); e.run_g_step(data, bi)
+        torch.cuda.synchronize()
+        return vae.WdT.clone(), vae.W_q0.clone(), disc.arena.clone(), e.words.clone(), e.kernels_launched
+
+    a = run(False)
+    b = run(True)
+    assert torch.equal(a[3], b[3]) and a[4] == b[4]
+    W0 = torch.as_tensor(s["params"][3]).t().cuda()
+    assert rel(b[0] - W0, a[0] - W0) < 2e-2
+    assert (a[1] - b[1]).abs().max().item() < 1e-3
+    assert (a[2] - b[2]).abs().max().item() < 1e-3
+
+
 def test_evaluate_matches_oracle_metrics(setup):
     from scipy import sparse
     s = setup
