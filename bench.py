@@ -142,6 +142,33 @@ class ClockSampler(object):
         return out
 
 
+def eval_throughput(engine, tabs, n_users=2000):
+    """SURVEY 8d asks for evaluation users/s beside the training metric: fold-in forward (dropout on, F4) + exact top-100
+    NDCG@100 / Recall@20,50 (engine.evaluate = train.py:333-348 / test.py:138-173) on the first n_users synthetic users, 80/20
+    split of each user's items. Host CSR upload and metric read-back are inside the time."""
+    import numpy as np
+    import torch
+    indptr = np.asarray(tabs["indptr"], dtype=np.int64)
+    indices = np.asarray(tabs["indices"], dtype=np.int32)
+    n = int(min(n_users, len(indptr) - 1))
+    tr, te, trp, tep = [], [], [0], [0]
+    for u in range(n):
+        it = indices[indptr[u]: indptr[u + 1]]
+        held = np.zeros(len(it), dtype=bool)
+        held[4::5] = True
+        tr.append(it[~held]); te.append(it[held])
+        trp.append(trp[-1] + len(tr[-1])); tep.append(tep[-1] + len(te[-1]))
+    args = (np.asarray(trp, dtype=np.int64), np.concatenate(tr), np.asarray(tep, dtype=np.int64), np.concatenate(te))
+    engine.evaluate(*args)   # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = engine.evaluate(*args)
+    dt = time.perf_counter() - t0
+    nd = res["ndcg@100"]
+    return dict(users_per_sec=n / dt, users=n, ms=dt * 1e3, users_with_heldout=len(nd), ndcg_at_100_random_init=float(np.mean(nd)) if nd else None,
+                what="fold-in forward + exact top-100 NDCG@100 / Recall@20,50 per user; host CSR upload and metric read-back included")
+
+
 def cpu_baseline(tabs, n_steps, n_items):
     """The reference's CPU data flow (oracle/cpu_step.py) on a bounded sample of the same workload."""
     import torch
@@ -415,6 +442,11 @@ def main():
             line["config"]["exchange"] = ("our kernels over NVLink peer memory (%s), flag barriers; no NCCL collective in the step"
                                           % ("NVLS multicast stores + in-switch reduction" if engine.peer["dWdT_mc"] else "unicast peer loads/stores")
                                           if engine.peer is not None else "NCCL collectives captured in the step graphs")
+        if world == 1:
+            try:   # reported beside the training metric; never allowed to take the bench line down
+                line["eval"] = eval_throughput(engine, tabs)
+            except Exception as e:  # noqa: BLE001
+                line["eval"] = dict(error=repr(e)[:200])
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(tabs, args.cpu_steps, I)
         print(json.dumps(line), flush=True)
