@@ -681,10 +681,13 @@ class GanEngine(object):
 
     def _g_step_dp(self, data, bi):
         """G update under user-sharded data parallelism with a row-sharded optimizer.
-        Collectives, in issue order (identical on every rank): all-reduce(sum y, cnt) -> reduce-scatter(dW_dec) ->
-        all-gather(bf16 W_dec) -> reduce-scatter(dW_enc) -> all-reduce(small grads) -> all-gather(bf16 W_enc).
-        The decoder reduce-scatter is issued from a side branch right after the weight-gradient GEMM, so it travels over NVLink
-        while the encoder-side backward is still computing."""
+        Peer-memory path (default on one NVLink node, see _setup_peer): in-place all-reduce of (sum y, cnt) in one small kernel ->
+        backward; on branch s1: barrier -> ltg_adam_peer (gradient rows pulled from every rank, bf16 rows stored to every rank);
+        on the main stream: push of dh1pre -> barrier -> shard gradient GEMM over the global batch -> ltg_enc_adam_peer; on branch
+        s2: barrier -> pull-sum of the small gradients -> Adam on the replicated small arena; one barrier closes the step.
+        NCCL path (LTG_DP_PEER=0 / no peer mapping), collectives in issue order, identical on every rank: all-reduce(sum y, cnt) ->
+        reduce-scatter(dW_dec) -> all-gather(bf16 W_dec) -> all-gather(dh1pre) or reduce-scatter(dW_enc) -> all-reduce(small grads)
+        -> all-gather(bf16 W_enc)."""
         import torch.distributed as dist
         v = self.vae
         self._g_forward(data, bi)
