@@ -55,3 +55,114 @@ def test_philox4x32_known_answers():
     out = philox.philox4x32_10(np.uint32(0xffffffff), np.uint32(0xffffffff), np.uint32(0xffffffff), np.uint32(0xffffffff),
                                np.uint32(0xffffffff), np.uint32(0xffffffff))
     assert [int(x) for x in out] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# The TF-graph part of the oracle is "parity unpinned" by the reference (no TensorFlow here, no recorded outputs). These
+# checks pin it against an independent float64 NumPy evaluation of SURVEY Appendix A (the reference's math written out
+# from MultiVAE.py / discriminator.py / train.py line by line) and against the closed-form gradient of the F3 term.
+# --------------------------------------------------------------------------------------------------------------------
+import torch  # noqa: E402
+from oracle import ltgan_oracle as orc  # noqa: E402
+
+
+def _np(t):
+    return t.detach().numpy().astype(np.float64)
+
+
+def test_vae_forward_matches_float64_appendix_a():
+    rng = np.random.RandomState(0)
+    I, B = 57, 5
+    params = orc.init_vae_params(I, seed=3)
+    params[5] = params[5] + 0.05 * torch.randn(params[5].shape, generator=torch.Generator().manual_seed(1))   # non-trivial logvar bias
+    X = (rng.rand(B, I) < 0.2).astype(np.float32); X[0, :3] = 1
+    keep = rng.rand(B, I) < 0.75
+    eps = rng.randn(B, orc.L).astype(np.float32)
+    out = orc.vae_forward(params, torch.from_numpy(X), torch.from_numpy(keep), 0.75, torch.from_numpy(eps), 1, 0.13)
+    W_q0, W_q1, W_p0, W_p1, b_q0, b_q1, b_p0, b_p1 = [_np(p) for p in params]
+    x = X.astype(np.float64)
+    h0 = x / np.sqrt(np.maximum((x * x).sum(1, keepdims=True), 1e-12))           # MultiVAE.py:148
+    h0 = h0 * keep / 0.75                                                         # :149
+    h1 = np.tanh(h0 @ W_q0 + b_q0)                                                # :151-155
+    ml = h1 @ W_q1 + b_q1                                                         # :157-158
+    mu, lv = ml[:, :orc.L], ml[:, orc.L:]
+    KL = np.mean(np.sum(0.5 * (-lv + np.exp(lv) + mu ** 2 - 1), axis=1))          # :161-162
+    z = mu + eps * np.exp(0.5 * lv)                                               # :160,178-181
+    h2 = np.tanh(z @ W_p0 + b_p0)
+    logits = h2 @ W_p1 + b_p1                                                     # :168-172
+    lse = np.log(np.exp(logits - logits.max(1, keepdims=True)).sum(1, keepdims=True)) + logits.max(1, keepdims=True)
+    neg_ll = -np.mean(np.sum((logits - lse) * x, axis=1))                         # :108-112
+    assert abs(out["KL"].item() - KL) < 1e-5 * max(1.0, abs(KL))
+    assert abs(out["neg_ll"].item() - neg_ll) < 1e-5 * abs(neg_ll)
+    assert abs(out["neg_ELBO"].item() - (neg_ll + 0.13 * KL)) < 1e-5 * abs(neg_ll)
+    assert np.abs(_np(out["probs"]) - np.exp(logits - lse)).max() < 1e-6
+    # inference mode (phase A / evaluation): z = mu, dropout still on (F4)
+    out0 = orc.vae_forward(params, torch.from_numpy(X), torch.from_numpy(keep), 0.75, torch.from_numpy(eps), 0, 0.0)
+    assert np.abs(_np(out0["z"]) - mu).max() < 1e-5
+
+
+def test_disc_forward_and_d_loss_float64():
+    rng = np.random.RandomState(1)
+    I, P = 40, 9
+    E, dp = orc.init_disc_params(I, 100, 150, 250, 300, seed=5)
+    pop = rng.randint(0, I, P); niche = rng.randint(0, I, P)
+    masks = [rng.rand(P, n) < 0.7 for n in (150, 250, 300)]
+    y = orc.disc_forward(E, dp, torch.from_numpy(pop), torch.from_numpy(niche), [torch.from_numpy(m) for m in masks], 0.7)
+    w1, b1, w2, b2, w3, b3, w4, b4 = [_np(p) for p in dp]
+    En = _np(E)
+    a1 = np.tanh(En[pop] @ w1 + b1) * masks[0] / 0.7                              # discriminator.py:25-30
+    a2 = np.tanh(En[niche] @ w2 + b2) * masks[1] / 0.7
+    a3 = np.tanh(np.concatenate([a1, a2], 1) @ w3 + b3) * masks[2] / 0.7          # :36-44
+    want = 1.0 / (1.0 + np.exp(-(a3 @ w4 + b4).reshape(-1)))                      # :45
+    assert np.abs(_np(y) - want).max() < 1e-6
+    d = orc.d_loss_fn(y[:4], y[4:]).item()                                        # train.py:142
+    assert abs(d - (-np.log(want[:4]).sum() - np.log(1 - want[4:]).sum())) < 1e-5 * abs(d)
+
+
+def test_gan_term_broadcast_quirk_and_its_gradient():
+    """F3: tf.multiply([K], [P,1]) broadcasts to [P,K]; the sum is (sum p)(sum y). Gradient w.r.t. the logits of user u:
+    -(lam/cnt)(sum y) * pi_u o (m_u - sum_i m_ui pi_ui)   (SURVEY Appendix A)."""
+    rng = np.random.RandomState(2)
+    B, I, P = 3, 11, 5
+    logits = torch.from_numpy(rng.randn(B, I)).requires_grad_(True)
+    mask = torch.from_numpy((rng.rand(B, I) < 0.3).astype(np.float64))
+    y = torch.from_numpy(rng.rand(P))
+    probs = torch.softmax(logits, dim=-1)
+    lam, cnt = 1.7, float(mask.sum().item())
+    a = orc.gan_term(probs, mask, y, lam, cnt, literal_outer=True)
+    b = orc.gan_term(probs, mask, y, lam, cnt, literal_outer=False)
+    assert abs(a.item() - b.item()) < 1e-12
+    assert abs(a.item() - (-(lam / cnt) * (probs * mask).sum().item() * y.sum().item())) < 1e-12
+    (g,) = torch.autograd.grad(a, logits)
+    pi = probs.detach().numpy(); m = mask.numpy()
+    want = -(lam / cnt) * y.sum().item() * pi * (m - (m * pi).sum(1, keepdims=True))
+    assert np.abs(g.numpy() - want).max() < 1e-12
+
+
+def test_tf_adam_formula_and_shared_step_counter():
+    """[ext] TF1 AdamOptimizer: lr_t = lr sqrt(1-b2^t)/(1-b1^t), epsilon OUTSIDE the bias correction; one optimizer object serves the
+    D and the G minimize() (train.py:160-164), so t advances on both (F6)."""
+    lr = 1e-4
+    for t in (1, 2, 7, 1000):
+        assert abs(orc.tf_adam_lr_t(lr, t) - lr * np.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)) < 1e-9
+    p = torch.tensor([0.5, -0.25]); m = torch.tensor([0.01, 0.0]); v = torch.tensor([1e-4, 0.0]); g = torch.tensor([0.2, 0.0])
+    orc.tf_adam_step(p, m, v, g, orc.tf_adam_lr_t(lr, 3))
+    m0 = 0.9 * 0.01 + 0.1 * 0.2
+    v0 = 0.999 * 1e-4 + 0.001 * 0.04
+    assert abs(m[0].item() - m0) < 1e-7 and abs(v[0].item() - v0) < 1e-9
+    assert abs(p[0].item() - (0.5 - orc.tf_adam_lr_t(lr, 3) * m0 / (np.sqrt(v0) + 1e-8))) < 1e-7
+    assert p[1].item() == -0.25                       # zero gradient, zero moments: the parameter does not move ...
+    m2 = torch.tensor([0.01]); v2 = torch.tensor([1e-4]); p2 = torch.tensor([1.0])
+    orc.tf_adam_step(p2, m2, v2, torch.tensor([0.0]), 1e-4)
+    assert p2.item() < 1.0                            # ... but with non-zero momentum it does (dense Adam, F7)
+    # first step from zero moments: displacement = lr * g / (|g| + eps*sqrt(1-b2)) ~ lr * sign(g)
+    p3 = torch.tensor([0.0]); m3 = torch.zeros(1); v3 = torch.zeros(1)
+    orc.tf_adam_step(p3, m3, v3, torch.tensor([3.0]), orc.tf_adam_lr_t(lr, 1))
+    assert abs(p3.item() + lr) < 1e-8
+
+
+def test_anneal_schedule():
+    assert orc.anneal_value(0) == 0.0                                             # train.py:319-324: pre-increment count
+    assert abs(orc.anneal_value(1000) - 0.05) < 1e-12
+    assert orc.anneal_value(4000) == 0.2 and orc.anneal_value(10 ** 6) == 0.2
+    assert orc.anneal_value(5, total_anneal_steps=0) == 0.2
