@@ -142,6 +142,36 @@ class ClockSampler(object):
         return out
 
 
+def step_roofline(n_items, batch, nnz_user, cand_user, pairs_real, pairs_gen, t_a, t_d, t_g, hbm_gbs, tc_tflops):
+    """Whole-step roofline of SURVEY 8d: algorithmic FLOPs and HBM bytes of phase A, the D update and the G update (the formulas of
+    that section, written out below), t_roof = max(FLOPs / tensor peak, bytes / HBM peak) per phase, fraction = t_roof / t_measured.
+    Times in ms, returns per-phase dicts and the step total. Pure arithmetic (also exercised by the CPU tests)."""
+    I, B = float(n_items), float(batch)
+    c = 2.0 * (600 * 400 + 200 * 600)              # the two middle layers, flops per user
+    d = 2.0 * 600 * I                               # decoder, flops per user
+    p_u = 0.5 * (pairs_real + pairs_gen) / B        # pairs of each kind per user
+    p_vae = 1201.0 * I + 361600.0
+    fl = dict(A=B * (2.0 * nnz_user * 600 + c + d),
+              D=B * p_u * 1923600.0,
+              G=B * (3.0 * (c + d) + 4.0 * nnz_user * 600 + p_u * 320600.0))
+    by = dict(A=2.0 * 600 * I + B * nnz_user * 1204.0 + 8.0 * B * cand_user,
+              D=1600.0 * (pairs_real + pairs_gen) + 26.0 * 161001.0,
+              G=26.0 * p_vae + 4.0 * 600 * I + 8.0 * 600 * I + 4.0 * B * I + B * nnz_user * 1204.0 + B * 1800 * 4.0)
+    meas = dict(A=t_a, D=t_d, G=t_g)
+    out, roof_total = {}, 0.0
+    for ph in ("A", "D", "G"):
+        t_tc = fl[ph] / (tc_tflops * 1e12) * 1e3
+        t_hbm = by[ph] / (hbm_gbs * 1e9) * 1e3
+        t_roof = max(t_tc, t_hbm)
+        roof_total += t_roof
+        out[ph] = dict(flops=fl[ph], bytes=by[ph], t_tensor_ms=t_tc, t_hbm_ms=t_hbm, bound="tensor" if t_tc > t_hbm else "hbm",
+                       t_roof_ms=t_roof, t_measured_ms=meas[ph], frac=t_roof / meas[ph] if meas[ph] > 0 else None)
+    t_meas = t_a + t_d + t_g
+    out["step"] = dict(t_roof_ms=roof_total, t_measured_ms=t_meas, frac=roof_total / t_meas if t_meas > 0 else None,
+                       note="SURVEY 8d algorithmic model (dense-Adam bytes dominate G); phases timed separately with CUDA events")
+    return out
+
+
 def eval_throughput(engine, tabs, n_users=2000):
     """SURVEY 8d asks for evaluation users/s beside the training metric: fold-in forward (dropout on, F4) + exact top-100
     NDCG@100 / Recall@20,50 (engine.evaluate = train.py:333-348 / test.py:138-173) on the first n_users synthetic users, 80/20
@@ -442,6 +472,16 @@ def main():
             line["config"]["exchange"] = ("our kernels over NVLink peer memory (%s), flag barriers; no NCCL collective in the step"
                                           % ("NVLS multicast stores + in-switch reduction" if engine.peer["dWdT_mc"] else "unicast peer loads/stores")
                                           if engine.peer is not None else "NCCL collectives captured in the step graphs")
+        try:   # whole-step roofline (north_star: fraction of roofline for the full GAN step), per GPU
+            hb, _ = measured_peaks("hbm_gbs")
+            tc, _ = measured_peaks("bf16_tflops")
+            n_u = BATCH * nb
+            ip = np.asarray(tabs["indptr"], dtype=np.int64); cp = np.asarray(tabs["cand_ptr"], dtype=np.int64)
+            line["step_roofline"] = step_roofline(I, BATCH, float(ip[n_u] - ip[0]) / n_u, float(cp[n_u] - cp[0]) / n_u,
+                                                  float(np.mean([b["Pr"] for b in data.batches])), float(np.mean([b["K"] for b in data.batches])),
+                                                  t_a, t_d, t_g, hb, tc)
+        except Exception as e:  # noqa: BLE001
+            line["step_roofline"] = dict(error=repr(e)[:200])
         if world == 1:
             try:   # reported beside the training metric; never allowed to take the bench line down
                 line["eval"] = eval_throughput(engine, tabs)
