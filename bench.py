@@ -27,6 +27,8 @@ if ROOT not in sys.path:
 CONFIG = "ml20m"
 BATCH = 500
 N_BENCH_BATCHES = 8   # distinct user batches cycled through by the timed steps (per GPU)
+MIN_TIMED_S = 0.5     # the K-step timed block is repeated until this much device time has accumulated (median block reported)
+MAX_REPEATS = 200
 H0, H1, H2, H3 = 100, 150, 250, 300   # config.ini h0..h3_size
 LR, LAM = 1e-4, 1.0                    # config.ini LEARNING_RATE, GANLAMBDA
 
@@ -50,7 +52,7 @@ def measured_peaks(key="hbm_gbs"):
         d = json.load(open(path))
         if key in d:
             return float(d[key]), "measured (MEASURED_PEAKS.json %s)" % key
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}[key], "fallback (B200_PROFILING.md)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1390.0}[key], "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler(object):
@@ -142,10 +144,13 @@ class ClockSampler(object):
         return out
 
 
-def step_roofline(n_items, batch, nnz_user, cand_user, pairs_real, pairs_gen, t_a, t_d, t_g, hbm_gbs, tc_tflops):
+def step_roofline(n_items, batch, nnz_user, cand_user, pairs_real, pairs_gen, t_a, t_d, t_g, hbm_gbs, tc_tflops, world=1, t_step=None):
     """Whole-step roofline of SURVEY 8d: algorithmic FLOPs and HBM bytes of phase A, the D update and the G update (the formulas of
     that section, written out below), t_roof = max(FLOPs / tensor peak, bytes / HBM peak) per phase, fraction = t_roof / t_measured.
-    Times in ms, returns per-phase dicts and the step total. Pure arithmetic (also exercised by the CPU tests)."""
+    Times in ms, returns per-phase dicts and the step total. Pure arithmetic (also exercised by the CPU tests).
+    world > 1 (data parallel, per-GPU view): the optimizer is row-sharded, so the dense-Adam bytes of the two [I,600] matrices are
+    divided by the number of ranks. t_step: the measured time of the whole step when its phases overlap (engine.run_step); the step
+    fraction is then roof / t_step, and the per-phase fractions remain those of the phases timed one by one."""
     I, B = float(n_items), float(batch)
     c = 2.0 * (600 * 400 + 200 * 600)              # the two middle layers, flops per user
     d = 2.0 * 600 * I                               # decoder, flops per user
@@ -156,7 +161,7 @@ def step_roofline(n_items, batch, nnz_user, cand_user, pairs_real, pairs_gen, t_
               G=B * (3.0 * (c + d) + 4.0 * nnz_user * 600 + p_u * 320600.0))
     by = dict(A=2.0 * 600 * I + B * nnz_user * 1204.0 + 8.0 * B * cand_user,
               D=1600.0 * (pairs_real + pairs_gen) + 26.0 * 161001.0,
-              G=26.0 * p_vae + 4.0 * 600 * I + 8.0 * 600 * I + 4.0 * B * I + B * nnz_user * 1204.0 + B * 1800 * 4.0)
+              G=26.0 * (1200.0 * I / world + I + 361600.0) + 4.0 * 600 * I + 8.0 * 600 * I + 4.0 * B * I + B * nnz_user * 1204.0 + B * 1800 * 4.0)
     meas = dict(A=t_a, D=t_d, G=t_g)
     out, roof_total = {}, 0.0
     for ph in ("A", "D", "G"):
@@ -166,9 +171,12 @@ def step_roofline(n_items, batch, nnz_user, cand_user, pairs_real, pairs_gen, t_
         roof_total += t_roof
         out[ph] = dict(flops=fl[ph], bytes=by[ph], t_tensor_ms=t_tc, t_hbm_ms=t_hbm, bound="tensor" if t_tc > t_hbm else "hbm",
                        t_roof_ms=t_roof, t_measured_ms=meas[ph], frac=t_roof / meas[ph] if meas[ph] > 0 else None)
-    t_meas = t_a + t_d + t_g
+    t_sum = t_a + t_d + t_g
+    t_meas = t_sum if t_step is None else t_step
     out["step"] = dict(t_roof_ms=roof_total, t_measured_ms=t_meas, frac=roof_total / t_meas if t_meas > 0 else None,
-                       note="SURVEY 8d algorithmic model (dense-Adam bytes dominate G); phases timed separately with CUDA events")
+                       t_sum_of_phases_ms=t_sum, frac_sum_of_phases=roof_total / t_sum if t_sum > 0 else None,
+                       note="SURVEY 8d algorithmic model (dense-Adam bytes dominate G); t_measured = the whole step (ms_per_step: one "
+                            "captured graph per batch, the G forward overlapping the D update); phases also timed one by one")
     return out
 
 
@@ -237,6 +245,9 @@ def run_reference(args, rank, world):
     """`--impl reference`: rank 0 times the reference's CPU path (port; TensorFlow is not installable here)."""
     if rank != 0:
         return
+    import torch
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the reference arm is a CPU job that owns the whole host
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
     syn = importlib.import_module("long-tail-gan_b200.synthetic")
     N, I, deg = syn.CONFIGS[CONFIG]
     n_steps = max(1, min(args.steps, 8))
@@ -261,7 +272,6 @@ def main():
     import torch
     import torch.distributed as dist
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -313,54 +323,80 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        step(i)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = engine.kernels_launched - k0
+    # The timed region is EXACTLY args.steps steps between two barriers; it is repeated (each repeat timed on its own, same
+    # bracketing) until at least MIN_TIMED_S of device time has accumulated, and the MEDIAN repeat is reported: one 20-step block is
+    # ~10 ms, too short for the clock sampler and for run-to-run noise to show.
+    block_ms = []
+    launches = 0
+    while True:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        k0 = engine.kernels_launched
+        e0.record()
+        for i in range(args.steps):
+            step(i)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)   # every rank sees the same number, so every rank stops after the same repeat
+        block_ms.append(float(t.item()))
+        launches = engine.kernels_launched - k0
+        if sum(block_ms) >= MIN_TIMED_S * 1e3 or len(block_ms) >= MAX_REPEATS:
+            break
+    ms = sorted(block_ms)[len(block_ms) // 2]
 
     # ---- end-to-end: the step's inputs come from pinned host memory, the losses go back to the host, every step ----
     # Software-pipelined like a real input pipeline: while step i computes, the inputs of step i+1 travel host->device on a
     # copy stream (into that batch's own device buffers), and the loss scalars of step i are read back asynchronously and
     # consumed by the host one step later. Every step's H2D and D2H traffic is inside the timed region.
-    host_scal = [torch.zeros(ops.NSCAL, dtype=torch.float32).pin_memory() for _ in range(2)]
+    host_scal = [torch.zeros(2, ops.NSCAL, dtype=torch.float32).pin_memory() for _ in range(2)]
     copy_stream = torch.cuda.Stream()
     comp = torch.cuda.current_stream()
-    up_done = [torch.cuda.Event() for _ in range(nb)]
-    step_done = [torch.cuda.Event() for _ in range(2)]
-    h2d = 0
-    losses_seen = 0
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    with torch.cuda.stream(copy_stream):
-        h2d += eng.upload_batch(data.batches[0])
-        up_done[0].record(copy_stream)
-    for i in range(args.steps):
-        bi = i % nb
-        if i + 1 < args.steps:
-            nxt = (i + 1) % nb
-            copy_stream.wait_event(step_done[(i + 1) % 2]) if i >= 1 else None   # the previous user of those buffers is long done
-            with torch.cuda.stream(copy_stream):
-                h2d += eng.upload_batch(data.batches[nxt])
-                up_done[nxt].record(copy_stream)
-        comp.wait_event(up_done[bi])
-        step(i)
-        host_scal[i % 2].copy_(engine.scal, non_blocking=True)
-        step_done[i % 2].record(comp)
-        if i >= 1:
-            step_done[(i - 1) % 2].synchronize()          # the host consumes the losses of the previous step
-            losses_seen += int(np.isfinite(host_scal[(i - 1) % 2][ops.S_NLL_SUM].item()))
-    step_done[(args.steps - 1) % 2].synchronize()
-    losses_seen += int(np.isfinite(host_scal[(args.steps - 1) % 2][ops.S_NLL_SUM].item()))
-    f1.record()
-    barrier()
-    ms_e2e = f0.elapsed_time(f1)
-    assert losses_seen == args.steps, "every step's loss must have been read back"
+
+    def e2e_block():
+        up_done = [torch.cuda.Event() for _ in range(nb)]
+        step_done = [torch.cuda.Event() for _ in range(2)]
+        h2d = 0
+        losses_seen = 0
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        with torch.cuda.stream(copy_stream):
+            h2d += eng.upload_batch(data.batches[0])
+            up_done[0].record(copy_stream)
+        for i in range(args.steps):
+            bi = i % nb
+            if i + 1 < args.steps:
+                nxt = (i + 1) % nb
+                copy_stream.wait_event(step_done[(i + 1) % 2]) if i >= 1 else None   # the previous user of those buffers is long done
+                with torch.cuda.stream(copy_stream):
+                    h2d += eng.upload_batch(data.batches[nxt])
+                    up_done[nxt].record(copy_stream)
+            comp.wait_event(up_done[bi])
+            step(i)
+            host_scal[i % 2].copy_(engine.scal_all, non_blocking=True)
+            step_done[i % 2].record(comp)
+            if i >= 1:
+                step_done[(i - 1) % 2].synchronize()          # the host consumes the losses of the previous step
+                losses_seen += int(np.isfinite(host_scal[(i - 1) % 2][0, ops.S_NLL_SUM].item()))
+        step_done[(args.steps - 1) % 2].synchronize()
+        losses_seen += int(np.isfinite(host_scal[(args.steps - 1) % 2][0, ops.S_NLL_SUM].item()))
+        f1.record()
+        barrier()
+        assert losses_seen == args.steps, "every step's loss must have been read back"
+        t = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), h2d
+
+    e2e_ms = []
+    while True:
+        t, h2d = e2e_block()
+        e2e_ms.append(t)
+        if sum(e2e_ms) >= MIN_TIMED_S * 1e3 or len(e2e_ms) >= MAX_REPEATS:
+            break
+    ms_e2e = sorted(e2e_ms)[len(e2e_ms) // 2]
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-phase split and the dominant kernel (fused Adam over the [I,600] decoder weight), CUDA events, same stream ----
@@ -463,23 +499,26 @@ def main():
                     warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="bf16", data="synthetic", config=workload_config(world),
                     e2e=dict(value=users / (ms_e2e * 1e-3), unit="users/s", h2d_bytes_per_step=h2d // args.steps,
-                             d2h_bytes_per_step=ops.NSCAL * 4, ms_per_step=ms_e2e / args.steps),
+                             d2h_bytes_per_step=2 * ops.NSCAL * 4, ms_per_step=ms_e2e / args.steps),
                     gpu_launches=launches, clocks=clocks, roofline=roof,
                     phases_ms=dict(A=t_a, D=t_d, G=t_g, epoch_weighted_users_per_sec=BATCH * world / ((t_a + 10 * t_d + 10 * t_g) * 1e-3)),
                     pairs_per_step=dict(real=int(np.mean([b["Pr"] for b in data.batches])), generated_slots=int(np.mean([b["K"] for b in data.batches]))),
-                    graphs=not args.no_graphs)
+                    graphs=not args.no_graphs,
+                    timing=dict(repeats=len(block_ms), block_ms_min=min(block_ms), block_ms_median=ms, block_ms_max=max(block_ms),
+                                e2e_repeats=len(e2e_ms), rule="the %d-step block is repeated until >= %.1f s of device time; median block reported"
+                                                              % (args.steps, MIN_TIMED_S)))
         if world > 1:
             line["config"]["exchange"] = ("our kernels over NVLink peer memory (%s), flag barriers; no NCCL collective in the step"
                                           % ("NVLS multicast stores + in-switch reduction" if engine.peer["dWdT_mc"] else "unicast peer loads/stores")
                                           if engine.peer is not None else "NCCL collectives captured in the step graphs")
         try:   # whole-step roofline (north_star: fraction of roofline for the full GAN step), per GPU
             hb, _ = measured_peaks("hbm_gbs")
-            tc, _ = measured_peaks("bf16_tflops")
+            tc, _ = measured_peaks("bf16_tflops_sustained")   # phases are timed inside a long step: the sustained figure applies
             n_u = BATCH * nb
             ip = np.asarray(tabs["indptr"], dtype=np.int64); cp = np.asarray(tabs["cand_ptr"], dtype=np.int64)
             line["step_roofline"] = step_roofline(I, BATCH, float(ip[n_u] - ip[0]) / n_u, float(cp[n_u] - cp[0]) / n_u,
                                                   float(np.mean([b["Pr"] for b in data.batches])), float(np.mean([b["K"] for b in data.batches])),
-                                                  t_a, t_d, t_g, hb, tc)
+                                                  t_a, t_d, t_g, hb, tc, world=world, t_step=ms / args.steps)
         except Exception as e:  # noqa: BLE001
             line["step_roofline"] = dict(error=repr(e)[:200])
         if world == 1:

@@ -50,9 +50,12 @@ int ltg_init(void);
  * writes LTG_S_LR_T / LTG_S_ANNEAL into `scal` after zeroing its accumulator slots [0, 8), so a captured graph needs no host values.
  *   kind: 0 = phase-A (rng only), 1 = D update (rng + Adam t), 2 = G update (rng + Adam t + anneal count)
  * zero_buf / zero_words: optional 4-byte-aligned buffer cleared by the same launch (the phase's atomically accumulated
- * gradients or counters), so no separate memset sits at the head of the phase.                                  */
+ * gradients or counters), so no separate memset sits at the head of the phase.
+ * step_snapshot: optional word that receives the new rng step; the phase's kernels take it as their `step_dev`, so phases whose
+ * kernels overlap in time (the G forward beside the D update of the same batch, engine.run_step) each see their own step. */
 int ltg_step_advance(uint32_t* words, float* scal, int kind, float lr, float beta1, float beta2,
-                     float anneal_cap, float total_anneal_steps, void* zero_buf, int64_t zero_words, void* stream);
+                     float anneal_cap, float total_anneal_steps, void* zero_buf, int64_t zero_words, uint32_t* step_snapshot,
+                     void* stream);
 
 /* ---- generic bf16 tensor-core GEMM (tcgen05/TMA/TMEM) ------------------------------------------------------------
  * D[M,N] = alpha * A * B^T with A given as [M,K] (a_mn=0, pitch lda) or stored transposed [K,M] (a_mn=1), B likewise
@@ -195,9 +198,15 @@ int ltg_enc_adam_peer(float* p, float* m, float* v, void* const* shadows_bf16, v
  * (act_ptr[n_active+1] delimits the item's entries in csc_row[] = batch row / csc_pos[] = offset into coef).                */
 int ltg_enc_wgrad_compact(float* G, int n_active, const int32_t* act_ptr, const int32_t* csc_row, const int32_t* csc_pos,
                           const float* coef, const float* dh1pre, int ld_dh1, void* stream);
-/* Dense TF-Adam sweep over W_q0 (every row moves, F7); row i takes gradient G[slot_of_item[i], :] (slot -1: zero).           */
+/* Dense TF-Adam sweep over W_q0 (every row moves, F7); row i takes gradient G[slot_of_item[i], :] (slot -1: zero).
+ * rows: 0 = every row; 1 = only the rows with slot -1 (zero gradient: needs nothing from the backward pass, so the engine
+ * issues it at the start of the G step); 2 = only the batch's active rows.                                                    */
 int ltg_enc_adam(float* p, float* m, float* v, void* shadow_bf16, int n_items, const int32_t* slot_of_item, const float* G,
-                 float lr_t, const float* scal, float beta1, float beta2, float eps, void* stream);
+                 float lr_t, const float* scal, float beta1, float beta2, float eps, int rows, void* stream);
+/* Restores the all-zero state of the dense coefficient matrix xc[B, ld_xc] that ltg_enc_gather_fwd filled for the batch rows
+ * indptr[0..B] (train.py:194-198 made this matrix dense on the host): one store per interaction. nnz_hint sizes the grid.   */
+int ltg_enc_xc_clear(const int32_t* indptr, const int32_t* indices, int B, int nnz_hint, const int32_t* slot_of_item, void* xc_bf16,
+                     int ld_xc, void* stream);
 /* Dense gradient of W_q0 (parity checks / data-parallel all-reduce path): dW[i, :] = G[slot_of_item[i], :] or 0.             */
 int ltg_enc_wgrad_expand(float* dW, int n_items, const int32_t* slot_of_item, const float* G, void* stream);
 

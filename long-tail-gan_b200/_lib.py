@@ -80,7 +80,7 @@ SIGNATURES = {
     "ltg_last_error": (ctypes.c_char_p, []),
     "ltg_version": (_I, []),
     "ltg_init": (_I, []),
-    "ltg_step_advance": (_I, [_P, _P, _I, _F, _F, _F, _F, _F, _P, _I64, _P]),
+    "ltg_step_advance": (_I, [_P, _P, _I, _F, _F, _F, _F, _F, _P, _I64, _P, _P]),
     "ltg_gemm_bf16": (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _F, _I, _F, _U64, _U32, _U32, _P, _I,
                            _I, _P, _P, _I, _F, _I64, _P]),
     "ltg_enc_gather_fwd": (_I, [_P, _P, _P, _I, _I, _I64, _P, _P, _F, _U64, _U32, _P, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P]),
@@ -96,7 +96,8 @@ SIGNATURES = {
     "ltg_dec_dlogits": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ltg_adam": (_I, [_P, _P, _P, _P, _I, _I64, _P, _I64, _F, _P, _F, _F, _F, _P]),
     "ltg_enc_wgrad_compact": (_I, [_P, _I, _P, _P, _P, _P, _P, _I, _P]),
-    "ltg_enc_adam": (_I, [_P, _P, _P, _P, _I, _P, _P, _F, _P, _F, _F, _F, _P]),
+    "ltg_enc_adam": (_I, [_P, _P, _P, _P, _I, _P, _P, _F, _P, _F, _F, _F, _I, _P]),
+    "ltg_enc_xc_clear": (_I, [_P, _P, _I, _I, _P, _P, _I, _P]),
     "ltg_enc_wgrad_expand": (_I, [_P, _I, _P, _P, _P]),
     "ltg_sample_pairs": (_I, [_P, _I, _I, _I, _I64, _P, _P, _P, _P, _P, _P, _U64, _U32, _P, _P, _P, _P, _P, _I, _P, _P]),
     "ltg_dec_row_bwd": (_I, [_P, _I, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -15,13 +15,14 @@ namespace {
 constexpr int H = LTG_H;
 
 __device__ __forceinline__ void adam_update4(float4& p, float4& m, float4& v, const float4 g, float lr_t, float b1, float b2, float eps) {
-  m.x = b1 * m.x + (1.f - b1) * g.x; m.y = b1 * m.y + (1.f - b1) * g.y;
-  m.z = b1 * m.z + (1.f - b1) * g.z; m.w = b1 * m.w + (1.f - b1) * g.w;
-  v.x = b2 * v.x + (1.f - b2) * g.x * g.x; v.y = b2 * v.y + (1.f - b2) * g.y * g.y;
-  v.z = b2 * v.z + (1.f - b2) * g.z * g.z; v.w = b2 * v.w + (1.f - b2) * g.w * g.w;
-  p.x -= lr_t * m.x / (sqrtf(v.x) + eps); p.y -= lr_t * m.y / (sqrtf(v.y) + eps);
-  p.z -= lr_t * m.z / (sqrtf(v.z) + eps); p.w -= lr_t * m.w / (sqrtf(v.w) + eps);
+  ltg_adam4(p, m, v, g, lr_t, b1, b2, eps);
 }
+
+// Non-persistent grid: every CTA owns one fixed chunk of ADAM_UN x 256 float4 and exits. The sweeps run on low-priority side
+// branches of the step graph beside the latency-bound critical chain; a grid-stride kernel with 8 resident CTAs per SM held every
+// thread slot of the GPU for its whole 60 us and the critical chain's kernels waited for it (timeline: vae_mid_bwd_b 58 us under the
+// sweep vs 12 us alone). With short-lived CTAs the block scheduler hands freed slots to the higher-priority kernels first.
+constexpr int ADAM_UN = 2;
 
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g, int n_partials,
@@ -29,31 +30,58 @@ adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
             float b2, float eps) {
   if (lr_t < 0.f) lr_t = scal[LTG_S_LR_T];
   const int64_t n4 = n >> 2;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    float4 pp = ld_stream_f4(p + 4 * i), mm = ld_stream_f4(m + 4 * i), vv = ld_stream_f4(v + 4 * i);
-    float4 gg = ld_stream_f4(g + 4 * i);
-    for (int sp = 1; sp < n_partials; ++sp) {  // split-K partials of the producing GEMM
-      const float4 o = ld_stream_f4(g + (size_t)sp * partial_stride + 4 * i);
-      gg.x += o.x; gg.y += o.y; gg.z += o.z; gg.w += o.w;
+  const int64_t base = (int64_t)blockIdx.x * (256 * ADAM_UN) + threadIdx.x;
+  float4 pp[ADAM_UN], mm[ADAM_UN], vv[ADAM_UN], gg[ADAM_UN];
+#pragma unroll
+  for (int u = 0; u < ADAM_UN; ++u) {          // all loads of the chunk first: 8 independent 16-byte requests per thread
+    const int64_t i = base + u * 256;
+    if (i < n4) {
+      pp[u] = ld_stream_f4(p + 4 * i); mm[u] = ld_stream_f4(m + 4 * i); vv[u] = ld_stream_f4(v + 4 * i);
+      gg[u] = ld_stream_f4(g + 4 * i);
     }
-    adam_update4(pp, mm, vv, gg, lr_t, b1, b2, eps);
-    st_stream_f4(p + 4 * i, pp); st_stream_f4(m + 4 * i, mm); st_stream_f4(v + 4 * i, vv);
+  }
+  if (n_partials > 1) {                        // split-K partials of the producing GEMM, four independent accumulation chains
+#pragma unroll
+    for (int u = 0; u < ADAM_UN; ++u) {
+      const int64_t i = base + u * 256;
+      if (i >= n4) continue;
+      float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a1, a3 = a1;
+      int sp = 1;
+      for (; sp + 3 <= n_partials; sp += 3) {
+        const float4 o1 = ld_stream_f4(g + (size_t)sp * partial_stride + 4 * i);
+        const float4 o2 = ld_stream_f4(g + (size_t)(sp + 1) * partial_stride + 4 * i);
+        const float4 o3 = ld_stream_f4(g + (size_t)(sp + 2) * partial_stride + 4 * i);
+        a1.x += o1.x; a1.y += o1.y; a1.z += o1.z; a1.w += o1.w;
+        a2.x += o2.x; a2.y += o2.y; a2.z += o2.z; a2.w += o2.w;
+        a3.x += o3.x; a3.y += o3.y; a3.z += o3.z; a3.w += o3.w;
+      }
+      for (; sp < n_partials; ++sp) {
+        const float4 o = ld_stream_f4(g + (size_t)sp * partial_stride + 4 * i);
+        a1.x += o.x; a1.y += o.y; a1.z += o.z; a1.w += o.w;
+      }
+      gg[u].x += (a1.x + a2.x) + a3.x; gg[u].y += (a1.y + a2.y) + a3.y; gg[u].z += (a1.z + a2.z) + a3.z; gg[u].w += (a1.w + a2.w) + a3.w;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < ADAM_UN; ++u) {
+    const int64_t i = base + u * 256;
+    if (i >= n4) continue;
+    adam_update4(pp[u], mm[u], vv[u], gg[u], lr_t, b1, b2, eps);
+    st_stream_f4(p + 4 * i, pp[u]); st_stream_f4(m + 4 * i, mm[u]); st_stream_f4(v + 4 * i, vv[u]);
     if (shadow != nullptr) {
-      uint2 s; s.x = pack_bf16x2(pp.x, pp.y); s.y = pack_bf16x2(pp.z, pp.w);
+      uint2 s; s.x = pack_bf16x2(pp[u].x, pp[u].y); s.y = pack_bf16x2(pp[u].z, pp[u].w);
       *reinterpret_cast<uint2*>(shadow + 4 * i) = s;
     }
   }
   // tail (n % 4)
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     const int64_t i = (n4 << 2) + threadIdx.x;
-    float gg = g[i];
-    for (int sp = 1; sp < n_partials; ++sp) gg += g[(size_t)sp * partial_stride + i];
-    const float mm = b1 * m[i] + (1.f - b1) * gg;
-    const float vv = b2 * v[i] + (1.f - b2) * gg * gg;
-    const float pp = p[i] - lr_t * mm / (sqrtf(vv) + eps);
-    m[i] = mm; v[i] = vv; p[i] = pp;
-    if (shadow != nullptr) shadow[i] = __float2bfloat16(pp);
+    float gt = g[i];
+    for (int sp = 1; sp < n_partials; ++sp) gt += g[(size_t)sp * partial_stride + i];
+    float mt = m[i], vt = v[i], pt = p[i];
+    ltg_adam1(pt, mt, vt, gt, lr_t, b1, b2, eps);
+    m[i] = mt; v[i] = vt; p[i] = pt;
+    if (shadow != nullptr) shadow[i] = __float2bfloat16(pt);
   }
 }
 
@@ -111,21 +139,36 @@ enc_wgrad_compact_kernel(float* __restrict__ G, const int32_t* __restrict__ act_
 __global__ void __launch_bounds__(256)
 enc_adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, __nv_bfloat16* __restrict__ shadow, int n_items,
                 const int32_t* __restrict__ slot_of_item, const float* __restrict__ G, float lr_t, const float* __restrict__ scal,
-                float b1, float b2, float eps) {
+                float b1, float b2, float eps, int rows) {
   if (lr_t < 0.f) lr_t = scal[LTG_S_LR_T];
   const int64_t n4 = (int64_t)n_items * H4;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+  const int64_t base = (int64_t)blockIdx.x * (256 * ADAM_UN) + threadIdx.x;   // one fixed chunk per CTA (see adam_kernel)
+  float4 pp[ADAM_UN], mm[ADAM_UN], vv[ADAM_UN], gg[ADAM_UN];
+  bool on[ADAM_UN];
+#pragma unroll
+  for (int u = 0; u < ADAM_UN; ++u) {
+    const int64_t i = base + u * 256;
+    on[u] = false;
+    if (i >= n4) continue;
     const int item = (int)(i / H4);
     const int c4 = (int)(i - (int64_t)item * H4);
-    float4 pp = ld_stream_f4(p + 4 * i), mm = ld_stream_f4(m + 4 * i), vv = ld_stream_f4(v + 4 * i);
     const int slot = __ldg(slot_of_item + item);
-    float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (slot >= 0) gg = __ldg(reinterpret_cast<const float4*>(G + (size_t)slot * H) + c4);
-    adam_update4(pp, mm, vv, gg, lr_t, b1, b2, eps);
-    st_stream_f4(p + 4 * i, pp); st_stream_f4(m + 4 * i, mm); st_stream_f4(v + 4 * i, vv);
+    // rows: 0 every row; 1 only rows without a gradient (their update needs nothing from this step's backward pass, so it can run
+    // while the forward chain leaves HBM idle); 2 only the batch's active rows
+    if ((rows == 1 && slot >= 0) || (rows == 2 && slot < 0)) continue;
+    on[u] = true;
+    pp[u] = ld_stream_f4(p + 4 * i); mm[u] = ld_stream_f4(m + 4 * i); vv[u] = ld_stream_f4(v + 4 * i);
+    gg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (slot >= 0) gg[u] = __ldg(reinterpret_cast<const float4*>(G + (size_t)slot * H) + c4);
+  }
+#pragma unroll
+  for (int u = 0; u < ADAM_UN; ++u) {
+    if (!on[u]) continue;
+    const int64_t i = base + u * 256;
+    adam_update4(pp[u], mm[u], vv[u], gg[u], lr_t, b1, b2, eps);
+    st_stream_f4(p + 4 * i, pp[u]); st_stream_f4(m + 4 * i, mm[u]); st_stream_f4(v + 4 * i, vv[u]);
     if (shadow != nullptr) {
-      uint2 s; s.x = pack_bf16x2(pp.x, pp.y); s.y = pack_bf16x2(pp.z, pp.w);
+      uint2 s; s.x = pack_bf16x2(pp[u].x, pp[u].y); s.y = pack_bf16x2(pp[u].z, pp[u].w);
       *reinterpret_cast<uint2*>(shadow + 4 * i) = s;
     }
   }
@@ -143,6 +186,21 @@ enc_wgrad_expand_kernel(float* __restrict__ dW, int n_items, const int32_t* __re
     float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
     if (slot >= 0) gg = __ldg(reinterpret_cast<const float4*>(G + (size_t)slot * H) + c4);
     st_stream_f4(dW + 4 * i, gg);
+  }
+}
+
+// Xc (dense bf16 coefficient matrix of the batch, written by ltg_enc_gather_fwd) back to all-zero after its consumer: clears
+// exactly the entries the forward wrote (one 2-byte store per interaction instead of a fill of the whole matrix)
+__global__ void __launch_bounds__(256)
+enc_xc_clear_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, int B, const int32_t* __restrict__ slot_of_item,
+                    __nv_bfloat16* __restrict__ xc, int ld_xc) {
+  const int e0 = indptr[0];
+  const int n = indptr[B] - e0;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    // row of entry e: binary search in indptr[0..B]
+    int lo = 0, hi = B;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (indptr[mid] - e0 <= e) lo = mid; else hi = mid; }
+    xc[(size_t)lo * ld_xc + slot_of_item[indices[e0 + e]]] = __float2bfloat16(0.f);
   }
 }
 
@@ -167,7 +225,7 @@ extern "C" int ltg_adam(float* p, float* m, float* v, const float* g, int n_part
                 reinterpret_cast<uintptr_t>(g)) & 15) == 0);
   LTG_REQUIRE((reinterpret_cast<uintptr_t>(shadow_bf16) & 7) == 0);
   if (n <= 0) return LTG_OK;
-  adam_kernel<<<grid_for(n >> 2, 256, kStreamBlocks), 256, 0, (cudaStream_t)stream>>>(
+  adam_kernel<<<grid_for(((n >> 2) + ADAM_UN - 1) / ADAM_UN, 256, 1 << 30), 256, 0, (cudaStream_t)stream>>>(
       p, m, v, g, n_partials, partial_stride, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n, lr_t, scal, beta1, beta2, eps);
   LTG_CHECK_LAUNCH();
   return LTG_OK;
@@ -184,13 +242,13 @@ extern "C" int ltg_enc_wgrad_compact(float* G, int n_active, const int32_t* act_
 }
 
 extern "C" int ltg_enc_adam(float* p, float* m, float* v, void* shadow_bf16, int n_items, const int32_t* slot_of_item, const float* G,
-                            float lr_t, const float* scal, float beta1, float beta2, float eps, void* stream) {
-  LTG_REQUIRE(p && m && v && slot_of_item && G);
+                            float lr_t, const float* scal, float beta1, float beta2, float eps, int rows, void* stream) {
+  LTG_REQUIRE(p && m && v && slot_of_item && G && rows >= 0 && rows <= 2);
   LTG_REQUIRE(lr_t >= 0.f || scal != nullptr);
   LTG_REQUIRE((reinterpret_cast<uintptr_t>(shadow_bf16) & 7) == 0);
   if (n_items <= 0) return LTG_OK;
-  enc_adam_kernel<<<grid_for((int64_t)n_items * H4, 256, kStreamBlocks), 256, 0, (cudaStream_t)stream>>>(
-      p, m, v, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n_items, slot_of_item, G, lr_t, scal, beta1, beta2, eps);
+  enc_adam_kernel<<<grid_for(((int64_t)n_items * H4 + ADAM_UN - 1) / ADAM_UN, 256, 1 << 30), 256, 0, (cudaStream_t)stream>>>(
+      p, m, v, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n_items, slot_of_item, G, lr_t, scal, beta1, beta2, eps, rows);
   LTG_CHECK_LAUNCH();
   return LTG_OK;
 }
@@ -199,6 +257,16 @@ extern "C" int ltg_enc_wgrad_expand(float* dW, int n_items, const int32_t* slot_
   LTG_REQUIRE(dW && slot_of_item && G);
   if (n_items <= 0) return LTG_OK;
   enc_wgrad_expand_kernel<<<grid_for((int64_t)n_items * H4, 256, kStreamBlocks), 256, 0, (cudaStream_t)stream>>>(dW, n_items, slot_of_item, G);
+  LTG_CHECK_LAUNCH();
+  return LTG_OK;
+}
+
+extern "C" int ltg_enc_xc_clear(const int32_t* indptr, const int32_t* indices, int B, int nnz_hint, const int32_t* slot_of_item, void* xc_bf16,
+                                int ld_xc, void* stream) {
+  LTG_REQUIRE(indptr && indices && slot_of_item && xc_bf16);
+  if (B <= 0 || nnz_hint <= 0) return LTG_OK;
+  enc_xc_clear_kernel<<<grid_for(nnz_hint, 256, kStreamBlocks), 256, 0, (cudaStream_t)stream>>>(
+      indptr, indices, B, slot_of_item, reinterpret_cast<__nv_bfloat16*>(xc_bf16), ld_xc);
   LTG_CHECK_LAUNCH();
   return LTG_OK;
 }

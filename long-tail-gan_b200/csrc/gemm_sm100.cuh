@@ -580,12 +580,7 @@ struct EpiAdam {
       if (col_ok && r < M) {
         const float gx = sw[rl * 17 + c4], gy = sw[rl * 17 + c4 + 1], gz = sw[rl * 17 + c4 + 2], gw = sw[rl * 17 + c4 + 3];
         float4 m4 = mm[j], v4 = vv[j], p4 = pp[j];
-        m4.x = p.b1 * m4.x + (1.f - p.b1) * gx; m4.y = p.b1 * m4.y + (1.f - p.b1) * gy;
-        m4.z = p.b1 * m4.z + (1.f - p.b1) * gz; m4.w = p.b1 * m4.w + (1.f - p.b1) * gw;
-        v4.x = p.b2 * v4.x + (1.f - p.b2) * gx * gx; v4.y = p.b2 * v4.y + (1.f - p.b2) * gy * gy;
-        v4.z = p.b2 * v4.z + (1.f - p.b2) * gz * gz; v4.w = p.b2 * v4.w + (1.f - p.b2) * gw * gw;
-        p4.x -= lr_t * m4.x / (sqrtf(v4.x) + p.eps); p4.y -= lr_t * m4.y / (sqrtf(v4.y) + p.eps);
-        p4.z -= lr_t * m4.z / (sqrtf(v4.z) + p.eps); p4.w -= lr_t * m4.w / (sqrtf(v4.w) + p.eps);
+        ltg_adam4(p4, m4, v4, make_float4(gx, gy, gz, gw), lr_t, p.b1, p.b2, p.eps);
         const size_t off = (size_t)r * p.ld + col0 + c4;
         st_stream_f4(p.p + off, p4); st_stream_f4(p.m + off, m4); st_stream_f4(p.v + off, v4);
         uint2 sh; sh.x = pack_bf16x2(p4.x, p4.y); sh.y = pack_bf16x2(p4.z, p4.w);

@@ -171,3 +171,18 @@ __device__ __forceinline__ float4 ld_stream_f4(const float* p) {
 __device__ __forceinline__ void st_stream_f4(float* p, float4 v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+
+// ---------------------------------------------------------------------------------------------
+// TF1 Adam on one element (train.py:160-164): the ONE definition every optimizer kernel uses (adam / enc_adam, the
+// peer variants, the GEMM epilogue). Explicit round-to-nearest intrinsics fix where the compiler may contract a multiply into an
+// FMA, so two kernels given the same inputs produce bit-identical parameters (the data-parallel ranks must stay in lock step).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ltg_adam1(float& p, float& m, float& v, float g, float lr_t, float b1, float b2, float eps) {
+  m = __fmaf_rn(b1, m, __fmul_rn(1.f - b1, g));
+  v = __fmaf_rn(b2, v, __fmul_rn(__fmul_rn(1.f - b2, g), g));
+  p = __fsub_rn(p, __fdiv_rn(__fmul_rn(lr_t, m), __fadd_rn(sqrtf(v), eps)));
+}
+__device__ __forceinline__ void ltg_adam4(float4& p, float4& m, float4& v, const float4 g, float lr_t, float b1, float b2, float eps) {
+  ltg_adam1(p.x, m.x, v.x, g.x, lr_t, b1, b2, eps); ltg_adam1(p.y, m.y, v.y, g.y, lr_t, b1, b2, eps);
+  ltg_adam1(p.z, m.z, v.z, g.z, lr_t, b1, b2, eps); ltg_adam1(p.w, m.w, v.w, g.w, lr_t, b1, b2, eps);
+}

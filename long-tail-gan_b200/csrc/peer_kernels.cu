@@ -154,12 +154,7 @@ adam_peer_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict
       for (int r = 1; r < PEER_MAX; ++r)
         if (r < world) { gg.x += g[r].x; gg.y += g[r].y; gg.z += g[r].z; gg.w += g[r].w; }   // rank order on every rank
     }
-    mm.x = b1 * mm.x + (1.f - b1) * gg.x; mm.y = b1 * mm.y + (1.f - b1) * gg.y;
-    mm.z = b1 * mm.z + (1.f - b1) * gg.z; mm.w = b1 * mm.w + (1.f - b1) * gg.w;
-    vv.x = b2 * vv.x + (1.f - b2) * gg.x * gg.x; vv.y = b2 * vv.y + (1.f - b2) * gg.y * gg.y;
-    vv.z = b2 * vv.z + (1.f - b2) * gg.z * gg.z; vv.w = b2 * vv.w + (1.f - b2) * gg.w * gg.w;
-    pp.x -= lr_t * mm.x / (sqrtf(vv.x) + eps); pp.y -= lr_t * mm.y / (sqrtf(vv.y) + eps);
-    pp.z -= lr_t * mm.z / (sqrtf(vv.z) + eps); pp.w -= lr_t * mm.w / (sqrtf(vv.w) + eps);
+    ltg_adam4(pp, mm, vv, gg, lr_t, b1, b2, eps);
     st_stream_f4(p + 4 * i, pp); st_stream_f4(m + 4 * i, mm); st_stream_f4(v + 4 * i, vv);
     uint2 s; s.x = pack_bf16x2(pp.x, pp.y); s.y = pack_bf16x2(pp.z, pp.w);
     if (shadows_mc != nullptr) {
@@ -190,12 +185,7 @@ enc_adam_peer_kernel(float* __restrict__ p, float* __restrict__ m, float* __rest
     const int slot = __ldg(slot_of_item + item);
     float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
     if (slot >= 0) gg = __ldg(reinterpret_cast<const float4*>(G + (size_t)slot * LTG_H) + c4);
-    mm.x = b1 * mm.x + (1.f - b1) * gg.x; mm.y = b1 * mm.y + (1.f - b1) * gg.y;
-    mm.z = b1 * mm.z + (1.f - b1) * gg.z; mm.w = b1 * mm.w + (1.f - b1) * gg.w;
-    vv.x = b2 * vv.x + (1.f - b2) * gg.x * gg.x; vv.y = b2 * vv.y + (1.f - b2) * gg.y * gg.y;
-    vv.z = b2 * vv.z + (1.f - b2) * gg.z * gg.z; vv.w = b2 * vv.w + (1.f - b2) * gg.w * gg.w;
-    pp.x -= lr_t * mm.x / (sqrtf(vv.x) + eps); pp.y -= lr_t * mm.y / (sqrtf(vv.y) + eps);
-    pp.z -= lr_t * mm.z / (sqrtf(vv.z) + eps); pp.w -= lr_t * mm.w / (sqrtf(vv.w) + eps);
+    ltg_adam4(pp, mm, vv, gg, lr_t, b1, b2, eps);
     st_stream_f4(p + 4 * i, pp); st_stream_f4(m + 4 * i, mm); st_stream_f4(v + 4 * i, vv);
     uint2 s; s.x = pack_bf16x2(pp.x, pp.y); s.y = pack_bf16x2(pp.z, pp.w);
     if (shadows_mc != nullptr) {

@@ -66,12 +66,16 @@ extern "C" int ltg_init(void) {
 // Also clears one caller-chosen buffer (the phase's atomically accumulated gradients / counters): one memset launch less at the
 // head of every phase's critical chain.
 __global__ void step_advance_kernel(uint32_t* words, float* scal, int kind, float lr, double beta1, double beta2,
-                                    float anneal_cap, float total_anneal_steps, uint32_t* zero_buf, int64_t zero_words) {
+                                    float anneal_cap, float total_anneal_steps, uint32_t* zero_buf, int64_t zero_words,
+                                    uint32_t* step_snapshot) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < zero_words; i += (int64_t)gridDim.x * blockDim.x) zero_buf[i] = 0u;
   if (blockIdx.x != 0) return;
   if (threadIdx.x < 8) scal[threadIdx.x] = 0.f;   // per-step accumulators (KL, NLL, sum p, sum y, cnt, d_loss)
   if (threadIdx.x != 0) return;
   words[0] += 1;
+  // a phase whose kernels may run beside another phase's (engine.run_step: the G forward beside the D update) reads its rng step
+  // from its own word instead of the live counter
+  if (step_snapshot != nullptr) *step_snapshot = words[0];
   if (kind >= 1) {
     const uint32_t t = ++words[1];
     // TF1 AdamOptimizer: lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t)   [ext, SURVEY F6]
@@ -89,14 +93,15 @@ __global__ void step_advance_kernel(uint32_t* words, float* scal, int kind, floa
 }
 
 extern "C" int ltg_step_advance(uint32_t* words, float* scal, int kind, float lr, float beta1, float beta2,
-                                float anneal_cap, float total_anneal_steps, void* zero_buf, int64_t zero_words, void* stream) {
+                                float anneal_cap, float total_anneal_steps, void* zero_buf, int64_t zero_words, uint32_t* step_snapshot,
+                                void* stream) {
   LTG_REQUIRE(words != nullptr && scal != nullptr && zero_words >= 0 && (zero_words == 0 || zero_buf != nullptr));
   LTG_REQUIRE((reinterpret_cast<uintptr_t>(zero_buf) & 3) == 0);
   int64_t blocks = (zero_words + 1023) / 1024;   // 256 threads x 4 words each
   if (blocks < 1) blocks = 1;
   if (blocks > 148) blocks = 148;
   step_advance_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(words, scal, kind, lr, (double)beta1, (double)beta2, anneal_cap,
-                                                                          total_anneal_steps, reinterpret_cast<uint32_t*>(zero_buf), zero_words);
+                                                                          total_anneal_steps, reinterpret_cast<uint32_t*>(zero_buf), zero_words, step_snapshot);
   LTG_CHECK_LAUNCH();
   return LTG_OK;
 }

@@ -204,17 +204,32 @@ class GanEngine(object):
         self.device = vae.device
         self.max_B, self.max_P = int(max_B), int(max(1, max_P))
         self.max_active = int(self.I if max_active is None else max(1, max_active))
-        self.words = torch.zeros(4, dtype=torch.int32, device=self.device)
-        self.scal = torch.zeros(ops.NSCAL, dtype=torch.float32, device=self.device)
+        # words[0] rng step, [1] Adam t, [2] G-update count; [4], [5], [6]: the rng step of the current phase A / D update / G update
+        # (snapshots written by ltg_step_advance: each phase's kernels read their own word, so the G forward may run beside the D update)
+        self.words = torch.zeros(8, dtype=torch.int32, device=self.device)
+        self.w_a, self.w_d, self.w_g = self.words[4:5], self.words[5:6], self.words[6:7]
+        # per-step scalars: row 0 for phase A and the G update, row 1 for the D update (same reason)
+        self.scal_all = torch.zeros(2, ops.NSCAL, dtype=torch.float32, device=self.device)
+        self.scal, self.scal_d = self.scal_all[0], self.scal_all[1]
         self._graphs = {}
-        # side streams: independent branches of a step (captured as parallel branches of the CUDA graph)
-        self.s1 = torch.cuda.Stream(device=self.device)
-        self.s2 = torch.cuda.Stream(device=self.device)
-        # graphs are captured on a high-priority stream: kernel nodes inherit it, so the critical chain (main) wins SMs over the
-        # HBM-bound sweeps and weight-gradient GEMMs of the side branches when both have CTAs ready (LTG_GRAPH_PRIORITY=0: off)
+        # Side streams: independent branches of a step (captured as parallel branches of the CUDA graph). Kernel nodes inherit the
+        # priority of the stream they were captured on: the critical chain (capture stream) is highest, the G forward that runs beside
+        # the D update next, then the small weight-gradient GEMMs, then the HBM-bound sweeps (decoder weight gradient + Adam, early
+        # encoder Adam), whose short-lived CTAs fill whatever the chain leaves free (LTG_GRAPH_PRIORITY=0: everything default priority)
         import os
-        self._cap_stream = torch.cuda.Stream(device=self.device, priority=-1) if os.environ.get("LTG_GRAPH_PRIORITY", "1") != "0" else None
+        prio = os.environ.get("LTG_GRAPH_PRIORITY", "1") != "0"
+        mk = lambda p: torch.cuda.Stream(device=self.device, priority=(p if prio else 0))  # noqa: E731
+        self.s1 = mk(-1)   # decoder weight gradient + Adam sweep / discriminator forward of the G update
+        self.s2 = mk(-2)   # small weight-gradient GEMMs
+        self.s3 = mk(-3)   # run_step: the G update's VAE forward beside the D update
+        self.s4 = mk(0)    # Adam over the encoder rows that get no gradient from this batch
+        self._cap_stream = mk(-5) if prio else None
         self.overlap = True
+        # The dense TF-Adam sweep over W_q0 (F7) moves every row, but rows of items absent from the batch (two thirds at batch 500)
+        # have a zero gradient: their update depends on nothing the step computes, so it is issued at the START of the G update and
+        # runs while the latency-bound forward chain leaves HBM idle; only the active rows wait for the backward pass.
+        self.early_adam = os.environ.get("LTG_EARLY_ADAM", "1") != "0"
+        self.overlap_dg = os.environ.get("LTG_OVERLAP_DG", "1") != "0"   # run_step: G forward beside the D update
         # Decoder wgrad GEMM with the Adam step as its epilogue (EpiAdam, ltg_wgrad_adam): correct (tests) and 96 MB/step less HBM
         # traffic, but measured SLOWER than wgrad GEMM (38 us) + streaming Adam (58 us): 112 us, 2.9 TB/s -- the 16 epilogue warps
         # walk load -> update -> store chunk by chunk and cannot keep enough HBM requests in flight. Kept off until the epilogue is
@@ -318,23 +333,24 @@ class GanEngine(object):
     def _vae_forward(self, data, bt, is_training, keep, stash=True, indptr=None, indices=None, coef=None, uid0=None, B=None, max_nnz=None):
         """MultiVAE.forward_pass (MultiVAE.py:175-186) up to the logits and their softmax statistics."""
         v = self.vae
+        wstep = self.w_g if is_training else self.w_a
         B = bt["B"] if B is None else B
         indptr = data.indptr[bt["b0"]: bt["b0"] + B + 1] if indptr is None else indptr
         indices = data.indices if indices is None else indices
         coef = data.coef if coef is None else coef
         uid0 = bt["uid0"] if uid0 is None else uid0
         # Xc (dense coefficient matrix, G step only) is all-zero here: the G backward clears it again right after its consumer
-        ops.enc_gather_fwd(indptr, indices, None, B, self.I, uid0, v.W_q0_b, v.view("b_q0"), keep, self.seed, 0, self.words, self.h1, coef,
+        ops.enc_gather_fwd(indptr, indices, None, B, self.I, uid0, v.W_q0_b, v.view("b_q0"), keep, self.seed, 0, wstep, self.h1, coef,
                            bt["max_nnz"] if max_nnz is None else max_nnz, self.enc_ws, self.enc_cnt,
                            bt["slot_of_item"] if is_training else None, self.Xc if is_training else None)
         if self.fused_mid:
             ops.vae_mid_fwd(self.h1, v.view("W_q1", "b"), v.view("b_q1"), v.view("W_p0", "b"), v.view("b_p0"),
-                            self.eps_inject if is_training else None, B, uid0, 1.0 if is_training else 0.0, self.seed, 0, self.words,
+                            self.eps_inject if is_training else None, B, uid0, 1.0 if is_training else 0.0, self.seed, 0, wstep,
                             self.mulv, self.z, self.zmu, self.h2, self.scal)
         else:
             ops.gemm(self.h1, v.view("W_q1", "b"), B, 2 * L, H, b_mn=True, bn=64, out_f32=self.mulv, bias=v.view("b_q1"))
             ops.latent_fwd(self.mulv, self.eps_inject if is_training else None, B, uid0, 1.0 if is_training else 0.0, self.seed, 0,
-                           self.words, self.z, self.zmu, self.scal)
+                           wstep, self.z, self.zmu, self.scal)
             ops.gemm(self.z, v.view("W_p0", "b"), B, H, L, b_mn=True, bn=64, out_bf16=self.h2, bias=v.view("b_p0"), act=1)
         ops.dec_logits_fwd(self.h2, v.WdT_b, v.view("b_p1"), B, self.I, self.logits if stash else None, self.partial)
         return indptr, indices
@@ -344,22 +360,23 @@ class GanEngine(object):
         d = self.disc
         seed, kd = self.seed, self.keep_d
         st = ops.STREAM_DISC_DROPOUT
+        words, scal = (self.w_d, self.scal_d) if backward else (self.w_g, self.scal)   # D update / G update
         ops.disc_gather(d.E_b, pop, niche, P, self.Xp, self.Xn)
         if self.fused_disc:
-            ops.disc_fwd_fused(self.Xp, self.Xn, P, d, label, kd, seed, st, self.words, self.Hd, self.y, self.scal,
+            ops.disc_fwd_fused(self.Xp, self.Xn, P, d, label, kd, seed, st, words, self.Hd, self.y, scal,
                                self.dz3 if backward else None, g_w4 if backward else None, g_b4 if backward else None)
             return
         k1 = d.h0 + 1  # embedding columns + the ones column (bias row of W1 / W2)
         ops.gemm(self.Xp, d.view("W1", "b"), P, d.h1, k1, lda=128, b_mn=True, bn=ops.pick_bn(P, d.h1), out_bf16=self.Hd, ld_bf16=d.k3,
-                 act=1, keep=kd, seed=seed, rng_stream=st, rng_step_dev=self.words, rng_ld=d.ld1)
+                 act=1, keep=kd, seed=seed, rng_stream=st, rng_step_dev=words, rng_ld=d.ld1)
         ops.gemm(self.Xn, d.view("W2", "b"), P, d.h2, k1, lda=128, b_mn=True, bn=ops.pick_bn(P, d.h2), out_bf16=self.Hd[:, d.off2:],
-                 ld_bf16=d.k3, act=1, keep=kd, seed=seed, rng_stream=st + 1, rng_step_dev=self.words, rng_ld=d.ld2)
+                 ld_bf16=d.k3, act=1, keep=kd, seed=seed, rng_stream=st + 1, rng_step_dev=words, rng_ld=d.ld2)
         ops.gemm(self.Hd, d.view("W3", "b"), P, d.h3, d.k3, b_mn=True, bn=ops.pick_bn(P, d.h3), out_bf16=self.Y3, act=1, keep=kd, seed=seed,
-                 rng_stream=st + 2, rng_step_dev=self.words, rng_ld=d.ld3)
+                 rng_stream=st + 2, rng_step_dev=words, rng_ld=d.ld3)
         if backward:
-            ops.disc_head(self.Y3, P, d.h3, d.view("w4"), d.view("b4"), label, kd, self.y, self.scal, self.dz3, g_w4, g_b4)
+            ops.disc_head(self.Y3, P, d.h3, d.view("w4"), d.view("b4"), label, kd, self.y, scal, self.dz3, g_w4, g_b4)
         else:
-            ops.disc_head(self.Y3, P, d.h3, d.view("w4"), d.view("b4"), label, kd, self.y, self.scal)
+            ops.disc_head(self.Y3, P, d.h3, d.view("w4"), d.view("b4"), label, kd, self.y, scal)
 
     # ------------------------------------------------------------------------------------------------------------
     # phase A: train.py:192-269
@@ -368,13 +385,13 @@ class GanEngine(object):
         bt = data.batches[bi]
         B = bt["B"]
         ops.step_advance(self.words, self.scal, 0, self.lr, anneal_cap=self.anneal_cap, total_anneal_steps=self.total_anneal_steps,
-                         zero=bt["cnt"])   # the sampler's per-user counters are cleared by the same launch
+                         zero=bt["cnt"], snap=self.w_a)   # the sampler's per-user counters are cleared by the same launch
         # train.py:200: sess.run(generator_out) with default placeholders: dropout 0.75 (F4), is_training 0
         self._vae_forward(data, bt, False, self.keep_vae)
         if bt["K"] > 0:
             Pr = bt["Pr"]
             ops.sample_pairs(self.logits, B, self.I, bt["uid0"], data.cand_ptr[bt["b0"]: bt["b0"] + B + 1], data.cand_items, bt["samp_ptr"],
-                             data.pop_ptr[bt["b0"]: bt["b0"] + B + 1], data.pop_items, data.item_valid, self.seed, 0, self.words,
+                             data.pop_ptr[bt["b0"]: bt["b0"] + B + 1], data.pop_items, data.item_valid, self.seed, 0, self.w_a,
                              bt["pair_niche"][Pr:], bt["pair_pop"][Pr:], bt["label"][Pr:], bt["cnt"], bt["max_cand"], bt["samp_order"])
 
     # ------------------------------------------------------------------------------------------------------------
@@ -384,13 +401,18 @@ class GanEngine(object):
         self._d_fwd_bwd(data, bi)
         self._d_update()
 
-    def _d_fwd_bwd(self, data, bi):
+    def _d_advance(self):
+        # (the w4 / b4 gradient slots of partial 0, accumulated by the head with atomics, are cleared by the same launch)
+        d = self.disc
+        ops.step_advance(self.words, self.scal_d, 1, self.lr, anneal_cap=self.anneal_cap, total_anneal_steps=self.total_anneal_steps,
+                         zero=self.arena_gp[0][d._off["w4"][0]:], snap=self.w_d)
+
+    def _d_fwd_bwd(self, data, bi, advance=True):
         bt = data.batches[bi]
         d = self.disc
         P = bt["P"]
-        # (the w4 / b4 gradient slots of partial 0, accumulated by the head with atomics, are cleared by the same launch)
-        ops.step_advance(self.words, self.scal, 1, self.lr, anneal_cap=self.anneal_cap, total_anneal_steps=self.total_anneal_steps,
-                         zero=self.arena_gp[0][d._off["w4"][0]:])
+        if advance:
+            self._d_advance()
         # autodiff of discriminator.py:25-55; every bias gradient is the ones-row of its weight-gradient GEMM.
         # Single GPU: the split-K partials of the three weight-gradient GEMMs go to arena_gp[s] and the Adam kernel sums them.
         # Data parallel: atomic accumulation into arena_g (which is what gets all-reduced).
@@ -424,10 +446,10 @@ class GanEngine(object):
     def _d_update(self):
         d = self.disc
         if self.world_size == 1:
-            ops.adam(d.arena, d.arena_m, d.arena_v, self.arena_gp, d.arena_b, scal=self.scal, n_partials=self._d_parts,
+            ops.adam(d.arena, d.arena_m, d.arena_v, self.arena_gp, d.arena_b, scal=self.scal_d, n_partials=self._d_parts,
                      partial_stride=d.arena_n)
         else:
-            ops.adam(d.arena, d.arena_m, d.arena_v, d.arena_g, d.arena_b, scal=self.scal)
+            ops.adam(d.arena, d.arena_m, d.arena_v, d.arena_g, d.arena_b, scal=self.scal_d)
 
     # ------------------------------------------------------------------------------------------------------------
     # G update: train.py:326
@@ -435,27 +457,44 @@ class GanEngine(object):
     def g_step(self, data, bi, update=True):
         """Single-GPU G update. The data-parallel variant (run_g_step with world_size > 1) runs the same three parts with
         the two exchange steps in between."""
-        self._g_forward(data, bi)
         self._fuse_update = bool(update) and self.world_size == 1
+        self._g_forward(data, bi)
         self._g_backward(data, bi)
         self._fuse_update = False
         if update and self.world_size > 1:
             self._g_update(data, bi)
 
+    def _g_advance(self):
+        ops.step_advance(self.words, self.scal, 2, self.lr, anneal_cap=self.anneal_cap, total_anneal_steps=self.total_anneal_steps,
+                         zero=self.vae.small_g, snap=self.w_g)   # bias gradients are accumulated atomically: cleared by the same launch
+
+    def _g_early(self, data, bi):
+        """Part of the G update that depends on nothing but the step counters: TF-Adam over the encoder rows without a gradient."""
+        self._early_done = False
+        if not (self.early_adam and self.world_size == 1 and getattr(self, "_fuse_update", False)):
+            return
+        v = self.vae
+        with self._fork(self.s4):
+            ops.enc_adam(v.W_q0, v.W_q0_m, v.W_q0_v, v.W_q0_b, self.I, data.batches[bi]["slot_of_item"], self.G_enc, scal=self.scal, rows=1)
+        self._early_done = True
+
+    def _g_disc_forward(self, data, bi):
+        # y_generated with fresh dropout masks (keep_prob 0.7 is fed in the G step too, train.py:326)
+        bt = data.batches[bi]
+        Pr, K = bt["Pr"], bt["K"]
+        if K > 0:
+            self._disc_forward(bt["pair_pop"][Pr:], bt["pair_niche"][Pr:], bt["label"][Pr:], K, False)
+
     def _g_forward(self, data, bi):
         bt = data.batches[bi]
-        v = self.vae
-        B, Pr, K = bt["B"], bt["Pr"], bt["K"]
-        ops.step_advance(self.words, self.scal, 2, self.lr, anneal_cap=self.anneal_cap, total_anneal_steps=self.total_anneal_steps,
-                         zero=v.small_g)   # bias gradients are accumulated atomically: cleared by the same launch
-        if K > 0:
-            # y_generated with fresh dropout masks (keep_prob 0.7 is fed in the G step too, train.py:326): independent of the
-            # generator forward, so it runs as a parallel branch
+        self._g_advance()
+        self._g_early(data, bi)
+        if bt["K"] > 0:
+            # independent of the generator forward, so it runs as a parallel branch
             with self._fork(self.s1):
-                self._disc_forward(bt["pair_pop"][Pr:], bt["pair_niche"][Pr:], bt["label"][Pr:], K, False)
-        indptr, indices = self._vae_forward(data, bt, True, self.keep_vae)
-        samp = (bt["samp_ptr"], bt["pair_niche"][Pr:], bt["label"][Pr:]) if K > 0 else (None, None, None)
-        if K > 0:
+                self._g_disc_forward(data, bi)
+        self._vae_forward(data, bt, True, self.keep_vae)
+        if bt["K"] > 0:
             self._join(self.s1)
         # the softmax statistics are fused into the backward's per-user kernel (ltg_dec_row_bwd)
 
@@ -562,7 +601,8 @@ class GanEngine(object):
         if not (self.world_size > 1 and getattr(self, "_dp_comm", False) and self.dp_tables is not None):
             ops.gemm(self.Xc, self.dh1pre_b, bt["n_active"], H, B, a_mn=True, b_mn=True, bn=ops.pick_bn(bt["n_active"], H), out_f32=self.G_enc)
         with self._fork(self.s2):
-            self.Xc.zero_()   # self-cleaning, off the critical path: the next G forward scatters into an all-zero matrix
+            # self-cleaning, off the critical path: the next G forward scatters into an all-zero matrix
+            ops.enc_xc_clear(indptr, indices, B, bt["nnz"], bt["slot_of_item"], self.Xc)
         act_exchange = dp_comm and self.dp_tables is not None
         if self.world_size > 1 and not act_exchange:
             ops.enc_wgrad_expand(self.dW_q0, self.I, bt["slot_of_item"], self.G_enc)
@@ -572,7 +612,7 @@ class GanEngine(object):
             tb = self.dp_tables[bi]
             self.Xc_glob.zero_()
             ops.enc_coef_scatter(tb["e_row"], tb["e_item"], tb["e_slot"], tb["row_uid"], tb["row_rnorm"], tb["n_entries"], self.I,
-                                 self.keep_vae, self.seed, 0, self.words, self.Xc_glob)
+                                 self.keep_vae, self.seed, 0, self.w_g, self.Xc_glob)
             if self.peer is not None:
                 nb_ = self.dh1pre_b.numel() * 2
                 ops.peer_push(self.dh1pre_b, nb_, self.peer["dh1"], self.rank * nb_, self.world_size, dst_mc=self.peer["dh1_mc"])
@@ -597,7 +637,11 @@ class GanEngine(object):
                 r0, nr = self.row0, self.nrows
                 ops.adam(v.W_q0[r0:r0 + nr], v.W_q0_m[r0:r0 + nr], v.W_q0_v[r0:r0 + nr], self.g_enc_shard, self.Wq0_b_shard, scal=self.scal)
         if fuse_update:
-            ops.enc_adam(v.W_q0, v.W_q0_m, v.W_q0_v, v.W_q0_b, self.I, bt["slot_of_item"], self.G_enc, scal=self.scal)
+            ops.enc_adam(v.W_q0, v.W_q0_m, v.W_q0_v, v.W_q0_b, self.I, bt["slot_of_item"], self.G_enc, scal=self.scal,
+                         rows=2 if getattr(self, "_early_done", False) else 0)
+            if getattr(self, "_early_done", False):
+                self._join(self.s4)
+                self._early_done = False
         self._join(self.s2)
         self._join(self.s1)
         if fuse_update:
@@ -657,7 +701,7 @@ class GanEngine(object):
             d = self.disc
             self._pbar(0)
             ops.peer_reduce(self.peer["arena_g"], 0, d.arena_g.numel(), self.world_size, self.arena_gsum, bufs_mc=self.peer["arena_g_mc"])
-            ops.adam(d.arena, d.arena_m, d.arena_v, self.arena_gsum, d.arena_b, scal=self.scal)
+            ops.adam(d.arena, d.arena_m, d.arena_v, self.arena_gsum, d.arena_b, scal=self.scal_d)
             return
         dist.all_reduce(self.disc.arena_g)                       # 161 k discriminator gradients: one small bucket
         self._d_update()
@@ -667,9 +711,31 @@ class GanEngine(object):
         reference's epoch schedule needs -- all of phase A first, then sub-epochs of D and G; a per-batch step is what the
         benchmark times, and one graph launch instead of three removes two launch gaps)."""
         if self.world_size == 1:
-            self._run(("adg", id(data), bi), lambda: (self.phase_a(data, bi), self.d_step(data, bi), self.g_step(data, bi)))
+            self._run(("adg", id(data), bi), lambda: self._step_fused(data, bi))
         else:
             self._run(("adgdp", id(data), bi), lambda: (self.phase_a(data, bi), self._d_step_dp(data, bi), self._g_step_dp(data, bi)))
+
+    def _step_fused(self, data, bi):
+        """A -> D -> G of one batch with the dependencies the data flow has, not the ones the call order suggests: the G update's VAE
+        forward (train.py:326, generator side) needs the weights phase A used and nothing from the D update, so it runs on a side
+        branch beside it; only y_generated (discriminator forward with the UPDATED weights) and everything behind it wait for D."""
+        if not (self.overlap and self.overlap_dg):
+            self.phase_a(data, bi); self.d_step(data, bi); self.g_step(data, bi)
+            return
+        bt = data.batches[bi]
+        self.phase_a(data, bi)
+        self._d_advance()          # the counters advance in the reference's order (D's Adam step, then G's) ...
+        self._fuse_update = True
+        self._g_advance()          # ... before either update's kernels start
+        self._g_early(data, bi)
+        with self._fork(self.s3):
+            self._vae_forward(data, bt, True, self.keep_vae)
+        self._d_fwd_bwd(data, bi, advance=False)
+        self._d_update()
+        self._g_disc_forward(data, bi)
+        self._join(self.s3)
+        self._g_backward(data, bi)
+        self._fuse_update = False
 
     def run_g_step(self, data, bi):
         if self.world_size == 1:
@@ -746,7 +812,8 @@ class GanEngine(object):
             self.WdT_b_full, peer["WdT_b"] = sym(self.WdT_b_full); peer["WdT_b_mc"] = mc[1]
             self.Wq0_b_full, peer["Wq0_b"] = sym(self.Wq0_b_full); peer["Wq0_b_mc"] = mc[2]
             self.dh1_glob, peer["dh1"] = sym(self.dh1_glob); peer["dh1_mc"] = mc[3]
-            self.scal, peer["scal"] = sym(self.scal)
+            self.scal_all, peer["scal"] = sym(self.scal_all)
+            self.scal, self.scal_d = self.scal_all[0], self.scal_all[1]
             self.disc.arena_g, peer["arena_g"] = sym(self.disc.arena_g); peer["arena_g_mc"] = mc[5]
             self.vae.small_g, peer["small_g"] = sym(self.vae.small_g); peer["small_g_mc"] = mc[6]
             pads = torch.zeros(ops.PEER_SLOTS * 8, dtype=torch.int32, device=self.device)
@@ -798,7 +865,8 @@ class GanEngine(object):
     # losses of the last step (host reads; train.py:303,329 print them once per sub-epoch)
     # ------------------------------------------------------------------------------------------------------------
     def last_losses(self, B, B_global=None):
-        s = self.scal.detach().cpu().numpy().astype(np.float64)
+        sa = self.scal_all.detach().cpu().numpy().astype(np.float64)
+        s = sa[0]
         Bg = B if B_global is None else B_global
         neg_ll = s[ops.S_NLL_SUM] / Bg
         kl = s[ops.S_KL_SUM] / Bg
@@ -806,7 +874,7 @@ class GanEngine(object):
         vae_loss = neg_ll + anneal * kl
         cnt = s[ops.S_CNT]
         gan = -(self.lam / cnt) * s[ops.S_SUM_P] * s[ops.S_SUM_Y] if cnt > 0 else 0.0
-        return dict(neg_ll=neg_ll, KL=kl, anneal=anneal, vae_loss=vae_loss, gan_loss=gan, g_loss=vae_loss + gan, d_loss=s[ops.S_D_LOSS],
+        return dict(neg_ll=neg_ll, KL=kl, anneal=anneal, vae_loss=vae_loss, gan_loss=gan, g_loss=vae_loss + gan, d_loss=sa[1][ops.S_D_LOSS],
                     cnt=cnt, sum_p=s[ops.S_SUM_P], sum_y=s[ops.S_SUM_Y])
 
     # ------------------------------------------------------------------------------------------------------------

@@ -46,13 +46,13 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def step_advance(words, scal, kind, lr, beta1=0.9, beta2=0.999, anneal_cap=0.2, total_anneal_steps=20000.0, zero=None):
+def step_advance(words, scal, kind, lr, beta1=0.9, beta2=0.999, anneal_cap=0.2, total_anneal_steps=20000.0, zero=None, snap=None):
     _count(1)
     zw = 0
     if zero is not None:
         assert zero.is_contiguous() and zero.element_size() == 4
         zw = zero.numel()
-    check(lib().ltg_step_advance(ptr(words), ptr(scal), kind, lr, beta1, beta2, anneal_cap, total_anneal_steps, ptr(zero), zw, _stream()))
+    check(lib().ltg_step_advance(ptr(words), ptr(scal), kind, lr, beta1, beta2, anneal_cap, total_anneal_steps, ptr(zero), zw, ptr(snap), _stream()))
 
 
 def pick_bn(M, N, splits_ok=False):
@@ -249,10 +249,15 @@ def enc_wgrad_compact(G, n_active, act_ptr, csc_row, csc_pos, coef, dh1pre):
                                       dh1pre.stride(0), _stream()))
 
 
-def enc_adam(p, m, v, shadow, n_items, slot_of_item, G, lr_t=-1.0, scal=None, beta1=0.9, beta2=0.999, eps=1e-8):
+def enc_adam(p, m, v, shadow, n_items, slot_of_item, G, lr_t=-1.0, scal=None, beta1=0.9, beta2=0.999, eps=1e-8, rows=0):
     _count(1)
     check(lib().ltg_enc_adam(ptr(p), ptr(m), ptr(v), ptr(shadow), n_items, ptr(slot_of_item), ptr(G), lr_t, ptr(scal), beta1, beta2,
-                             eps, _stream()))
+                             eps, rows, _stream()))
+
+
+def enc_xc_clear(indptr, indices, B, nnz, slot_of_item, xc):
+    _count(1)
+    check(lib().ltg_enc_xc_clear(ptr(indptr), ptr(indices), B, nnz, ptr(slot_of_item), ptr(xc), xc.stride(0), _stream()))
 
 
 def enc_wgrad_expand(dW, n_items, slot_of_item, G):

@@ -66,7 +66,8 @@ def run_epochs(tabs, vad, cfg, init, n_epochs, seed=0, log=None):
                 t += 1
                 d_loss, _ = orc.d_step(E, dparams, dm, dv, tp, masks(len(pairs["x_niche"])), masks(pairs["cnt"]), 0.7, orc.tf_adam_lr_t(lr, t))
         g = None
-        for _ in range(cfg["NUM_SUB_EPOCHS"]):                         # train.py:307-329
+        diag = dict(sp=[], ybar=[], vae=[], gan=[])                    # last G sub-epoch: what the adversarial term acts on
+        for j_gen in range(cfg["NUM_SUB_EPOCHS"]):                     # train.py:307-329
             for bi in order:
                 X, pairs = cache[bi]
                 tp = {k: torch.from_numpy(pairs[k]) for k in ("x_popular_n", "x_niche", "x_popular_g", "x_generated")}
@@ -77,6 +78,9 @@ def run_epochs(tabs, vad, cfg, init, n_epochs, seed=0, log=None):
                 eps = torch.from_numpy(rng.randn(X.shape[0], orc.L).astype(np.float32))
                 g = orc.g_step(params, gm, gv, E, dparams, X, keep, 0.75, eps, anneal, torch.from_numpy(pairs["mask"].astype(np.float32)), tp,
                                masks(pairs["cnt"]), 0.7, lam, pairs["cnt"], orc.tf_adam_lr_t(lr, t), literal_outer=False)
+                if j_gen == cfg["NUM_SUB_EPOCHS"] - 1:
+                    diag["sp"].append(float((g["probs"] * torch.from_numpy(pairs["mask"].astype(np.float32))).sum()) / pairs["cnt"])
+                    diag["ybar"].append(float(g["y_gen"].mean())); diag["vae"].append(g["vae_loss"]); diag["gan"].append(g["gan_loss"])
         # validation, dropout still on (train.py:333-348)
         Nv = len(vad[0]) - 1
         Xv = _dense(vad[0], vad[1], 0, Nv, I)
@@ -86,7 +90,9 @@ def run_epochs(tabs, vad, cfg, init, n_epochs, seed=0, log=None):
         pred[Xv.numpy().nonzero()] = -np.inf
         rec = dict(epoch=ep, ndcg=float(np.mean(orc.ndcg_binary_at_k_batch(pred, te, 100))),
                    r20=float(np.mean(orc.recall_at_k_batch(pred, te, 20)[0])), r50=float(np.mean(orc.recall_at_k_batch(pred, te, 50)[0])),
-                   d_loss=float(d_loss), g_loss=None if g is None else g["g_loss"])
+                   d_loss=float(d_loss), g_loss=None if g is None else g["g_loss"],
+                   sp_mean=float(np.mean(diag["sp"])) if diag["sp"] else None, ybar_mean=float(np.mean(diag["ybar"])) if diag["ybar"] else None,
+                   vae_loss_mean=float(np.mean(diag["vae"])) if diag["vae"] else None, gan_loss_mean=float(np.mean(diag["gan"])) if diag["gan"] else None)
         history.append(rec)
         if log:
             log(rec)
