@@ -116,6 +116,15 @@ int ltg_vae_mid_fwd(const void* h1_bf16, int ld_h1, const void* Wq1_bf16, const 
 int ltg_vae_mid_bwd(const void* dh2pre_bf16, const void* Wp0_bf16, const void* Wq1_bf16, const float* mulv, const float* zmu,
                     const void* h1_bf16, int ld_h1, int B, int B_global, float anneal, const float* scal, void* dmulv_bf16,
                     float* dh1pre, void* dh1pre_bf16, float* db_q1, float* db_q0, void* stream);
+/* The same two operators on the tcgen05 tensor cores (mid_tc.cu): one launch each, a CTA owns 128 batch rows and chains both GEMMs
+ * through TMEM / shared memory; identical arguments and results (bf16 operands, fp32 accumulate).                               */
+int ltg_vae_mid_fwd_tc(const void* h1_bf16, int ld_h1, const void* Wq1_bf16, const float* b_q1, const void* Wp0_bf16,
+                       const float* b_p0, const float* eps, int B, int64_t uid0, float is_training, uint64_t seed, uint32_t step,
+                       const uint32_t* step_dev, float* mulv, void* z_bf16, int ld_z, float* zmu, void* h2_bf16, int ld_h2,
+                       float* scal, void* stream);
+int ltg_vae_mid_bwd_tc(const void* dh2pre_bf16, const void* Wp0_bf16, const void* Wq1_bf16, const float* mulv, const float* zmu,
+                       const void* h1_bf16, int ld_h1, int B, int B_global, float anneal, const float* scal, void* dmulv_bf16,
+                       float* dh1pre, void* dh1pre_bf16, float* db_q1, float* db_q0, void* stream);
 
 /* dx = dy * (1 - y^2) for y = tanh(.) stored as bf16 [B, ld_y]; outputs bf16 and/or fp32; column sums -> dbias (atomic).
  * dy may be given as n_partials split-K partial buffers (dy + s*partial_stride), which are summed on the fly.             */

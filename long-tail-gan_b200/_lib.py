@@ -16,7 +16,7 @@ _INCLUDE = os.path.join(_ROOT, "include")
 LIB_PATH = os.path.join(_HERE, "libltgan.so")
 
 SOURCES = ["runtime.cu", "gemm_ops.cu", "vae_kernels.cu", "adam_kernels.cu", "sampler_kernels.cu", "disc_kernels.cu",
-           "topk_kernels.cu", "mid_kernels.cu", "disc_fused.cu", "peer_kernels.cu"]
+           "topk_kernels.cu", "mid_kernels.cu", "mid_tc.cu", "disc_fused.cu", "peer_kernels.cu"]
 HEADERS = ["ltg_common.cuh", "gemm_sm100.cuh"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
@@ -89,6 +89,8 @@ SIGNATURES = {
     "ltg_latent_bwd": (_I, [_P, _P, _P, _I, _I, _F, _P, _P, _I, _P, _P]),
     "ltg_vae_mid_fwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _I, _I64, _F, _U64, _U32, _P, _P, _P, _I, _P, _P, _I, _P, _P]),
     "ltg_vae_mid_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
+    "ltg_vae_mid_fwd_tc": (_I, [_P, _I, _P, _P, _P, _P, _P, _I, _I64, _F, _U64, _U32, _P, _P, _P, _I, _P, _P, _I, _P, _P]),
+    "ltg_vae_mid_bwd_tc": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
     "ltg_tanh_bwd": (_I, [_P, _I, _I, _I64, _P, _I, _I, _I, _P, _I, _P, _I, _P, _P]),
     "ltg_dec_logits_fwd": (_I, [_P, _I, _P, _P, _I, _I, _P, _I, _P, _P]),
     "ltg_dec_row_stats": (_I, [_P, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -7,6 +7,7 @@
 //
 // Pure streaming kernels: 16-byte loads/stores with L1 no-allocate, 26 B of HBM traffic per parameter
 // (p,m,v read + write, bf16 shadow write) plus 4 B for an explicit gradient.
+#include <stdlib.h>
 #include "ltg_common.cuh"
 #include "../../include/ltgan.h"
 
@@ -216,6 +217,22 @@ int grid_for(int64_t work_items, int threads, int max_blocks) {
 // 148 SMs x 8 resident 256-thread CTAs: one full wave, grid-stride over the rest
 static const int kStreamBlocks = 148 * 8;
 
+// Dynamic shared memory requested by the Adam sweeps only to bound how many of their CTAs an SM holds at once (LTG_ADAM_CTAS_PER_SM,
+// default 8 = no bound): a sweep that keeps fewer bytes in flight leaves HBM queues shorter for the latency-bound kernels beside it.
+static size_t adam_throttle_smem() {
+  static long v = -1;
+  if (v < 0) {
+    const char* e = getenv("LTG_ADAM_CTAS_PER_SM");
+    const int n = e != nullptr ? atoi(e) : 8;
+    v = (n >= 8 || n <= 0) ? 0 : (long)((227 * 1024) / n - 1024) / 1024 * 1024;
+    if (v > 0) {
+      cudaFuncSetAttribute(adam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v);
+      cudaFuncSetAttribute(enc_adam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v);
+    }
+  }
+  return (size_t)v;
+}
+
 extern "C" int ltg_adam(float* p, float* m, float* v, const float* g, int n_partials, int64_t partial_stride, void* shadow_bf16, int64_t n,
                         float lr_t, const float* scal, float beta1, float beta2, float eps, void* stream) {
   LTG_REQUIRE(p && m && v && g && n_partials >= 1);
@@ -225,7 +242,7 @@ extern "C" int ltg_adam(float* p, float* m, float* v, const float* g, int n_part
                 reinterpret_cast<uintptr_t>(g)) & 15) == 0);
   LTG_REQUIRE((reinterpret_cast<uintptr_t>(shadow_bf16) & 7) == 0);
   if (n <= 0) return LTG_OK;
-  adam_kernel<<<grid_for(((n >> 2) + ADAM_UN - 1) / ADAM_UN, 256, 1 << 30), 256, 0, (cudaStream_t)stream>>>(
+  adam_kernel<<<grid_for(((n >> 2) + ADAM_UN - 1) / ADAM_UN, 256, 1 << 30), 256, n > (1 << 20) ? adam_throttle_smem() : 0, (cudaStream_t)stream>>>(
       p, m, v, g, n_partials, partial_stride, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n, lr_t, scal, beta1, beta2, eps);
   LTG_CHECK_LAUNCH();
   return LTG_OK;
@@ -247,7 +264,7 @@ extern "C" int ltg_enc_adam(float* p, float* m, float* v, void* shadow_bf16, int
   LTG_REQUIRE(lr_t >= 0.f || scal != nullptr);
   LTG_REQUIRE((reinterpret_cast<uintptr_t>(shadow_bf16) & 7) == 0);
   if (n_items <= 0) return LTG_OK;
-  enc_adam_kernel<<<grid_for(((int64_t)n_items * H4 + ADAM_UN - 1) / ADAM_UN, 256, 1 << 30), 256, 0, (cudaStream_t)stream>>>(
+  enc_adam_kernel<<<grid_for(((int64_t)n_items * H4 + ADAM_UN - 1) / ADAM_UN, 256, 1 << 30), 256, adam_throttle_smem(), (cudaStream_t)stream>>>(
       p, m, v, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n_items, slot_of_item, G, lr_t, scal, beta1, beta2, eps, rows);
   LTG_CHECK_LAUNCH();
   return LTG_OK;

@@ -223,6 +223,8 @@ class GanEngine(object):
         self.s2 = mk(-2)   # small weight-gradient GEMMs
         self.s3 = mk(-3)   # run_step: the G update's VAE forward beside the D update
         self.s4 = mk(0)    # Adam over the encoder rows that get no gradient from this batch
+        self.s5 = mk(-1)   # decoder Adam, chunk by chunk behind the weight-gradient GEMM of branch s1
+        self.dec_chunks = int(os.environ.get("LTG_DEC_CHUNKS", "1"))
         self._cap_stream = mk(-5) if prio else None
         self.overlap = True
         # The dense TF-Adam sweep over W_q0 (F7) moves every row, but rows of items absent from the batch (two thirds at batch 500)
@@ -236,7 +238,12 @@ class GanEngine(object):
         # restructured (TMA-staged p/m/v tiles).
         self.fused_wgrad_adam = False
         self.fused_disc = ops.disc_fused_supported(self.disc)   # one tcgen05 kernel for the discriminator forward (disc_fused.cu)
-        self.fused_mid = True   # fused 600->400->200->600 middle (mid_kernels.cu) instead of two GEMMs + element-wise launches
+        self.fused_mid = True   # fused 600->400->200->600 middle instead of two GEMMs + element-wise launches ...
+        # ... on tcgen05 (mid_tc.cu: one CTA per 128 rows x column third) for large batches, where streaming the weights once per 128
+        # rows pays; at batch 500 the 12 CTAs of that kernel are a serial L2-latency chain (38 us vs 16 us measured) and the mma.sync
+        # kernels (mid_kernels.cu, 160 CTAs) win. LTG_MID_TC=0/1 forces either.
+        mt = os.environ.get("LTG_MID_TC", "")
+        self.mid_tc = (self.max_B >= 4096) if mt == "" else (mt != "0")
         self._alloc()
         self.eps_inject = None  # optional [B, L] fp32 tensor used instead of the Philox normal (parity tests)
 
@@ -346,7 +353,7 @@ class GanEngine(object):
         if self.fused_mid:
             ops.vae_mid_fwd(self.h1, v.view("W_q1", "b"), v.view("b_q1"), v.view("W_p0", "b"), v.view("b_p0"),
                             self.eps_inject if is_training else None, B, uid0, 1.0 if is_training else 0.0, self.seed, 0, wstep,
-                            self.mulv, self.z, self.zmu, self.h2, self.scal)
+                            self.mulv, self.z, self.zmu, self.h2, self.scal, tc=self.mid_tc)
         else:
             ops.gemm(self.h1, v.view("W_q1", "b"), B, 2 * L, H, b_mn=True, bn=64, out_f32=self.mulv, bias=v.view("b_q1"))
             ops.latent_fwd(self.mulv, self.eps_inject if is_training else None, B, uid0, 1.0 if is_training else 0.0, self.seed, 0,
@@ -420,9 +427,10 @@ class GanEngine(object):
         part = True   # data parallel sums the partials into arena_g before the all-reduce (see _d_step_dp)
         bn3 = ops.pick_bn(d.k3, d.h3, True)
         # fixed split counts (empty splits store zeros): dW3 has 8 output tiles -> 16 splits fill the machine; dW1/dW2 have one tile
-        sp3 = 16 if part else ops.pick_splits(d.k3, d.h3, P, bn3)
-        sp = self.d_splits_max if part else ops.pick_splits(k1, d.h2, P, 256)
-        self._d_parts = self.d_splits_max if part else 1
+        import os
+        sp3 = int(os.environ.get("LTG_D_SP3", "12")) if part else ops.pick_splits(d.k3, d.h3, P, bn3)
+        sp = int(os.environ.get("LTG_D_SP", "16")) if part else ops.pick_splits(k1, d.h2, P, 256)
+        self._d_parts = max(sp, sp3) if part else 1
         if part:
             gW = lambda name: self.arena_gp[0][d._off[name][0]: d._off[name][0] + d._off[name][1]]  # noqa: E731
             kw = dict(split_stride=d.arena_n)
@@ -515,10 +523,22 @@ class GanEngine(object):
         fuse_update = self.world_size == 1 and getattr(self, "_fuse_update", False)
         dp_comm = self.world_size > 1 and getattr(self, "_dp_comm", False)
         fused_wa = fuse_update and self.fused_wgrad_adam
+        # single GPU: the decoder weight gradient and its Adam sweep are cut into row chunks of the catalog and pipelined -- Adam on
+        # chunk c (branch s5) runs beside the weight-gradient GEMM of chunk c+1 (branch s1), and reads a gradient chunk that is still
+        # in L2 (8 MB per chunk instead of a 48 MB round trip through HBM)
+        chunked = fuse_update and not fused_wa and self.dec_chunks > 1
+        self._dec_ev = []
         if not fused_wa:
             with self._fork(self.s1):
-                ops.gemm(self.dl, self.h2, self.I, H + 1, B, a_mn=True, b_mn=True, bn=128, out_f32=self.dWdT, ld_f32=H, aux_col=H,
-                         aux_out=v.view("b_p1", "g"))
+                if chunked:
+                    for r0, nr in self._dec_chunk_rows():
+                        ops.gemm(self.dl[:, r0:], self.h2, nr, H + 1, B, a_mn=True, b_mn=True, bn=128, out_f32=self.dWdT[r0:r0 + nr], ld_f32=H,
+                                 aux_col=H, aux_out=v.view("b_p1", "g")[r0:])
+                        ev = torch.cuda.Event(); ev.record()
+                        self._dec_ev.append(ev)
+                else:
+                    ops.gemm(self.dl, self.h2, self.I, H + 1, B, a_mn=True, b_mn=True, bn=128, out_f32=self.dWdT, ld_f32=H, aux_col=H,
+                             aux_out=v.view("b_p1", "g"))
                 if dp_comm and self.peer is None:
                     import torch.distributed as dist
                     dist.reduce_scatter_tensor(self.g_dec_shard, self.dWdT_full)
@@ -565,8 +585,18 @@ class GanEngine(object):
             # the Adam sweep rewrites the bf16 decoder weights the dgrad GEMM above reads: order it after dgrad
             if self.overlap:
                 self.s1.wait_stream(torch.cuda.current_stream())
-            with (torch.cuda.stream(self.s1) if self.overlap else torch.cuda.stream(torch.cuda.current_stream())):
-                ops.adam(v.WdT, v.WdT_m, v.WdT_v, self.dWdT, v.WdT_b, scal=self.scal)
+            if chunked:
+                side = self.s5 if self.overlap else torch.cuda.current_stream()
+                if self.overlap:
+                    self.s5.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for (r0, nr), ev in zip(self._dec_chunk_rows(), self._dec_ev):
+                        if self.overlap:
+                            side.wait_event(ev)
+                        ops.adam(v.WdT[r0:r0 + nr], v.WdT_m[r0:r0 + nr], v.WdT_v[r0:r0 + nr], self.dWdT[r0:r0 + nr], v.WdT_b[r0:r0 + nr], scal=self.scal)
+            else:
+                with (torch.cuda.stream(self.s1) if self.overlap else torch.cuda.stream(torch.cuda.current_stream())):
+                    ops.adam(v.WdT, v.WdT_m, v.WdT_v, self.dWdT, v.WdT_b, scal=self.scal)
         if self.fused_mid:
             # split-K sum + tanh' with full-machine parallelism, then two fused kernels (dz + latent backward; dh1 + tanh' + db_q0);
             # the two weight-gradient GEMMs (contractions over the batch) run on side branches
@@ -575,7 +605,7 @@ class GanEngine(object):
             with self._fork(self.s2):
                 ops.gemm(self.z, self.dh2pre, L, H, B, a_mn=True, b_mn=True, bn=64, out_f32=v.view("W_p0", "g"))
             ops.vae_mid_bwd(self.dh2pre, v.view("W_p0", "b"), v.view("W_q1", "b"), self.mulv, self.zmu, self.h1, B, Bg, -1.0, self.scal,
-                            self.dmulv, self.dh1pre, self.dh1pre_b, v.view("b_q1", "g"), v.view("b_q0", "g"))
+                            self.dmulv, self.dh1pre, self.dh1pre_b, v.view("b_q1", "g"), v.view("b_q0", "g"), tc=self.mid_tc)
             self._join(self.s2)
             with self._fork(self.s2):
                 ops.gemm(self.h1, self.dmulv, H, 2 * L, B, a_mn=True, b_mn=True, bn=64, out_f32=v.view("W_q1", "g"))
@@ -644,8 +674,15 @@ class GanEngine(object):
                 self._early_done = False
         self._join(self.s2)
         self._join(self.s1)
+        if chunked:
+            self._join(self.s5)
         if fuse_update:
             ops.adam(v.small, v.small_m, v.small_v, v.small_g, v.small_b, scal=self.scal)
+
+    def _dec_chunk_rows(self):
+        """Row chunks [(r0, n_rows)] of the decoder matrix for the pipelined weight gradient + Adam (multiples of 128 rows)."""
+        per = max(128, (-(-self.I // self.dec_chunks) + 127) // 128 * 128)
+        return [(r0, min(per, self.I - r0)) for r0 in range(0, self.I, per)]
 
     def _g_update(self, data, bi):
         bt = data.batches[bi]

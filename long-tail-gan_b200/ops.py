@@ -136,16 +136,19 @@ def latent_bwd(dz, mulv, zmu, B, B_global, anneal, scal, dmulv, db_q1):
                                _stream()))
 
 
-def vae_mid_fwd(h1, Wq1_b, b_q1, Wp0_b, b_p0, eps, B, uid0, is_training, seed, step, step_dev, mulv, z, zmu, h2, scal):
-    _count(2)
-    check(lib().ltg_vae_mid_fwd(ptr(h1), h1.stride(0), ptr(Wq1_b), ptr(b_q1), ptr(Wp0_b), ptr(b_p0), ptr(eps), B, uid0, float(is_training),
+def vae_mid_fwd(h1, Wq1_b, b_q1, Wp0_b, b_p0, eps, B, uid0, is_training, seed, step, step_dev, mulv, z, zmu, h2, scal, tc=False):
+    """tc: the tcgen05 kernel (mid_tc.cu, one launch) instead of the two mma.sync kernels (mid_kernels.cu)."""
+    _count(1 if tc else 2)
+    fn = lib().ltg_vae_mid_fwd_tc if tc else lib().ltg_vae_mid_fwd
+    check(fn(ptr(h1), h1.stride(0), ptr(Wq1_b), ptr(b_q1), ptr(Wp0_b), ptr(b_p0), ptr(eps), B, uid0, float(is_training),
                                 seed, step, ptr(step_dev), ptr(mulv), ptr(z), z.stride(0), ptr(zmu), ptr(h2), h2.stride(0), ptr(scal),
                                 _stream()))
 
 
-def vae_mid_bwd(dh2pre, Wp0_b, Wq1_b, mulv, zmu, h1, B, B_global, anneal, scal, dmulv, dh1pre, dh1pre_b, db_q1, db_q0):
-    _count(2)
-    check(lib().ltg_vae_mid_bwd(ptr(dh2pre), ptr(Wp0_b), ptr(Wq1_b), ptr(mulv), ptr(zmu), ptr(h1), h1.stride(0), B, B_global, anneal,
+def vae_mid_bwd(dh2pre, Wp0_b, Wq1_b, mulv, zmu, h1, B, B_global, anneal, scal, dmulv, dh1pre, dh1pre_b, db_q1, db_q0, tc=False):
+    _count(1 if tc else 2)
+    fn = lib().ltg_vae_mid_bwd_tc if tc else lib().ltg_vae_mid_bwd
+    check(fn(ptr(dh2pre), ptr(Wp0_b), ptr(Wq1_b), ptr(mulv), ptr(zmu), ptr(h1), h1.stride(0), B, B_global, anneal,
                                 ptr(scal), ptr(dmulv), ptr(dh1pre), ptr(dh1pre_b), ptr(db_q1), ptr(db_q0), _stream()))
 
 

@@ -677,3 +677,72 @@ def test_wgrad_adam_epilogue_matches_gemm_then_adam(ops):
     for a, b in ((p, p2), (m, m2), (v, v2)):
         assert (a - b).abs().max().item() <= 1e-6 * max(1.0, b.abs().max().item())
     assert (sh.float() - sh2.float()).abs().max().item() <= 1e-2 * 0.5 and (sh != sh2).float().mean().item() < 1e-3
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# VAE middle on tcgen05 (mid_tc.cu) against a torch fp32 restatement of MultiVAE.py:151-181 / its autodiff, and against the
+# mma.sync kernels (mid_kernels.cu) on the same inputs
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B", [500, 77, 128, 1])
+def test_vae_mid_tc_forward_backward(ops, B):
+    torch.manual_seed(5 + B)
+    H, L = 600, 200
+    h1 = (torch.randn(B, H, device="cuda") * 0.5).tanh().bfloat16()
+    Wq1 = (torch.randn(H, 2 * L, device="cuda") * 0.05).bfloat16(); bq1 = torch.randn(2 * L, device="cuda") * 0.01
+    Wp0 = (torch.randn(L, H, device="cuda") * 0.08).bfloat16(); bp0 = torch.randn(H, device="cuda") * 0.01
+    eps = torch.randn(B, L, device="cuda")
+    outs = {}
+    for tc in (False, True):
+        mulv = torch.zeros(B, 2 * L, device="cuda"); z = torch.zeros(B, L, device="cuda", dtype=torch.bfloat16)
+        zmu = torch.zeros(B, L, device="cuda"); h2 = torch.zeros(B, 608, device="cuda", dtype=torch.bfloat16); scal = torch.zeros(16, device="cuda")
+        ops.vae_mid_fwd(h1, Wq1, bq1, Wp0, bp0, eps, B, 0, 1.0, 0, 0, None, mulv, z, zmu, h2, scal, tc=tc)
+        torch.cuda.synchronize()
+        outs[tc] = (mulv, z, zmu, h2, scal)
+    # fp32 reference on the bf16-rounded operands
+    mv = h1.float() @ Wq1.float() + bq1
+    mu, lv = mv[:, :L], mv[:, L:]
+    kl = (0.5 * (-lv + lv.exp() + mu * mu - 1.0)).sum()
+    d = eps * (0.5 * lv).exp()
+    zr = (mu + d)
+    h2r = (zr.bfloat16().float() @ Wp0.float() + bp0).tanh()
+    for tc in (False, True):
+        mulv, z, zmu, h2, scal = outs[tc]
+        assert (mulv - mv).abs().max().item() < 2e-3, tc
+        assert (zmu - d).abs().max().item() < 2e-3, tc
+        assert (z.float() - zr).abs().max().item() < 2e-2, tc
+        assert (h2[:, :H].float() - h2r).abs().max().item() < 2e-2, tc
+        assert abs(scal[ops.S_KL_SUM].item() - kl.item()) < 1e-3 * abs(kl.item()) + 1e-3, tc
+    # tensor-core version against the mma.sync version: same operands, same accumulation type
+    assert (outs[True][0] - outs[False][0]).abs().max().item() < 1e-4
+    assert (outs[True][3].float() - outs[False][3].float()).abs().max().item() < 1e-2
+    # inference mode (phase A / evaluation): z = mu, Philox path not taken
+    mulv, z, zmu, h2, scal = [torch.zeros_like(t) for t in outs[True]]
+    ops.vae_mid_fwd(h1, Wq1, bq1, Wp0, bp0, None, B, 7, 0.0, 3, 1, None, mulv, z, zmu, h2, scal, tc=True)
+    assert (z.float() - mu).abs().max().item() < 2e-2 and zmu.abs().max().item() == 0.0
+
+    # ---- backward
+    mulv, z, zmu, h2, scal = outs[True]
+    dh2pre = (torch.randn(B, H, device="cuda") * 0.01).bfloat16()
+    anneal, Bg = 0.13, max(B, 2)
+    res = {}
+    for tc in (False, True):
+        dmulv = torch.zeros(B, 2 * L, device="cuda", dtype=torch.bfloat16); dh1pre = torch.zeros(B, H, device="cuda")
+        dh1pre_b = torch.zeros(B, H, device="cuda", dtype=torch.bfloat16); dbq1 = torch.zeros(2 * L, device="cuda"); dbq0 = torch.zeros(H, device="cuda")
+        ops.vae_mid_bwd(dh2pre, Wp0, Wq1, mulv, zmu, h1, B, Bg, anneal, scal, dmulv, dh1pre, dh1pre_b, dbq1, dbq0, tc=tc)
+        torch.cuda.synchronize()
+        res[tc] = (dmulv, dh1pre, dh1pre_b, dbq1, dbq0)
+    dz = dh2pre.float() @ Wp0.float().t()
+    dmu = dz + anneal * mulv[:, :L] / Bg
+    dlv = dz * zmu * 0.5 + anneal * 0.5 * (mulv[:, L:].exp() - 1.0) / Bg
+    dmv = torch.cat([dmu, dlv], 1)
+    dh1 = dmv.bfloat16().float() @ Wq1.float().t()
+    dh1p = dh1 * (1.0 - h1.float() ** 2)
+    sc = dh1p.abs().max().item()
+    for tc in (False, True):
+        dmulv, dh1pre, dh1pre_b, dbq1, dbq0 = res[tc]
+        assert (dmulv.float() - dmv).abs().max().item() < 1e-2 * dmv.abs().max().item() + 1e-6, tc
+        assert (dh1pre - dh1p).abs().max().item() < 2e-2 * sc + 1e-7, tc
+        assert (dh1pre_b.float() - dh1pre).abs().max().item() < 1e-2 * sc + 1e-7, tc
+        assert (dbq1 - dmv.sum(0)).abs().max().item() < 2e-2 * dmv.sum(0).abs().max().item() + 1e-6, tc
+        assert (dbq0 - dh1p.sum(0)).abs().max().item() < 2e-2 * dh1p.sum(0).abs().max().item() + 1e-6, tc
+    assert (res[True][1] - res[False][1]).abs().max().item() < 1e-3 * sc + 1e-8
