@@ -32,13 +32,14 @@ adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
   if (lr_t < 0.f) lr_t = scal[LTG_S_LR_T];
   const int64_t n4 = n >> 2;
   const int64_t base = (int64_t)blockIdx.x * (256 * ADAM_UN) + threadIdx.x;
+  const uint64_t pol = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
   float4 pp[ADAM_UN], mm[ADAM_UN], vv[ADAM_UN], gg[ADAM_UN];
 #pragma unroll
   for (int u = 0; u < ADAM_UN; ++u) {          // all loads of the chunk first: 8 independent 16-byte requests per thread
     const int64_t i = base + u * 256;
     if (i < n4) {
-      pp[u] = ld_stream_f4(p + 4 * i); mm[u] = ld_stream_f4(m + 4 * i); vv[u] = ld_stream_f4(v + 4 * i);
-      gg[u] = ld_stream_f4(g + 4 * i);
+      pp[u] = ld_stream_f4_hint(p + 4 * i, pol); mm[u] = ld_stream_f4_hint(m + 4 * i, pol); vv[u] = ld_stream_f4_hint(v + 4 * i, pol);
+      gg[u] = ld_stream_f4_hint(g + 4 * i, pol);
     }
   }
   if (n_partials > 1) {                        // split-K partials of the producing GEMM, four independent accumulation chains
@@ -68,10 +69,10 @@ adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
     const int64_t i = base + u * 256;
     if (i >= n4) continue;
     adam_update4(pp[u], mm[u], vv[u], gg[u], lr_t, b1, b2, eps);
-    st_stream_f4(p + 4 * i, pp[u]); st_stream_f4(m + 4 * i, mm[u]); st_stream_f4(v + 4 * i, vv[u]);
+    st_stream_f4_hint(p + 4 * i, pp[u], pol); st_stream_f4_hint(m + 4 * i, mm[u], pol); st_stream_f4_hint(v + 4 * i, vv[u], pol);
     if (shadow != nullptr) {
       uint2 s; s.x = pack_bf16x2(pp[u].x, pp[u].y); s.y = pack_bf16x2(pp[u].z, pp[u].w);
-      *reinterpret_cast<uint2*>(shadow + 4 * i) = s;
+      st_b64_hint(shadow + 4 * i, s, pol_keep);
     }
   }
   // tail (n % 4)
@@ -144,6 +145,7 @@ enc_adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict_
   if (lr_t < 0.f) lr_t = scal[LTG_S_LR_T];
   const int64_t n4 = (int64_t)n_items * H4;
   const int64_t base = (int64_t)blockIdx.x * (256 * ADAM_UN) + threadIdx.x;   // one fixed chunk per CTA (see adam_kernel)
+  const uint64_t pol = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
   float4 pp[ADAM_UN], mm[ADAM_UN], vv[ADAM_UN], gg[ADAM_UN];
   bool on[ADAM_UN];
 #pragma unroll
@@ -158,7 +160,7 @@ enc_adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict_
     // while the forward chain leaves HBM idle); 2 only the batch's active rows
     if ((rows == 1 && slot >= 0) || (rows == 2 && slot < 0)) continue;
     on[u] = true;
-    pp[u] = ld_stream_f4(p + 4 * i); mm[u] = ld_stream_f4(m + 4 * i); vv[u] = ld_stream_f4(v + 4 * i);
+    pp[u] = ld_stream_f4_hint(p + 4 * i, pol); mm[u] = ld_stream_f4_hint(m + 4 * i, pol); vv[u] = ld_stream_f4_hint(v + 4 * i, pol);
     gg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (slot >= 0) gg[u] = __ldg(reinterpret_cast<const float4*>(G + (size_t)slot * H) + c4);
   }
@@ -167,10 +169,10 @@ enc_adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict_
     if (!on[u]) continue;
     const int64_t i = base + u * 256;
     adam_update4(pp[u], mm[u], vv[u], gg[u], lr_t, b1, b2, eps);
-    st_stream_f4(p + 4 * i, pp[u]); st_stream_f4(m + 4 * i, mm[u]); st_stream_f4(v + 4 * i, vv[u]);
+    st_stream_f4_hint(p + 4 * i, pp[u], pol); st_stream_f4_hint(m + 4 * i, mm[u], pol); st_stream_f4_hint(v + 4 * i, vv[u], pol);
     if (shadow != nullptr) {
       uint2 s; s.x = pack_bf16x2(pp[u].x, pp[u].y); s.y = pack_bf16x2(pp[u].z, pp[u].w);
-      *reinterpret_cast<uint2*>(shadow + 4 * i) = s;
+      st_b64_hint(shadow + 4 * i, s, pol_keep);
     }
   }
 }

@@ -319,13 +319,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int split = rest / shape.n_blocks;
       const int n0 = n_blk * BN;
       const int row = m_blk * GEMM_BM + sub * 32 + lane;
+      // The epilogue functor may need global data per chunk that does not depend on the accumulator (bias slice, stored activation for
+      // the fused tanh'/dropout backward). ncu (round 2) showed the epilogue warps stalled on exactly those loads, one L2 round trip
+      // per chunk (30% of all samples of the dz12 GEMM, 21% of the decoder forward): they are software pipelined -- the first chunk's
+      // loads are issued BEFORE waiting for the accumulator, chunk i+1's before chunk i is processed.
+      Epi epi(ep, row, n0, n_blk * 4 + quarter, split, shape, epi_scratch);
+      int c = quarter * GEMM_CW;
+      bool have = c < BN && n0 + c < shape.N;   // warp-uniform
+      if (have) epi.preload(n0 + c);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      Epi epi(ep, row, n0, n_blk * 4 + quarter, split, shape, epi_scratch);
       const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c = quarter * GEMM_CW; c < BN; c += 4 * GEMM_CW) {
-        if (n0 + c >= shape.N) break;  // warp-uniform
+      while (have) {
+        const int cn = c + 4 * GEMM_CW;
+        const bool next = cn < BN && n0 + cn < shape.N;
         float v[GEMM_CW];
         if (split * shape.kb_per_split < shape.k_blocks) {
           tmem_ld16(taddr + c, v);
@@ -333,7 +341,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int i = 0; i < GEMM_CW; ++i) v[i] = 0.f;  // empty split: nothing was accumulated
         }
-        epi.chunk(n0 + c, v);
+        epi.chunk(n0 + c, v, next ? n0 + cn : -1);
+        c = cn; have = next;
       }
       epi.finish();
       tc_fence_before();
@@ -385,7 +394,19 @@ struct EpiStore {
   uint32_t thr16, key;
   float inv_keep;
   bool drop;
+  uint4 pre0, pre1;   // stored activation of the NEXT chunk (dact_src), loaded one chunk ahead
+  bool pre_vec;
   static constexpr int kSmem = 0;
+  __device__ __forceinline__ void preload(int col0) {
+    pre_vec = false;
+    if (p.dact_src == nullptr || row >= M) return;
+    const __nv_bfloat16* src = p.dact_src + (size_t)row * p.dact_ld + col0;
+    if (col0 + GEMM_CW <= N && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+      pre0 = __ldg(reinterpret_cast<const uint4*>(src));
+      pre1 = __ldg(reinterpret_cast<const uint4*>(src) + 1);
+      pre_vec = true;
+    }
+  }
   __device__ EpiStore(const Params& p_, int row_, int, int, int split_, const GemmShape& s, uint8_t*) : p(p_), row(row_), M(s.M), N(s.N), split(split_) {
     drop = p.keep > 0.f && p.keep < 1.f;
     thr16 = drop ? ltg_keep_threshold16(p.keep) : 65536u;
@@ -393,10 +414,13 @@ struct EpiStore {
     key = 0;
     if (drop) key = ltg_hash_key(p.seed, p.rng_stream, p.rng_step + (p.rng_step_dev != nullptr ? *p.rng_step_dev : 0u));
   }
-  __device__ void chunk(int col0, float (&v)[GEMM_CW]) {
+  __device__ void chunk(int col0, float (&v)[GEMM_CW], int next_col0) {
     if (row >= M) return;
     constexpr int CW = GEMM_CW;
     const bool full = col0 + CW <= N;
+    const uint4 cur0 = pre0, cur1 = pre1;
+    const bool cur_vec = pre_vec;
+    if (next_col0 >= 0) preload(next_col0);
     if (p.bias != nullptr) {
       if (full && ((reinterpret_cast<uintptr_t>(p.bias + col0) & 15) == 0)) {
         const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
@@ -423,10 +447,10 @@ struct EpiStore {
       const __nv_bfloat16* src = p.dact_src + (size_t)row * p.dact_ld + col0;
       const bool dd = p.dact_keep > 0.f && p.dact_keep < 1.f;
       const float kk = dd ? p.dact_keep : 1.0f, ik = 1.0f / kk;
-      if (full && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+      if (cur_vec) {
 #pragma unroll
         for (int q = 0; q < CW / 8; ++q) {
-          const uint4 u = __ldg(reinterpret_cast<const uint4*>(src) + q);
+          const uint4 u = q == 0 ? cur0 : cur1;
           const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -550,7 +574,8 @@ struct EpiAdam {
   // The accumulator arrives with thread == row (64 B per thread per array, 2400 B apart: 32 half-used sectors per request, measured
   // 3x slower than the separate Adam sweep). The warp therefore transposes its 32 x 16 chunk through shared memory so that four
   // lanes cover the 64 contiguous bytes of a row and a request touches 8 rows x 64 B = 16 full sectors.
-  __device__ void chunk(int col0, float (&g)[GEMM_CW]) {
+  __device__ __forceinline__ void preload(int) {}
+  __device__ void chunk(int col0, float (&g)[GEMM_CW], int) {
     const int lane = threadIdx.x & 31;
     if (row < M && p.aux_col >= col0 && p.aux_col < col0 + GEMM_CW) {
 #pragma unroll
@@ -604,21 +629,37 @@ struct EpiLogitsStats {
   const Params& p;
   int row, M, N, slot;
   float mx, sum;
+  float4 pb[GEMM_CW / 4];   // bias slice of the NEXT chunk, loaded one chunk ahead
+  bool pre_vec;
   static constexpr int kSmem = 0;
+  __device__ __forceinline__ void preload(int col0) {
+    pre_vec = false;
+    if (row >= M) return;
+    if (col0 + GEMM_CW <= N && ((reinterpret_cast<uintptr_t>(p.bias + col0) & 15) == 0)) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+      for (int i = 0; i < GEMM_CW / 4; ++i) pb[i] = __ldg(b4 + i);
+      pre_vec = true;
+    }
+  }
   __device__ EpiLogitsStats(const Params& p_, int row_, int, int slot_, int, const GemmShape& s, uint8_t*)
       : p(p_), row(row_), M(s.M), N(s.N), slot(slot_), mx(-INFINITY), sum(0.f) {}
-  __device__ void chunk(int col0, float (&v)[GEMM_CW]) {
+  __device__ void chunk(int col0, float (&v)[GEMM_CW], int next_col0) {
     if (row >= M) return;
     constexpr int CW = GEMM_CW;
     constexpr float LOG2E = 1.4426950408889634f;
-    if (col0 + CW <= N && ((reinterpret_cast<uintptr_t>(p.bias + col0) & 15) == 0)) {
-      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+    if (pre_vec) {
+      float4 cb[CW / 4];
+#pragma unroll
+      for (int i = 0; i < CW / 4; ++i) cb[i] = pb[i];
+      if (next_col0 >= 0) preload(next_col0);
 #pragma unroll
       for (int i = 0; i < CW / 4; ++i) {
-        const float4 b = __ldg(b4 + i);
+        const float4 b = cb[i];
         v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
       }
     } else {
+      if (next_col0 >= 0) preload(next_col0);
 #pragma unroll
       for (int i = 0; i < CW; ++i) v[i] = (col0 + i < N) ? v[i] + __ldg(p.bias + col0 + i) : -INFINITY;
     }

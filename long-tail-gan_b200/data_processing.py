@@ -90,15 +90,51 @@ def load_user_items(csv_file_path):
 
 
 class OverlapCoeffs(object):
-    """OVERLAP_COEFFS[a][b] = |U_a & U_b| / min(|U_a|, |U_b|) (data_processing.py:100-107) backed by a dense float64
-    matrix; indexable like the reference's dict of dicts."""
+    """OVERLAP_COEFFS of the reference (a dict of dicts, data_processing.py:110-167) held SPARSE: the co-occurrence counts
+    C = X^T X as CSR plus the item degrees; a coefficient C[a,b] / min(C[a,a], C[b,b]) is formed only for the (niche x niche) and
+    (niche x popular) blocks the two consumers read. (Round 1 densified C into an I x I float64 matrix and ~4 temporaries of the same
+    size: 13-16 GB at the ML-20M catalog, impossible at 1 M items.) `OV[a]` still yields the dense row a, `OV[a][b]` a coefficient."""
 
-    def __init__(self, matrix, present):
-        self.matrix = matrix
-        self.present = present
+    DENSE_LIMIT = 30000   # `.matrix` (dense I x I float64, compatibility / tests) is refused above this catalog size
+
+    def __init__(self, C, deg):
+        self.C = C.tocsr()
+        self.C.sort_indices()
+        self.deg = np.asarray(deg, dtype=np.float64)
+        self.present = self.deg > 0
+        self.n_items = self.C.shape[0]
+
+    def block(self, rows, cols):
+        """Dense float64 block M[rows][:, cols] (the same division the reference performs; 0 where an item never occurs)."""
+        rows = np.asarray(rows, dtype=np.int64); cols = np.asarray(cols, dtype=np.int64)
+        c = np.asarray(self.C[rows][:, cols].todense(), dtype=np.float64)
+        denom = np.minimum(self.deg[rows][:, None], self.deg[cols][None, :])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return np.where(denom > 0, c / denom, 0.0)
+
+    def colmax(self, rows, n_cols_mask=None):
+        """max over `rows` of M[rows, j] for every item j (length n_items), touching only the non-zeros of those rows."""
+        rows = np.asarray(rows, dtype=np.int64)
+        sub = self.C[rows]
+        best = np.zeros(self.n_items, dtype=np.float64)
+        if sub.nnz:
+            r_of = np.repeat(rows, np.diff(sub.indptr))
+            denom = np.minimum(self.deg[r_of], self.deg[sub.indices])
+            with np.errstate(divide="ignore", invalid="ignore"):
+                val = np.where(denom > 0, sub.data.astype(np.float64) / denom, 0.0)
+            np.maximum.at(best, sub.indices, val)
+        return best
+
+    @property
+    def matrix(self):
+        if self.n_items > self.DENSE_LIMIT:
+            raise MemoryError("OverlapCoeffs.matrix would be a dense %d x %d float64 array; use block()/colmax() (catalogs above %d items "
+                              "are served sparse)" % (self.n_items, self.n_items, self.DENSE_LIMIT))
+        allr = np.arange(self.n_items)
+        return self.block(allr, allr)
 
     def __getitem__(self, a):
-        return self.matrix[a]
+        return self.block([int(a)], np.arange(self.n_items))[0]
 
     def __contains__(self, a):
         return bool(self.present[a])
@@ -108,8 +144,8 @@ class OverlapCoeffs(object):
 
 
 def load_overlap_coeff(show2id_path, user_tag_matrix_path):
-    """data_processing.py:110-167 as one sparse product: C = X^T X on the binary user x item matrix of item_counts.csv,
-    coefficient = C[a,b] / min(C[a,a], C[b,b]) in float64 (the same division the reference performs)."""
+    """data_processing.py:110-167 as one sparse product: C = X^T X on the binary user x item matrix of item_counts.csv, kept sparse;
+    coefficient = C[a,b] / min(C[a,a], C[b,b]) in float64 (the same division the reference performs), formed on demand."""
     SHOW2ID = _read_show2id(show2id_path)
     tp = pd.read_csv(user_tag_matrix_path, dtype=str)
     users = tp.iloc[:, 0].to_numpy()
@@ -119,24 +155,22 @@ def load_overlap_coeff(show2id_path, user_tag_matrix_path):
     item = np.asarray([int(SHOW2ID[t]) for t in tags], dtype=np.int64)
     _, uidx = np.unique(users, return_inverse=True)
     n_items = int(max(int(v) for v in SHOW2ID.values())) + 1
-    X = sparse.csr_matrix((np.ones(len(item), dtype=np.int64), (uidx, item)), shape=(uidx.max() + 1, n_items))
-    X.data[:] = 1  # sets: a (user, item) pair counts once
+    return overlap_from_interactions(uidx, item, n_items)
+
+
+def overlap_from_interactions(uidx, item, n_items):
+    """Sparse OverlapCoeffs from (user index, item id) interaction pairs (a pair counts once: the reference builds sets)."""
+    X = sparse.csr_matrix((np.ones(len(item), dtype=np.int64), (uidx, item)), shape=(int(np.max(uidx)) + 1 if len(uidx) else 1, n_items))
     X.sum_duplicates()
     X.data[:] = 1
-    C = (X.T @ X).toarray().astype(np.float64)
-    deg = np.diag(C).copy()
-    present = deg > 0
-    denom = np.minimum(deg[:, None], deg[None, :])
-    with np.errstate(divide="ignore", invalid="ignore"):
-        M = np.where(denom > 0, C / denom, 0.0)
-    return OverlapCoeffs(M, present)
+    C = (X.T @ X).tocsr()
+    return OverlapCoeffs(C, C.diagonal())
 
 
 def load_items_to_sample(user_popular_data, user_niche_data, NICHE_TAGS, OVERLAP_COEFFS, N):
     """data_processing.py:170-224: candidates = the user's niche items + the top max(2n, 10-n) other niche items ranked by
     their best overlap with any of the user's niche items (stable: ties keep ascending item id, which is the iteration
     order of the reference's `NICHE_TAGS - curr_niche_tags` set of small ints)."""
-    M = OVERLAP_COEFFS.matrix
     niche_sorted = np.asarray(sorted(NICHE_TAGS), dtype=np.int64)
     out = {}
     for user_idx in range(N):
@@ -146,7 +180,7 @@ def load_items_to_sample(user_popular_data, user_niche_data, NICHE_TAGS, OVERLAP
         n = len(cur)
         num_sample = max(2 * n, 10 - n)
         others = niche_sorted[~np.isin(niche_sorted, cur)]
-        best = M[np.ix_(cur, others)].max(axis=0) if len(others) else np.zeros(0)
+        best = OVERLAP_COEFFS.colmax(cur)[others] if len(others) else np.zeros(0)
         order = np.argsort(-best, kind="stable")[: min(num_sample, len(others))]
         out[user_idx] = np.sort(np.concatenate([cur, others[order]]))
     return out
@@ -155,14 +189,13 @@ def load_items_to_sample(user_popular_data, user_niche_data, NICHE_TAGS, OVERLAP
 def load_vectors(user_popular_data, user_niche_data, OVERLAP_COEFFS, ITEM_FEATURE_DICT, N):
     """data_processing.py:227-271: for each niche item of the user the popular item of the user with the highest overlap
     (first maximum in list order), dropped when either id is not in ITEM_FEATURE_DICT."""
-    M = OVERLAP_COEFFS.matrix
     x_niche, x_pop = {}, {}
     for user_idx in range(N):
         if user_idx not in user_popular_data or user_idx not in user_niche_data:
             continue
         pops = np.asarray(user_popular_data[user_idx], dtype=np.int64)
         niches = np.asarray(user_niche_data[user_idx], dtype=np.int64)
-        best = pops[np.argmax(M[np.ix_(niches, pops)], axis=1)]
+        best = pops[np.argmax(OVERLAP_COEFFS.block(niches, pops), axis=1)]
         cn, cp = [], []
         for a, b in zip(niches.tolist(), best.tolist()):
             if a in ITEM_FEATURE_DICT and b in ITEM_FEATURE_DICT:

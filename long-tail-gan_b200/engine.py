@@ -232,12 +232,17 @@ class GanEngine(object):
         # runs while the latency-bound forward chain leaves HBM idle; only the active rows wait for the backward pass.
         self.early_adam = os.environ.get("LTG_EARLY_ADAM", "1") != "0"
         self.overlap_dg = os.environ.get("LTG_OVERLAP_DG", "1") != "0"   # run_step: G forward beside the D update
+        self.adam_after_mid = os.environ.get("LTG_ADAM_AFTER_MID", "0") != "0"
         # Decoder wgrad GEMM with the Adam step as its epilogue (EpiAdam, ltg_wgrad_adam): correct (tests) and 96 MB/step less HBM
         # traffic, but measured SLOWER than wgrad GEMM (38 us) + streaming Adam (58 us): 112 us, 2.9 TB/s -- the 16 epilogue warps
         # walk load -> update -> store chunk by chunk and cannot keep enough HBM requests in flight. Kept off until the epilogue is
         # restructured (TMA-staged p/m/v tiles).
         self.fused_wgrad_adam = False
         self.fused_disc = ops.disc_fused_supported(self.disc)   # one tcgen05 kernel for the discriminator forward (disc_fused.cu)
+        # ... and optionally the backward down to dz12 in the same tile (fourth MMA on the resident dz3 tile). Measured at the bench shape:
+        # 98 us for forward + dz12 fused vs 65 + 36 us as two kernels, step 0.519 vs 0.513 ms -- the tile is bound by its epilogue warps
+        # (tools/disc_trace.py: 30 of 40 us per tile are tanh/dropout/head/dact epilogues at IPC ~1.2), not by the GEMM it absorbs: off.
+        self.fused_dz12 = os.environ.get("LTG_FUSED_DZ12", "0") != "0"
         self.fused_mid = True   # fused 600->400->200->600 middle instead of two GEMMs + element-wise launches ...
         # ... on tcgen05 (mid_tc.cu: one CTA per 128 rows x column third) for large batches, where streaming the weights once per 128
         # rows pays; at batch 500 the 12 CTAs of that kernel are a serial L2-latency chain (38 us vs 16 us measured) and the mma.sync
@@ -371,7 +376,8 @@ class GanEngine(object):
         ops.disc_gather(d.E_b, pop, niche, P, self.Xp, self.Xn)
         if self.fused_disc:
             ops.disc_fwd_fused(self.Xp, self.Xn, P, d, label, kd, seed, st, words, self.Hd, self.y, scal,
-                               self.dz3 if backward else None, g_w4 if backward else None, g_b4 if backward else None)
+                               self.dz3 if backward else None, g_w4 if backward else None, g_b4 if backward else None,
+                               self.dz12 if (backward and self.fused_dz12) else None)
             return
         k1 = d.h0 + 1  # embedding columns + the ones column (bias row of W1 / W2)
         ops.gemm(self.Xp, d.view("W1", "b"), P, d.h1, k1, lda=128, b_mn=True, bn=ops.pick_bn(P, d.h1), out_bf16=self.Hd, ld_bf16=d.k3,
@@ -441,8 +447,9 @@ class GanEngine(object):
         self._disc_forward(bt["pair_pop"], bt["pair_niche"], bt["label"], P, True, g_w4=gW("w4"), g_b4=gW("b4"))
         with self._fork(self.s1):
             ops.gemm(self.Hd, self.dz3, d.k3, d.h3, P, a_mn=True, b_mn=True, splits=sp3, bn=bn3, out_f32=gW("W3"), ld_f32=d.ld3, **kw)  # dW3 (+db3)
-        ops.gemm(self.dz3, d.view("W3", "b"), P, d.k3, d.h3, bn=ops.pick_bn(P, d.k3), out_bf16=self.dz12, dact_src=self.Hd,
-                 dact_keep=self.keep_d)                                                            # dz12 = (dz3 W3^T) * dact(Hd)
+        if not (self.fused_disc and self.fused_dz12):   # (the fused kernel has already produced dz12 as its fourth MMA)
+            ops.gemm(self.dz3, d.view("W3", "b"), P, d.k3, d.h3, bn=ops.pick_bn(P, d.k3), out_bf16=self.dz12, dact_src=self.Hd,
+                     dact_keep=self.keep_d)                                                        # dz12 = (dz3 W3^T) * dact(Hd)
         with self._fork(self.s2):
             ops.gemm(self.Xp, self.dz12, k1, d.h1, P, a_mn=True, b_mn=True, splits=sp, bn=ops.pick_bn(k1, d.h1, True), out_f32=gW("W1"),
                      ld_f32=d.ld1, **kw)                                                           # dW1 (+db1) = Xp^T dz1
@@ -594,6 +601,8 @@ class GanEngine(object):
                         if self.overlap:
                             side.wait_event(ev)
                         ops.adam(v.WdT[r0:r0 + nr], v.WdT_m[r0:r0 + nr], v.WdT_v[r0:r0 + nr], self.dWdT[r0:r0 + nr], v.WdT_b[r0:r0 + nr], scal=self.scal)
+            elif self.adam_after_mid and self.overlap and self.fused_mid:
+                self._dec_adam_pending = True   # issued below, behind the latency-bound middle of the backward chain
             else:
                 with (torch.cuda.stream(self.s1) if self.overlap else torch.cuda.stream(torch.cuda.current_stream())):
                     ops.adam(v.WdT, v.WdT_m, v.WdT_v, self.dWdT, v.WdT_b, scal=self.scal)
@@ -606,6 +615,14 @@ class GanEngine(object):
                 ops.gemm(self.z, self.dh2pre, L, H, B, a_mn=True, b_mn=True, bn=64, out_f32=v.view("W_p0", "g"))
             ops.vae_mid_bwd(self.dh2pre, v.view("W_p0", "b"), v.view("W_q1", "b"), self.mulv, self.zmu, self.h1, B, Bg, -1.0, self.scal,
                             self.dmulv, self.dh1pre, self.dh1pre_b, v.view("b_q1", "g"), v.view("b_q0", "g"), tc=self.mid_tc)
+            if getattr(self, "_dec_adam_pending", False):
+                # The decoder Adam sweep saturates HBM for ~60 us; the two middle kernels above are L2-latency chains that ran 2.5x
+                # slower beside it (34 + 34 us instead of 15 + 12, timeline of round 2). It starts once they are done and then shares
+                # HBM with the other bandwidth-bound tail of the step (encoder weight gradient + Adam over the active rows).
+                self._dec_adam_pending = False
+                self.s1.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self.s1):
+                    ops.adam(v.WdT, v.WdT_m, v.WdT_v, self.dWdT, v.WdT_b, scal=self.scal)
             self._join(self.s2)
             with self._fork(self.s2):
                 ops.gemm(self.h1, self.dmulv, H, 2 * L, B, a_mn=True, b_mn=True, bn=64, out_f32=v.view("W_q1", "g"))

@@ -531,7 +531,7 @@ def test_disc_gather_head_and_backward(ops):
 
 
 @pytest.mark.parametrize("P,backward,sizes", [(333, True, (100, 150, 250, 300)), (1000, False, (100, 150, 250, 300)), (128, True, (100, 150, 250, 300)),
-                                              (260, True, (40, 24, 56, 64))])
+                                              (260, True, (40, 24, 56, 64)), (40000, True, (100, 150, 250, 300)), (40000, False, (100, 150, 250, 300))])
 def test_disc_fused_forward_matches_unfused_chain(ops, P, backward, sizes):
     """disc_fused.cu (one tcgen05 kernel: branch layers -> fc1 -> head through TMEM / shared memory) against the chain of
     ltg_gemm_bf16 + ltg_disc_head launches it replaces. The dropout masks are the same counter hash, so the hidden activation
@@ -562,8 +562,9 @@ def test_disc_fused_forward_matches_unfused_chain(ops, P, backward, sizes):
         dz3 = torch.zeros(P, d.ld3, **bf) if backward else None
         dw4 = torch.zeros(d.ld3, device="cuda") if backward else None
         db4 = torch.zeros(4, device="cuda") if backward else None
+        dz12 = torch.zeros(P, d.k3, **bf) if backward else None
         if fused:
-            ops.disc_fwd_fused(Xp, Xn, P, d, label, keep, seed, st, words, Hd, y, scal, dz3, dw4, db4)
+            ops.disc_fwd_fused(Xp, Xn, P, d, label, keep, seed, st, words, Hd, y, scal, dz3, dw4, db4, dz12)
         else:
             Y3 = torch.zeros(P, d.ld3, **bf)
             ops.gemm(Xp, d.view("W1", "b"), P, d.h1, k1, lda=128, b_mn=True, bn=ops.pick_bn(P, d.h1), out_bf16=Hd, ld_bf16=d.k3, act=1,
@@ -573,11 +574,13 @@ def test_disc_fused_forward_matches_unfused_chain(ops, P, backward, sizes):
             ops.gemm(Hd, d.view("W3", "b"), P, d.h3, d.k3, b_mn=True, bn=ops.pick_bn(P, d.h3), out_bf16=Y3, act=1, keep=keep, seed=seed,
                      rng_stream=st + 2, rng_step_dev=words, rng_ld=d.ld3)
             ops.disc_head(Y3, P, d.h3, d.view("w4"), d.view("b4"), label, keep, y, scal, dz3, dw4, db4)
+            if backward:   # the backward GEMM the fused kernel's fourth MMA replaces
+                ops.gemm(dz3, d.view("W3", "b"), P, d.k3, d.h3, bn=ops.pick_bn(P, d.k3), out_bf16=dz12, dact_src=Hd, dact_keep=keep)
         torch.cuda.synchronize()
-        return Hd, y, scal, dz3, dw4, db4
+        return Hd, y, scal, dz3, dw4, db4, dz12
 
-    Hu, yu, su, dzu, dwu, dbu = run(False)
-    Hf, yf, sf, dzf, dwf, dbf = run(True)
+    Hu, yu, su, dzu, dwu, dbu, d12u = run(False)
+    Hf, yf, sf, dzf, dwf, dbf, d12f = run(True)
     # same dropout pattern and the ones column / padding layout
     assert torch.equal(Hu == 0, Hf == 0)
     assert (Hf[:, d.one3] == 1).all() and (Hf[:, d.one3 + 1:] == 0).all() and (Hf[:, d.h1:d.off2] == 0).all()
@@ -593,6 +596,14 @@ def test_disc_fused_forward_matches_unfused_chain(ops, P, backward, sizes):
         assert (dzf[label.long() < 0] == 0).all()
         assert (dwu - dwf).abs().max().item() < 2e-3 * max(1.0, dwu.abs().max().item())
         assert abs(dbu[0].item() - dbf[0].item()) < 1e-3 * max(1.0, abs(dbu[0].item()))
+        # dz12 = (dz3 W3^T) * dact(Hd): fused fourth MMA against the GEMM path, and against fp32 on the fused kernel's own dz3 / Hd
+        used = list(range(d.h1)) + list(range(d.off2, d.off2 + d.h2))   # the columns the weight-gradient GEMMs read
+        s12 = d12u.float()[:, used].abs().max().item() + 1e-9
+        assert (d12u.float()[:, used] - d12f.float()[:, used]).abs().max().item() < 4e-2 * s12
+        Hff = Hf.float()
+        dact = torch.where(Hff != 0, (1 - (Hff * keep) ** 2) / keep, torch.zeros_like(Hff))
+        want = (dzf[:, : d.h3].float() @ d.view("W3", "b").float()[:, : d.h3].t()) * dact
+        assert (d12f.float()[:, used] - want[:, used]).abs().max().item() < 2e-2 * want[:, used].abs().max().item() + 1e-7
     # independent fp32 restatement of the head on the fused kernel's own hidden activation
     W3 = d.view("W3", "b").float()[:, : d.h3]
     a3 = torch.tanh(Hf.float() @ W3)
