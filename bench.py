@@ -26,7 +26,20 @@ if ROOT not in sys.path:
 
 CONFIG = "ml20m"
 BATCH = 500
+# BASELINE.json `configs`: the headline (what the driver runs with no --config) is configs[1]; the others are run with --config and
+# their lines are kept under profiles/. batch = users per GPU per step (weak scaling).
+BENCH_CONFIGS = {
+    "ml20m": dict(batch=500, label="ML-20M-shaped synthetic"),
+    # batch is free for the throughput configs: 8192 users per GPU puts the G step on the tensor side of its roofline
+    "netflix": dict(batch=8192, label="Netflix-shaped synthetic"),
+    # "GAN sampling + discriminator at full batch, 8 B200": one eighth of the 571,355 users per GPU and step
+    "msd": dict(batch=71420, label="MSD-shaped synthetic (full batch / 8 per GPU)"),
+    # the bundled dataset (tests/golden/askubuntu_sample.npz = the reference loaders' outputs on Dataset/Askubuntu_Sample), config.ini batch
+    "askubuntu": dict(batch=100, label="bundled Askubuntu sample (real data)"),
+}
+GOLD = os.path.join(ROOT, "tests", "golden", "askubuntu_sample.npz")
 N_BENCH_BATCHES = 8   # distinct user batches cycled through by the timed steps (per GPU)
+CPU_BATCH_CAP = 1000  # users per step of the CPU baseline sample (dense fp32 [B, I] tensors)
 MIN_TIMED_S = 0.5     # the K-step timed block is repeated until this much device time has accumulated (median block reported)
 MAX_REPEATS = 200
 H0, H1, H2, H3 = 100, 150, 250, 300   # config.ini h0..h3_size
@@ -39,6 +52,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=48)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default=os.environ.get("LTG_BENCH_CONFIG", "ml20m"), choices=sorted(BENCH_CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="users per GPU per step (default: the config's)")
+    ap.add_argument("--no-dp-check", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=6, help="steps of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true")
@@ -213,28 +229,54 @@ def cpu_baseline(tabs, n_steps, n_items):
     from oracle.cpu_step import CpuGanStep
     step = CpuGanStep(n_items, H0, H1, H2, H3, LR, LAM)
     N = len(tabs["indptr"]) - 1
-    step.step(tabs, 0, min(BATCH, N))  # warm-up (thread pools, allocator)
+    cb = min(BATCH, CPU_BATCH_CAP)   # the dense fp32 [B, I] restatement is bounded to CPU_BATCH_CAP users per step
+    step.step(tabs, 0, min(cb, N))  # warm-up (thread pools, allocator)
     t0 = time.perf_counter()
     users = 0
     parts = {"t_a": 0.0, "t_d": 0.0, "t_g": 0.0}
     for i in range(n_steps):
-        b0 = ((i + 1) * BATCH) % max(BATCH, N - BATCH + 1)
-        r = step.step(tabs, b0, min(N, b0 + BATCH))
-        users += min(N, b0 + BATCH) - b0
+        b0 = ((i + 1) * cb) % max(cb, N - cb + 1)
+        r = step.step(tabs, b0, min(N, b0 + cb))
+        users += min(N, b0 + cb) - b0
         for k in parts:
             parts[k] += r[k]
     dt = time.perf_counter() - t0
     return dict(value=users / dt, unit="users/s", cores=torch.get_num_threads(), kind="port",
                 sample="%d GAN steps (A+D+G) of %d users at the %s shape, dense fp32 PyTorch-CPU restatement of the TF graph + the "
                        "reference's host sampling loop; %.2f s/step (A %.2f, D %.2f, G %.2f)"
-                       % (n_steps, BATCH, CONFIG, dt / n_steps, parts["t_a"] / n_steps, parts["t_d"] / n_steps, parts["t_g"] / n_steps),
+                       % (n_steps, cb, CONFIG, dt / n_steps, parts["t_a"] / n_steps, parts["t_d"] / n_steps, parts["t_g"] / n_steps),
                 host_cpu_count=os.cpu_count())
 
 
-def workload_config(world):
+def config_shape():
+    """(n_users, n_items) of the selected configuration."""
+    if CONFIG == "askubuntu":
+        return 10001, 1000
     syn = importlib.import_module("long-tail-gan_b200.synthetic")
     N, I, deg = syn.CONFIGS[CONFIG]
-    return dict(workload="ML-20M-shaped synthetic: %d users x %d items, VAE 600-200, batch %d per GPU, GAN step = A + D + G" % (N, I, BATCH),
+    return N, I
+
+
+def config_tables(n_users):
+    """Side tables of the first n_users users of the selected configuration."""
+    if CONFIG == "askubuntu":
+        import numpy as np
+        dp = importlib.import_module("long-tail-gan_b200.data_processing")
+        tabs = dp.tables_from_golden(np.load(GOLD))
+        return tabs
+    syn = importlib.import_module("long-tail-gan_b200.synthetic")
+    return syn.make_config(CONFIG, n_users=n_users)
+
+
+def select_config(args):
+    global CONFIG, BATCH
+    CONFIG = args.config
+    BATCH = args.batch if args.batch > 0 else BENCH_CONFIGS[CONFIG]["batch"]
+
+
+def workload_config(world):
+    N, I = config_shape()
+    return dict(workload="%s: %d users x %d items, VAE 600-200, batch %d per GPU, GAN step = A + D + G" % (BENCH_CONFIGS[CONFIG]["label"], N, I, BATCH),
                 users=N, items=I, batch_per_gpu=BATCH, global_batch=BATCH * world, parallelism="dp%d" % world,
                 disc="h0..h3 = %d/%d/%d/%d" % (H0, H1, H2, H3), ganlambda=LAM,
                 l2_policy="per-step working set (weights + Adam state, ~0.8 GB touched) exceeds the 126 MB L2; timed steps cycle over "
@@ -248,20 +290,21 @@ def run_reference(args, rank, world):
     import torch
     # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the reference arm is a CPU job that owns the whole host
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    syn = importlib.import_module("long-tail-gan_b200.synthetic")
-    N, I, deg = syn.CONFIGS[CONFIG]
+    N, I = config_shape()
     n_steps = max(1, min(args.steps, 8))
-    tabs = syn.make_config(CONFIG, n_users=BATCH * (n_steps + 2))
+    cpu_batch = min(BATCH, CPU_BATCH_CAP)
+    tabs = config_tables(cpu_batch * (n_steps + 2))
     cb = cpu_baseline(tabs, n_steps, I)
     line = dict(impl="reference", metric="gan_step_users_per_sec", value=cb["value"], unit="users/s", n_gpus=world, steps=n_steps,
-                warmup=1, ms_per_step=1e3 * BATCH / cb["value"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="fp32",
-                data="synthetic", config=workload_config(world), cpu_baseline=cb,
+                warmup=1, ms_per_step=1e3 * min(BATCH, CPU_BATCH_CAP) / cb["value"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="fp32",
+                data="real (bundled sample)" if CONFIG == "askubuntu" else "synthetic", config=workload_config(world), cpu_baseline=cb,
                 e2e=dict(value=cb["value"], unit="users/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
 
 
 def main():
     args = parse()
+    select_config(args)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -289,10 +332,10 @@ def main():
     ops = importlib.import_module("long-tail-gan_b200.ops")
     ops.init()
 
-    N, I, deg = syn.CONFIGS[CONFIG]
-    nb = N_BENCH_BATCHES
+    N, I = config_shape()
+    nb = max(1, min(N_BENCH_BATCHES, N // (BATCH * world)))
     # every rank owns its own contiguous slice of users (user-sharded data parallel, weak scaling)
-    tabs = syn.make_config(CONFIG, n_users=BATCH * nb * world)
+    tabs = config_tables(BATCH * nb * world)
     data = eng.TrainData(batch_size=BATCH, first_batch=rank * nb, max_batches=nb, **tabs)
     vae = gen.MultiVAE([200, 600, I], lam=0.0, random_seed=98765)
     vae.init_weights(98765)
@@ -442,6 +485,15 @@ def main():
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ms, ms_e2e, t_a, t_d, t_g, t_adam, t_enc_adam, t_df_d, t_df_g = [float(x) for x in times.cpu()]
 
+    dp_res = None
+    if world > 1 and not args.no_dp_check:
+        # driver-visible correctness of the data-parallel step: same global batch on N ranks and on one GPU (dp_check.py)
+        dpc = importlib.import_module("long-tail-gan_b200.dp_check")
+        bq = min(BATCH, 512)
+        try:
+            dp_res = dpc.run_check(config_tables(bq * world), I, bq, rank, world, steps=2, lr=1e-3, use_graphs=not args.no_graphs)
+        except Exception as e:  # noqa: BLE001
+            dp_res = dict(ok=False, error=repr(e)[:300])
     if rank == 0:
         peak, peak_src = measured_peaks()
         users = BATCH * world * args.steps
@@ -497,7 +549,7 @@ def main():
             adam_roof.pop("others", None)
         line = dict(metric="gan_step_users_per_sec", value=users / (ms * 1e-3), unit="users/s", n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype="bf16", data="synthetic", config=workload_config(world),
+                    dtype="bf16", data="real (bundled sample)" if CONFIG == "askubuntu" else "synthetic", config=workload_config(world),
                     e2e=dict(value=users / (ms_e2e * 1e-3), unit="users/s", h2d_bytes_per_step=h2d // args.steps,
                              d2h_bytes_per_step=2 * ops.NSCAL * 4, ms_per_step=ms_e2e / args.steps),
                     gpu_launches=launches, clocks=clocks, roofline=roof,
@@ -508,6 +560,8 @@ def main():
                                 e2e_repeats=len(e2e_ms), rule="the %d-step block is repeated until >= %.1f s of device time; median block reported"
                                                               % (args.steps, MIN_TIMED_S)))
         if world > 1:
+            line["dp_check"] = dp_res
+            line["comm"] = dict(world_size=dist.get_world_size(), backend=dist.get_backend(), nccl_version=".".join(str(x) for x in torch.cuda.nccl.version()))
             line["config"]["exchange"] = ("our kernels over NVLink peer memory (%s), flag barriers; no NCCL collective in the step"
                                           % ("NVLS multicast stores + in-switch reduction" if engine.peer["dWdT_mc"] else "unicast peer loads/stores")
                                           if engine.peer is not None else "NCCL collectives captured in the step graphs")

@@ -212,6 +212,10 @@ int ltg_enc_wgrad_compact(float* G, int n_active, const int32_t* act_ptr, const 
  * issues it at the start of the G step); 2 = only the batch's active rows.                                                    */
 int ltg_enc_adam(float* p, float* m, float* v, void* shadow_bf16, int n_items, const int32_t* slot_of_item, const float* G,
                  float lr_t, const float* scal, float beta1, float beta2, float eps, int rows, void* stream);
+/* out[i] = sum over s < n_partials of src[s * stride + i] (n, stride multiples of 4): split-K partials -> one gradient buffer.   */
+int ltg_sum_partials(const float* src, int n_partials, int64_t stride, int64_t n, float* out, void* stream);
+/* Data parallel: zeroes the entries ltg_enc_coef_scatter wrote (same e_row / e_slot arrays) once the shard GEMM has read them.   */
+int ltg_enc_coef_clear(const int32_t* e_row, const int32_t* e_slot, int n_entries, void* xc_bf16, int ld_xc, void* stream);
 /* Restores the all-zero state of the dense coefficient matrix xc[B, ld_xc] that ltg_enc_gather_fwd filled for the batch rows
  * indptr[0..B] (train.py:194-198 made this matrix dense on the host): one store per interaction. nnz_hint sizes the grid.   */
 int ltg_enc_xc_clear(const int32_t* indptr, const int32_t* indices, int B, int nnz_hint, const int32_t* slot_of_item, void* xc_bf16,

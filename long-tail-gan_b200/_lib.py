@@ -99,6 +99,8 @@ SIGNATURES = {
     "ltg_adam": (_I, [_P, _P, _P, _P, _I, _I64, _P, _I64, _F, _P, _F, _F, _F, _P]),
     "ltg_enc_wgrad_compact": (_I, [_P, _I, _P, _P, _P, _P, _P, _I, _P]),
     "ltg_enc_adam": (_I, [_P, _P, _P, _P, _I, _P, _P, _F, _P, _F, _F, _F, _I, _P]),
+    "ltg_sum_partials": (_I, [_P, _I, _I64, _I64, _P, _P]),
+    "ltg_enc_coef_clear": (_I, [_P, _P, _I, _P, _I, _P]),
     "ltg_enc_xc_clear": (_I, [_P, _P, _I, _I, _P, _P, _I, _P]),
     "ltg_enc_wgrad_expand": (_I, [_P, _I, _P, _P, _P]),
     "ltg_sample_pairs": (_I, [_P, _I, _I, _I, _I64, _P, _P, _P, _P, _P, _P, _U64, _U32, _P, _P, _P, _P, _P, _I, _P, _P]),

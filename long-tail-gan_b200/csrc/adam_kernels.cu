@@ -289,3 +289,35 @@ extern "C" int ltg_enc_xc_clear(const int32_t* indptr, const int32_t* indices, i
   LTG_CHECK_LAUNCH();
   return LTG_OK;
 }
+
+// out[i] = sum_s src[s * stride + i]: the split-K partials of the discriminator weight-gradient GEMMs folded into the one gradient
+// arena the data-parallel exchange reads (replaces a torch.sum launch inside the captured step)
+namespace {
+__global__ void __launch_bounds__(256)
+sum_partials_kernel(const float* __restrict__ src, int n_partials, int64_t stride, int64_t n4, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 a = ld_stream_f4(src + 4 * i), b = make_float4(0.f, 0.f, 0.f, 0.f), c = b, d = b;
+  int sp = 1;
+  for (; sp + 3 <= n_partials; sp += 3) {
+    const float4 x = ld_stream_f4(src + (size_t)sp * stride + 4 * i), y = ld_stream_f4(src + (size_t)(sp + 1) * stride + 4 * i),
+                 z = ld_stream_f4(src + (size_t)(sp + 2) * stride + 4 * i);
+    b.x += x.x; b.y += x.y; b.z += x.z; b.w += x.w; c.x += y.x; c.y += y.y; c.z += y.z; c.w += y.w; d.x += z.x; d.y += z.y; d.z += z.z; d.w += z.w;
+  }
+  for (; sp < n_partials; ++sp) {
+    const float4 x = ld_stream_f4(src + (size_t)sp * stride + 4 * i);
+    b.x += x.x; b.y += x.y; b.z += x.z; b.w += x.w;
+  }
+  *reinterpret_cast<float4*>(out + 4 * i) = make_float4((a.x + b.x) + (c.x + d.x), (a.y + b.y) + (c.y + d.y), (a.z + b.z) + (c.z + d.z), (a.w + b.w) + (c.w + d.w));
+}
+}  // namespace
+
+extern "C" int ltg_sum_partials(const float* src, int n_partials, int64_t stride, int64_t n, float* out, void* stream) {
+  LTG_REQUIRE(src && out && n_partials >= 1 && n % 4 == 0 && stride % 4 == 0);
+  LTG_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(out)) & 15) == 0);
+  if (n <= 0) return LTG_OK;
+  const int64_t n4 = n / 4;
+  sum_partials_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, n_partials, stride, n4, out);
+  LTG_CHECK_LAUNCH();
+  return LTG_OK;
+}

@@ -558,6 +558,13 @@ __global__ void enc_coef_scatter_kernel(const int32_t* __restrict__ e_row, const
   xc[(size_t)r * ld_xc + e_slot[e]] = __float2bfloat16(c);
 }
 
+// the same entries back to zero after the shard's weight-gradient GEMM has consumed the matrix (replaces a fill of the whole matrix)
+__global__ void enc_coef_clear_kernel(const int32_t* __restrict__ e_row, const int32_t* __restrict__ e_slot, int n_entries,
+                                      __nv_bfloat16* __restrict__ xc, int ld_xc) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n_entries) xc[(size_t)e_row[e] * ld_xc + e_slot[e]] = __float2bfloat16(0.f);
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -691,6 +698,14 @@ extern "C" int ltg_enc_coef_scatter(const int32_t* e_row, const int32_t* e_item,
   if (n_entries <= 0) return LTG_OK;
   enc_coef_scatter_kernel<<<(n_entries + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
       e_row, e_item, e_slot, row_uid, row_rnorm, n_entries, n_items, keep, seed, step, step_dev, reinterpret_cast<__nv_bfloat16*>(xc_bf16), ld_xc);
+  LTG_CHECK_LAUNCH();
+  return LTG_OK;
+}
+
+extern "C" int ltg_enc_coef_clear(const int32_t* e_row, const int32_t* e_slot, int n_entries, void* xc_bf16, int ld_xc, void* stream) {
+  LTG_REQUIRE(e_row && e_slot && xc_bf16);
+  if (n_entries <= 0) return LTG_OK;
+  enc_coef_clear_kernel<<<(n_entries + 255) / 256, 256, 0, (cudaStream_t)stream>>>(e_row, e_slot, n_entries, reinterpret_cast<__nv_bfloat16*>(xc_bf16), ld_xc);
   LTG_CHECK_LAUNCH();
   return LTG_OK;
 }

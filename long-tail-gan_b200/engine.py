@@ -657,7 +657,6 @@ class GanEngine(object):
             # encoder gradient of THIS rank's item shard over the GLOBAL batch: only dh1pre (bf16 [B,600] per rank) is exchanged
             import torch.distributed as dist
             tb = self.dp_tables[bi]
-            self.Xc_glob.zero_()
             ops.enc_coef_scatter(tb["e_row"], tb["e_item"], tb["e_slot"], tb["row_uid"], tb["row_rnorm"], tb["n_entries"], self.I,
                                  self.keep_vae, self.seed, 0, self.w_g, self.Xc_glob)
             if self.peer is not None:
@@ -669,6 +668,8 @@ class GanEngine(object):
             if tb["n_active"] > 0:
                 ops.gemm(self.Xc_glob, self.dh1_glob, tb["n_active"], H, self.world_size * self.max_B, a_mn=True, b_mn=True,
                          bn=ops.pick_bn(tb["n_active"], H), out_f32=self.G_shard)
+            with self._fork(self.s2):   # self-cleaning, off the critical path: the next step scatters into an all-zero matrix
+                ops.enc_coef_clear(tb["e_row"], tb["e_slot"], tb["n_entries"], self.Xc_glob)
             if self.nrows > 0:
                 r0, nr = self.row0, self.nrows
                 if self.peer is not None:   # Adam on the shard rows, bf16 rows stored straight into every rank's encoder shadow
@@ -748,9 +749,14 @@ class GanEngine(object):
         self._run(("ddp", id(data), bi), lambda: self._d_step_dp(data, bi))
 
     def _d_step_dp(self, data, bi):
-        import torch.distributed as dist
         self._d_fwd_bwd(data, bi)
-        torch.sum(self.arena_gp, dim=0, out=self.disc.arena_g)   # split-K partials -> one gradient arena
+        self._d_update_dp()
+
+    def _d_update_dp(self):
+        import torch.distributed as dist
+        d = self.disc
+        # split-K partials -> the one gradient arena the exchange reads (arena_n is padded to a multiple of 4)
+        ops.sum_partials(self.arena_gp, self._d_parts, d.arena_n, d.arena_g.numel(), d.arena_g)
         if self.peer is not None:
             d = self.disc
             self._pbar(0)
@@ -767,28 +773,39 @@ class GanEngine(object):
         if self.world_size == 1:
             self._run(("adg", id(data), bi), lambda: self._step_fused(data, bi))
         else:
-            self._run(("adgdp", id(data), bi), lambda: (self.phase_a(data, bi), self._d_step_dp(data, bi), self._g_step_dp(data, bi)))
+            self._run(("adgdp", id(data), bi), lambda: self._step_fused(data, bi))
 
     def _step_fused(self, data, bi):
         """A -> D -> G of one batch with the dependencies the data flow has, not the ones the call order suggests: the G update's VAE
         forward (train.py:326, generator side) needs the weights phase A used and nothing from the D update, so it runs on a side
         branch beside it; only y_generated (discriminator forward with the UPDATED weights) and everything behind it wait for D."""
+        dp = self.world_size > 1
         if not (self.overlap and self.overlap_dg):
-            self.phase_a(data, bi); self.d_step(data, bi); self.g_step(data, bi)
+            self.phase_a(data, bi)
+            if dp:
+                self._d_step_dp(data, bi); self._g_step_dp(data, bi)
+            else:
+                self.d_step(data, bi); self.g_step(data, bi)
             return
         bt = data.batches[bi]
         self.phase_a(data, bi)
         self._d_advance()          # the counters advance in the reference's order (D's Adam step, then G's) ...
-        self._fuse_update = True
+        self._fuse_update = not dp
         self._g_advance()          # ... before either update's kernels start
         self._g_early(data, bi)
         with self._fork(self.s3):
             self._vae_forward(data, bt, True, self.keep_vae)
         self._d_fwd_bwd(data, bi, advance=False)
-        self._d_update()
+        if dp:
+            self._d_update_dp()    # (its gradient exchange involves the peers; the G forward on branch s3 is rank-local)
+        else:
+            self._d_update()
         self._g_disc_forward(data, bi)
         self._join(self.s3)
-        self._g_backward(data, bi)
+        if dp:
+            self._g_rest_dp(data, bi)
+        else:
+            self._g_backward(data, bi)
         self._fuse_update = False
 
     def run_g_step(self, data, bi):
@@ -808,9 +825,12 @@ class GanEngine(object):
         NCCL path (LTG_DP_PEER=0 / no peer mapping), collectives in issue order, identical on every rank: all-reduce(sum y, cnt) ->
         reduce-scatter(dW_dec) -> all-gather(bf16 W_dec) -> all-gather(dh1pre) or reduce-scatter(dW_enc) -> all-reduce(small grads)
         -> all-gather(bf16 W_enc)."""
+        self._g_forward(data, bi)
+        self._g_rest_dp(data, bi)
+
+    def _g_rest_dp(self, data, bi):
         import torch.distributed as dist
         v = self.vae
-        self._g_forward(data, bi)
         # F3: the adversarial term multiplies GLOBAL sums; Ybar = sum y / cnt must be global before the backward pass starts
         if self.peer is not None:
             pr = self.peer
@@ -918,8 +938,18 @@ class GanEngine(object):
     # ------------------------------------------------------------------------------------------------------------
     # losses of the last step (host reads; train.py:303,329 print them once per sub-epoch)
     # ------------------------------------------------------------------------------------------------------------
-    def last_losses(self, B, B_global=None):
-        sa = self.scal_all.detach().cpu().numpy().astype(np.float64)
+    def last_losses(self, B, B_global=None, reduce=False):
+        """reduce (data parallel): sums the per-rank NLL / KL / sum p / d_loss over the ranks (sum y and cnt already are global) and
+        normalises by the global batch -- a collective, every rank must call it."""
+        sa_t = self.scal_all.detach().clone()
+        if reduce and self.world_size > 1:
+            import torch.distributed as dist
+            loc = torch.stack([sa_t[0, ops.S_NLL_SUM], sa_t[0, ops.S_KL_SUM], sa_t[0, ops.S_SUM_P], sa_t[1, ops.S_D_LOSS]])
+            dist.all_reduce(loc)
+            sa_t[0, ops.S_NLL_SUM], sa_t[0, ops.S_KL_SUM], sa_t[0, ops.S_SUM_P], sa_t[1, ops.S_D_LOSS] = loc[0], loc[1], loc[2], loc[3]
+            if B_global is None:
+                B_global = self.B_global
+        sa = sa_t.cpu().numpy().astype(np.float64)
         s = sa[0]
         Bg = B if B_global is None else B_global
         neg_ll = s[ops.S_NLL_SUM] / Bg

@@ -258,6 +258,16 @@ def enc_adam(p, m, v, shadow, n_items, slot_of_item, G, lr_t=-1.0, scal=None, be
                              eps, rows, _stream()))
 
 
+def sum_partials(src, n_partials, stride, n, out):
+    _count(1)
+    check(lib().ltg_sum_partials(ptr(src), n_partials, stride, n, ptr(out), _stream()))
+
+
+def enc_coef_clear(e_row, e_slot, n_entries, xc):
+    _count(1)
+    check(lib().ltg_enc_coef_clear(ptr(e_row), ptr(e_slot), n_entries, ptr(xc), xc.stride(0), _stream()))
+
+
 def enc_xc_clear(indptr, indices, B, nnz, slot_of_item, xc):
     _count(1)
     check(lib().ltg_enc_xc_clear(ptr(indptr), ptr(indices), B, nnz, ptr(slot_of_item), ptr(xc), xc.stride(0), _stream()))

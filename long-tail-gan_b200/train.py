@@ -26,6 +26,8 @@ from .discriminator import discriminator                 # noqa: E402
 from .engine import GanEngine, TrainData                 # noqa: E402
 from .generator import generator_VAECF as generator      # noqa: E402
 from .generator import MultiVAE                          # noqa: E402
+from .dist import env_rank_world as dist_env_rank_world  # noqa: E402
+from .dist import shard_range as dist_shard_range        # noqa: E402
 
 
 def _load_dataset(dataset):
@@ -78,10 +80,27 @@ def _load_dataset(dataset):
     return tabs, vad, n_items, generator(pro_dir)
 
 
+def _dist_setup():
+    """One process per GPU under torch.distributed.run (RANK / WORLD_SIZE / LOCAL_RANK in the environment): user-sharded data
+    parallelism. Returns (rank, world). A plain `python train.py` run is (0, 1) and touches no process group."""
+    rank, world, local = dist_env_rank_world()
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        if not dist.is_initialized():
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world
+
+
 def train_GAN(h0_size, h1_size, h2_size, h3_size, NUM_EPOCH, NUM_SUB_EPOCHS, BATCH_SIZE, DISPLAY_ITER, LEARNING_RATE, to_restore,
-              model_name, dataset, GANLAMBDA, seed=0, max_epochs=None, save=True, quiet=False, init=None):
-    """train.py:30-356. Extra keyword arguments (seed, max_epochs, save, quiet, init=(vae params, E, d_params)) are ours."""
-    log = (lambda *a, **k: None) if quiet else print
+              model_name, dataset, GANLAMBDA, seed=0, max_epochs=None, save=True, quiet=False, init=None, diag=False):
+    """train.py:30-356. Extra keyword arguments (seed, max_epochs, save, quiet, init=(vae params, E, d_params), diag) are ours.
+    Launched under torch.distributed.run with N ranks, every global batch of BATCH_SIZE users is split over the ranks (BATCH_SIZE / N
+    users each; gradients exchanged inside the step, engine._g_step_dp); rank 0 prints the reference's lines and writes checkpoints.
+    to_restore = 1 (parsed and ignored by the reference, train.py:374) resumes from the newest model_<epoch> under the output path."""
+    rank, world = _dist_setup()
+    log = (lambda *a, **k: None) if (quiet or rank != 0) else print
     dataset_name = dataset.split("/")[-1].strip()
     if dataset_name == "":
         dataset_name = dataset.split("/")[-2].strip()
@@ -93,7 +112,15 @@ def train_GAN(h0_size, h1_size, h2_size, h3_size, NUM_EPOCH, NUM_SUB_EPOCHS, BAT
 
     tabs, vad, n_items, gen = _load_dataset(dataset)
     generator_network, generator_out, g_vae_loss, g_params, p_dims, total_anneal_steps, anneal_cap = gen
-    data = TrainData(batch_size=BATCH_SIZE, **tabs)
+    if world > 1:
+        if BATCH_SIZE % world != 0:
+            raise ValueError("BATCH_SIZE (%d) must be a multiple of the number of ranks (%d)" % (BATCH_SIZE, world))
+        B_local = BATCH_SIZE // world
+        n_local_total = int(np.ceil(float(len(tabs["indptr"]) - 1) / B_local))
+        first, count = dist_shard_range(n_local_total, rank, world)   # contiguous block of local batches per rank; the tail is dropped
+        data = TrainData(batch_size=B_local, first_batch=first, max_batches=count, **tabs)
+    else:
+        data = TrainData(batch_size=BATCH_SIZE, **tabs)
     N = data.N
     log("Number of Users: ", N)
     batches_per_epoch = int(np.ceil(float(N) / BATCH_SIZE))
@@ -101,20 +128,46 @@ def train_GAN(h0_size, h1_size, h2_size, h3_size, NUM_EPOCH, NUM_SUB_EPOCHS, BAT
     y_data, y_generated, d_params, x_generated_id, x_popular_n_id, x_popular_g_id, x_niche_id, item_feature_arr, keep_prob = \
         discriminator(n_items, n_items, h0_size, h1_size, h2_size, h3_size)
     disc = y_data.owner
+    if world > 1:
+        # the reference leaves the discriminator initialiser unseeded (discriminator.py:14-41): every rank would draw its own
+        import torch.distributed as dist
+        for t in (disc.arena, disc.E):
+            dist.broadcast(t, 0)
+        disc.load_state_dict(dict(arena=disc.arena.clone(), E=disc.E.clone()))
     if init is not None:
         generator_network.set_params(init[0]); generator_network.reset_optimizer()
         disc.set_params(init[1], init[2])
+    start_epoch, restored_words = 0, None
+    if to_restore and save:
+        found = latest_checkpoint(output_path)
+        if found is not None:
+            start_epoch, ck = found[0] + 1, torch.load(found[1], map_location="cpu")
+            generator_network.load_state_dict(ck["vae"]); disc.load_state_dict(ck["disc"])
+            restored_words = ck["words"]
+            log("Restored", found[1], "-> resuming at global-epoch", start_epoch)
     engine = GanEngine(generator_network, disc, max(data.max_B, 1), data.max_P, seed=seed, lr=LEARNING_RATE, lam=GANLAMBDA,
-                       total_anneal_steps=total_anneal_steps, anneal_cap=anneal_cap, max_active=data.max_active)
+                       total_anneal_steps=total_anneal_steps, anneal_cap=anneal_cap, max_active=data.max_active, world_size=world, rank=rank,
+                       B_global=(data.batch_size * world if world > 1 else None))
+    if restored_words is not None:   # rng step, the shared Adam step t (F6) and the G-update count behind the KL anneal
+        engine.words[: len(restored_words)].copy_(restored_words.to(engine.words.device))
+    if world > 1:
+        import torch.distributed as dist
+        from .engine import build_dp_shard_tables
+        engine.attach_dp_tables(build_dp_shard_tables(data, tabs["indptr"], tabs["indices"], world, rank, len(data.batches), engine.R))
     rng = np.random.RandomState(seed)
+    for _ in range(start_epoch):      # the batch order of a resumed run continues the original shuffle sequence
+        rng.shuffle(np.arange(len(data.batches)))
     history = []
     n_epochs = NUM_EPOCH if max_epochs is None else min(NUM_EPOCH, max_epochs)
-    for i in range(n_epochs):
+    for i in range(start_epoch, n_epochs):
         # ---- phase A (train.py:192-278): sample generated pairs for every batch with the epoch-start generator ----
         for bi in range(len(data.batches)):
             engine.run_phase_a(data, bi)
         torch.cuda.synchronize()
-        cnts = [int(bt["cnt"].item()) for bt in data.batches]
+        cnts = torch.stack([bt["cnt"][0] for bt in data.batches]).to(torch.int64)
+        if world > 1:
+            dist.all_reduce(cnts)     # a global batch is skipped only when no rank produced a pair for it (train.py:254-255)
+        cnts = cnts.cpu().tolist()
         user_err_cnt = int((~np.asarray(tabs["eligible"], dtype=bool)).sum())
         log("global-epoch:", i, "Data Creation Finished", "user_err_cnt:", user_err_cnt)
         indices = np.asarray([bi for bi, c in enumerate(cnts) if c > 0])   # train.py:254-255: batches without pairs are skipped
@@ -124,15 +177,21 @@ def train_GAN(h0_size, h1_size, h2_size, h3_size, NUM_EPOCH, NUM_SUB_EPOCHS, BAT
             for bi in indices:
                 engine.run_d_step(data, int(bi))
             if len(indices):
-                curr_d_loss = engine.last_losses(data.batches[int(indices[-1])]["B"])["d_loss"]
+                curr_d_loss = engine.last_losses(data.batches[int(indices[-1])]["B"], reduce=True)["d_loss"]
             log("global-epoch:%s, discr-epoch:%s, d_loss:%.5f" % (i, j_disc, curr_d_loss))
         log("")
         j_gen = 0
+        dg = dict(sp=[], ybar=[], vae=[], gan=[])
         for j_gen in range(NUM_SUB_EPOCHS):                                # train.py:307-329
             for bi in indices:
                 engine.run_g_step(data, int(bi))
+                if diag and j_gen == NUM_SUB_EPOCHS - 1:   # what the adversarial term acts on, over the last G sub-epoch (parity runs)
+                    Ld = engine.last_losses(data.batches[int(bi)]["B"], reduce=True)
+                    if Ld["cnt"] > 0:
+                        dg["sp"].append(Ld["sum_p"] / Ld["cnt"]); dg["ybar"].append(Ld["sum_y"] / Ld["cnt"])
+                        dg["vae"].append(Ld["vae_loss"]); dg["gan"].append(Ld["gan_loss"])
             if len(indices):
-                L = engine.last_losses(data.batches[int(indices[-1])]["B"])
+                L = engine.last_losses(data.batches[int(indices[-1])]["B"], reduce=True)
                 log("global-epoch:%s, generator-epoch:%s, g_loss:%.5f (vae_loss: %.5f + gan_loss: %.5f, anneal: %.5f)"
                     % (i, j_gen, L["g_loss"], L["vae_loss"], L["gan_loss"], L["anneal"]))
         log("")
@@ -141,13 +200,30 @@ def train_GAN(h0_size, h1_size, h2_size, h3_size, NUM_EPOCH, NUM_SUB_EPOCHS, BAT
         log("global-epoch:", i, "gen-epoch:", j_gen, "Vad: NDCG:", np.mean(ndcg_vad), "Recall@20:", np.mean(recall_at_20), "Recall@50:",
             np.mean(recall_at_50), "Num_users:", len(ndcg_vad), len(recall_at_20), len(recall_at_50))
         log("")
-        history.append(dict(epoch=i, ndcg=float(np.mean(ndcg_vad)), r20=float(np.mean(recall_at_20)), r50=float(np.mean(recall_at_50)),
-                            d_loss=curr_d_loss))
+        rec = dict(epoch=i, ndcg=float(np.mean(ndcg_vad)), r20=float(np.mean(recall_at_20)), r50=float(np.mean(recall_at_50)),
+                   d_loss=curr_d_loss)
+        if diag:
+            rec.update(sp_mean=float(np.mean(dg["sp"])) if dg["sp"] else None, ybar_mean=float(np.mean(dg["ybar"])) if dg["ybar"] else None,
+                       vae_loss_mean=float(np.mean(dg["vae"])) if dg["vae"] else None, gan_loss_mean=float(np.mean(dg["gan"])) if dg["gan"] else None)
+        history.append(rec)
         if save:
-            save_checkpoint(os.path.join(output_path, "model_" + str(i)), generator_network, disc, engine, p_dims,
-                            (h0_size, h1_size, h2_size, h3_size))
+            engine.gather_master()   # data parallel: the fp32 masters and Adam moments are row-sharded; no-op on one GPU
+            if rank == 0:
+                save_checkpoint(os.path.join(output_path, "model_" + str(i)), generator_network, disc, engine, p_dims,
+                                (h0_size, h1_size, h2_size, h3_size))
             log("Model saved at global-epoch", i)
     return dict(history=history, vae=generator_network, disc=disc, engine=engine, data=data)
+
+
+def latest_checkpoint(output_path):
+    """(epoch, path) of the newest model_<epoch> file under output_path, or None."""
+    best = None
+    if os.path.isdir(output_path):
+        for name in os.listdir(output_path):
+            if name.startswith("model_") and name[6:].isdigit():
+                if best is None or int(name[6:]) > best[0]:
+                    best = (int(name[6:]), os.path.join(output_path, name))
+    return best
 
 
 def save_checkpoint(path, vae, disc, engine, p_dims, hs):
@@ -170,4 +246,10 @@ def read_config(path="config.ini"):
 if __name__ == "__main__":
     cfg = read_config("config.ini")
     cfg["dataset"] = sys.argv[1]
-    train_GAN(**cfg)
+    me = os.environ.get("LTG_MAX_EPOCHS")   # (ours) bound the run without editing NUM_EPOCH, which also sets NUM_SUB_EPOCHS
+    train_GAN(max_epochs=int(me) if me else None, **cfg)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        torch.cuda.synchronize(); dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)   # graphs hold captured exchange kernels; leave without tearing the process group down under them

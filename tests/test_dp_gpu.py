@@ -1,0 +1,66 @@
+"""Data-parallel device path on REAL GPUs (needs >= 2 visible devices, skipped otherwise): two ranks over NCCL / NVLink peer memory
+against the single-GPU engine on the same global batch (long-tail-gan_b200/dp_check.py), and the torchrun form of the train.py CLI."""
+import importlib
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden", "askubuntu_sample.npz")
+pytestmark = pytest.mark.gpu
+
+needs2 = pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs two GPUs")
+
+
+def _torchrun(n, script_args, timeout=600, env=None):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+           "--master-port", "29611"] + script_args
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout, env=e)
+
+
+@needs2
+@pytest.mark.parametrize("peer", ["1", "0"])
+def test_two_rank_step_equals_single_gpu_step(tmp_path, peer):
+    """Peer-memory exchange kernels (peer=1) and the NCCL-collective fallback (peer=0)."""
+    out = str(tmp_path / "dp.json")
+    r = _torchrun(2, [os.path.join(ROOT, "tools", "dp_check.py"), out], env={"LTG_DP_PEER": peer})
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    res = json.load(open(out))
+    assert res["ok"] and res["world"] == 2
+    assert res["shadows_equal_rounded_masters"] and max(res["shadow_max_abs_diff_vs_rank0"].values()) == 0.0
+    assert res["losses_dp"]["cnt"] == res["losses_single_gpu"]["cnt"] > 0
+    for k in ("nll", "kl", "sum_p", "d_loss", "sum_y"):
+        assert res["loss_rel_diff"][k] < 2e-2, (k, res["loss_rel_diff"])
+    assert max(res["displacement_mismatch"].values()) < 0.05, res["displacement_mismatch"]
+    assert ("peer" in res["exchange"]) == (peer == "1")
+
+
+@needs2
+def test_train_cli_two_ranks(tmp_path):
+    """`torchrun ... train.py <dataset>`: batches sharded over two ranks, rank 0 prints the reference's lines and writes the
+    checkpoint; test.py restores it on one GPU."""
+    (tmp_path / "config.ini").write_text("[Long-Tail-GAN]\nh0_size = 100\nh1_size = 150\nh2_size = 250\nh3_size = 300\nNUM_EPOCH = 8\n"
+                                         "BATCH_SIZE = 100\nDISPLAY_ITER = 50\nLEARNING_RATE = 0.001\nto_restore = 0\nmodel_name = LT_GAN\nGANLAMBDA = 1.0\n")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port",
+           "29612", os.path.join(ROOT, "long-tail-gan_b200", "train.py"), GOLD]
+    env = dict(os.environ); env["LTG_MAX_EPOCHS"] = "2"
+    r = subprocess.run(cmd, cwd=str(tmp_path), capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if "Vad: NDCG:" in l]
+    assert len(lines) == 2, r.stdout[-2000:]      # one validation line per epoch, printed once (rank 0 only)
+    ndcg = float(lines[-1].split("Vad: NDCG:")[1].split()[0])
+    assert ndcg > 0.12
+    ck = tmp_path / "chkpt" / "askubuntu_sample_LT_GAN_1.0" / "model_1"
+    assert ck.exists()
+    test = importlib.import_module("long-tail-gan_b200.test")
+    train = importlib.import_module("long-tail-gan_b200.train")
+    cfg = train.read_config(str(tmp_path / "config.ini"))
+    n100, r20, r50 = test.test_GAN(dataset=GOLD, output_path=str(ck), quiet=True, **cfg)
+    assert abs(n100 - ndcg) < 0.03 and r50 > r20 > 0
