@@ -36,7 +36,11 @@ BENCH_CONFIGS = {
     "msd": dict(batch=71420, label="MSD-shaped synthetic (full batch / 8 per GPU)"),
     # the bundled dataset (tests/golden/askubuntu_sample.npz = the reference loaders' outputs on Dataset/Askubuntu_Sample), config.ini batch
     "askubuntu": dict(batch=100, label="bundled Askubuntu sample (real data)"),
+    # configs[4]: 1 M items x 5 M users, catalog-sharded (vocab-parallel) decoder/softmax/top-k: every rank holds I / N items and all
+    # ranks process the same 500 users per step (strong scaling over the catalog); N = 1 holds the whole catalog on one GPU
+    "x1m": dict(batch=500, label="1M-item synthetic catalog, catalog-sharded"),
 }
+X1M_ITEMS, X1M_USERS, X1M_DEG = 1000000, 5000000, 50.0
 GOLD = os.path.join(ROOT, "tests", "golden", "askubuntu_sample.npz")
 N_BENCH_BATCHES = 8   # distinct user batches cycled through by the timed steps (per GPU)
 CPU_BATCH_CAP = 1000  # users per step of the CPU baseline sample (dense fp32 [B, I] tensors)
@@ -252,6 +256,8 @@ def config_shape():
     """(n_users, n_items) of the selected configuration."""
     if CONFIG == "askubuntu":
         return 10001, 1000
+    if CONFIG == "x1m":
+        return X1M_USERS, X1M_ITEMS
     syn = importlib.import_module("long-tail-gan_b200.synthetic")
     N, I, deg = syn.CONFIGS[CONFIG]
     return N, I
@@ -265,6 +271,9 @@ def config_tables(n_users):
         tabs = dp.tables_from_golden(np.load(GOLD))
         return tabs
     syn = importlib.import_module("long-tail-gan_b200.synthetic")
+    if CONFIG == "x1m":
+        indptr, indices = syn.make_interactions(n_users, X1M_ITEMS, X1M_DEG, seed=7)
+        return syn.make_side_tables(indptr, indices, X1M_ITEMS, seed=7)
     return syn.make_config(CONFIG, n_users=n_users)
 
 
@@ -302,6 +311,149 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def run_x1m(args, rank, world, local_rank):
+    """BASELINE configs[4]: the catalog-sharded engine (vocab_parallel.py). Same timing contract; `value` = users per second of the
+    whole job (every rank works on the same users, each on its item shard: strong scaling over the catalog)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pkg = importlib.import_module("long-tail-gan_b200")
+    pkg._lib.build()
+    syn = importlib.import_module("long-tail-gan_b200.synthetic")
+    dis = importlib.import_module("long-tail-gan_b200.discriminator")
+    eng = importlib.import_module("long-tail-gan_b200.engine")
+    vp = importlib.import_module("long-tail-gan_b200.vocab_parallel")
+    ops = importlib.import_module("long-tail-gan_b200.ops")
+    ops.init()
+    I, nb = X1M_ITEMS, 4
+    indptr, indices = syn.make_interactions(BATCH * nb, I, X1M_DEG, seed=7)
+    tabs = syn.make_side_tables(indptr, indices, I, seed=7)
+    data, vae, lo, hi = vp.build_shard(tabs, I, rank, world, BATCH)
+    disc = dis.Discriminator(I, I, H0, H1, H2, H3, seed=4242)
+    engine = vp.CatalogShardedEngine(vae, disc, data.max_B, data.max_P, I, lo, rank, world, seed=2026, lr=LR, lam=LAM, max_active=data.max_active)
+    eng.pin_host_inputs(data)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i):
+        engine.run_step(data, i % nb)
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    block_ms = []
+    launches = 0
+    while True:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        k0 = ops.kernel_launches
+        e0.record()
+        for i in range(args.steps):
+            step(i)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        block_ms.append(float(t.item()))
+        launches = ops.kernel_launches - k0
+        if sum(block_ms) >= MIN_TIMED_S * 1e3 or len(block_ms) >= MAX_REPEATS:
+            break
+    ms = sorted(block_ms)[len(block_ms) // 2]
+    # end to end: the batch's index arrays come from pinned host memory, the loss scalars go back, every step
+    host_scal = torch.zeros(2, ops.NSCAL, dtype=torch.float32).pin_memory()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h2d = 0
+    f0.record()
+    for i in range(args.steps):
+        h2d += eng.upload_batch(data.batches[i % nb])
+        step(i)
+        host_scal.copy_(engine.scal_all, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        assert np.isfinite(host_scal[0, ops.S_NLL_SUM].item())
+    f1.record()
+    barrier()
+    t = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    def timed(fn, n):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(n):
+            fn(i)
+        b.record()
+        barrier()
+        tt = torch.tensor([a.elapsed_time(b) / n], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+    t_a = timed(lambda i: engine.run_phase_a(data, i % nb), 8)
+    t_d = timed(lambda i: engine.run_d_step(data, i % nb), 8)
+    t_g = timed(lambda i: engine.run_g_step(data, i % nb), 8)
+    # ranking evaluation over the sharded catalog: local top-100 per shard + merge
+    tr_p, tr_i, te_p, te_i = syn.make_eval_split(1000, I, X1M_DEG)
+    engine.evaluate(tr_p, tr_i, te_p, te_i)
+    barrier()
+    t0 = time.perf_counter()
+    m = engine.evaluate(tr_p, tr_i, te_p, te_i)
+    barrier()
+    t_eval = time.perf_counter() - t0
+    L = engine.last_losses(BATCH)
+    if rank == 0:
+        hb, _ = measured_peaks("hbm_gbs")
+        tc, _ = measured_peaks("bf16_tflops_sustained")
+        users = BATCH * args.steps
+        n_u = BATCH * nb
+        ip = np.asarray(tabs["indptr"], dtype=np.int64); cp = np.asarray(tabs["cand_ptr"], dtype=np.int64)
+        roof = step_roofline(hi - lo, BATCH, float(ip[n_u] - ip[0]) / n_u / world, float(cp[n_u] - cp[0]) / n_u,
+                             float(np.mean([b["Pr"] for b in data.batches])) / world, float(np.mean([b["K"] for b in data.batches])) / world,
+                             t_a, t_d, t_g, hb, tc, world=1, t_step=ms / args.steps)
+        cfg = dict(workload="%s: %d users x %d items over %d GPU(s) (%d items per shard), VAE 600-200, batch %d (the same users on every rank), "
+                            "GAN step = A + D + G" % (BENCH_CONFIGS[CONFIG]["label"], X1M_USERS, I, world, hi - lo, BATCH),
+                   users=X1M_USERS, items=I, items_per_gpu=hi - lo, batch_per_gpu=BATCH, global_batch=BATCH, parallelism="vp%d" % world,
+                   disc="h0..h3 = %d/%d/%d/%d" % (H0, H1, H2, H3), ganlambda=LAM,
+                   exchange="torch.distributed (NCCL) all-reduce of [B,600] activations x2, all-gather of per-row softmax statistics [B,4], "
+                            "all-reduce of the candidate logits and of the 161 k discriminator gradients; no weight or weight-gradient traffic",
+                   l2_policy="per-step working set (shard weights + Adam state, %.1f GB) exceeds the 126 MB L2; %d distinct batches" %
+                             (30.0 * 1200 * (hi - lo) / 1e9, nb))
+        line = dict(metric="gan_step_users_per_sec", value=users / (ms * 1e-3), unit="users/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="bf16", data="synthetic",
+                    gpu_launches=launches, config=cfg, clocks=clocks,
+                    e2e=dict(value=users / (ms_e2e * 1e-3), unit="users/s", h2d_bytes_per_step=h2d // args.steps, d2h_bytes_per_step=2 * ops.NSCAL * 4,
+                             ms_per_step=ms_e2e / args.steps),
+                    phases_ms=dict(A=t_a, D=t_d, G=t_g), step_roofline=roof, graphs=False,
+                    roofline=dict(bound=roof["G"]["bound"], kernel="G update of the catalog shard (per GPU; SURVEY 8d model on the shard)",
+                                  achieved=(roof["G"]["bytes"] / (t_g * 1e-3) / 1e9) if roof["G"]["bound"] == "hbm" else roof["G"]["flops"] / (t_g * 1e-3) / 1e12,
+                                  peak=hb if roof["G"]["bound"] == "hbm" else tc, unit="GB/s" if roof["G"]["bound"] == "hbm" else "TFLOP/s",
+                                  frac=roof["G"]["frac"], traffic=None),
+                    eval=dict(users_per_sec=1000 / t_eval, users=1000, ms=t_eval * 1e3, ndcg_at_100_random_init=float(np.mean(m["ndcg@100"])),
+                              what="fold-in forward over the shards + local exact top-100 per shard + all-gather/merge of 100 (score, id) pairs per rank"),
+                    losses_last_step={k: float(v) for k, v in L.items()},
+                    timing=dict(repeats=len(block_ms), block_ms_min=min(block_ms), block_ms_median=ms, block_ms_max=max(block_ms)))
+        if world > 1:
+            line["comm"] = dict(world_size=dist.get_world_size(), backend=dist.get_backend())
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.cuda.synchronize(); dist.barrier()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
+
+
 def main():
     args = parse()
     select_config(args)
@@ -310,6 +462,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if CONFIG == "x1m":
+        run_x1m(args, rank, world, local_rank)
         return
     import numpy as np
     import torch

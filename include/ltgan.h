@@ -84,6 +84,17 @@ int ltg_enc_gather_fwd(const int32_t* indptr, const int32_t* indices, const floa
                        const uint32_t* step_dev, void* h1_bf16, int ld_h1, float* coef, int max_row_nnz, float* pre_ws,
                        int32_t* counters, const int32_t* slot_of_item, void* xc_bf16, int ld_xc, void* stream);
 
+/* Catalog-sharded layout: the same gather-sum over THIS rank's item shard. indices hold shard-local item ids
+ * (rows of W_shard), item_offset + id is the global id (dropout key), n_items_global the whole catalog; row_rnorm[B] =
+ * rsqrt(|x_u|^2) over the user's whole row. The fp32 partial pre-activation is ADDED into pre_sum [B, H] (zeroed by the caller); the
+ * ranks all-reduce pre_sum and finish with ltg_bias_tanh. coef / xc as in ltg_enc_gather_fwd.                                     */
+int ltg_enc_gather_partial(const int32_t* indptr, const int32_t* indices, int B, int n_items_global, int item_offset, int64_t uid0,
+                           const void* W_shard_bf16, const float* row_rnorm, float keep, uint64_t seed, uint32_t step,
+                           const uint32_t* step_dev, float* pre_sum, float* coef, int max_row_nnz, const int32_t* slot_of_item,
+                           void* xc_bf16, int ld_xc, void* stream);
+/* out = bf16(tanh(pre + bias)) row-wise, N % 4 == 0 (MultiVAE.py:152-155 after the cross-shard sum).                               */
+int ltg_bias_tanh(const float* pre, int ld, const float* bias, int B, int N, void* out_bf16, int ld_out, void* stream);
+
 /* Data-parallel encoder gradient: rebuilds the forward coefficients of the GLOBAL batch's interactions that fall into this
  * rank's item shard (entry e: global batch row e_row[e], item e_item[e], shard slot e_slot[e]; row_uid / row_rnorm per global
  * row) and scatters them into xc_bf16[row, slot] (zeroed by the caller). The dropout bits are recomputed, not communicated.  */
@@ -236,6 +247,14 @@ int ltg_sample_pairs(const void* logits_bf16, int ld_logits, int B, int n_items,
                      uint64_t seed, uint32_t step, const uint32_t* step_dev,
                      int32_t* samp_items, int32_t* samp_partner, int32_t* samp_valid, int32_t* cnt, int max_cand,
                      const int32_t* user_order, void* stream);
+/* Same, with the candidates' logits given explicitly (cand_vals[j] belongs to cand_items[j]; catalog-sharded layout: every rank
+ * contributes the logits of the candidates it owns and the sum is all-reduced); logits_bf16 may then be NULL.                 */
+int ltg_sample_pairs_vals(const void* logits_bf16, int ld_logits, const float* cand_vals, int B, int n_items, int64_t uid0,
+                          const int32_t* cand_ptr, const int32_t* cand_items, const int32_t* samp_ptr,
+                          const int32_t* pop_ptr, const int32_t* pop_items, const uint8_t* item_valid,
+                          uint64_t seed, uint32_t step, const uint32_t* step_dev,
+                          int32_t* samp_items, int32_t* samp_partner, int32_t* samp_valid, int32_t* cnt, int max_cand,
+                          const int32_t* user_order, void* stream);
 
 /* ---- a11/a12: discriminator (discriminator.py:14-55, train.py:142) --------------------------------------------------
  * Frozen embedding gather (F5): rows of E_bf16 [n_items, 128] (cols 100.. are zero) -> Xp, Xn bf16 [P, 128].            */

@@ -35,13 +35,30 @@ def _newest(paths):
 
 
 def build(force=False, verbose=False):
-    """Compile every .cu under csrc/ for sm_100a and link libltgan.so (no GPU needed: nvcc cross-compiles)."""
+    """Compile every .cu under csrc/ for sm_100a and link libltgan.so (no GPU needed: nvcc cross-compiles). Safe to call from
+    several processes at once (torchrun ranks): the build runs under an exclusive file lock and the library is moved into place
+    atomically; the other ranks find it up to date when they get the lock."""
     srcs = [os.path.join(_CSRC, s) for s in SOURCES]
     deps = srcs + [os.path.join(_CSRC, h) for h in HEADERS] + [os.path.join(_INCLUDE, "ltgan.h")]
-    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= _newest(deps):
+
+    def fresh():
+        return os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= _newest(deps)
+    if not force and fresh():
         return LIB_PATH
+    import fcntl
     objdir = os.path.join(_HERE, "build")
     os.makedirs(objdir, exist_ok=True)
+    with open(os.path.join(objdir, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and fresh():
+                return LIB_PATH
+            return _build_locked(srcs, objdir, force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(srcs, objdir, force, verbose):
     nvcc = _nvcc()
 
     def compile_one(src):
@@ -59,10 +76,12 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs
+    tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    os.replace(tmp, LIB_PATH)
     return LIB_PATH
 
 
@@ -84,6 +103,8 @@ SIGNATURES = {
     "ltg_gemm_bf16": (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _F, _I, _F, _U64, _U32, _U32, _P, _I,
                            _I, _P, _P, _I, _F, _I64, _P]),
     "ltg_enc_gather_fwd": (_I, [_P, _P, _P, _I, _I, _I64, _P, _P, _F, _U64, _U32, _P, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P]),
+    "ltg_enc_gather_partial": (_I, [_P, _P, _I, _I, _I, _I64, _P, _P, _F, _U64, _U32, _P, _P, _P, _I, _P, _P, _I, _P]),
+    "ltg_bias_tanh": (_I, [_P, _I, _P, _I, _I, _P, _I, _P]),
     "ltg_enc_coef_scatter": (_I, [_P, _P, _P, _P, _P, _I, _I, _F, _U64, _U32, _P, _P, _I, _P]),
     "ltg_latent_fwd": (_I, [_P, _P, _I, _I64, _F, _U64, _U32, _P, _P, _I, _P, _P, _P]),
     "ltg_latent_bwd": (_I, [_P, _P, _P, _I, _I, _F, _P, _P, _I, _P, _P]),
@@ -104,6 +125,7 @@ SIGNATURES = {
     "ltg_enc_xc_clear": (_I, [_P, _P, _I, _I, _P, _P, _I, _P]),
     "ltg_enc_wgrad_expand": (_I, [_P, _I, _P, _P, _P]),
     "ltg_sample_pairs": (_I, [_P, _I, _I, _I, _I64, _P, _P, _P, _P, _P, _P, _U64, _U32, _P, _P, _P, _P, _P, _I, _P, _P]),
+    "ltg_sample_pairs_vals": (_I, [_P, _I, _P, _I, _I, _I64, _P, _P, _P, _P, _P, _P, _U64, _U32, _P, _P, _P, _P, _P, _I, _P, _P]),
     "ltg_dec_row_bwd": (_I, [_P, _I, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ltg_wgrad_adam": (_I, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _P, _F, _P, _F, _F, _F, _P]),
     "ltg_peer_barrier": (_I, [_P, _I, _I, _I, _P, _P]),
@@ -129,8 +151,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        build()
+    build()   # no-op when libltgan.so is newer than every source (mtime check), so an edited kernel is never loaded stale
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing: loud by design

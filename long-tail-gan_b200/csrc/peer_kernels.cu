@@ -58,6 +58,8 @@ __device__ __forceinline__ void mm_st_b128(void* mc, uint4 v) {
                "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w)) : "memory");
 }
 
+constexpr unsigned long long PEER_SPIN_LIMIT_NS = 20ull * 1000ull * 1000ull * 1000ull;   // 20 s
+
 // Executed by the first warp of ONE CTA. `e` is the barrier number (the same on every rank).
 __device__ __forceinline__ void peer_barrier_warp(const PeerPtrs& pads, int rank, int world, int slot, uint32_t e) {
   const int lane = threadIdx.x & 31;
@@ -65,7 +67,19 @@ __device__ __forceinline__ void peer_barrier_warp(const PeerPtrs& pads, int rank
   if (lane < world) {
     st_release_sys(reinterpret_cast<uint32_t*>(pads.p[lane]) + slot * PEER_MAX + rank, e);
     const uint32_t* mine = reinterpret_cast<const uint32_t*>(pads.p[rank]) + slot * PEER_MAX + lane;
-    while ((int32_t)(ld_acquire_sys(mine) - e) < 0) { __nanosleep(20); }
+    // A peer that died (exception on its host, lost process) never arrives: after PEER_SPIN_LIMIT_NS the kernel traps, so the hang
+    // surfaces as a CUDA error on this rank instead of a captured graph that spins forever.
+    unsigned long long t0 = 0;
+    uint32_t spins = 0;
+    while ((int32_t)(ld_acquire_sys(mine) - e) < 0) {
+      __nanosleep(20);
+      if ((++spins & 0x3FFu) == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > PEER_SPIN_LIMIT_NS) __trap();
+      }
+    }
   }
   __syncwarp();
   __threadfence_system();

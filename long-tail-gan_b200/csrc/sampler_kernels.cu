@@ -53,7 +53,7 @@ sample_pairs_kernel(const __nv_bfloat16* __restrict__ logits, int ld, int n_item
                     const int32_t* __restrict__ pop_ptr, const int32_t* __restrict__ pop_items, const uint8_t* __restrict__ item_valid,
                     uint64_t seed, uint32_t step, const uint32_t* __restrict__ step_dev,
                     int32_t* __restrict__ samp_items, int32_t* __restrict__ samp_partner, int32_t* __restrict__ samp_valid,
-                    int32_t* __restrict__ cnt_out, const int32_t* __restrict__ user_order) {
+                    int32_t* __restrict__ cnt_out, const int32_t* __restrict__ user_order, const float* __restrict__ cand_vals) {
   extern __shared__ uint32_t s_keys[];  // [max_cand]
   __shared__ uint32_t s_hist[256];
   __shared__ uint32_t s_sel[2];          // digit, remaining-k
@@ -75,12 +75,14 @@ sample_pairs_kernel(const __nv_bfloat16* __restrict__ logits, int ld, int n_item
   if (n > C) n = C;  // sample.py:51-61 would shrink the draw; cannot happen when own niche items are candidates
 
   // keys
-  const __nv_bfloat16* row = logits + (size_t)u * ld;
+  const __nv_bfloat16* row = logits != nullptr ? logits + (size_t)u * ld : nullptr;
   for (int c = tid; c < C; c += SAMP_THREADS) {
     const int item = cand_items[c0 + c];
     const uint32_t r = ltg_rand_u32(seed, LTG_STREAM_SAMPLE, step, ubase + (uint64_t)item);
     const float g = -__logf(-__logf(ltg_u01(r)));
-    s_keys[c] = float_to_ordered(__bfloat162float(row[item]) + g);
+    // cand_vals (catalog-sharded layout): the candidates' logits gathered across the item shards, aligned with cand_items
+    const float lg = cand_vals != nullptr ? cand_vals[c0 + c] : __bfloat162float(row[item]);
+    s_keys[c] = float_to_ordered(lg + g);
   }
   if (tid == 0) s_nvalid = 0;
   __syncthreads();
@@ -186,7 +188,17 @@ extern "C" int ltg_sample_pairs(const void* logits_bf16, int ld_logits, int B, i
                                 uint64_t seed, uint32_t step, const uint32_t* step_dev,
                                 int32_t* samp_items, int32_t* samp_partner, int32_t* samp_valid, int32_t* cnt, int max_cand, const int32_t* user_order,
                                 void* stream) {
-  LTG_REQUIRE(logits_bf16 && cand_ptr && cand_items && samp_ptr && pop_ptr && pop_items && item_valid);
+  return ltg_sample_pairs_vals(logits_bf16, ld_logits, nullptr, B, n_items, uid0, cand_ptr, cand_items, samp_ptr, pop_ptr, pop_items, item_valid, seed,
+                               step, step_dev, samp_items, samp_partner, samp_valid, cnt, max_cand, user_order, stream);
+}
+
+extern "C" int ltg_sample_pairs_vals(const void* logits_bf16, int ld_logits, const float* cand_vals, int B, int n_items, int64_t uid0,
+                                     const int32_t* cand_ptr, const int32_t* cand_items, const int32_t* samp_ptr,
+                                     const int32_t* pop_ptr, const int32_t* pop_items, const uint8_t* item_valid,
+                                     uint64_t seed, uint32_t step, const uint32_t* step_dev,
+                                     int32_t* samp_items, int32_t* samp_partner, int32_t* samp_valid, int32_t* cnt, int max_cand,
+                                     const int32_t* user_order, void* stream) {
+  LTG_REQUIRE((logits_bf16 || cand_vals) && cand_ptr && cand_items && samp_ptr && pop_ptr && pop_items && item_valid);
   LTG_REQUIRE(samp_items && samp_partner && samp_valid);
   LTG_REQUIRE(max_cand >= 0 && (size_t)max_cand * 4 <= 200 * 1024);
   if (B <= 0) return LTG_OK;
@@ -199,7 +211,7 @@ extern "C" int ltg_sample_pairs(const void* logits_bf16, int ld_logits, int B, i
   }
   sample_pairs_kernel<<<B, SAMP_THREADS, smem, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(logits_bf16), ld_logits, n_items, uid0, cand_ptr, cand_items, samp_ptr, pop_ptr, pop_items,
-      item_valid, seed, step, step_dev, samp_items, samp_partner, samp_valid, cnt, user_order);
+      item_valid, seed, step, step_dev, samp_items, samp_partner, samp_valid, cnt, user_order, cand_vals);
   LTG_CHECK_LAUNCH();
   return LTG_OK;
 }

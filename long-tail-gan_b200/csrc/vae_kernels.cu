@@ -21,12 +21,18 @@ constexpr int HV = H / 8;  // 75 16-byte vectors per bf16 weight row
 constexpr int ENC_THREADS = 96;
 constexpr int ENC_CHUNK = 128;  // nonzeros per CTA (64 was tried: more atomics, no gain)
 
+// PARTIAL (catalog-sharded layout): the CSR row holds only the interactions whose item lies in this rank's shard
+// (local item ids, W = the shard's rows); the row norm comes from row_rnorm[] (it is over the user's WHOLE row), the dropout bit is
+// keyed by the global item id (item + item_offset), and the fp32 partial pre-activation sum is ADDED into pre_ws[u] (zeroed by the
+// caller) -- bias and tanh follow the cross-rank all-reduce (ltg_bias_tanh).
+template <bool PARTIAL>
 __global__ void __launch_bounds__(ENC_THREADS)
 enc_gather_fwd_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
                       int n_items, int64_t uid0, const uint4* __restrict__ W, const float* __restrict__ bias, float keep,
                       uint64_t seed, uint32_t step, const uint32_t* __restrict__ step_dev, __nv_bfloat16* __restrict__ h1,
                       int ld_h1, float* __restrict__ coef, float* __restrict__ pre_ws, int* __restrict__ counters,
-                      const int32_t* __restrict__ slot_of_item, __nv_bfloat16* __restrict__ xc, int ld_xc) {
+                      const int32_t* __restrict__ slot_of_item, __nv_bfloat16* __restrict__ xc, int ld_xc,
+                      const float* __restrict__ row_rnorm, int item_offset) {
   __shared__ int s_item[ENC_CHUNK];
   __shared__ float s_coef[ENC_CHUNK];
   __shared__ float s_red[ENC_THREADS / 32];
@@ -50,7 +56,7 @@ enc_gather_fwd_kernel(const int32_t* __restrict__ indptr, const int32_t* __restr
   } else {
     ss = (float)(end - beg);
   }
-  const float rs = rsqrtf(fmaxf(ss, 1e-12f));
+  const float rs = PARTIAL ? row_rnorm[u] : rsqrtf(fmaxf(ss, 1e-12f));
   const bool drop = keep > 0.f && keep < 1.f;
   const uint32_t thr = drop ? ltg_keep_threshold(keep) : 0xFFFFFFFFu;
   const float scale = drop ? rs / keep : rs;
@@ -66,7 +72,8 @@ enc_gather_fwd_kernel(const int32_t* __restrict__ indptr, const int32_t* __restr
     const float val = values != nullptr ? values[c0 + j] : 1.0f;
     float c = val * scale;
     if (drop) {
-      const uint32_t r = ltg_rand_u32(seed, LTG_STREAM_ENC_DROPOUT, step, (uint64_t)(uid0 + u) * (uint64_t)n_items + (uint64_t)item);
+      const uint32_t r = ltg_rand_u32(seed, LTG_STREAM_ENC_DROPOUT, step,
+                                      (uint64_t)(uid0 + u) * (uint64_t)n_items + (uint64_t)(item + (PARTIAL ? item_offset : 0)));
       if (r >= thr) c = 0.f;
     }
     s_item[j] = item;
@@ -107,6 +114,14 @@ enc_gather_fwd_kernel(const int32_t* __restrict__ indptr, const int32_t* __restr
         acc[6] = fmaf(c, e.x, acc[6]); acc[7] = fmaf(c, e.y, acc[7]);
       }
     }
+  }
+  if constexpr (PARTIAL) {
+    float* ws = pre_ws + (size_t)u * H;
+    if (tid < HV && cnt > 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(ws + tid * 8 + i, acc[i]);
+    }
+    return;
   }
   if (nchunks > 1) {
     // multi-CTA row: accumulate into the fp32 workspace, last arrival finishes
@@ -580,9 +595,46 @@ extern "C" int ltg_enc_gather_fwd(const int32_t* indptr, const int32_t* indices,
   LTG_REQUIRE(xc_bf16 == nullptr || slot_of_item != nullptr);
   if (B <= 0) return LTG_OK;
   const int chunks = max_row_nnz <= ENC_CHUNK ? 1 : (max_row_nnz + ENC_CHUNK - 1) / ENC_CHUNK;
-  enc_gather_fwd_kernel<<<dim3(B, chunks), ENC_THREADS, 0, (cudaStream_t)stream>>>(
+  enc_gather_fwd_kernel<false><<<dim3(B, chunks), ENC_THREADS, 0, (cudaStream_t)stream>>>(
       indptr, indices, values, n_items, uid0, reinterpret_cast<const uint4*>(W_enc_bf16), b_q0, keep, seed, step, step_dev,
-      reinterpret_cast<__nv_bfloat16*>(h1_bf16), ld_h1, coef, pre_ws, counters, slot_of_item, reinterpret_cast<__nv_bfloat16*>(xc_bf16), ld_xc);
+      reinterpret_cast<__nv_bfloat16*>(h1_bf16), ld_h1, coef, pre_ws, counters, slot_of_item, reinterpret_cast<__nv_bfloat16*>(xc_bf16), ld_xc,
+      nullptr, 0);
+  LTG_CHECK_LAUNCH();
+  return LTG_OK;
+}
+
+extern "C" int ltg_enc_gather_partial(const int32_t* indptr, const int32_t* indices, int B, int n_items_global, int item_offset, int64_t uid0,
+                                      const void* W_shard_bf16, const float* row_rnorm, float keep, uint64_t seed, uint32_t step,
+                                      const uint32_t* step_dev, float* pre_sum, float* coef, int max_row_nnz, const int32_t* slot_of_item,
+                                      void* xc_bf16, int ld_xc, void* stream) {
+  LTG_REQUIRE(indptr && indices && W_shard_bf16 && row_rnorm && pre_sum && coef);
+  LTG_REQUIRE(xc_bf16 == nullptr || slot_of_item != nullptr);
+  if (B <= 0) return LTG_OK;
+  const int chunks = max_row_nnz <= ENC_CHUNK ? 1 : (max_row_nnz + ENC_CHUNK - 1) / ENC_CHUNK;
+  enc_gather_fwd_kernel<true><<<dim3(B, chunks), ENC_THREADS, 0, (cudaStream_t)stream>>>(
+      indptr, indices, nullptr, n_items_global, uid0, reinterpret_cast<const uint4*>(W_shard_bf16), nullptr, keep, seed, step, step_dev, nullptr, 0,
+      coef, pre_sum, nullptr, slot_of_item, reinterpret_cast<__nv_bfloat16*>(xc_bf16), ld_xc, row_rnorm, item_offset);
+  LTG_CHECK_LAUNCH();
+  return LTG_OK;
+}
+
+namespace {
+__global__ void bias_tanh_kernel(const float* __restrict__ pre, int ld, const float* __restrict__ bias, int B, int N, __nv_bfloat16* __restrict__ out,
+                                 int ld_out) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4, r = blockIdx.y;
+  if (c >= N || r >= B) return;
+  const float4 x = *reinterpret_cast<const float4*>(pre + (size_t)r * ld + c);
+  const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c));
+  uint2 o;
+  o.x = pack_bf16x2(tanhf(x.x + b.x), tanhf(x.y + b.y)); o.y = pack_bf16x2(tanhf(x.z + b.z), tanhf(x.w + b.w));
+  *reinterpret_cast<uint2*>(out + (size_t)r * ld_out + c) = o;
+}
+}  // namespace
+
+extern "C" int ltg_bias_tanh(const float* pre, int ld, const float* bias, int B, int N, void* out_bf16, int ld_out, void* stream) {
+  LTG_REQUIRE(pre && bias && out_bf16 && N % 4 == 0 && ld % 4 == 0 && ld_out % 4 == 0);
+  if (B <= 0) return LTG_OK;
+  bias_tanh_kernel<<<dim3((N / 4 + 127) / 128, B), 128, 0, (cudaStream_t)stream>>>(pre, ld, bias, B, N, reinterpret_cast<__nv_bfloat16*>(out_bf16), ld_out);
   LTG_CHECK_LAUNCH();
   return LTG_OK;
 }

@@ -247,6 +247,10 @@ def build_train_tables(train_data, user_popular_data, user_niche_data, user_x_ni
     N = train_data.shape[0]
     csr = train_data.tocsr()
     csr.sort_indices()
+    if csr.nnz and float(csr.data.max()) != 1.0:
+        # csr_matrix((ones,(rows,cols))) sums duplicate (uid, sid) rows (data_processing.py:13-15): the device tables are binary
+        raise ValueError("train_GAN.csv holds repeated (uid, sid) rows (max count %g); the device tables carry binary interactions -- "
+                         "deduplicate the file or pass the counts through TrainData/ltg_enc_gather_fwd `values`" % float(csr.data.max()))
     pop_ptr, pop_items = _ragged(user_popular_data, N)
     cand_ptr, cand_items = _ragged(USER_TAGS_TO_SAMPLE, N)
     real_ptr, real_niche = _ragged(user_x_niche_vectors, N)

@@ -9,6 +9,9 @@ from . import ops
 from .engine import metrics_from_counts
 
 
+MAX_K = 128
+
+
 def _run(X_pred, heldout_batch, k, recall_ks):
     ops.init()
     if isinstance(X_pred, np.ndarray):
@@ -23,7 +26,10 @@ def _run(X_pred, heldout_batch, k, recall_ks):
     hi = torch.as_tensor((held.indices if held.nnz else np.zeros(1)).astype(np.int32)).cuda()
     dcg = torch.zeros(n, dtype=torch.float64, device="cuda")
     hits = torch.zeros(n, max(1, len(recall_ks)), dtype=torch.int32, device="cuda")
-    kk = min(k, 128)
+    if k > MAX_K:
+        raise ValueError("k = %d: the device top-k kernel ranks at most %d items per user (the reference calls these functions with "
+                         "k = 100, 20 and 50: train.py:342-346, test.py:151-157)" % (k, MAX_K))
+    kk = k
     ops.topk_metrics(scores, n, n_items, None, None, hp, hi, kk, recall_ks, None, dcg, hits)
     torch.cuda.synchronize()
     return metrics_from_counts(dcg.cpu().numpy(), hits.cpu().numpy(), np.diff(held.indptr.astype(np.int64)), kk, recall_ks)
@@ -31,7 +37,7 @@ def _run(X_pred, heldout_batch, k, recall_ks):
 
 def NDCG_binary_at_k_batch(X_pred, heldout_batch, k=100):
     """eval_functions.py:11-38: list of NDCG@k over the users with a non-empty held-out set."""
-    return _run(X_pred, heldout_batch, k, [])["ndcg@%d" % min(k, 128)]
+    return _run(X_pred, heldout_batch, k, [])["ndcg@%d" % k]
 
 
 def Recall_at_k_batch(X_pred, heldout_batch, k=100):

@@ -118,6 +118,19 @@ def enc_gather_fwd(indptr, indices, values, B, n_items, uid0, W_enc_bf16, b_q0, 
                                    ptr(slot_of_item), ptr(xc), xc.stride(0) if xc is not None else 0, _stream()))
 
 
+def enc_gather_partial(indptr, indices, B, n_items_global, item_offset, uid0, W_shard_bf16, row_rnorm, keep, seed, step, step_dev, pre_sum, coef,
+                       max_row_nnz=0, slot_of_item=None, xc=None):
+    _count(1)
+    check(lib().ltg_enc_gather_partial(ptr(indptr), ptr(indices), B, n_items_global, item_offset, uid0, ptr(W_shard_bf16), ptr(row_rnorm), keep,
+                                       seed, step, ptr(step_dev), ptr(pre_sum), ptr(coef), max_row_nnz, ptr(slot_of_item), ptr(xc),
+                                       xc.stride(0) if xc is not None else 0, _stream()))
+
+
+def bias_tanh(pre, bias, B, N, out):
+    _count(1)
+    check(lib().ltg_bias_tanh(ptr(pre), pre.stride(0), ptr(bias), B, N, ptr(out), out.stride(0), _stream()))
+
+
 def enc_coef_scatter(e_row, e_item, e_slot, row_uid, row_rnorm, n_entries, n_items, keep, seed, step, step_dev, xc):
     _count(1)
     check(lib().ltg_enc_coef_scatter(ptr(e_row), ptr(e_item), ptr(e_slot), ptr(row_uid), ptr(row_rnorm), n_entries, n_items, keep, seed,
@@ -279,11 +292,12 @@ def enc_wgrad_expand(dW, n_items, slot_of_item, G):
 
 
 def sample_pairs(logits, B, n_items, uid0, cand_ptr, cand_items, samp_ptr, pop_ptr, pop_items, item_valid, seed, step, step_dev,
-                 samp_items, samp_partner, samp_valid, cnt, max_cand, user_order=None):
+                 samp_items, samp_partner, samp_valid, cnt, max_cand, user_order=None, cand_vals=None):
+    """cand_vals (fp32, aligned with cand_items): the candidates' logits given explicitly (catalog-sharded layout); logits may be None."""
     _count(1)
-    check(lib().ltg_sample_pairs(ptr(logits), logits.stride(0), B, n_items, uid0, ptr(cand_ptr), ptr(cand_items), ptr(samp_ptr),
-                                 ptr(pop_ptr), ptr(pop_items), ptr(item_valid), seed, step, ptr(step_dev), ptr(samp_items),
-                                 ptr(samp_partner), ptr(samp_valid), ptr(cnt), max_cand, ptr(user_order), _stream()))
+    check(lib().ltg_sample_pairs_vals(ptr(logits), logits.stride(0) if logits is not None else 0, ptr(cand_vals), B, n_items, uid0, ptr(cand_ptr),
+                                      ptr(cand_items), ptr(samp_ptr), ptr(pop_ptr), ptr(pop_items), ptr(item_valid), seed, step, ptr(step_dev),
+                                      ptr(samp_items), ptr(samp_partner), ptr(samp_valid), ptr(cnt), max_cand, ptr(user_order), _stream()))
 
 
 def disc_gather(E_bf16, pop_ids, niche_ids, P, Xp, Xn):

@@ -1,0 +1,80 @@
+"""Catalog-sharded (vocab-parallel) engine, SURVEY 8e / BASELINE configs[4]: the sharded code path against the single-GPU engine on the
+same batch and weights (long-tail-gan_b200/vp_check.py). One shard on one GPU runs everywhere; two shards need two GPUs."""
+import importlib
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pytestmark = pytest.mark.gpu
+
+
+def _check(res):
+    assert res["ok"], res
+    assert res["cnt_equal"]
+    for k, v in res["loss_rel_diff"].items():
+        assert v < 2e-2, (k, v)           # per-step losses: north_star asks for 1e-3 on the VAE loss ...
+    assert res["loss_rel_diff"]["vae_loss"] < 1e-3 and res["loss_rel_diff"]["neg_ll"] < 1e-3
+    m = res["displacement_mismatch"]
+    assert m["W_dec"] < 0.05 and m["W_enc"] < 0.05 and m["disc"] < 0.05 and m["small"] < 1e-3
+    assert res["eval_users"][0] == res["eval_users"][1] and abs(res["eval_ndcg"][0] - res["eval_ndcg"][1]) < 5e-3
+
+
+def test_one_shard_equals_single_gpu_engine():
+    vpc = importlib.import_module("long-tail-gan_b200.vp_check")
+    _check(vpc.run_check(2400, 96, 0, 1))
+
+
+def test_partial_gather_sums_to_full_encoder():
+    """ltg_enc_gather_partial over two item shards + ltg_bias_tanh == ltg_enc_gather_fwd over the whole catalog (same dropout bits:
+    the hash is keyed by the global item id)."""
+    pkg = importlib.import_module("long-tail-gan_b200")
+    pkg._lib.build()
+    ops = importlib.import_module("long-tail-gan_b200.ops")
+    vp = importlib.import_module("long-tail-gan_b200.vocab_parallel")
+    ops.init()
+    rng = np.random.RandomState(4)
+    B, I, H = 70, 1536, 600
+    indptr = [0]; idx = []
+    for u in range(B):
+        n = int(rng.randint(1, 300 if u % 9 == 0 else 40))
+        idx.append(np.sort(rng.choice(I, n, replace=False))); indptr.append(indptr[-1] + n)
+    indptr = np.asarray(indptr, dtype=np.int32); indices = np.concatenate(idx).astype(np.int32)
+    W = (torch.randn(I, H, device="cuda") * 0.05).bfloat16(); bias = torch.randn(H, device="cuda") * 0.01
+    words = torch.tensor([5], dtype=torch.int32, device="cuda")
+    dev = lambda a: torch.as_tensor(a).cuda()  # noqa: E731
+    h1 = torch.zeros(B, H, device="cuda", dtype=torch.bfloat16); coef = torch.zeros(len(indices), device="cuda")
+    ws = torch.zeros(B, H, device="cuda"); cn = torch.zeros(B, dtype=torch.int32, device="cuda")
+    max_nnz = int(np.diff(indptr).max())
+    ops.enc_gather_fwd(dev(indptr), dev(indices), None, B, I, 1000, W, bias, 0.75, 77, 0, words, h1, coef, max_nnz, ws, cn)
+    pre = torch.zeros(B, H, device="cuda")
+    tabs = dict(indptr=indptr, indices=indices)
+    for lo, hi in vp.shard_bounds(I, 2):
+        t = vp.shard_tables(tabs, lo, hi)
+        c = torch.zeros(max(1, len(t["indices"])), device="cuda")
+        ops.enc_gather_partial(dev(t["indptr"]), dev(t["indices"]) if len(t["indices"]) else torch.zeros(1, dtype=torch.int32, device="cuda"), B, I, lo,
+                               1000, W[lo:hi].contiguous(), dev(t["row_rnorm"]), 0.75, 77, 0, words, pre, c,
+                               int(np.diff(t["indptr"]).max()))
+    out = torch.zeros(B, H, device="cuda", dtype=torch.bfloat16)
+    ops.bias_tanh(pre, bias, B, H, out)
+    torch.cuda.synchronize()
+    assert (out.float() - h1.float()).abs().max().item() < 1e-2     # one bf16 ulp of tanh (summation order differs)
+    assert (out.float() - h1.float()).abs().mean().item() < 2e-4
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_shards_equal_single_gpu_engine(tmp_path):
+    out = str(tmp_path / "vp.json")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port",
+           "29621", os.path.join(ROOT, "tools", "vp_check.py"), out]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    res = json.load(open(out))
+    assert res["world"] == 2
+    _check(res)
