@@ -405,6 +405,8 @@ def run_x1m(args, rank, world, local_rank):
     t_a = timed(lambda i: engine.run_phase_a(data, i % nb), 8)
     t_d = timed(lambda i: engine.run_d_step(data, i % nb), 8)
     t_g = timed(lambda i: engine.run_g_step(data, i % nb), 8)
+    step(0)
+    L = engine.last_losses(BATCH)
     # ranking evaluation over the sharded catalog: local top-100 per shard + merge
     tr_p, tr_i, te_p, te_i = syn.make_eval_split(1000, I, X1M_DEG)
     engine.evaluate(tr_p, tr_i, te_p, te_i)
@@ -413,7 +415,6 @@ def run_x1m(args, rank, world, local_rank):
     m = engine.evaluate(tr_p, tr_i, te_p, te_i)
     barrier()
     t_eval = time.perf_counter() - t0
-    L = engine.last_losses(BATCH)
     if rank == 0:
         hb, _ = measured_peaks("hbm_gbs")
         tc, _ = measured_peaks("bf16_tflops_sustained")

@@ -52,6 +52,9 @@ def test_train_cli_two_ranks(tmp_path):
            "29612", os.path.join(ROOT, "long-tail-gan_b200", "train.py"), GOLD]
     env = dict(os.environ); env["LTG_MAX_EPOCHS"] = "2"
     r = subprocess.run(cmd, cwd=str(tmp_path), capture_output=True, text=True, timeout=900, env=env)
+    if r.returncode != 0:   # the rendezvous port can still be held by the previous test's workers for a moment: one retry on another port
+        cmd[cmd.index("29612")] = "29613"
+        r = subprocess.run(cmd, cwd=str(tmp_path), capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     lines = [l for l in r.stdout.splitlines() if "Vad: NDCG:" in l]
     assert len(lines) == 2, r.stdout[-2000:]      # one validation line per epoch, printed once (rank 0 only)
