@@ -78,11 +78,15 @@ int ltg_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int 
  * (fp32 [B, H]) and counters (int32 [B]) are zero-initialised workspaces that the kernel leaves zeroed again.
  * Optional (training): xc_bf16 [B, ld_xc] (zeroed by the caller) receives coef at column slot_of_item[item] -- the dense
  * coefficient matrix over the batch's active items, i.e. the A operand of the encoder weight-gradient GEMM
- * dW_q0[active] = Xc^T dh1pre (autodiff of MultiVAE.py:152).                                                                  */
+ * dW_q0[active] = Xc^T dh1pre (autodiff of MultiVAE.py:152).
+ * Optional work list (NULL: a 2-D grid of B x ceil(max_row_nnz/128) CTAs, most of which exit at once when few rows are long):
+ * work[n_work], one entry (chunk << 20 | row) per non-empty 128-nonzero chunk of every row (rows without interactions: chunk 0),
+ * so the grid holds exactly the chunks that exist; B < 2^20.                                                                     */
 int ltg_enc_gather_fwd(const int32_t* indptr, const int32_t* indices, const float* values, int B, int n_items, int64_t uid0,
                        const void* W_enc_bf16, const float* b_q0, float keep, uint64_t seed, uint32_t step,
                        const uint32_t* step_dev, void* h1_bf16, int ld_h1, float* coef, int max_row_nnz, float* pre_ws,
-                       int32_t* counters, const int32_t* slot_of_item, void* xc_bf16, int ld_xc, void* stream);
+                       int32_t* counters, const int32_t* slot_of_item, void* xc_bf16, int ld_xc, const int32_t* work, int n_work,
+                       void* stream);
 
 /* Catalog-sharded layout: the same gather-sum over THIS rank's item shard. indices hold shard-local item ids
  * (rows of W_shard), item_offset + id is the global id (dropout key), n_items_global the whole catalog; row_rnorm[B] =

@@ -102,7 +102,7 @@ SIGNATURES = {
     "ltg_step_advance": (_I, [_P, _P, _I, _F, _F, _F, _F, _F, _P, _I64, _P, _P]),
     "ltg_gemm_bf16": (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _F, _I, _F, _U64, _U32, _U32, _P, _I,
                            _I, _P, _P, _I, _F, _I64, _P]),
-    "ltg_enc_gather_fwd": (_I, [_P, _P, _P, _I, _I, _I64, _P, _P, _F, _U64, _U32, _P, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P]),
+    "ltg_enc_gather_fwd": (_I, [_P, _P, _P, _I, _I, _I64, _P, _P, _F, _U64, _U32, _P, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _I, _P]),
     "ltg_enc_gather_partial": (_I, [_P, _P, _I, _I, _I, _I64, _P, _P, _F, _U64, _U32, _P, _P, _P, _I, _P, _P, _I, _P]),
     "ltg_bias_tanh": (_I, [_P, _I, _P, _I, _I, _P, _I, _P]),
     "ltg_enc_coef_scatter": (_I, [_P, _P, _P, _P, _P, _I, _I, _F, _U64, _U32, _P, _P, _I, _P]),

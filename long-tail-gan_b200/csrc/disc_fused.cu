@@ -37,7 +37,8 @@ constexpr int DF_R2 = DF_KB3_MAX * 16384;   // region 2 (112 KB)
 constexpr int DF_W3_STAGE = 5 * 8192;       // one 64-k block of W3 (MN-major): five 64-column boxes
 constexpr int DF_W3T_HALF = DF_N4 * 128;    // one 64-k' block of W3^T rows [0,208) or [208,416), K-major: 26 KB
 constexpr int DF_W3T_STAGE = 2 * DF_W3T_HALF;
-constexpr size_t DF_SMEM = 1024 + DF_R1 + DF_R2 + 256 + 4 * 128 * 4 + DF_MAXH3 * 4 + 32;
+constexpr int DF_W4_PAD = (DF_MAXH3 + 15) / 16 * 16 + 16;   // head weights staged in shared memory (zero beyond ld3)
+constexpr size_t DF_SMEM = 1024 + DF_R1 + DF_R2 + 256 + 4 * 128 * 4 + DF_MAXH3 * 4 + 32 + DF_W4_PAD * 4;
 constexpr int DF_CH3 = (DF_MAXH3 + 63) / 64;   // fc1 chunks per epilogue warp (5)
 static_assert(DF_W3_STAGE * 2 <= DF_R1 && DF_W3T_STAGE * 2 <= DF_R2 && DF_KB4 * 16384 <= DF_R1, "region sizes");
 
@@ -74,17 +75,12 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
   return u;
 }
 
-// w4[c .. c+16) (zero beyond n); c is a multiple of 16 and w4 is 16-byte aligned
-__device__ __forceinline__ void load_w16(float (&w)[16], const float* __restrict__ w4, int c, int n) {
-  if (c + 16 <= n) {   // warp-uniform
+// w4[c .. c+16) from the zero-padded shared-memory copy; c is a multiple of 16 (warp-uniform address: broadcast reads)
+__device__ __forceinline__ void load_w16(float (&w)[16], const float* s_w4, int c) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 t = __ldg(reinterpret_cast<const float4*>(w4 + c) + i);
-      w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) w[i] = c + i < n ? __ldg(w4 + c + i) : 0.f;
+  for (int i = 0; i < 4; ++i) {
+    const float4 t = reinterpret_cast<const float4*>(s_w4 + c)[i];
+    w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
   }
 }
 
@@ -97,7 +93,7 @@ __device__ __forceinline__ void tile_store(uint8_t* tile, int r, int g0, uint4 u
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 disc_fused_kernel(const __grid_constant__ CUtensorMap tmXp, const __grid_constant__ CUtensorMap tmXn, const __grid_constant__ CUtensorMap tmW1,
                   const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmW3, const __grid_constant__ CUtensorMap tmW3T,
-                  const __grid_constant__ DiscFusedParams p) {
+                  const __grid_constant__ CUtensorMap tmHd, const __grid_constant__ DiscFusedParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* r1 = smem;                        // [96 KB]
@@ -116,6 +112,7 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmXp, const __grid_constan
   float* s_part = reinterpret_cast<float*>(r2 + DF_R2 + 256);   // [4][128] per-quarter partial dot products
   float* s_dw4 = s_part + 4 * 128;                               // [DF_MAXH3]
   float* s_acc = s_dw4 + DF_MAXH3;                               // loss, sum_y, sum ds, n_generated
+  float* s_w4 = s_acc + 8;                                       // [DF_W4_PAD] head weights (16-byte aligned: DF_MAXH3 % 4 == 0)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool bwd = p.dz3 != nullptr;
@@ -124,7 +121,7 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmXp, const __grid_constan
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmXp); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmXn); tma_prefetch_desc(&tmW2); tma_prefetch_desc(&tmW3);
-    if (bwd4) tma_prefetch_desc(&tmW3T);
+    if (bwd4) tma_prefetch_desc(&tmW3T); else tma_prefetch_desc(&tmHd);
     mbar_init(&bar_ld[0], 1); mbar_init(&bar_ld[1], 1);
     for (int i = 0; i < 4; ++i) mbar_init(&bar_mma[i], 1);
     mbar_init(bar_hd, GEMM_EPI_WARPS); mbar_init(bar_dz3, GEMM_EPI_WARPS); mbar_init(bar_done, GEMM_EPI_WARPS);
@@ -133,6 +130,9 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmXp, const __grid_constan
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   for (int j = threadIdx.x; j < DF_MAXH3 + 4; j += GEMM_THREADS) s_dw4[j] = 0.f;   // s_dw4 and s_acc are contiguous
+  // The head weights are read by every epilogue thread for every chunk, twice per tile in the D update: from global memory that was one
+  // L1/L2 round trip per chunk in front of the FMAs (ncu source view, round 2: the top long-scoreboard lines of the kernel)
+  for (int j = threadIdx.x; j < DF_W4_PAD; j += GEMM_THREADS) s_w4[j] = j < p.ld3 ? __ldg(p.w4 + j) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -222,6 +222,14 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmXp, const __grid_constan
         mbar_wait(bar_hd, par);                  // Hd tile complete in R2, TMEM columns 0..447 drained
         DF_STAMP(11);
         tc_fence_after();
+        // The hidden activation leaves the CTA as TMA tile stores of the very tile MMA 3 reads (same 128B-swizzled K-major blocks):
+        // full 128-byte lines written by the copy engine instead of 16 bytes per thread and row from the epilogue warps (204 store
+        // instructions of 32 sectors each per tile). Rows >= P and columns >= k3 are clipped by the tensor map. (With MMA 4 in the kernel
+        // the epilogue warps keep their own stores: they read the activation back through the generic proxy.)
+        if (!bwd4) {
+          for (int kb = 0; kb < p.kb3; ++kb) tma_store_2d(&tmHd, r2 + kb * 16384, kb * 64, t * GEMM_BM);
+          bulk_commit();
+        }
         for (int kb = 0; kb < p.kb3; ++kb) {
           mbar_wait(&full3[st3], ph3);
           tc_fence_after();
@@ -235,6 +243,7 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmXp, const __grid_constan
           umma_commit(&empty3[st3]);
           if (++st3 == 2) { st3 = 0; ph3 ^= 1; }
         }
+        if (!bwd4) bulk_wait_read0();            // R2 is handed back to the producer by the commit below: the tile stores have read it
         umma_commit(&bar_mma[2]);
         DF_STAMP(12);
         if (bwd4) {
@@ -258,6 +267,7 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmXp, const __grid_constan
           DF_STAMP(14);
         }
       }
+      bulk_wait0();                              // the last tile's activation stores are complete before the CTA retires
     }
   } else {
     // ===================== epilogue =====================
@@ -295,7 +305,7 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmXp, const __grid_constan
           if (g0 < p.off2) {
             const uint4 u = pack8(v + 8 * h);
             tile_store(r2, rl, g0, u);
-            if (row_ok) *reinterpret_cast<uint4*>(hrow + g0) = u;
+            if (bwd4 && row_ok) *reinterpret_cast<uint4*>(hrow + g0) = u;
           }
         }
       }
@@ -323,7 +333,7 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmXp, const __grid_constan
           if (g0 < p.k3) {
             const uint4 u = pack8(v + 8 * h);
             tile_store(r2, rl, g0, u);
-            if (row_ok) *reinterpret_cast<uint4*>(hrow + g0) = u;
+            if (bwd4 && row_ok) *reinterpret_cast<uint4*>(hrow + g0) = u;
           }
         }
       }
@@ -352,7 +362,7 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmXp, const __grid_constan
           for (int i = 0; i < 16; ++i) v[i] = tanh_approx(v[i]);
           if (drop) drop16(v, key3, thr16, inv_keep, row, p.ld3, c);
           float w[16];
-          load_w16(w, p.w4, c, p.ld3);
+          load_w16(w, s_w4, c);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const uint32_t u = pack_bf16x2(v[2 * i], v[2 * i + 1]);
@@ -396,7 +406,7 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmXp, const __grid_constan
           const int c = quarter * 16 + 64 * j;
           if (c < p.ld3) {                       // warp-uniform
             float d[16], gw[16], w[16];
-            load_w16(w, p.w4, c, p.ld3);
+            load_w16(w, s_w4, c);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float2 f = unpack_bf16x2(yq[j][i]);
@@ -543,7 +553,7 @@ extern "C" int ltg_disc_fwd_fused(const void* Xp_bf16, const void* Xn_bf16, int 
   LTG_REQUIRE(dz12_bf16 == nullptr || dz3_bf16 != nullptr);
   LTG_REQUIRE(ltg_disc_fused_supported(k1, ld1, ld2, ld3, off2, one3, h2, k3));
   if (P <= 0) return LTG_OK;
-  CUtensorMap tmXp, tmXn, tmW1, tmW2, tmW3, tmW3T;
+  CUtensorMap tmXp, tmXn, tmW1, tmW2, tmW3, tmW3T, tmHd;
   int rc;
   if ((rc = make_tmap_bf16(&tmXp, Xp_bf16, 128, (uint64_t)P, 128, 64, GEMM_BM))) return rc;
   if ((rc = make_tmap_bf16(&tmXn, Xn_bf16, 128, (uint64_t)P, 128, 64, GEMM_BM))) return rc;
@@ -552,6 +562,8 @@ extern "C" int ltg_disc_fwd_fused(const void* Xp_bf16, const void* Xn_bf16, int 
   if ((rc = make_tmap_bf16(&tmW3, W3_bf16, (uint64_t)ld3, (uint64_t)k3, (uint64_t)ld3, 64, 64))) return rc;
   // the same W3 [k3, ld3] seen as the K-major B operand of dz12 = dz3 W3^T: rows = output column k, 64-wide slices of n
   if ((rc = make_tmap_bf16(&tmW3T, W3_bf16, (uint64_t)ld3, (uint64_t)k3, (uint64_t)ld3, 64, DF_N4))) return rc;
+  // the activation Hd [P, k3] as the destination of the tile stores: the 64-column K blocks of the shared-memory tile
+  if ((rc = make_tmap_bf16(&tmHd, Hd_bf16, (uint64_t)k3, (uint64_t)P, (uint64_t)k3, 64, GEMM_BM))) return rc;
   DiscFusedParams p;
   p.P = P; p.ld1 = ld1; p.ld2 = ld2; p.ld3 = ld3; p.off2 = off2; p.one3 = one3; p.h2 = h2; p.k3 = k3; p.kb3 = (k3 + 63) / 64;
   p.w4 = w4; p.b4 = b4; p.label = label; p.keep = keep; p.seed = seed; p.rng_stream = rng_stream; p.rng_step = rng_step;
@@ -566,7 +578,7 @@ extern "C" int ltg_disc_fwd_fused(const void* Xp_bf16, const void* Xn_bf16, int 
   }
   const int n_tiles = (P + GEMM_BM - 1) / GEMM_BM;
   const int grid = n_tiles < ltg_num_sms() ? n_tiles : ltg_num_sms();
-  disc_fused_kernel<<<grid, GEMM_THREADS, DF_SMEM, (cudaStream_t)stream>>>(tmXp, tmXn, tmW1, tmW2, tmW3, tmW3T, p);
+  disc_fused_kernel<<<grid, GEMM_THREADS, DF_SMEM, (cudaStream_t)stream>>>(tmXp, tmXn, tmW1, tmW2, tmW3, tmW3T, tmHd, p);
   LTG_CHECK_LAUNCH();
   return LTG_OK;
 }

@@ -11,20 +11,39 @@ constexpr int HV = H / 8;  // 75 16-byte vectors per bf16 weight row
 
 // ---------------------------------------------------------------------------------------------
 // a3: encoder. CTA (u, c) owns chunk c (ENC_CHUNK nonzeros) of user u's CSR row: it turns the chunk into
-// (item, coef) pairs in shared memory (norm, Philox dropout bit per nonzero), then 75 threads each own
-// one 16-byte column slice of the 1200-byte bf16 W_q0 rows and stream the surviving rows with 4 loads in
-// flight. Users that fit one chunk (the common case) are finished in place; longer rows (heavy users,
-// up to 2000 interactions) are spread over several CTAs that accumulate into an fp32 workspace row, and
-// the last CTA to arrive applies bias + tanh and clears the workspace again (self-cleaning, no memset).
+// (item, coef) pairs in shared memory (norm, Philox dropout bit per nonzero), then streams the surviving
+// 1200-byte bf16 W_q0 rows. The kernel is a latency chain, not a bandwidth problem (ncu, round 2: 14 % occupancy, 0.45 TB/s,
+// IPC 0.9 -- every CTA walks its rows in rounds of 8 loads per thread, one L2/HBM round trip per round, 12 rounds for a full
+// chunk), so the chunk is spread over ENC_GROUPS groups of 80 threads: thread l < 75 of group g owns the 16-byte column slice l
+// of the rows g, g+4, g+8, ... with 8 loads in flight, i.e. 32 rows per round trip and at most 4 rounds per chunk; the groups'
+// partial sums meet in shared memory in a fixed order (deterministic). Users that fit one chunk (the common case) are finished in
+// place; longer rows (heavy users, up to 2000 interactions) are spread over several CTAs that accumulate into an fp32 workspace
+// row, and the last CTA to arrive applies bias + tanh and clears the workspace again (self-cleaning, no memset).
+// Grid: 2-D (user, chunk) -- CTAs beyond a user's last chunk exit at once -- or, with a host-built work list (TrainData: one entry
+// (chunk << 20 | user) per non-empty chunk, full chunks first), 1-D over exactly the chunks that exist.
 // Restates MultiVAE.py:148 (l2_normalize), 149 (dropout), 152-155 (matmul + bias + tanh).
 // ---------------------------------------------------------------------------------------------
-constexpr int ENC_THREADS = 96;
+constexpr int ENC_GROUPS = 4;
+constexpr int ENC_GSZ = 80;     // threads per group; the first HV = 75 of them load
+constexpr int ENC_THREADS = ENC_GROUPS * ENC_GSZ;
 constexpr int ENC_CHUNK = 128;  // nonzeros per CTA (64 was tried: more atomics, no gain)
+static_assert(ENC_GSZ >= HV && ENC_THREADS % 32 == 0 && ENC_THREADS >= ENC_CHUNK, "group size");
 
 // PARTIAL (catalog-sharded layout): the CSR row holds only the interactions whose item lies in this rank's shard
 // (local item ids, W = the shard's rows); the row norm comes from row_rnorm[] (it is over the user's WHOLE row), the dropout bit is
 // keyed by the global item id (item + item_offset), and the fp32 partial pre-activation sum is ADDED into pre_ws[u] (zeroed by the
 // caller) -- bias and tanh follow the cross-rank all-reduce (ltg_bias_tanh).
+// 16-byte global -> shared copy that bypasses the register file (LDGSTS). A round of 8 row slices per thread written as register
+// loads was serialised by ptxas into load -> use -> load with one or two requests in flight, whatever the source order (SASS check,
+// round 2); an asynchronous copy has no result register to schedule around, so all 8 requests of a round are in flight at once.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 template <bool PARTIAL>
 __global__ void __launch_bounds__(ENC_THREADS)
 enc_gather_fwd_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
@@ -32,16 +51,20 @@ enc_gather_fwd_kernel(const int32_t* __restrict__ indptr, const int32_t* __restr
                       uint64_t seed, uint32_t step, const uint32_t* __restrict__ step_dev, __nv_bfloat16* __restrict__ h1,
                       int ld_h1, float* __restrict__ coef, float* __restrict__ pre_ws, int* __restrict__ counters,
                       const int32_t* __restrict__ slot_of_item, __nv_bfloat16* __restrict__ xc, int ld_xc,
-                      const float* __restrict__ row_rnorm, int item_offset) {
+                      const float* __restrict__ row_rnorm, int item_offset, const int32_t* __restrict__ work) {
   __shared__ int s_item[ENC_CHUNK];
   __shared__ float s_coef[ENC_CHUNK];
   __shared__ float s_red[ENC_THREADS / 32];
+  __shared__ float4 s_acc[ENC_GROUPS - 1][HV][2];
+  __shared__ int s_wcnt[ENC_CHUNK / 32];
   __shared__ int s_last;
-  const int u = blockIdx.x;
+  __shared__ uint4 s_stage[8 * ENC_GROUPS * HV];   // [slot of the round][group][column slice]: each thread reads back only its own slots
+  int u = blockIdx.x, chunk = blockIdx.y;
+  if (work != nullptr) { const int w = work[blockIdx.x]; u = w & 0xFFFFF; chunk = w >> 20; }
   const int tid = threadIdx.x;
   const int beg = indptr[u], end = indptr[u + 1];
   const int nchunks = max(1, (end - beg + ENC_CHUNK - 1) / ENC_CHUNK);
-  if ((int)blockIdx.y >= nchunks) return;
+  if (chunk >= nchunks) return;
   if (step_dev != nullptr) step += *step_dev;
 
   // squared norm of the whole row (values == NULL: binary row)
@@ -51,7 +74,9 @@ enc_gather_fwd_kernel(const int32_t* __restrict__ indptr, const int32_t* __restr
     ss = warp_sum(ss);
     if ((tid & 31) == 0) s_red[tid >> 5] = ss;
     __syncthreads();
-    ss = s_red[0] + s_red[1] + s_red[2];
+    ss = 0.f;
+#pragma unroll
+    for (int w = 0; w < ENC_THREADS / 32; ++w) ss += s_red[w];
     __syncthreads();
   } else {
     ss = (float)(end - beg);
@@ -65,54 +90,76 @@ enc_gather_fwd_kernel(const int32_t* __restrict__ indptr, const int32_t* __restr
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
 
-  const int c0 = beg + blockIdx.y * ENC_CHUNK;
+  const int c0 = beg + chunk * ENC_CHUNK;
   const int cnt = min(ENC_CHUNK, end - c0);
-  for (int j = tid; j < cnt; j += ENC_THREADS) {
-    const int item = indices[c0 + j];
-    const float val = values != nullptr ? values[c0 + j] : 1.0f;
-    float c = val * scale;
+  // thread j < cnt prepares nonzero j of the chunk (cnt <= ENC_CHUNK <= ENC_THREADS); the survivors of the dropout are compacted
+  // in order (ballot + per-warp offsets: deterministic), so the load rounds below carry no empty slots
+  int item = 0;
+  float c = 0.f;
+  if (tid < cnt) {
+    item = indices[c0 + tid];
+    const float val = values != nullptr ? values[c0 + tid] : 1.0f;
+    c = val * scale;
     if (drop) {
       const uint32_t r = ltg_rand_u32(seed, LTG_STREAM_ENC_DROPOUT, step,
                                       (uint64_t)(uid0 + u) * (uint64_t)n_items + (uint64_t)(item + (PARTIAL ? item_offset : 0)));
       if (r >= thr) c = 0.f;
     }
-    s_item[j] = item;
-    s_coef[j] = c;
-    coef[c0 + j] = c;
+    coef[c0 + tid] = c;
     // dense bf16 coefficient matrix over the batch's active items: the A operand of the encoder weight-gradient GEMM
     if (xc != nullptr) xc[(size_t)u * ld_xc + slot_of_item[item]] = __float2bfloat16(c);
   }
+  const unsigned live = __ballot_sync(0xffffffffu, c != 0.f);
+  if ((tid & 31) == 0 && tid < ENC_CHUNK) s_wcnt[tid >> 5] = __popc(live);
   __syncthreads();
-  if (tid < HV) {
-    int j = 0;
-    constexpr int EU = 8;  // 16-byte loads in flight per thread
-    for (; j + EU <= cnt; j += EU) {
-      uint4 w[EU]; float c[EU];
+  int nlive = 0;
+#pragma unroll
+  for (int w = 0; w < ENC_CHUNK / 32; ++w) {
+    if (w == (tid >> 5) && c != 0.f) {
+      const int pos = nlive + __popc(live & ((1u << (tid & 31)) - 1u));
+      s_item[pos] = item;
+      s_coef[pos] = c;
+    }
+    nlive += s_wcnt[w];
+  }
+  __syncthreads();
+  const int grp = tid / ENC_GSZ, l = tid - grp * ENC_GSZ;
+  if (l < HV) {
+    constexpr int EU = 8;  // 16-byte copies in flight per thread
+    uint4* st = s_stage + grp * HV + l;
+    for (int j = grp; j < nlive; j += EU * ENC_GROUPS) {
 #pragma unroll
       for (int q = 0; q < EU; ++q) {
-        c[q] = s_coef[j + q];
-        w[q] = make_uint4(0, 0, 0, 0);
-        if (c[q] != 0.f) w[q] = __ldg(W + (size_t)s_item[j + q] * HV + tid);
+        const int jj = j + q * ENC_GROUPS;
+        if (jj < nlive) cp_async16(st + q * (ENC_GROUPS * HV), W + (size_t)s_item[jj] * HV + l);
       }
+      cp_async_wait_all();
 #pragma unroll
       for (int q = 0; q < EU; ++q) {
-        float2 a = unpack_bf16x2(w[q].x), b = unpack_bf16x2(w[q].y), d = unpack_bf16x2(w[q].z), e = unpack_bf16x2(w[q].w);
-        acc[0] = fmaf(c[q], a.x, acc[0]); acc[1] = fmaf(c[q], a.y, acc[1]);
-        acc[2] = fmaf(c[q], b.x, acc[2]); acc[3] = fmaf(c[q], b.y, acc[3]);
-        acc[4] = fmaf(c[q], d.x, acc[4]); acc[5] = fmaf(c[q], d.y, acc[5]);
-        acc[6] = fmaf(c[q], e.x, acc[6]); acc[7] = fmaf(c[q], e.y, acc[7]);
+        const int jj = j + q * ENC_GROUPS;
+        if (jj < nlive) {
+          const float cf = s_coef[jj];
+          const uint4 w = st[q * (ENC_GROUPS * HV)];
+          float2 a = unpack_bf16x2(w.x), b = unpack_bf16x2(w.y), d = unpack_bf16x2(w.z), e = unpack_bf16x2(w.w);
+          acc[0] = fmaf(cf, a.x, acc[0]); acc[1] = fmaf(cf, a.y, acc[1]);
+          acc[2] = fmaf(cf, b.x, acc[2]); acc[3] = fmaf(cf, b.y, acc[3]);
+          acc[4] = fmaf(cf, d.x, acc[4]); acc[5] = fmaf(cf, d.y, acc[5]);
+          acc[6] = fmaf(cf, e.x, acc[6]); acc[7] = fmaf(cf, e.y, acc[7]);
+        }
       }
     }
-    for (; j < cnt; ++j) {
-      const float c = s_coef[j];
-      if (c != 0.f) {
-        const uint4 w = __ldg(W + (size_t)s_item[j] * HV + tid);
-        float2 a = unpack_bf16x2(w.x), b = unpack_bf16x2(w.y), d = unpack_bf16x2(w.z), e = unpack_bf16x2(w.w);
-        acc[0] = fmaf(c, a.x, acc[0]); acc[1] = fmaf(c, a.y, acc[1]);
-        acc[2] = fmaf(c, b.x, acc[2]); acc[3] = fmaf(c, b.y, acc[3]);
-        acc[4] = fmaf(c, d.x, acc[4]); acc[5] = fmaf(c, d.y, acc[5]);
-        acc[6] = fmaf(c, e.x, acc[6]); acc[7] = fmaf(c, e.y, acc[7]);
-      }
+    if (grp > 0) {
+      s_acc[grp - 1][l][0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      s_acc[grp - 1][l][1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+  }
+  __syncthreads();
+  if (tid < HV) {   // group 0 collects the other groups' partial sums (fixed order)
+#pragma unroll
+    for (int g = 0; g < ENC_GROUPS - 1; ++g) {
+      const float4 x = s_acc[g][tid][0], y = s_acc[g][tid][1];
+      acc[0] += x.x; acc[1] += x.y; acc[2] += x.z; acc[3] += x.w;
+      acc[4] += y.x; acc[5] += y.y; acc[6] += y.z; acc[7] += y.w;
     }
   }
   if constexpr (PARTIAL) {
@@ -588,17 +635,20 @@ __global__ void enc_coef_clear_kernel(const int32_t* __restrict__ e_row, const i
 extern "C" int ltg_enc_gather_fwd(const int32_t* indptr, const int32_t* indices, const float* values, int B, int n_items, int64_t uid0,
                                   const void* W_enc_bf16, const float* b_q0, float keep, uint64_t seed, uint32_t step,
                                   const uint32_t* step_dev, void* h1_bf16, int ld_h1, float* coef, int max_row_nnz, float* pre_ws,
-                                  int32_t* counters, const int32_t* slot_of_item, void* xc_bf16, int ld_xc, void* stream) {
+                                  int32_t* counters, const int32_t* slot_of_item, void* xc_bf16, int ld_xc, const int32_t* work, int n_work,
+                                  void* stream) {
   LTG_REQUIRE(indptr && indices && W_enc_bf16 && b_q0 && h1_bf16 && coef);
+  LTG_REQUIRE(work == nullptr || (n_work >= B && B < (1 << 20)));
   LTG_REQUIRE(ld_h1 % 8 == 0 && ld_h1 >= H);
   LTG_REQUIRE(max_row_nnz <= ENC_CHUNK || (pre_ws != nullptr && counters != nullptr));
   LTG_REQUIRE(xc_bf16 == nullptr || slot_of_item != nullptr);
   if (B <= 0) return LTG_OK;
   const int chunks = max_row_nnz <= ENC_CHUNK ? 1 : (max_row_nnz + ENC_CHUNK - 1) / ENC_CHUNK;
-  enc_gather_fwd_kernel<false><<<dim3(B, chunks), ENC_THREADS, 0, (cudaStream_t)stream>>>(
+  const dim3 grid = work != nullptr ? dim3(n_work) : dim3(B, chunks);
+  enc_gather_fwd_kernel<false><<<grid, ENC_THREADS, 0, (cudaStream_t)stream>>>(
       indptr, indices, values, n_items, uid0, reinterpret_cast<const uint4*>(W_enc_bf16), b_q0, keep, seed, step, step_dev,
       reinterpret_cast<__nv_bfloat16*>(h1_bf16), ld_h1, coef, pre_ws, counters, slot_of_item, reinterpret_cast<__nv_bfloat16*>(xc_bf16), ld_xc,
-      nullptr, 0);
+      nullptr, 0, work);
   LTG_CHECK_LAUNCH();
   return LTG_OK;
 }
@@ -613,7 +663,7 @@ extern "C" int ltg_enc_gather_partial(const int32_t* indptr, const int32_t* indi
   const int chunks = max_row_nnz <= ENC_CHUNK ? 1 : (max_row_nnz + ENC_CHUNK - 1) / ENC_CHUNK;
   enc_gather_fwd_kernel<true><<<dim3(B, chunks), ENC_THREADS, 0, (cudaStream_t)stream>>>(
       indptr, indices, nullptr, n_items_global, uid0, reinterpret_cast<const uint4*>(W_shard_bf16), nullptr, keep, seed, step, step_dev, nullptr, 0,
-      coef, pre_sum, nullptr, slot_of_item, reinterpret_cast<__nv_bfloat16*>(xc_bf16), ld_xc, row_rnorm, item_offset);
+      coef, pre_sum, nullptr, slot_of_item, reinterpret_cast<__nv_bfloat16*>(xc_bf16), ld_xc, row_rnorm, item_offset, nullptr);
   LTG_CHECK_LAUNCH();
   return LTG_OK;
 }

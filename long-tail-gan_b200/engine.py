@@ -89,8 +89,9 @@ class TrainData(object):
         label = np.full(max(P, 1), -1, dtype=np.int32)
         pair_pop[:Pr] = real_pop[r0:r1]; pair_niche[:Pr] = real_niche[r0:r1]; label[:Pr] = 0
         t = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(dev)  # noqa: E731
+        enc_work = ops.enc_work_list(self.h_indptr[b0:b1 + 1]) if B > 0 else np.zeros(1, dtype=np.int32)
         self._last_host = dict(act_ptr=act_ptr, slot_of_item=slot_of_item, csc_row=rows[order], csc_pos=order + e0, samp_ptr=samp_ptr,
-                               pair_pop=pair_pop[:max(Pr, 1)],
+                               enc_work=enc_work, pair_pop=pair_pop[:max(Pr, 1)],
                                pair_niche=pair_niche[:max(Pr, 1)], label=label[:max(Pr, 1)])
         return dict(b0=b0, B=B, uid0=self.uid_start + b0, nnz=e1 - e0, Pr=Pr, K=K, P=P, e0=e0, e1=e1,
                     host_src={k: np.ascontiguousarray(v, dtype=np.int32) for k, v in self._last_host.items()},
@@ -101,6 +102,7 @@ class TrainData(object):
                     cnt=torch.zeros(1, dtype=torch.int32, device=dev),
                     max_cand=int(cand_len[b0:b1].max()) if B > 0 else 0,
                     samp_order=t(np.argsort(-cand_len[b0:b1], kind="stable")),
+                    enc_work=t(enc_work) if B > 0 else None,
                     max_nnz=int(np.diff(self.h_indptr[b0:b1 + 1]).max()) if B > 0 else 0)
 
 
@@ -166,8 +168,9 @@ def pin_host_inputs(data):
         add(data.pop_items[p0:p1], h["pop_items"][p0:p1])
         hs = bt["host_src"]
         Pr = bt["Pr"]
-        for k in ("act_ptr", "slot_of_item", "csc_row", "csc_pos", "samp_ptr"):
-            add(bt[k], hs[k])
+        for k in ("act_ptr", "slot_of_item", "csc_row", "csc_pos", "samp_ptr", "enc_work"):
+            if bt[k] is not None:
+                add(bt[k], hs[k])
         if Pr > 0:
             for k in ("pair_pop", "pair_niche", "label"):
                 add(bt[k][:Pr], hs[k][:Pr])
@@ -346,15 +349,17 @@ class GanEngine(object):
         """MultiVAE.forward_pass (MultiVAE.py:175-186) up to the logits and their softmax statistics."""
         v = self.vae
         wstep = self.w_g if is_training else self.w_a
+        own_rows = indptr is None and B is None      # the batch's own CSR rows: its precomputed chunk list applies
         B = bt["B"] if B is None else B
         indptr = data.indptr[bt["b0"]: bt["b0"] + B + 1] if indptr is None else indptr
         indices = data.indices if indices is None else indices
         coef = data.coef if coef is None else coef
         uid0 = bt["uid0"] if uid0 is None else uid0
+        work = bt.get("enc_work") if own_rows else None
         # Xc (dense coefficient matrix, G step only) is all-zero here: the G backward clears it again right after its consumer
         ops.enc_gather_fwd(indptr, indices, None, B, self.I, uid0, v.W_q0_b, v.view("b_q0"), keep, self.seed, 0, wstep, self.h1, coef,
                            bt["max_nnz"] if max_nnz is None else max_nnz, self.enc_ws, self.enc_cnt,
-                           bt["slot_of_item"] if is_training else None, self.Xc if is_training else None)
+                           bt["slot_of_item"] if is_training else None, self.Xc if is_training else None, work=work)
         if self.fused_mid:
             ops.vae_mid_fwd(self.h1, v.view("W_q1", "b"), v.view("b_q1"), v.view("W_p0", "b"), v.view("b_p0"),
                             self.eps_inject if is_training else None, B, uid0, 1.0 if is_training else 0.0, self.seed, 0, wstep,

@@ -111,11 +111,31 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, splits=1,
 
 
 def enc_gather_fwd(indptr, indices, values, B, n_items, uid0, W_enc_bf16, b_q0, keep, seed, step, step_dev, h1, coef, max_row_nnz=0,
-                   pre_ws=None, counters=None, slot_of_item=None, xc=None):
+                   pre_ws=None, counters=None, slot_of_item=None, xc=None, work=None):
     _count(1)
     check(lib().ltg_enc_gather_fwd(ptr(indptr), ptr(indices), ptr(values), B, n_items, uid0, ptr(W_enc_bf16), ptr(b_q0), keep, seed,
                                    step, ptr(step_dev), ptr(h1), h1.stride(0), ptr(coef), max_row_nnz, ptr(pre_ws), ptr(counters),
-                                   ptr(slot_of_item), ptr(xc), xc.stride(0) if xc is not None else 0, _stream()))
+                                   ptr(slot_of_item), ptr(xc), xc.stride(0) if xc is not None else 0, ptr(work),
+                                   work.numel() if work is not None else 0, _stream()))
+
+
+ENC_CHUNK = 128   # nonzeros per CTA of ltg_enc_gather_fwd (csrc/vae_kernels.cu)
+
+
+def enc_work_list(indptr):
+    """Host-side work list of ltg_enc_gather_fwd for the CSR rows indptr[0..B]: one int32 (chunk << 20 | row) per non-empty
+    128-nonzero chunk (rows without interactions keep their chunk 0: they still need bias + tanh), full chunks first."""
+    import numpy as np
+    deg = np.diff(np.asarray(indptr, dtype=np.int64))
+    B = len(deg)
+    assert B < (1 << 20)
+    nch = np.maximum(1, -(-deg // ENC_CHUNK))
+    rows = np.repeat(np.arange(B, dtype=np.int64), nch)
+    first = np.concatenate([[0], np.cumsum(nch)[:-1]])
+    chunk = np.arange(len(rows), dtype=np.int64) - np.repeat(first, nch)
+    size = np.minimum(ENC_CHUNK, deg[rows] - chunk * ENC_CHUNK)
+    order = np.argsort(-size, kind="stable")
+    return ((chunk[order] << 20) | rows[order]).astype(np.int32)
 
 
 def enc_gather_partial(indptr, indices, B, n_items_global, item_offset, uid0, W_shard_bf16, row_rnorm, keep, seed, step, step_dev, pre_sum, coef,

@@ -339,3 +339,77 @@ def test_edge_batches_single_user_and_no_pairs():
                 assert L["cnt"] == 0 and L["gan_loss"] == 0.0 and L["d_loss"] == 0.0
     torch.cuda.synchronize()
     assert torch.isfinite(vae.WdT).all() and torch.isfinite(vae.W_q0).all() and torch.isfinite(disc.arena).all()
+
+
+def test_ten_step_drift_vs_oracle(setup):
+    """Ten consecutive A -> D -> G updates, device vs oracle, WITHOUT re-synchronising the oracle's parameters from the device: the
+    oracle keeps its own fp32 weights and Adam moments from step 0 on and is fed only what the reference's host code would hand the
+    graph (the device's sampled pairs, the mirrored dropout bits, the injected eps). Every step's losses must stay within the
+    north_star tolerance (1e-3 relative; 2e-2 for the small adversarial term), i.e. bf16-operand rounding does not compound, and the
+    accumulated parameter displacement after ten TF-Adam updates must agree in direction and size."""
+    s = setup
+    eng = s["eng"]
+    gen = importlib.import_module("long-tail-gan_b200.generator")
+    dis = importlib.import_module("long-tail-gan_b200.discriminator")
+    tabs = s["tabs"]
+    lr = 1e-4
+    vae = gen.MultiVAE([200, 600, I], lam=0.0, random_seed=98765)
+    vae.set_params(s["params"]); vae.reset_optimizer()
+    disc = dis.Discriminator(I, I, H0, H1, H2, H3, seed=1)
+    disc.set_params(s["E"], s["dparams"])
+    data = eng.TrainData(batch_size=BATCH, **tabs)
+    e = eng.GanEngine(vae, disc, data.max_B, data.max_P, seed=SEED, lr=lr, lam=1.0, use_graphs=False, max_active=data.max_active)
+    g0 = [p.clone().cpu().contiguous() for p in vae.params]
+    d0 = [p.clone().cpu() for p in disc.d_params]
+    gp = [p.clone() for p in g0]; gm = [torch.zeros_like(p) for p in g0]; gv = [torch.zeros_like(p) for p in g0]
+    dp = [p.clone() for p in d0]; dm = [torch.zeros_like(p) for p in d0]; dv = [torch.zeros_like(p) for p in d0]
+    worst = dict(d_loss=0.0, vae_loss=0.0, g_loss=0.0, gan_loss=0.0)
+    for it in range(10):
+        bi = it % 2
+        bt = data.batches[bi]
+        b0, B, Pr, K, P = bt["b0"], bt["B"], bt["Pr"], bt["K"], bt["P"]
+        e.phase_a(data, bi)
+        e.d_step(data, bi)
+        torch.cuda.synchronize()
+        step = int(e.words[0].item()); t = int(e.words[1].item())
+        pairs, gen_rows = _oracle_pairs(bt)
+        masks = disc_masks(step, P, disc)
+        d_loss, _ = orc.d_step(s["E"], dp, dm, dv, pairs, [m[:Pr] for m in masks], [m[Pr:][gen_rows] for m in masks], 0.7,
+                               orc.tf_adam_lr_t(lr, t))
+        got_d = e.last_losses(B)["d_loss"]
+        worst["d_loss"] = max(worst["d_loss"], abs(got_d - d_loss) / abs(d_loss))
+        eps = torch.randn(B, 200, generator=torch.Generator().manual_seed(100 + it))
+        e.eps_inject = eps.cuda()
+        e.g_step(data, bi)
+        torch.cuda.synchronize()
+        step = int(e.words[0].item()); t = int(e.words[1].item())
+        got = e.last_losses(B)
+        X = torch.from_numpy(helpers.dense_rows(tabs["indptr"], tabs["indices"], b0, b0 + B, I))
+        idx = (np.uint64(bt["uid0"]) + np.arange(B, dtype=np.uint64))[:, None] * np.uint64(I) + np.arange(I, dtype=np.uint64)[None, :]
+        keep_mask = torch.from_numpy(philox.keep_mask(SEED, philox.STREAM_ENC_DROPOUT, step, idx, 0.75))
+        m_gen = [m[gen_rows] for m in disc_masks(step, K, disc)]
+        sp = bt["samp_ptr"].cpu().numpy()
+        niche = bt["pair_niche"].cpu().numpy()[Pr:]; lab = bt["label"].cpu().numpy()[Pr:]
+        rows = np.repeat(np.arange(B), np.diff(sp))
+        mask = torch.zeros(B, I)
+        mask[rows[lab > 0], niche[lab > 0]] = 1.0
+        cnt = int((lab > 0).sum())
+        ref = orc.g_step(gp, gm, gv, s["E"], dp, X, keep_mask, 0.75, eps, got["anneal"], mask, pairs, m_gen, 0.7, 1.0, cnt,
+                         orc.tf_adam_lr_t(lr, t))
+        assert got["cnt"] == cnt
+        for key in ("vae_loss", "g_loss"):
+            worst[key] = max(worst[key], abs(got[key] - ref[key]) / abs(ref[key]))
+        worst["gan_loss"] = max(worst["gan_loss"], abs(got["gan_loss"] - ref["gan_loss"]) / (abs(ref["gan_loss"]) + 1e-6))
+    e.eps_inject = None
+    print("ten-step drift, worst relative loss error:", worst)
+    assert worst["d_loss"] < 1e-3 and worst["vae_loss"] < 1e-3 and worst["g_loss"] < 1e-3 and worst["gan_loss"] < 2e-2, worst
+    # accumulated displacement after ten updates: cosine with the oracle's displacement and ratio of the norms
+    drift = {}
+    for name, dev, ref_p, p0 in list(zip("W_q0 W_q1 W_p0 W_p1".split(), vae.params, gp, g0)) + \
+            list(zip("w1 w2 w3 w4".split(), disc.d_params[0::2], dp[0::2], d0[0::2])):
+        a = (dev.detach().cpu().double().reshape(p0.shape) - p0.double()).reshape(-1)
+        b = (ref_p.double() - p0.double()).reshape(-1)
+        drift[name] = (float(a @ b / (a.norm() * b.norm() + 1e-30)), float(a.norm() / (b.norm() + 1e-30)))
+    print("ten-step drift, (cosine, norm ratio) of the accumulated displacement:", drift)
+    for name, (cos, ratio) in drift.items():
+        assert cos > 0.9 and 0.9 < ratio < 1.1, (name, cos, ratio)

@@ -174,6 +174,15 @@ def test_enc_gather_long_row_and_values(ops):
     want = np.tanh((x / np.sqrt((x * x).sum())) @ Wb.float().cpu().numpy())
     assert np.abs(h1[0].float().cpu().numpy() - want).max() < 1e-2
     assert (h1[1:].float().abs().max().item()) == 0.0  # empty rows: tanh(0 + 0)
+    # the same call over a host-built work list (one CTA per existing chunk instead of a rows x max-chunks grid)
+    work = ops.enc_work_list(indptr)
+    assert len(work) == 11 + 2 and sorted(int(w) & 0xFFFFF for w in work) == [0] * 11 + [1, 2]
+    h1w = torch.full((3, 600), 7.0, device="cuda", dtype=torch.bfloat16)
+    coefw = torch.zeros(n, device="cuda")
+    ops.enc_gather_fwd(dev(indptr), dev(indices), dev(vals), 3, I, 0, Wb, dev(b), 1.0, 1, 0, None, h1w, coefw, n, ws, cn, work=dev(work))
+    torch.cuda.synchronize()
+    assert ws.abs().max().item() == 0.0 and cn.abs().max().item() == 0
+    assert torch.equal(coefw, coef) and (h1w.float() - h1.float()).abs().max().item() < 4e-3   # (float atomics: order may differ)
 
 
 def test_latent_fwd_bwd(ops):

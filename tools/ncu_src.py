@@ -8,8 +8,9 @@ def main():
     rep, kern = sys.argv[1], sys.argv[2]
     skip = sys.argv[3] if len(sys.argv) > 3 else "0"
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 30
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern, "--launch-skip", skip,
-                          "--launch-count", "1"], capture_output=True, text=True).stdout
+    # names are matched against the demangled name WITH template arguments (bool arguments print as 0 / 1)
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name-base", "demangled", "--kernel-name", "regex:" + kern,
+                          "--launch-skip", skip, "--launch-count", "1"], capture_output=True, text=True).stdout
     lines = [l for l in out.splitlines() if l.strip()]
     print(lines[0][:200])
     rd = [r for r in csv.DictReader(lines[1:]) if (r.get("# Samples") or "0").replace(".", "").isdigit()]
