@@ -56,6 +56,13 @@ int ltg_init(void);
 int ltg_step_advance(uint32_t* words, float* scal, int kind, float lr, float beta1, float beta2,
                      float anneal_cap, float total_anneal_steps, void* zero_buf, int64_t zero_words, uint32_t* step_snapshot,
                      void* stream);
+/* The advances of one whole A -> D -> G step in one launch: identical in effect to ltg_step_advance with kind 0, 1, 2 in this order
+ * on three DISTINCT scalar rows (phase A's row is scratch: train.py:200 fetches no loss), each with its own cleared buffer and rng-step
+ * snapshot. Used by the per-batch step graph (train.py:192-329 for one batch), where it takes two launches off the critical chain.  */
+int ltg_step_advance3(uint32_t* words, float* scal_a, float* scal_d, float* scal_g, float lr, float beta1, float beta2,
+                      float anneal_cap, float total_anneal_steps, void* zero_a, int64_t zero_a_words, void* zero_d,
+                      int64_t zero_d_words, void* zero_g, int64_t zero_g_words, uint32_t* snap_a, uint32_t* snap_d,
+                      uint32_t* snap_g, void* stream);
 
 /* ---- generic bf16 tensor-core GEMM (tcgen05/TMA/TMEM) ------------------------------------------------------------
  * D[M,N] = alpha * A * B^T with A given as [M,K] (a_mn=0, pitch lda) or stored transposed [K,M] (a_mn=1), B likewise
@@ -148,7 +155,11 @@ int ltg_tanh_bwd(const float* dy, int ld_dy, int n_partials, int64_t partial_str
 
 /* ---- a5/a6: decoder + catalog softmax (MultiVAE.py:169,108-112,143) -------------------------------------------------
  * logits = h2 * W_dec + b_dec through the tcgen05 GEMM with the softmax-statistics epilogue: bf16 logits stash
- * [B, ld_logits] (NULL = statistics only) and partial (max,sumexp) pairs: partial[4*ceil(n_items/256)][B] float2.     */
+ * [B, ld_logits] (NULL = statistics only) and partial (max,sumexp) pairs: partial[n_blocks][B] float2 with
+ * n_blocks = ltg_dec_logits_nblk(B, n_items) = 4 x the number of column tiles the launch uses for this shape (the tile width is
+ * chosen per shape against wave quantisation; never more than 4*ceil(n_items/128) rows). The row passes below take n_blocks.
+ * partial may be NULL when only the logits are wanted (phase A, train.py:200: the sampler needs no normaliser).                */
+int ltg_dec_logits_nblk(int B, int n_items);
 int ltg_dec_logits_fwd(const void* h2_bf16, int ld_h2, const void* WdT_bf16, const float* b_dec, int B, int n_items,
                        void* logits_bf16, int ld_logits, float* partial, void* stream);
 /* Row pass: lse[B]; nll: scal[NLL_SUM] += -sum_i x_ui (logit_ui - lse_u); sampled-probability sum per user s_u[B] and

@@ -100,6 +100,7 @@ SIGNATURES = {
     "ltg_version": (_I, []),
     "ltg_init": (_I, []),
     "ltg_step_advance": (_I, [_P, _P, _I, _F, _F, _F, _F, _F, _P, _I64, _P, _P]),
+    "ltg_step_advance3": (_I, [_P, _P, _P, _P, _F, _F, _F, _F, _F, _P, _I64, _P, _I64, _P, _I64, _P, _P, _P, _P]),
     "ltg_gemm_bf16": (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _F, _I, _F, _U64, _U32, _U32, _P, _I,
                            _I, _P, _P, _I, _F, _I64, _P]),
     "ltg_enc_gather_fwd": (_I, [_P, _P, _P, _I, _I, _I64, _P, _P, _F, _U64, _U32, _P, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _I, _P]),
@@ -113,6 +114,7 @@ SIGNATURES = {
     "ltg_vae_mid_fwd_tc": (_I, [_P, _I, _P, _P, _P, _P, _P, _I, _I64, _F, _U64, _U32, _P, _P, _P, _I, _P, _P, _I, _P, _P]),
     "ltg_vae_mid_bwd_tc": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
     "ltg_tanh_bwd": (_I, [_P, _I, _I, _I64, _P, _I, _I, _I, _P, _I, _P, _I, _P, _P]),
+    "ltg_dec_logits_nblk": (_I, [_I, _I]),
     "ltg_dec_logits_fwd": (_I, [_P, _I, _P, _P, _I, _I, _P, _I, _P, _P]),
     "ltg_dec_row_stats": (_I, [_P, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ltg_dec_probs": (_I, [_P, _I, _P, _I, _I, _P, _I, _P]),

@@ -42,26 +42,25 @@ adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
       gg[u] = ld_stream_f4_hint(g + 4 * i, pol);
     }
   }
-  if (n_partials > 1) {                        // split-K partials of the producing GEMM, four independent accumulation chains
+  if (n_partials > 1) {
+    // split-K partials of the producing GEMM: rounds of 4 partials x ADAM_UN chunks = 8 independent 16-byte requests per thread
+    // (the discriminator update sums 16 partials on the critical chain of the step: 5 dependent rounds of 3 before)
+    constexpr int PR = 4;
+    for (int sp = 1; sp < n_partials; sp += PR) {
+      float4 o[PR][ADAM_UN];
 #pragma unroll
-    for (int u = 0; u < ADAM_UN; ++u) {
-      const int64_t i = base + u * 256;
-      if (i >= n4) continue;
-      float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a1, a3 = a1;
-      int sp = 1;
-      for (; sp + 3 <= n_partials; sp += 3) {
-        const float4 o1 = ld_stream_f4(g + (size_t)sp * partial_stride + 4 * i);
-        const float4 o2 = ld_stream_f4(g + (size_t)(sp + 1) * partial_stride + 4 * i);
-        const float4 o3 = ld_stream_f4(g + (size_t)(sp + 2) * partial_stride + 4 * i);
-        a1.x += o1.x; a1.y += o1.y; a1.z += o1.z; a1.w += o1.w;
-        a2.x += o2.x; a2.y += o2.y; a2.z += o2.z; a2.w += o2.w;
-        a3.x += o3.x; a3.y += o3.y; a3.z += o3.z; a3.w += o3.w;
+      for (int q = 0; q < PR; ++q)
+#pragma unroll
+        for (int u = 0; u < ADAM_UN; ++u) {
+          const int64_t i = base + u * 256;
+          o[q][u] = (sp + q < n_partials && i < n4) ? ld_stream_f4(g + (size_t)(sp + q) * partial_stride + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+      for (int u = 0; u < ADAM_UN; ++u) {
+        const float4 a = o[0][u], b = o[1][u], c = o[2][u], d = o[3][u];
+        gg[u].x += (a.x + b.x) + (c.x + d.x); gg[u].y += (a.y + b.y) + (c.y + d.y);
+        gg[u].z += (a.z + b.z) + (c.z + d.z); gg[u].w += (a.w + b.w) + (c.w + d.w);
       }
-      for (; sp < n_partials; ++sp) {
-        const float4 o = ld_stream_f4(g + (size_t)sp * partial_stride + 4 * i);
-        a1.x += o.x; a1.y += o.y; a1.z += o.z; a1.w += o.w;
-      }
-      gg[u].x += (a1.x + a2.x) + a3.x; gg[u].y += (a1.y + a2.y) + a3.y; gg[u].z += (a1.z + a2.z) + a3.z; gg[u].w += (a1.w + a2.w) + a3.w;
     }
   }
 #pragma unroll

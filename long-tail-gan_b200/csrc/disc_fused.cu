@@ -139,8 +139,8 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmXp, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp in the loop, one elected lane issues: see elect_one) =====================
+    {
       int st3 = 0; uint32_t ph3 = 0; int st4 = 0; uint32_t ph4 = 0;
       int it = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
@@ -150,28 +150,34 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmXp, const __grid_constan
         DF_STAMP(0);
         if (it > 0) mbar_wait(&bar_mma[bwd4 ? 3 : 2], prev);
         DF_STAMP(1);
-        {  // R2: X_pop [2 x 16 KB] + W1 [2 k blocks x three 64-column boxes]
-          uint8_t* xs = r2; uint8_t* ws = r2 + 32768;
-          mbar_expect_tx(&bar_ld[0], 32768 + 2 * 3 * 8192);
-          for (int kb = 0; kb < 2; ++kb) {
-            tma_load_2d(xs + kb * 16384, &tmXp, &bar_ld[0], kb * 64, m0);
-            for (int j = 0; j < 3; ++j) tma_load_2d(ws + kb * (3 * 8192) + j * 8192, &tmW1, &bar_ld[0], j * 64, kb * 64);
+        if (elect_one()) {
+          {  // R2: X_pop [2 x 16 KB] + W1 [2 k blocks x three 64-column boxes]
+            uint8_t* xs = r2; uint8_t* ws = r2 + 32768;
+            mbar_expect_tx(&bar_ld[0], 32768 + 2 * 3 * 8192);
+            for (int kb = 0; kb < 2; ++kb) {
+              tma_load_2d(xs + kb * 16384, &tmXp, &bar_ld[0], kb * 64, m0);
+              for (int j = 0; j < 3; ++j) tma_load_2d(ws + kb * (3 * 8192) + j * 8192, &tmW1, &bar_ld[0], j * 64, kb * 64);
+            }
+          }
+          {  // R1: X_niche + W2 [2 k blocks x four boxes]
+            uint8_t* xs = r1; uint8_t* ws = r1 + 32768;
+            mbar_expect_tx(&bar_ld[1], 32768 + 2 * 4 * 8192);
+            for (int kb = 0; kb < 2; ++kb) {
+              tma_load_2d(xs + kb * 16384, &tmXn, &bar_ld[1], kb * 64, m0);
+              for (int j = 0; j < 4; ++j) tma_load_2d(ws + kb * (4 * 8192) + j * 8192, &tmW2, &bar_ld[1], j * 64, kb * 64);
+            }
           }
         }
-        {  // R1: X_niche + W2 [2 k blocks x four boxes]
-          uint8_t* xs = r1; uint8_t* ws = r1 + 32768;
-          mbar_expect_tx(&bar_ld[1], 32768 + 2 * 4 * 8192);
-          for (int kb = 0; kb < 2; ++kb) {
-            tma_load_2d(xs + kb * 16384, &tmXn, &bar_ld[1], kb * 64, m0);
-            for (int j = 0; j < 4; ++j) tma_load_2d(ws + kb * (4 * 8192) + j * 8192, &tmW2, &bar_ld[1], j * 64, kb * 64);
-          }
-        }
+        __syncwarp();
         mbar_wait(&bar_mma[1], par);             // MMA 2 has read R1: it becomes the W3 ring
         DF_STAMP(2);
         for (int kb = 0; kb < p.kb3; ++kb) {
           mbar_wait(&empty3[st3], ph3 ^ 1);
-          mbar_expect_tx(&full3[st3], DF_W3_STAGE);
-          for (int j = 0; j < 5; ++j) tma_load_2d(r1 + st3 * DF_W3_STAGE + j * 8192, &tmW3, &full3[st3], j * 64, kb * 64);
+          if (elect_one()) {
+            mbar_expect_tx(&full3[st3], DF_W3_STAGE);
+            for (int j = 0; j < 5; ++j) tma_load_2d(r1 + st3 * DF_W3_STAGE + j * 8192, &tmW3, &full3[st3], j * 64, kb * 64);
+          }
+          __syncwarp();
           if (++st3 == 2) { st3 = 0; ph3 ^= 1; }
         }
         if (bwd4) {
@@ -180,17 +186,20 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmXp, const __grid_constan
           DF_STAMP(4);
           for (int kb = 0; kb < DF_KB4; ++kb) {
             mbar_wait(&empty4[st4], ph4 ^ 1);
-            mbar_expect_tx(&full4[st4], DF_W3T_STAGE);
-            tma_load_2d(r2 + st4 * DF_W3T_STAGE, &tmW3T, &full4[st4], kb * 64, 0);
-            tma_load_2d(r2 + st4 * DF_W3T_STAGE + DF_W3T_HALF, &tmW3T, &full4[st4], kb * 64, DF_N4);
+            if (elect_one()) {
+              mbar_expect_tx(&full4[st4], DF_W3T_STAGE);
+              tma_load_2d(r2 + st4 * DF_W3T_STAGE, &tmW3T, &full4[st4], kb * 64, 0);
+              tma_load_2d(r2 + st4 * DF_W3T_STAGE + DF_W3T_HALF, &tmW3T, &full4[st4], kb * 64, DF_N4);
+            }
+            __syncwarp();
             if (++st4 == 2) { st4 = 0; ph4 ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp in the loop, one elected lane issues) =====================
+    {
       constexpr uint32_t ID1 = umma_idesc(GEMM_BM, DF_N1, false, true), ID2 = umma_idesc(GEMM_BM, DF_N2, false, true);
       constexpr uint32_t ID3A = umma_idesc(GEMM_BM, DF_N3A, false, true), ID3B = umma_idesc(GEMM_BM, DF_N3B, false, true);
       constexpr uint32_t ID4 = umma_idesc(GEMM_BM, DF_N4, false, false);
@@ -204,21 +213,27 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmXp, const __grid_constan
         mbar_wait(&bar_ld[0], par);
         DF_STAMP(9);
         tc_fence_after();
-        for (int kb = 0; kb < 2; ++kb)
+        if (elect_one()) {
+          for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base, umma_desc_k(a2 + kb * 16384 + k * 32), umma_desc_mn(a2 + 32768 + kb * (3 * 8192) + k * 2048, 8192), ID1,
-                      (kb | k) ? 1u : 0u);
-        umma_commit(&bar_mma[0]);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base, umma_desc_k(a2 + kb * 16384 + k * 32), umma_desc_mn(a2 + 32768 + kb * (3 * 8192) + k * 2048, 8192), ID1,
+                        (kb | k) ? 1u : 0u);
+          umma_commit(&bar_mma[0]);
+        }
+        __syncwarp();
         mbar_wait(&bar_ld[1], par);
         DF_STAMP(10);
         tc_fence_after();
-        for (int kb = 0; kb < 2; ++kb)
+        if (elect_one()) {
+          for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + DF_N1, umma_desc_k(a1 + kb * 16384 + k * 32), umma_desc_mn(a1 + 32768 + kb * (4 * 8192) + k * 2048, 8192), ID2,
-                      (kb | k) ? 1u : 0u);
-        umma_commit(&bar_mma[1]);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + DF_N1, umma_desc_k(a1 + kb * 16384 + k * 32), umma_desc_mn(a1 + 32768 + kb * (4 * 8192) + k * 2048, 8192), ID2,
+                        (kb | k) ? 1u : 0u);
+          umma_commit(&bar_mma[1]);
+        }
+        __syncwarp();
         mbar_wait(bar_hd, par);                  // Hd tile complete in R2, TMEM columns 0..447 drained
         DF_STAMP(11);
         tc_fence_after();
@@ -226,25 +241,32 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmXp, const __grid_constan
         // full 128-byte lines written by the copy engine instead of 16 bytes per thread and row from the epilogue warps (204 store
         // instructions of 32 sectors each per tile). Rows >= P and columns >= k3 are clipped by the tensor map. (With MMA 4 in the kernel
         // the epilogue warps keep their own stores: they read the activation back through the generic proxy.)
-        if (!bwd4) {
+        // lane 0 issues the stores and later waits for them (a bulk async-group belongs to the thread that committed it)
+        if (!bwd4 && lane == 0) {
           for (int kb = 0; kb < p.kb3; ++kb) tma_store_2d(&tmHd, r2 + kb * 16384, kb * 64, t * GEMM_BM);
           bulk_commit();
         }
+        __syncwarp();
         for (int kb = 0; kb < p.kb3; ++kb) {
           mbar_wait(&full3[st3], ph3);
           tc_fence_after();
           const uint32_t w3 = a1 + st3 * DF_W3_STAGE;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t da = umma_desc_k(a2 + kb * 16384 + k * 32);
-            umma_bf16(tmem_base, da, umma_desc_mn(w3 + k * 2048, 8192), ID3A, (kb | k) ? 1u : 0u);
-            umma_bf16(tmem_base + DF_N3A, da, umma_desc_mn(w3 + 4 * 8192 + k * 2048, 8192), ID3B, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da = umma_desc_k(a2 + kb * 16384 + k * 32);
+              umma_bf16(tmem_base, da, umma_desc_mn(w3 + k * 2048, 8192), ID3A, (kb | k) ? 1u : 0u);
+              umma_bf16(tmem_base + DF_N3A, da, umma_desc_mn(w3 + 4 * 8192 + k * 2048, 8192), ID3B, (kb | k) ? 1u : 0u);
+            }
+            umma_commit(&empty3[st3]);
           }
-          umma_commit(&empty3[st3]);
+          __syncwarp();
           if (++st3 == 2) { st3 = 0; ph3 ^= 1; }
         }
-        if (!bwd4) bulk_wait_read0();            // R2 is handed back to the producer by the commit below: the tile stores have read it
-        umma_commit(&bar_mma[2]);
+        if (!bwd4 && lane == 0) bulk_wait_read0();   // R2 is handed back to the producer by the commit below: the tile stores have read it
+        __syncwarp();
+        if (elect_one()) umma_commit(&bar_mma[2]);
+        __syncwarp();
         DF_STAMP(12);
         if (bwd4) {
           mbar_wait(bar_dz3, par);               // dz3 tile complete in R1, fc1 accumulators drained
@@ -254,20 +276,24 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmXp, const __grid_constan
             mbar_wait(&full4[st4], ph4);
             tc_fence_after();
             const uint32_t w = a2 + st4 * DF_W3T_STAGE;
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t da = umma_desc_k(a1 + kb * 16384 + k * 32);
-              umma_bf16(tmem_base, da, umma_desc_k(w + k * 32), ID4, (kb | k) ? 1u : 0u);
-              umma_bf16(tmem_base + DF_N4, da, umma_desc_k(w + DF_W3T_HALF + k * 32), ID4, (kb | k) ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t da = umma_desc_k(a1 + kb * 16384 + k * 32);
+                umma_bf16(tmem_base, da, umma_desc_k(w + k * 32), ID4, (kb | k) ? 1u : 0u);
+                umma_bf16(tmem_base + DF_N4, da, umma_desc_k(w + DF_W3T_HALF + k * 32), ID4, (kb | k) ? 1u : 0u);
+              }
+              umma_commit(&empty4[st4]);
             }
-            umma_commit(&empty4[st4]);
+            __syncwarp();
             if (++st4 == 2) { st4 = 0; ph4 ^= 1; }
           }
-          umma_commit(&bar_mma[3]);
+          if (elect_one()) umma_commit(&bar_mma[3]);
+          __syncwarp();
           DF_STAMP(14);
         }
       }
-      bulk_wait0();                              // the last tile's activation stores are complete before the CTA retires
+      if (lane == 0) bulk_wait0();               // the last tile's activation stores are complete before the CTA retires
     }
   } else {
     // ===================== epilogue =====================

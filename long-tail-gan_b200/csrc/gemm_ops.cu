@@ -47,18 +47,67 @@ extern "C" int ltg_gemm_bf16(const void* A, int lda, int a_mn, const void* B, in
   }
 }
 
+// Tile shape of the decoder forward. The kernel is epilogue-bound (ncu, round 2), so a tile costs about its width, and at batch 500
+// the catalog gives only a few tiles per SM: what matters is how many waves of (cluster) tiles the grid needs. 256-wide tiles in
+// clusters of four -- the round-1 choice -- put 79 cluster tiles on 33 clusters (4-CTA clusters reach 132 of the 148 SMs): 3 waves of
+// 256 columns, the last one a third full; 192-wide tiles in CTA pairs are 210 cluster tiles on 74 pairs: 3 waves of 192.
+// cost = waves x (BN + per-tile overhead); ties go to the wider tile.
+static void logits_tile_shape(int B, int n_items, int* bn_out, int* cm_out) {
+  const int m_blocks = (B + GEMM_BM - 1) / GEMM_BM;
+  const int sms = ltg_num_sms();
+  static const int cand[][2] = {{256, 4}, {256, 2}, {192, 2}, {128, 2}, {256, 1}, {192, 1}, {128, 1}};
+  long best = -1;
+  for (const auto& c : cand) {
+    const int bn = c[0], cm = c[1];
+    if (cm > 1 && m_blocks < cm) continue;            // no row blocks to share the B tile with
+    if (cm == 1 && m_blocks > 1) continue;            // (clusters save L2 -> SM operand traffic whenever there is something to share)
+    if (cm == 4 && m_blocks != 3 && m_blocks != 4) continue;
+    const int clusters = cm == 4 ? sms * 33 / 148 : sms / cm;
+    const long tiles = (long)((m_blocks + cm - 1) / cm) * ((n_items + bn - 1) / bn);
+    const long cost = ((tiles + clusters - 1) / clusters) * (bn + 48);
+    if (best < 0 || cost < best) { best = cost; *bn_out = bn; *cm_out = cm; }
+  }
+}
+
+extern "C" int ltg_dec_logits_nblk(int B, int n_items) {
+  if (B <= 0 || n_items <= 0) return 0;
+  int bn = 256, cm = 1;
+  logits_tile_shape(B, n_items, &bn, &cm);
+  return 4 * ((n_items + bn - 1) / bn);
+}
+
+template <int BN>
+static int launch_logits(int cm, const __nv_bfloat16* A, int lda, const __nv_bfloat16* Bm, int B, int n_items, const EpiLogitsStats::Params& ep,
+                         cudaStream_t stream) {
+  GemmShape s;
+  s.M = B; s.N = n_items; s.K = LTG_H;
+  s.m_blocks = (B + GEMM_BM - 1) / GEMM_BM;
+  s.n_blocks = (n_items + BN - 1) / BN;
+  s.k_blocks = (LTG_H + GEMM_BK - 1) / GEMM_BK;
+  s.kb_per_split = s.k_blocks;
+  s.splits = 1;
+  if (cm == 4) return launch_gemm_cm<BN, false, false, 4, EpiLogitsStats>(A, lda, Bm, LTG_H, s, ep, stream);
+  if (cm == 2) return launch_gemm_cm<BN, false, false, 2, EpiLogitsStats>(A, lda, Bm, LTG_H, s, ep, stream);
+  return launch_gemm_cm<BN, false, false, 1, EpiLogitsStats>(A, lda, Bm, LTG_H, s, ep, stream);
+}
+
 extern "C" int ltg_dec_logits_fwd(const void* h2_bf16, int ld_h2, const void* WdT_bf16, const float* b_dec, int B, int n_items,
                                   void* logits_bf16, int ld_logits, float* partial, void* stream) {
-  LTG_REQUIRE(h2_bf16 != nullptr && WdT_bf16 != nullptr && b_dec != nullptr && partial != nullptr);
+  LTG_REQUIRE(h2_bf16 != nullptr && WdT_bf16 != nullptr && b_dec != nullptr && (partial != nullptr || logits_bf16 != nullptr));
   LTG_REQUIRE(logits_bf16 == nullptr || ld_logits >= n_items);
+  if (B <= 0 || n_items <= 0) return LTG_OK;
   EpiLogitsStats::Params ep;
   ep.logits = reinterpret_cast<__nv_bfloat16*>(logits_bf16);
   ep.ld = ld_logits;
   ep.bias = b_dec;
   ep.partial = reinterpret_cast<float2*>(partial);
-  return launch_gemm<256, false, false, EpiLogitsStats>(reinterpret_cast<const __nv_bfloat16*>(h2_bf16), ld_h2,
-                                                        reinterpret_cast<const __nv_bfloat16*>(WdT_bf16), LTG_H, B, n_items, LTG_H, 1,
-                                                        ep, (cudaStream_t)stream);
+  int bn = 256, cm = 1;
+  logits_tile_shape(B, n_items, &bn, &cm);
+  const __nv_bfloat16* A = reinterpret_cast<const __nv_bfloat16*>(h2_bf16);
+  const __nv_bfloat16* W = reinterpret_cast<const __nv_bfloat16*>(WdT_bf16);
+  if (bn == 256) return launch_logits<256>(cm, A, ld_h2, W, B, n_items, ep, (cudaStream_t)stream);
+  if (bn == 192) return launch_logits<192>(cm, A, ld_h2, W, B, n_items, ep, (cudaStream_t)stream);
+  return launch_logits<128>(cm, A, ld_h2, W, B, n_items, ep, (cudaStream_t)stream);
 }
 
 // dW = A^T-layout GEMM (A stored [K][M], B stored [K][N]) with the Adam step fused into the epilogue; see EpiAdam.

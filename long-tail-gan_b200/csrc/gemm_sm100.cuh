@@ -83,6 +83,21 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // sources reusable
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }             // writes complete
+// One lane of a converged warp (elect.sync). The single-thread roles (TMA producer, MMA issuer) run their loops with the WHOLE warp and
+// gate only the issuing instructions with this predicate: every operand (shared-memory descriptors, TMEM address, barrier address) is
+// then warp-uniform and lives in uniform registers. Written as `if (lane == 0) { loop }` the same code made the compiler treat every
+// operand as divergent -- five R2UR.BROADCAST + ELECT + a BRA.U.ANY "waterfall" loop per tcgen05.mma, ~120 dependent scalar
+// instructions per k block in ONE thread: ncu (round 2) showed the MMA warp busy issuing, the producer waiting for free slots, the
+// epilogue warps waiting for accumulators, and 323 cycles per 128x256x16 MMA against a tensor-pipe floor of 128.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -239,8 +254,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int tile_stride = gridDim.x / CM;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp in the loop, one elected lane issues) =====================
+    {
       int stage = 0; uint32_t phase = 0;
       for (int t = tile0; t < num_tiles; t += tile_stride) {
         const int m_blk = (t % m_groups) * CM + (int)crank;
@@ -252,65 +267,75 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int m0 = m_blk * GEMM_BM, n0 = n_blk * BN;   // m0 may lie beyond M for the padding block of the last group: TMA zero-fills
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
-          uint8_t* sa = smem_a + stage * A_BYTES;
-          uint8_t* sb = smem_b + stage * B_BYTES;
-          const int k0 = kb * GEMM_BK;
-          if constexpr (A_MN) {
+          if (elect_one()) {
+            mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
+            uint8_t* sa = smem_a + stage * A_BYTES;
+            uint8_t* sb = smem_b + stage * B_BYTES;
+            const int k0 = kb * GEMM_BK;
+            if constexpr (A_MN) {
 #pragma unroll
-            for (int j = 0; j < GEMM_BM / 64; ++j) tma_load_2d(sa + j * 8192, &tmA, &full_bar[stage], m0 + j * 64, k0);
-          } else {
-            tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);
-          }
-          if constexpr (CM == 1) {
-            if constexpr (B_MN) {
-#pragma unroll
-              for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, &full_bar[stage], n0 + j * 64, k0);
+              for (int j = 0; j < GEMM_BM / 64; ++j) tma_load_2d(sa + j * 8192, &tmA, &full_bar[stage], m0 + j * 64, k0);
             } else {
-              tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);
+              tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);
             }
-          } else if constexpr (B_MN) {
-            // every 64(n) x 64(k) box is split along k: this CTA fetches k rows [crank*64/CM, +64/CM) of each box for everybody
-            constexpr int KR = 64 / CM;
+            if constexpr (CM == 1) {
+              if constexpr (B_MN) {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d_mc(sb + j * 8192 + crank * (KR * 128), &tmB, &full_bar[stage], n0 + j * 64, k0 + (int)crank * KR, MC_MASK);
-          } else {
-            // the BN x 64(k) tile is split along n: this CTA fetches rows [crank*BN/CM, +BN/CM) for everybody
-            constexpr int NR = BN / CM;
-            tma_load_2d_mc(sb + crank * (NR * 128), &tmB, &full_bar[stage], k0, n0 + (int)crank * NR, MC_MASK);
+                for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, &full_bar[stage], n0 + j * 64, k0);
+              } else {
+                tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);
+              }
+            } else if constexpr (B_MN) {
+              // every 64(n) x 64(k) box is split along k: this CTA fetches k rows [crank*64/CM, +64/CM) of each box for everybody
+              constexpr int KR = 64 / CM;
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_2d_mc(sb + j * 8192 + crank * (KR * 128), &tmB, &full_bar[stage], n0 + j * 64, k0 + (int)crank * KR, MC_MASK);
+            } else {
+              // the BN x 64(k) tile is split along n: this CTA fetches rows [crank*BN/CM, +BN/CM) for everybody
+              constexpr int NR = BN / CM;
+              tma_load_2d_mc(sb + crank * (NR * 128), &tmB, &full_bar[stage], k0, n0 + (int)crank * NR, MC_MASK);
+            }
           }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp in the loop, one elected lane issues) =====================
+    {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+      const uint32_t sa0 = smem_u32(smem_a), sb0 = smem_u32(smem_b);
       for (int t = tile0; t < num_tiles; t += tile_stride) {
         const int split = (t / m_groups) / shape.n_blocks;
         const int kb0 = split * shape.kb_per_split;
         const int kb1 = min(shape.k_blocks, kb0 + shape.kb_per_split);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        if (kb0 >= kb1) umma_commit(&tfull_bar[acc]);  // empty split (fixed split count, short K): the epilogue stores zeros
+        if (kb0 >= kb1) {  // empty split (fixed split count, short K): the epilogue stores zeros
+          if (elect_one()) umma_commit(&tfull_bar[acc]);
+          __syncwarp();
+        }
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem_a + stage * A_BYTES);
-          const uint32_t sb = smem_u32(smem_b + stage * B_BYTES);
+          const uint32_t sa = sa0 + stage * A_BYTES;
+          const uint32_t sb = sb0 + stage * B_BYTES;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            const uint64_t da = A_MN ? umma_desc_mn(sa + k * 2048, 8192) : umma_desc_k(sa + k * 32);
-            const uint64_t db = B_MN ? umma_desc_mn(sb + k * 2048, 8192) : umma_desc_k(sb + k * 32);
-            umma_bf16(tmem_d, da, db, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < GEMM_BK / 16; ++k) {
+              const uint64_t da = A_MN ? umma_desc_mn(sa + k * 2048, 8192) : umma_desc_k(sa + k * 32);
+              const uint64_t db = B_MN ? umma_desc_mn(sb + k * 2048, 8192) : umma_desc_k(sb + k * 32);
+              umma_bf16(tmem_d, da, db, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            if constexpr (CM == 1) umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+            else umma_commit_mc(&empty_bar[stage], MC_MASK);       // ... in every CTA of the cluster
+            if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
           }
-          if constexpr (CM == 1) umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
-          else umma_commit_mc(&empty_bar[stage], MC_MASK);       // ... in every CTA of the cluster
-          if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -378,6 +403,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// MUFU.EX2 without the denormal-range fix-up exp2f() wraps around it (FSETP + two FMULs per call: a quarter of the arithmetic of the
+// catalog-softmax epilogue in the ncu instruction mix of round 2). Arguments here are <= 0 and results feed a sum of at least one 1.0.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
@@ -633,7 +666,7 @@ struct EpiLogitsStats {
   struct Params {
     __nv_bfloat16* logits; int ld;   // [M, ld] bf16 (may be null: statistics only)
     const float* bias;               // [N]
-    float2* partial;                 // [4*n_blocks, M] (max, sumexp): one entry per (n block, chunk phase)
+    float2* partial;                 // [4*n_blocks, M] (max, sumexp): one entry per (n block, chunk phase); null: logits only
   };
   const Params& p;
   int row, M, N, slot;
@@ -672,22 +705,24 @@ struct EpiLogitsStats {
 #pragma unroll
       for (int i = 0; i < CW; ++i) v[i] = (col0 + i < N) ? v[i] + __ldg(p.bias + col0 + i) : -INFINITY;
     }
-    // four independent chains for the max and for the sum
-    float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
+    if (p.partial != nullptr) {   // (phase A only samples from the logits: no statistics wanted)
+      // four independent chains for the max and for the sum
+      float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
 #pragma unroll
-    for (int i = 4; i < CW; i += 4) {
-      m0 = fmaxf(m0, v[i]); m1 = fmaxf(m1, v[i + 1]); m2 = fmaxf(m2, v[i + 2]); m3 = fmaxf(m3, v[i + 3]);
-    }
-    const float nm = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));  // finite: every processed chunk has col0 < N
-    const float nml = nm * LOG2E;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      for (int i = 4; i < CW; i += 4) {
+        m0 = fmaxf(m0, v[i]); m1 = fmaxf(m1, v[i + 1]); m2 = fmaxf(m2, v[i + 2]); m3 = fmaxf(m3, v[i + 3]);
+      }
+      const float nm = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));  // finite: every processed chunk has col0 < N
+      const float nml = nm * LOG2E;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-    for (int i = 0; i < CW; i += 4) {
-      s0 += exp2f(fmaf(v[i], LOG2E, -nml)); s1 += exp2f(fmaf(v[i + 1], LOG2E, -nml));
-      s2 += exp2f(fmaf(v[i + 2], LOG2E, -nml)); s3 += exp2f(fmaf(v[i + 3], LOG2E, -nml));
+      for (int i = 0; i < CW; i += 4) {
+        s0 += ex2_approx(fmaf(v[i], LOG2E, -nml)); s1 += ex2_approx(fmaf(v[i + 1], LOG2E, -nml));
+        s2 += ex2_approx(fmaf(v[i + 2], LOG2E, -nml)); s3 += ex2_approx(fmaf(v[i + 3], LOG2E, -nml));
+      }
+      sum = sum * ex2_approx((mx - nm) * LOG2E) + ((s0 + s1) + (s2 + s3));   // first chunk: mx = -inf -> factor 0
+      mx = nm;
     }
-    sum = sum * exp2f((mx - nm) * LOG2E) + ((s0 + s1) + (s2 + s3));
-    mx = nm;
     if (p.logits != nullptr) {
       __nv_bfloat16* o = p.logits + (size_t)row * p.ld + col0;
       if (col0 + CW <= N && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
@@ -706,7 +741,7 @@ struct EpiLogitsStats {
     }
   }
   __device__ void finish() {
-    if (row < M) p.partial[(size_t)slot * M + row] = make_float2(mx, sum);
+    if (row < M && p.partial != nullptr) p.partial[(size_t)slot * M + row] = make_float2(mx, sum);
   }
 };
 

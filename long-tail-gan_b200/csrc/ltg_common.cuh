@@ -30,6 +30,35 @@
 void ltg_set_last_error(const char* msg, const char* file, int line);
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL). One GAN step is a chain of ~25 dependent kernels, most of them a few microseconds long, and
+// each pays its own launch gap and prologue (barrier init, TMEM allocation, cluster sync, descriptor prefetch) after the previous
+// kernel has drained. With LTG_PDL=1 (default) the kernels of the step are launched with the programmatic-stream-serialization
+// attribute (ltg_launch below; the edges survive CUDA-graph capture), every kernel
+//   * calls pdl_trigger() first: its in-stream successor may be launched as soon as all of OUR blocks have started, and
+//   * calls pdl_wait() before its first global-memory access: it blocks until every prerequisite grid has completed and its
+//     writes are visible -- so data dependencies (and write-after-read hazards) are exactly those of an ordinary launch;
+// what overlaps is the successor's launch latency and prologue with this kernel's tail. Both instructions are no-ops for a kernel
+// launched without the attribute, so a kernel that contains them is safe under any launch.
+// RULE: a kernel may be passed to ltg_launch ONLY if it executes pdl_wait() before touching global memory.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool ltg_pdl_enabled();   // runtime.cu: env LTG_PDL (default on)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t ltg_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ltg_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Philox4x32-10, stateless. key = (seed_lo, seed_hi); counter = (c0, c1, c2, c3).
 // The numpy mirror lives in oracle/philox.py and tests/ check bit equality of the streams.
 // ---------------------------------------------------------------------------------------------

@@ -141,26 +141,34 @@ mid_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // (both single-thread roles run their loops with the whole warp and gate the issuing instructions with elect_one(): operands stay
+  // warp-uniform, see gemm_sm100.cuh)
   if (warp == 0) {
-    if (lane == 0) {
+    {
       for (int kb = 0; kb < KB_H; ++kb) {
         const int st = kb & 1;
         if (kb >= 2) mbar_wait(&empty[st], ((kb >> 1) - 1) & 1);
-        mbar_expect_tx(&full[st], F_STAGE);
-        uint8_t* sa = ring + st * F_STAGE;
-        uint8_t* sb = sa + F_A_BYTES;
-        tma_load_2d(sa, &tmH1, &full[st], kb * 64, m0);
+        if (elect_one()) {
+          mbar_expect_tx(&full[st], F_STAGE);
+          uint8_t* sa = ring + st * F_STAGE;
+          uint8_t* sb = sa + F_A_BYTES;
+          tma_load_2d(sa, &tmH1, &full[st], kb * 64, m0);
 #pragma unroll
-        for (int j = 0; j < 7; ++j) tma_load_2d(sb + j * 8192, &tmWq1, &full[st], j * 64, kb * 64);
+          for (int j = 0; j < 7; ++j) tma_load_2d(sb + j * 8192, &tmWq1, &full[st], j * 64, kb * 64);
+        }
+        __syncwarp();
       }
       mbar_wait(bar_acc1, 0);            // GEMM 1 has read the whole ring: it now receives this CTA's third of W_p0
-      mbar_expect_tx(bar_w2, KB_L * 4 * 8192);
-      for (int kb = 0; kb < KB_L; ++kb)
+      if (elect_one()) {
+        mbar_expect_tx(bar_w2, KB_L * 4 * 8192);
+        for (int kb = 0; kb < KB_L; ++kb)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) tma_load_2d(ring + kb * 32768 + j * 8192, &tmWp0, bar_w2, n0 + j * 64, kb * 64);
+          for (int j = 0; j < 4; ++j) tma_load_2d(ring + kb * 32768 + j * 8192, &tmWp0, bar_w2, n0 + j * 64, kb * 64);
+      }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t ID_A = umma_idesc(GEMM_BM, 256, false, true), ID_B = umma_idesc(GEMM_BM, 144, false, true);
       constexpr uint32_t ID_2 = umma_idesc(GEMM_BM, NQ, false, true);
       for (int kb = 0; kb < KB_H; ++kb) {
@@ -168,24 +176,30 @@ mid_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_constan
         mbar_wait(&full[st], (kb >> 1) & 1);
         tc_fence_after();
         const uint32_t sa = smem_u32(ring + st * F_STAGE), sb = sa + F_A_BYTES;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t da = umma_desc_k(sa + k * 32);
-          umma_bf16(tmem_base, da, umma_desc_mn(sb + k * 2048, 8192), ID_A, (kb | k) ? 1u : 0u);                    // columns 0..255
-          umma_bf16(tmem_base + 256, da, umma_desc_mn(sb + 4 * 8192 + k * 2048, 8192), ID_B, (kb | k) ? 1u : 0u);   // columns 256..399
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = umma_desc_k(sa + k * 32);
+            umma_bf16(tmem_base, da, umma_desc_mn(sb + k * 2048, 8192), ID_A, (kb | k) ? 1u : 0u);                    // columns 0..255
+            umma_bf16(tmem_base + 256, da, umma_desc_mn(sb + 4 * 8192 + k * 2048, 8192), ID_B, (kb | k) ? 1u : 0u);   // columns 256..399
+          }
+          umma_commit(&empty[st]);
+          if (kb == KB_H - 1) umma_commit(bar_acc1);
         }
-        umma_commit(&empty[st]);
+        __syncwarp();
       }
-      umma_commit(bar_acc1);
       mbar_wait(bar_z, 0);               // z tile complete in shared memory, TMEM columns 0..399 drained
       mbar_wait(bar_w2, 0);
       tc_fence_after();
       const uint32_t zs = smem_u32(zt), ws = smem_u32(ring);
-      for (int ks = 0; ks < (L + 15) / 16; ++ks) {   // 13 k steps of 16 (columns >= 200 of the z tile are zero)
-        const int kb = ks >> 2, k = ks & 3;
-        umma_bf16(tmem_base, umma_desc_k(zs + kb * 16384 + k * 32), umma_desc_mn(ws + kb * 32768 + k * 2048, 8192), ID_2, ks ? 1u : 0u);
+      if (elect_one()) {
+        for (int ks = 0; ks < (L + 15) / 16; ++ks) {   // 13 k steps of 16 (columns >= 200 of the z tile are zero)
+          const int kb = ks >> 2, k = ks & 3;
+          umma_bf16(tmem_base, umma_desc_k(zs + kb * 16384 + k * 32), umma_desc_mn(ws + kb * 32768 + k * 2048, 8192), ID_2, ks ? 1u : 0u);
+        }
+        umma_commit(bar_acc2);
       }
-      umma_commit(bar_acc2);
+      __syncwarp();
     }
   } else {
     const int sub = warp & 3, half = (warp - 2) >> 2;
@@ -320,43 +334,47 @@ mid_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmD2, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       for (int kb = 0; kb < KB_ALL; ++kb) {
         const int st = kb & 1;
         if (kb >= 2) mbar_wait(&empty[st], ((kb >> 1) - 1) & 1);
-        uint8_t* sa = ring + st * B_STAGE;
-        uint8_t* sb = sa + B_A_BYTES;
-        if (kb < KB_H) {
-          mbar_expect_tx(&full[st], B_STAGE);
-          tma_load_2d(sa, &tmD2, &full[st], kb * 64, m0);
-          tma_load_2d(sb, &tmWp0, &full[st], kb * 64, 0);
-        } else {
-          mbar_expect_tx(&full[st], B_B_BYTES);
-          tma_load_2d(sb, &tmWq1, &full[st], (kb - KB_H) * 64, n0);
+        if (elect_one()) {
+          uint8_t* sa = ring + st * B_STAGE;
+          uint8_t* sb = sa + B_A_BYTES;
+          if (kb < KB_H) {
+            mbar_expect_tx(&full[st], B_STAGE);
+            tma_load_2d(sa, &tmD2, &full[st], kb * 64, m0);
+            tma_load_2d(sb, &tmWp0, &full[st], kb * 64, 0);
+          } else {
+            mbar_expect_tx(&full[st], B_B_BYTES);
+            tma_load_2d(sb, &tmWq1, &full[st], (kb - KB_H) * 64, n0);
+          }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t ID = umma_idesc(GEMM_BM, NQ, false, false);
       const uint32_t ds = smem_u32(dt);
       for (int kb = 0; kb < KB_ALL; ++kb) {
         const int st = kb & 1;
-        if (kb == KB_H) {
-          umma_commit(bar_acc1);
-          mbar_wait(bar_d, 0);          // dmulv tile complete in shared memory
-        }
+        if (kb == KB_H) mbar_wait(bar_d, 0);          // dmulv tile complete in shared memory
         mbar_wait(&full[st], (kb >> 1) & 1);
         tc_fence_after();
         const uint32_t sa = smem_u32(ring + st * B_STAGE), sb = sa + B_A_BYTES;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (kb < KB_H) umma_bf16(tmem_base, umma_desc_k(sa + k * 32), umma_desc_k(sb + k * 32), ID, (kb | k) ? 1u : 0u);
-          else umma_bf16(tmem_base + ACC2, umma_desc_k(ds + (kb - KB_H) * 16384 + k * 32), umma_desc_k(sb + k * 32), ID, ((kb - KB_H) | k) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            if (kb < KB_H) umma_bf16(tmem_base, umma_desc_k(sa + k * 32), umma_desc_k(sb + k * 32), ID, (kb | k) ? 1u : 0u);
+            else umma_bf16(tmem_base + ACC2, umma_desc_k(ds + (kb - KB_H) * 16384 + k * 32), umma_desc_k(sb + k * 32), ID, ((kb - KB_H) | k) ? 1u : 0u);
+          }
+          umma_commit(&empty[st]);
+          if (kb == KB_H - 1) umma_commit(bar_acc1);
+          if (kb == KB_ALL - 1) umma_commit(bar_acc2);
         }
-        umma_commit(&empty[st]);
+        __syncwarp();
       }
-      umma_commit(bar_acc2);
     }
   } else {
     const int sub = warp & 3, half = (warp - 2) >> 2;

@@ -198,7 +198,8 @@ class GanEngine(object):
         self.vae, self.disc = vae, disc
         self.I = vae.n_items
         self.ld = _pad(self.I, 8)
-        self.nblk = 4 * ((self.I + 255) // 256)  # softmax partials per row: (256-column block) x (chunk phase)
+        self.nblk = ops.dec_logits_nblk_max(self.I)  # softmax partials per row: at most (128-column tile) x (chunk phase); a launch
+        # writes ops.dec_logits_nblk(B, I) of them (tile width chosen per shape) and the row passes are told that count
         self.seed, self.lr, self.lam = int(seed), float(lr), float(lam)
         self.keep_vae, self.keep_d = float(keep_vae), float(keep_d)
         self.total_anneal_steps, self.anneal_cap = float(total_anneal_steps), float(anneal_cap)
@@ -211,9 +212,10 @@ class GanEngine(object):
         # (snapshots written by ltg_step_advance: each phase's kernels read their own word, so the G forward may run beside the D update)
         self.words = torch.zeros(8, dtype=torch.int32, device=self.device)
         self.w_a, self.w_d, self.w_g = self.words[4:5], self.words[5:6], self.words[6:7]
-        # per-step scalars: row 0 for phase A and the G update, row 1 for the D update (same reason)
-        self.scal_all = torch.zeros(2, ops.NSCAL, dtype=torch.float32, device=self.device)
-        self.scal, self.scal_d = self.scal_all[0], self.scal_all[1]
+        # per-step scalars: row 0 for the G update, row 1 for the D update (same reason), row 2 scratch for phase A (its forward
+        # accumulates a KL sum nobody reads: train.py:200 fetches generator_out only)
+        self.scal_all = torch.zeros(3, ops.NSCAL, dtype=torch.float32, device=self.device)
+        self.scal, self.scal_d, self.scal_a = self.scal_all[0], self.scal_all[1], self.scal_all[2]
         self._graphs = {}
         # Side streams: independent branches of a step (captured as parallel branches of the CUDA graph). Kernel nodes inherit the
         # priority of the stream they were captured on: the critical chain (capture stream) is highest, the G forward that runs beside
@@ -349,6 +351,7 @@ class GanEngine(object):
         """MultiVAE.forward_pass (MultiVAE.py:175-186) up to the logits and their softmax statistics."""
         v = self.vae
         wstep = self.w_g if is_training else self.w_a
+        scal = self.scal if is_training else self.scal_a
         own_rows = indptr is None and B is None      # the batch's own CSR rows: its precomputed chunk list applies
         B = bt["B"] if B is None else B
         indptr = data.indptr[bt["b0"]: bt["b0"] + B + 1] if indptr is None else indptr
@@ -363,13 +366,15 @@ class GanEngine(object):
         if self.fused_mid:
             ops.vae_mid_fwd(self.h1, v.view("W_q1", "b"), v.view("b_q1"), v.view("W_p0", "b"), v.view("b_p0"),
                             self.eps_inject if is_training else None, B, uid0, 1.0 if is_training else 0.0, self.seed, 0, wstep,
-                            self.mulv, self.z, self.zmu, self.h2, self.scal, tc=self.mid_tc)
+                            self.mulv, self.z, self.zmu, self.h2, scal, tc=self.mid_tc)
         else:
             ops.gemm(self.h1, v.view("W_q1", "b"), B, 2 * L, H, b_mn=True, bn=64, out_f32=self.mulv, bias=v.view("b_q1"))
             ops.latent_fwd(self.mulv, self.eps_inject if is_training else None, B, uid0, 1.0 if is_training else 0.0, self.seed, 0,
-                           wstep, self.z, self.zmu, self.scal)
+                           wstep, self.z, self.zmu, scal)
             ops.gemm(self.z, v.view("W_p0", "b"), B, H, L, b_mn=True, bn=64, out_bf16=self.h2, bias=v.view("b_p0"), act=1)
-        ops.dec_logits_fwd(self.h2, v.WdT_b, v.view("b_p1"), B, self.I, self.logits if stash else None, self.partial)
+        # (phase A samples with Gumbel-top-k straight from the logits: the softmax statistics are computed by the G forward only)
+        ops.dec_logits_fwd(self.h2, v.WdT_b, v.view("b_p1"), B, self.I, self.logits if stash else None,
+                           self.partial if (is_training or not stash) else None)
         return indptr, indices
 
     def _disc_forward(self, pop, niche, label, P, backward, g_w4=None, g_b4=None):
@@ -399,11 +404,12 @@ class GanEngine(object):
     # ------------------------------------------------------------------------------------------------------------
     # phase A: train.py:192-269
     # ------------------------------------------------------------------------------------------------------------
-    def phase_a(self, data, bi):
+    def phase_a(self, data, bi, advance=True):
         bt = data.batches[bi]
         B = bt["B"]
-        ops.step_advance(self.words, self.scal, 0, self.lr, anneal_cap=self.anneal_cap, total_anneal_steps=self.total_anneal_steps,
-                         zero=bt["cnt"], snap=self.w_a)   # the sampler's per-user counters are cleared by the same launch
+        if advance:
+            ops.step_advance(self.words, self.scal_a, 0, self.lr, anneal_cap=self.anneal_cap, total_anneal_steps=self.total_anneal_steps,
+                             zero=bt["cnt"], snap=self.w_a)   # the sampler's per-user counters are cleared by the same launch
         # train.py:200: sess.run(generator_out) with default placeholders: dropout 0.75 (F4), is_training 0
         self._vae_forward(data, bt, False, self.keep_vae)
         if bt["K"] > 0:
@@ -527,7 +533,7 @@ class GanEngine(object):
         indices = data.indices
         lam = self.lam if (K > 0 or self.world_size > 1) else 0.0
         samp = (bt["samp_ptr"], bt["pair_niche"][Pr:], bt["label"][Pr:]) if K > 0 else (None, None, None)
-        ops.dec_row_bwd(self.partial, self.nblk, self.logits, B, self.I, Bg, lam, indptr, indices, None, samp[0], samp[1], samp[2],
+        ops.dec_row_bwd(self.partial, ops.dec_logits_nblk(B, self.I), self.logits, B, self.I, Bg, lam, indptr, indices, None, samp[0], samp[1], samp[2],
                         self.lse, self.scal, self.dl)
         # decoder backward: dh2 = dl W_p1^T (split-K over the catalog), dW_p1^T = dl^T [h2 | 1].
         # Branch s1: decoder weight gradient (+ its Adam sweep when the update is fused into this graph, single GPU) -- HBM-bound,
@@ -793,10 +799,14 @@ class GanEngine(object):
                 self.d_step(data, bi); self.g_step(data, bi)
             return
         bt = data.batches[bi]
-        self.phase_a(data, bi)
-        self._d_advance()          # the counters advance in the reference's order (D's Adam step, then G's) ...
+        # the three advances of the step in one launch: the counters move in the reference's order (phase A, D's Adam step, G's)
+        # before any of the step's kernels start
+        d = self.disc
+        ops.step_advance3(self.words, self.scal_a, self.scal_d, self.scal, self.lr, bt["cnt"], self.arena_gp[0][d._off["w4"][0]:],
+                          self.vae.small_g, self.w_a, self.w_d, self.w_g, anneal_cap=self.anneal_cap,
+                          total_anneal_steps=self.total_anneal_steps)
+        self.phase_a(data, bi, advance=False)
         self._fuse_update = not dp
-        self._g_advance()          # ... before either update's kernels start
         self._g_early(data, bi)
         with self._fork(self.s3):
             self._vae_forward(data, bt, True, self.keep_vae)
@@ -892,7 +902,7 @@ class GanEngine(object):
             self.Wq0_b_full, peer["Wq0_b"] = sym(self.Wq0_b_full); peer["Wq0_b_mc"] = mc[2]
             self.dh1_glob, peer["dh1"] = sym(self.dh1_glob); peer["dh1_mc"] = mc[3]
             self.scal_all, peer["scal"] = sym(self.scal_all)
-            self.scal, self.scal_d = self.scal_all[0], self.scal_all[1]
+            self.scal, self.scal_d, self.scal_a = self.scal_all[0], self.scal_all[1], self.scal_all[2]
             self.disc.arena_g, peer["arena_g"] = sym(self.disc.arena_g); peer["arena_g_mc"] = mc[5]
             self.vae.small_g, peer["small_g"] = sym(self.vae.small_g); peer["small_g_mc"] = mc[6]
             pads = torch.zeros(ops.PEER_SLOTS * 8, dtype=torch.int32, device=self.device)
@@ -1043,7 +1053,7 @@ class Session(object):
             ops.latent_fwd(e.mulv, None, B, b0, is_training, e.seed, 0, e.words, e.z, e.zmu, e.scal)
             ops.gemm(e.z, v.view("W_p0", "b"), B, H, L, b_mn=True, bn=64, out_bf16=e.h2, bias=v.view("b_p0"), act=1)
             ops.dec_logits_fwd(e.h2, v.WdT_b, v.view("b_p1"), B, e.I, e.logits, e.partial)
-            ops.dec_row_stats(e.partial, e.nblk, e.logits, B, ipb, idx, val, None, None, None, e.lse, e.xw, None, e.scal)
+            ops.dec_row_stats(e.partial, ops.dec_logits_nblk(B, e.I), e.logits, B, ipb, idx, val, None, None, None, e.lse, e.xw, None, e.scal)
             ops.dec_probs(e.logits, e.lse, B, e.I, out_dev)
             torch.cuda.synchronize()
             probs[b0: b0 + B] = out_dev[:B].cpu().numpy()

@@ -55,6 +55,18 @@ def step_advance(words, scal, kind, lr, beta1=0.9, beta2=0.999, anneal_cap=0.2, 
     check(lib().ltg_step_advance(ptr(words), ptr(scal), kind, lr, beta1, beta2, anneal_cap, total_anneal_steps, ptr(zero), zw, ptr(snap), _stream()))
 
 
+def step_advance3(words, scal_a, scal_d, scal_g, lr, zero_a, zero_d, zero_g, snap_a, snap_d, snap_g, beta1=0.9, beta2=0.999, anneal_cap=0.2,
+                  total_anneal_steps=20000.0):
+    """Phase A, D-update and G-update advances of one step in one launch (same state as three step_advance calls, kinds 0, 1, 2)."""
+    _count(1)
+    for z in (zero_a, zero_d, zero_g):
+        assert z is None or (z.is_contiguous() and z.element_size() == 4)
+    nw = lambda z: 0 if z is None else z.numel()  # noqa: E731
+    check(lib().ltg_step_advance3(ptr(words), ptr(scal_a), ptr(scal_d), ptr(scal_g), lr, beta1, beta2, anneal_cap, total_anneal_steps,
+                                  ptr(zero_a), nw(zero_a), ptr(zero_d), nw(zero_d), ptr(zero_g), nw(zero_g), ptr(snap_a), ptr(snap_d),
+                                  ptr(snap_g), _stream()))
+
+
 def pick_bn(M, N, splits_ok=False):
     """Tile width for the tcgen05 GEMM. Large-M problems take the widest tile that wastes the fewest padded columns (fewer
     tiles, A streamed once per n-block); problems with only a handful of 128-row blocks take 64-wide tiles so that the tile
@@ -191,6 +203,15 @@ def tanh_bwd(dy, y_bf16, B, N, dx_bf16=None, dx_f32=None, dbias=None, n_partials
                              ptr(dx_bf16),
                              dx_bf16.stride(0) if dx_bf16 is not None else 0, ptr(dx_f32),
                              dx_f32.stride(0) if dx_f32 is not None else 0, ptr(dbias), _stream()))
+
+
+def dec_logits_nblk(B, n_items):
+    """Rows of the (max, sumexp) partial buffer ltg_dec_logits_fwd writes for this shape (what the row passes must be told)."""
+    return int(lib().ltg_dec_logits_nblk(int(B), int(n_items)))
+
+
+def dec_logits_nblk_max(n_items):
+    return 4 * ((int(n_items) + 127) // 128)
 
 
 def dec_logits_fwd(h2, WdT_bf16, b_dec, B, n_items, logits, partial):

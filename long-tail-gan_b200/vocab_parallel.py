@@ -188,7 +188,7 @@ class CatalogShardedEngine(GanEngine):
             samp = (None, None, None)
         # local softmax statistics -> global (lse, sum x, sum of sampled probabilities) per user
         self.scal[ops.S_SUM_P].zero_()
-        ops.dec_row_stats(self.partial, self.nblk, self.logits, B, indptr, data.indices, None, samp[0], samp[1], samp[2], self.lse, self.xw,
+        ops.dec_row_stats(self.partial, ops.dec_logits_nblk(B, self.I), self.logits, B, indptr, data.indices, None, samp[0], samp[1], samp[2], self.lse, self.xw,
                           self.su if K > 0 else None, self.scal)
         st = self.stats[:B]
         st[:, 0] = self.lse[:B]; st[:, 1] = self.xw[:B]; st[:, 2] = self.su[:B] if K > 0 else 0.0

@@ -232,7 +232,8 @@ def test_decoder_logits_stats_and_dlogits(ops):
     WdT = (torch.randn(I, 600, device="cuda") * 0.08).bfloat16()
     bd = torch.randn(I, device="cuda") * 0.1
     logits = torch.zeros(B, ld, device="cuda", dtype=torch.bfloat16)
-    nblk = 4 * ((I + 255) // 256)
+    nblk = ops.dec_logits_nblk(B, I)
+    assert 0 < nblk <= ops.dec_logits_nblk_max(I)
     partial = torch.zeros(nblk, B, 2, device="cuda")
     ops.dec_logits_fwd(h2, WdT, bd, B, I, logits, partial)
     ref = h2.float() @ WdT.float().t() + bd

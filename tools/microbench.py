@@ -33,7 +33,7 @@ def main():
     WdT = (torch.randn(I, H, device=dev) * 0.05).bfloat16()
     bd = torch.zeros(I, device=dev)
     logits = torch.zeros(B, ld, device=dev, dtype=torch.bfloat16)
-    nblk = 4 * ((I + 255) // 256)
+    nblk = ops.dec_logits_nblk(B, I)
     partial = torch.zeros(nblk, B, 2, device=dev)
     t = timeit(lambda: ops.dec_logits_fwd(h2, WdT, bd, B, I, logits, partial))
     fl = 2.0 * B * H * I
