@@ -13,7 +13,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 _ROOT = os.path.dirname(_HERE)
 _INCLUDE = os.path.join(_ROOT, "include")
-LIB_PATH = os.path.join(_HERE, "libltgan.so")
+# experiments: LTG_LIB_SUFFIX=_x LTG_NVCC_EXTRA="-DFOO=1" builds and loads libltgan_x.so beside the product library
+_SUFFIX = os.environ.get("LTG_LIB_SUFFIX", "")
+LIB_PATH = os.path.join(_HERE, "libltgan%s.so" % _SUFFIX)
 
 SOURCES = ["runtime.cu", "gemm_ops.cu", "vae_kernels.cu", "adam_kernels.cu", "sampler_kernels.cu", "disc_kernels.cu",
            "topk_kernels.cu", "mid_kernels.cu", "mid_tc.cu", "disc_fused.cu", "peer_kernels.cu"]
@@ -46,7 +48,7 @@ def build(force=False, verbose=False):
     if not force and fresh():
         return LIB_PATH
     import fcntl
-    objdir = os.path.join(_HERE, "build")
+    objdir = os.path.join(_HERE, "build" + _SUFFIX)
     os.makedirs(objdir, exist_ok=True)
     with open(os.path.join(objdir, ".lock"), "w") as lock:
         fcntl.flock(lock, fcntl.LOCK_EX)
@@ -66,7 +68,7 @@ def _build_locked(srcs, objdir, force, verbose):
         hdr_deps = [os.path.join(_CSRC, h) for h in HEADERS] + [os.path.join(_INCLUDE, "ltgan.h")]
         if not force and os.path.exists(obj) and os.path.getmtime(obj) >= _newest([src] + hdr_deps):
             return obj
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("LTG_NVCC_EXTRA", "").split() + ["-c", src, "-o", obj]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -29,6 +29,8 @@ __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g, int n_partials,
             int64_t partial_stride, __nv_bfloat16* __restrict__ shadow, int64_t n, float lr_t, const float* __restrict__ scal, float b1,
             float b2, float eps) {
+  pdl_trigger();
+  pdl_wait_cta();
   if (lr_t < 0.f) lr_t = scal[LTG_S_LR_T];
   const int64_t n4 = n >> 2;
   const int64_t base = (int64_t)blockIdx.x * (256 * ADAM_UN) + threadIdx.x;
@@ -141,6 +143,8 @@ __global__ void __launch_bounds__(256)
 enc_adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, __nv_bfloat16* __restrict__ shadow, int n_items,
                 const int32_t* __restrict__ slot_of_item, const float* __restrict__ G, float lr_t, const float* __restrict__ scal,
                 float b1, float b2, float eps, int rows) {
+  pdl_trigger();
+  pdl_wait_cta();
   if (lr_t < 0.f) lr_t = scal[LTG_S_LR_T];
   const int64_t n4 = (int64_t)n_items * H4;
   const int64_t base = (int64_t)blockIdx.x * (256 * ADAM_UN) + threadIdx.x;   // one fixed chunk per CTA (see adam_kernel)
@@ -196,6 +200,8 @@ enc_wgrad_expand_kernel(float* __restrict__ dW, int n_items, const int32_t* __re
 __global__ void __launch_bounds__(256)
 enc_xc_clear_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, int B, const int32_t* __restrict__ slot_of_item,
                     __nv_bfloat16* __restrict__ xc, int ld_xc) {
+  pdl_trigger();
+  pdl_wait_cta();
   const int e0 = indptr[0];
   const int n = indptr[B] - e0;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
@@ -243,7 +249,7 @@ extern "C" int ltg_adam(float* p, float* m, float* v, const float* g, int n_part
                 reinterpret_cast<uintptr_t>(g)) & 15) == 0);
   LTG_REQUIRE((reinterpret_cast<uintptr_t>(shadow_bf16) & 7) == 0);
   if (n <= 0) return LTG_OK;
-  adam_kernel<<<grid_for(((n >> 2) + ADAM_UN - 1) / ADAM_UN, 256, 1 << 30), 256, n > (1 << 20) ? adam_throttle_smem() : 0, (cudaStream_t)stream>>>(
+  ltg_launch(adam_kernel, dim3(grid_for(((n >> 2) + ADAM_UN - 1) / ADAM_UN, 256, 1 << 30)), dim3(256), n > (1 << 20) ? adam_throttle_smem() : 0, (cudaStream_t)stream, 
       p, m, v, g, n_partials, partial_stride, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n, lr_t, scal, beta1, beta2, eps);
   LTG_CHECK_LAUNCH();
   return LTG_OK;
@@ -265,7 +271,7 @@ extern "C" int ltg_enc_adam(float* p, float* m, float* v, void* shadow_bf16, int
   LTG_REQUIRE(lr_t >= 0.f || scal != nullptr);
   LTG_REQUIRE((reinterpret_cast<uintptr_t>(shadow_bf16) & 7) == 0);
   if (n_items <= 0) return LTG_OK;
-  enc_adam_kernel<<<grid_for(((int64_t)n_items * H4 + ADAM_UN - 1) / ADAM_UN, 256, 1 << 30), 256, adam_throttle_smem(), (cudaStream_t)stream>>>(
+  ltg_launch(enc_adam_kernel, dim3(grid_for(((int64_t)n_items * H4 + ADAM_UN - 1) / ADAM_UN, 256, 1 << 30)), dim3(256), adam_throttle_smem(), (cudaStream_t)stream, 
       p, m, v, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n_items, slot_of_item, G, lr_t, scal, beta1, beta2, eps, rows);
   LTG_CHECK_LAUNCH();
   return LTG_OK;
@@ -283,7 +289,7 @@ extern "C" int ltg_enc_xc_clear(const int32_t* indptr, const int32_t* indices, i
                                 int ld_xc, void* stream) {
   LTG_REQUIRE(indptr && indices && slot_of_item && xc_bf16);
   if (B <= 0 || nnz_hint <= 0) return LTG_OK;
-  enc_xc_clear_kernel<<<grid_for(nnz_hint, 256, kStreamBlocks), 256, 0, (cudaStream_t)stream>>>(
+  ltg_launch(enc_xc_clear_kernel, dim3(grid_for(nnz_hint, 256, kStreamBlocks)), dim3(256), 0, (cudaStream_t)stream, 
       indptr, indices, B, slot_of_item, reinterpret_cast<__nv_bfloat16*>(xc_bf16), ld_xc);
   LTG_CHECK_LAUNCH();
   return LTG_OK;

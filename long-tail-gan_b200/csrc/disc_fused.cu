@@ -119,6 +119,7 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmXp, const __grid_constan
   const bool bwd4 = bwd && p.dz12 != nullptr;   // MMA 4 / dz12 in this kernel
   const int n_tiles = (p.P + GEMM_BM - 1) / GEMM_BM;
 
+  pdl_trigger();   // (PDL, ltg_common.cuh) barrier init / TMEM allocation overlap the previous kernel's tail
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmXp); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmXn); tma_prefetch_desc(&tmW2); tma_prefetch_desc(&tmW3);
     if (bwd4) tma_prefetch_desc(&tmW3T); else tma_prefetch_desc(&tmHd);
@@ -130,6 +131,7 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmXp, const __grid_constan
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   for (int j = threadIdx.x; j < DF_MAXH3 + 4; j += GEMM_THREADS) s_dw4[j] = 0.f;   // s_dw4 and s_acc are contiguous
+  pdl_wait_cta();      // the head weights below are the first global data this kernel reads
   // The head weights are read by every epilogue thread for every chunk, twice per tile in the D update: from global memory that was one
   // L1/L2 round trip per chunk in front of the FMAs (ncu source view, round 2: the top long-scoreboard lines of the kernel)
   for (int j = threadIdx.x; j < DF_W4_PAD; j += GEMM_THREADS) s_w4[j] = j < p.ld3 ? __ldg(p.w4 + j) : 0.f;
@@ -604,7 +606,7 @@ extern "C" int ltg_disc_fwd_fused(const void* Xp_bf16, const void* Xn_bf16, int 
   }
   const int n_tiles = (P + GEMM_BM - 1) / GEMM_BM;
   const int grid = n_tiles < ltg_num_sms() ? n_tiles : ltg_num_sms();
-  disc_fused_kernel<<<grid, GEMM_THREADS, DF_SMEM, (cudaStream_t)stream>>>(tmXp, tmXn, tmW1, tmW2, tmW3, tmW3T, tmHd, p);
+  ltg_launch(disc_fused_kernel, dim3(grid), dim3(GEMM_THREADS), DF_SMEM, (cudaStream_t)stream, tmXp, tmXn, tmW1, tmW2, tmW3, tmW3T, tmHd, p);
   LTG_CHECK_LAUNCH();
   return LTG_OK;
 }

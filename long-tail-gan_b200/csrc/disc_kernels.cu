@@ -11,6 +11,8 @@ namespace {
 
 __global__ void disc_gather_kernel(const uint4* __restrict__ E, const int32_t* __restrict__ pop, const int32_t* __restrict__ niche, int P,
                                    uint4* __restrict__ Xp, uint4* __restrict__ Xn) {
+  pdl_trigger();
+  pdl_wait_cta();
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte vector each; 16 per row
   const int64_t row = t >> 4;
   const int v = (int)(t & 15);
@@ -140,7 +142,7 @@ extern "C" int ltg_disc_gather(const void* E_bf16, const int32_t* pop_ids, const
   LTG_REQUIRE(E_bf16 && pop_ids && niche_ids && Xp && Xn);
   if (P <= 0) return LTG_OK;
   const int64_t n = (int64_t)P * 16;
-  disc_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(E_bf16), pop_ids, niche_ids, P,
+  ltg_launch(disc_gather_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const uint4*>(E_bf16), pop_ids, niche_ids, P,
                                                                                      reinterpret_cast<uint4*>(Xp), reinterpret_cast<uint4*>(Xn));
   LTG_CHECK_LAUNCH();
   return LTG_OK;

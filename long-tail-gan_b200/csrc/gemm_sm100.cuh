@@ -233,6 +233,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  pdl_trigger();   // (PDL, ltg_common.cuh) the prologue below touches no global data: it overlaps the previous kernel's tail
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -246,6 +247,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if constexpr (CM > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait_cta();      // every prerequisite grid has completed and its writes are visible from here on
 
   // cluster tiles: (group of CM row blocks, n block, split); CTA `crank` of the cluster takes row block m_group*CM + crank
   const int m_groups = (shape.m_blocks + CM - 1) / CM;
@@ -794,14 +796,16 @@ int launch_gemm_cm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int 
   static int max_clusters = 0;  // per instantiation
   const size_t smem = gemm_smem_bytes<BN, Epi::kSmem>();
   cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CM; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = ltg_pdl_enabled() ? 2 : 1;
   if (max_clusters == 0) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { ltg_set_last_error(cudaGetErrorString(e), __FILE__, __LINE__); return LTG_ERR_CUDA; }

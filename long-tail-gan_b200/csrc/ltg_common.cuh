@@ -30,19 +30,37 @@
 void ltg_set_last_error(const char* msg, const char* file, int line);
 
 // ---------------------------------------------------------------------------------------------
-// Programmatic dependent launch (PDL). One GAN step is a chain of ~25 dependent kernels, most of them a few microseconds long, and
-// each pays its own launch gap and prologue (barrier init, TMEM allocation, cluster sync, descriptor prefetch) after the previous
-// kernel has drained. With LTG_PDL=1 (default) the kernels of the step are launched with the programmatic-stream-serialization
-// attribute (ltg_launch below; the edges survive CUDA-graph capture), every kernel
+// Programmatic dependent launch (PDL) -- OPTIONAL, off by default (LTG_PDL=1 turns it on). One GAN step is a chain of ~25 dependent
+// kernels, most of them a few microseconds long, and each pays its own launch gap and prologue (barrier init, TMEM allocation, cluster
+// sync, descriptor prefetch) after the previous kernel has drained. With LTG_PDL=1 the kernels of the step are launched with the
+// programmatic-stream-serialization attribute (ltg_launch below; the edges survive CUDA-graph capture), every kernel
 //   * calls pdl_trigger() first: its in-stream successor may be launched as soon as all of OUR blocks have started, and
-//   * calls pdl_wait() before its first global-memory access: it blocks until every prerequisite grid has completed and its
+//   * calls pdl_wait_cta() before its first global-memory access: it blocks until every prerequisite grid has completed and its
 //     writes are visible -- so data dependencies (and write-after-read hazards) are exactly those of an ordinary launch;
 // what overlaps is the successor's launch latency and prologue with this kernel's tail. Both instructions are no-ops for a kernel
 // launched without the attribute, so a kernel that contains them is safe under any launch.
+// MEASURED (round 2, B200, bench shape; all 58 GPU tests pass either way): early trigger 0.570 ms/step, implicit trigger at block exit
+// (-DLTG_PDL_EARLY=0) 0.509 ms, PDL off 0.504 ms. The step graph is not one chain: blocks of the critical chain that are launched
+// early sit on the SMs (a GEMM block holds 200 KB of shared memory while it waits) and keep the short-lived blocks of the HBM-bound
+// side branches (Adam sweeps, weight-gradient GEMMs) from being scheduled, which lengthens the G update by 60 us; without the early
+// trigger nothing is left to overlap. Hence off.
 // RULE: a kernel may be passed to ltg_launch ONLY if it executes pdl_wait() before touching global memory.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#ifndef LTG_PDL_EARLY
+#define LTG_PDL_EARLY 1   // 1: explicit trigger at the top of every kernel; 0: implicit trigger when a block exits
+#endif
+__device__ __forceinline__ void pdl_trigger() {
+#if LTG_PDL_EARLY
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// One thread waits for the prerequisite grids, the rest of the block parks at the barrier: a block that was launched early sits on its
+// SM until its inputs exist, and 18 warps polling the dependency stole issue slots from the kernel still running there.
+__device__ __forceinline__ void pdl_wait_cta() {
+  if (threadIdx.x == 0) pdl_wait();
+  __syncthreads();
+}
 
 bool ltg_pdl_enabled();   // runtime.cu: env LTG_PDL (default on)
 

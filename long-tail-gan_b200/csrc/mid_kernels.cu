@@ -155,6 +155,8 @@ vae_mid_fwd_a_kernel(const __nv_bfloat16* __restrict__ h1, int ld_h1, const __nv
                      const float* __restrict__ eps, int B, int64_t uid0, float is_training, uint64_t seed, uint32_t step,
                      const uint32_t* __restrict__ step_dev, float* __restrict__ mulv, __nv_bfloat16* __restrict__ z, int ld_z,
                      float* __restrict__ zmu, float* __restrict__ scal) {
+  pdl_trigger();
+  pdl_wait_cta();
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(smem_raw);          // [16][PA_H]  h1 tile
   __nv_bfloat16* sW = sA + MT * PA_H;
@@ -221,6 +223,8 @@ vae_mid_fwd_a_kernel(const __nv_bfloat16* __restrict__ h1, int ld_h1, const __nv
 __global__ void __launch_bounds__(MID_THREADS)
 vae_mid_fwd_b_kernel(const __nv_bfloat16* __restrict__ z, int ld_z, const __nv_bfloat16* __restrict__ Wp0, const float* __restrict__ bp0, int B,
                      __nv_bfloat16* __restrict__ h2, int ld_h2) {
+  pdl_trigger();
+  pdl_wait_cta();
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __nv_bfloat16* sZ = reinterpret_cast<__nv_bfloat16*>(smem_raw);          // [16][PA_L]
   __nv_bfloat16* sW = sZ + MT * PA_L;
@@ -257,6 +261,8 @@ __global__ void __launch_bounds__(MID_THREADS)
 vae_mid_bwd_a_kernel(const __nv_bfloat16* __restrict__ dh2pre, const __nv_bfloat16* __restrict__ Wp0, const float* __restrict__ mulv,
                      const float* __restrict__ zmu, int B, float inv_bg, float anneal, const float* __restrict__ scal,
                      __nv_bfloat16* __restrict__ dmulv, float* __restrict__ db_q1) {
+  pdl_trigger();
+  pdl_wait_cta();
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(smem_raw);          // [16][PA_H]   dh2pre tile
   __nv_bfloat16* sW = sA + MT * PA_H;
@@ -310,6 +316,8 @@ vae_mid_bwd_a_kernel(const __nv_bfloat16* __restrict__ dh2pre, const __nv_bfloat
 __global__ void __launch_bounds__(MID_THREADS)
 vae_mid_bwd_b_kernel(const __nv_bfloat16* __restrict__ dmulv, const __nv_bfloat16* __restrict__ Wq1, const __nv_bfloat16* __restrict__ h1,
                      int ld_h1, int B, float* __restrict__ dh1pre, __nv_bfloat16* __restrict__ dh1pre_b, float* __restrict__ db_q0) {
+  pdl_trigger();
+  pdl_wait_cta();
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __nv_bfloat16* sD = reinterpret_cast<__nv_bfloat16*>(smem_raw);          // [16][PA_2L]  dmulv tile
   __nv_bfloat16* sW = sD + MT * PA_2L;
@@ -366,11 +374,11 @@ extern "C" int ltg_vae_mid_fwd(const void* h1_bf16, int ld_h1, const void* Wq1_b
   rc = opt_in_smem(vae_mid_fwd_b_kernel, FWD_B_SMEM, &o2);
   if (rc) return rc;
   const dim3 grid((B + MT - 1) / MT, NG);
-  vae_mid_fwd_a_kernel<<<grid, MID_THREADS, FWD_A_SMEM, (cudaStream_t)stream>>>(
+  ltg_launch(vae_mid_fwd_a_kernel, dim3(grid), dim3(MID_THREADS), FWD_A_SMEM, (cudaStream_t)stream, 
       reinterpret_cast<const __nv_bfloat16*>(h1_bf16), ld_h1, reinterpret_cast<const __nv_bfloat16*>(Wq1_bf16), b_q1, eps, B, uid0, is_training,
       seed, step, step_dev, mulv, reinterpret_cast<__nv_bfloat16*>(z_bf16), ld_z, zmu, scal);
   LTG_CHECK_LAUNCH();
-  vae_mid_fwd_b_kernel<<<grid, MID_THREADS, FWD_B_SMEM, (cudaStream_t)stream>>>(
+  ltg_launch(vae_mid_fwd_b_kernel, dim3(grid), dim3(MID_THREADS), FWD_B_SMEM, (cudaStream_t)stream, 
       reinterpret_cast<const __nv_bfloat16*>(z_bf16), ld_z, reinterpret_cast<const __nv_bfloat16*>(Wp0_bf16), b_p0, B,
       reinterpret_cast<__nv_bfloat16*>(h2_bf16), ld_h2);
   LTG_CHECK_LAUNCH();
@@ -390,11 +398,11 @@ extern "C" int ltg_vae_mid_bwd(const void* dh2pre_bf16, const void* Wp0_bf16, co
   rc = opt_in_smem(vae_mid_bwd_b_kernel, BWD_B_SMEM, &o2);
   if (rc) return rc;
   const dim3 grid((B + MT - 1) / MT, NG);
-  vae_mid_bwd_a_kernel<<<grid, MID_THREADS, BWD_A_SMEM, (cudaStream_t)stream>>>(
+  ltg_launch(vae_mid_bwd_a_kernel, dim3(grid), dim3(MID_THREADS), BWD_A_SMEM, (cudaStream_t)stream, 
       reinterpret_cast<const __nv_bfloat16*>(dh2pre_bf16), reinterpret_cast<const __nv_bfloat16*>(Wp0_bf16), mulv, zmu, B,
       1.0f / (float)B_global, anneal, scal, reinterpret_cast<__nv_bfloat16*>(dmulv_bf16), db_q1);
   LTG_CHECK_LAUNCH();
-  vae_mid_bwd_b_kernel<<<grid, MID_THREADS, BWD_B_SMEM, (cudaStream_t)stream>>>(
+  ltg_launch(vae_mid_bwd_b_kernel, dim3(grid), dim3(MID_THREADS), BWD_B_SMEM, (cudaStream_t)stream, 
       reinterpret_cast<const __nv_bfloat16*>(dmulv_bf16), reinterpret_cast<const __nv_bfloat16*>(Wq1_bf16),
       reinterpret_cast<const __nv_bfloat16*>(h1_bf16), ld_h1, B, dh1pre, reinterpret_cast<__nv_bfloat16*>(dh1pre_bf16), db_q0);
   LTG_CHECK_LAUNCH();

@@ -15,7 +15,7 @@ bool ltg_pdl_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("LTG_PDL");
-    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
   }
   return v != 0;
 }
@@ -77,6 +77,8 @@ extern "C" int ltg_init(void) {
 __global__ void step_advance_kernel(uint32_t* words, float* scal, int kind, float lr, double beta1, double beta2,
                                     float anneal_cap, float total_anneal_steps, uint32_t* zero_buf, int64_t zero_words,
                                     uint32_t* step_snapshot) {
+  pdl_trigger();
+  pdl_wait_cta();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < zero_words; i += (int64_t)gridDim.x * blockDim.x) zero_buf[i] = 0u;
   if (blockIdx.x != 0) return;
   if (threadIdx.x < 8) scal[threadIdx.x] = 0.f;   // per-step accumulators (KL, NLL, sum p, sum y, cnt, d_loss)
@@ -107,6 +109,8 @@ __global__ void step_advance_kernel(uint32_t* words, float* scal, int kind, floa
 struct StepPhase { float* scal; uint32_t* zero_buf; int64_t zero_words; uint32_t* snapshot; };
 __global__ void step_advance3_kernel(uint32_t* words, StepPhase pa, StepPhase pd, StepPhase pg, float lr, double beta1, double beta2,
                                      float anneal_cap, float total_anneal_steps) {
+  pdl_trigger();
+  pdl_wait_cta();
   const StepPhase ph[3] = {pa, pd, pg};
 #pragma unroll
   for (int q = 0; q < 3; ++q)
@@ -151,7 +155,7 @@ extern "C" int ltg_step_advance3(uint32_t* words, float* scal_a, float* scal_d, 
   int64_t blocks = (mx + 1023) / 1024;
   if (blocks < 1) blocks = 1;
   if (blocks > 148) blocks = 148;
-  step_advance3_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(words, pa, pd, pg, lr, (double)beta1, (double)beta2, anneal_cap,
+  ltg_launch(step_advance3_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, words, pa, pd, pg, lr, (double)beta1, (double)beta2, anneal_cap,
                                                                            total_anneal_steps);
   LTG_CHECK_LAUNCH();
   return LTG_OK;
@@ -165,7 +169,7 @@ extern "C" int ltg_step_advance(uint32_t* words, float* scal, int kind, float lr
   int64_t blocks = (zero_words + 1023) / 1024;   // 256 threads x 4 words each
   if (blocks < 1) blocks = 1;
   if (blocks > 148) blocks = 148;
-  step_advance_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(words, scal, kind, lr, (double)beta1, (double)beta2, anneal_cap,
+  ltg_launch(step_advance_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, words, scal, kind, lr, (double)beta1, (double)beta2, anneal_cap,
                                                                           total_anneal_steps, reinterpret_cast<uint32_t*>(zero_buf), zero_words, step_snapshot);
   LTG_CHECK_LAUNCH();
   return LTG_OK;

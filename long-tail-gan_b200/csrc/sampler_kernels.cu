@@ -54,6 +54,8 @@ sample_pairs_kernel(const __nv_bfloat16* __restrict__ logits, int ld, int n_item
                     uint64_t seed, uint32_t step, const uint32_t* __restrict__ step_dev,
                     int32_t* __restrict__ samp_items, int32_t* __restrict__ samp_partner, int32_t* __restrict__ samp_valid,
                     int32_t* __restrict__ cnt_out, const int32_t* __restrict__ user_order, const float* __restrict__ cand_vals) {
+  pdl_trigger();
+  pdl_wait_cta();
   extern __shared__ uint32_t s_keys[];  // [max_cand]
   __shared__ uint32_t s_hist[256];
   __shared__ uint32_t s_sel[2];          // digit, remaining-k
@@ -209,7 +211,7 @@ extern "C" int ltg_sample_pairs_vals(const void* logits_bf16, int ld_logits, con
     if (e != cudaSuccess) { ltg_set_last_error(cudaGetErrorString(e), __FILE__, __LINE__); return LTG_ERR_CUDA; }
     smem_opted = smem;
   }
-  sample_pairs_kernel<<<B, SAMP_THREADS, smem, (cudaStream_t)stream>>>(
+  ltg_launch(sample_pairs_kernel, dim3(B), dim3(SAMP_THREADS), smem, (cudaStream_t)stream, 
       reinterpret_cast<const __nv_bfloat16*>(logits_bf16), ld_logits, n_items, uid0, cand_ptr, cand_items, samp_ptr, pop_ptr, pop_items,
       item_valid, seed, step, step_dev, samp_items, samp_partner, samp_valid, cnt, user_order, cand_vals);
   LTG_CHECK_LAUNCH();

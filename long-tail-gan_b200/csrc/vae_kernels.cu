@@ -52,6 +52,8 @@ enc_gather_fwd_kernel(const int32_t* __restrict__ indptr, const int32_t* __restr
                       int ld_h1, float* __restrict__ coef, float* __restrict__ pre_ws, int* __restrict__ counters,
                       const int32_t* __restrict__ slot_of_item, __nv_bfloat16* __restrict__ xc, int ld_xc,
                       const float* __restrict__ row_rnorm, int item_offset, const int32_t* __restrict__ work) {
+  pdl_trigger();
+  pdl_wait_cta();
   __shared__ int s_item[ENC_CHUNK];
   __shared__ float s_coef[ENC_CHUNK];
   __shared__ float s_red[ENC_THREADS / 32];
@@ -276,6 +278,8 @@ __global__ void latent_bwd_kernel(const float* __restrict__ dz, const float* __r
 __global__ void tanh_bwd_kernel(const float* __restrict__ dy, int ld_dy, int n_partials, int64_t partial_stride,
                                 const __nv_bfloat16* __restrict__ y, int ld_y, int B, int N,
                                 __nv_bfloat16* __restrict__ dxb, int ld_dxb, float* __restrict__ dxf, int ld_dxf, float* __restrict__ db) {
+  pdl_trigger();
+  pdl_wait_cta();
   constexpr int ROWS = 4;   // small row tile: this kernel sits on the critical path of the backward chain, parallelism first
   const int r0 = blockIdx.x * ROWS;
   const int r1 = min(B, r0 + ROWS);
@@ -310,6 +314,8 @@ constexpr int TB4_MAXP = 8;
 __global__ void __launch_bounds__(160)
 tanh_bwd4_kernel(const float* __restrict__ dy, int ld_dy, int n_partials, int64_t partial_stride, const __nv_bfloat16* __restrict__ y, int ld_y,
                  int B, int N, __nv_bfloat16* __restrict__ dxb, int ld_dxb, float* __restrict__ dxf, int ld_dxf, float* __restrict__ db) {
+  pdl_trigger();
+  pdl_wait_cta();
   const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
   if (c >= N) return;
   const int r0 = blockIdx.x * TB4_ROWS;
@@ -492,6 +498,8 @@ dec_row_bwd_kernel(const float2* __restrict__ partial, int n_blocks, const __nv_
                    const float* __restrict__ values, const int32_t* __restrict__ samp_ptr, const int32_t* __restrict__ samp_items,
                    const int32_t* __restrict__ samp_valid, float* __restrict__ lse_out, float* __restrict__ scal,
                    __nv_bfloat16* __restrict__ dl) {
+  pdl_trigger();
+  pdl_wait_cta();
   __shared__ float s_red[ROWBWD_THREADS / 32];
   const int u = blockIdx.x, tid = threadIdx.x;
   auto bsum = [&](float v) {
@@ -645,7 +653,7 @@ extern "C" int ltg_enc_gather_fwd(const int32_t* indptr, const int32_t* indices,
   if (B <= 0) return LTG_OK;
   const int chunks = max_row_nnz <= ENC_CHUNK ? 1 : (max_row_nnz + ENC_CHUNK - 1) / ENC_CHUNK;
   const dim3 grid = work != nullptr ? dim3(n_work) : dim3(B, chunks);
-  enc_gather_fwd_kernel<false><<<grid, ENC_THREADS, 0, (cudaStream_t)stream>>>(
+  ltg_launch(enc_gather_fwd_kernel<false>, dim3(grid), dim3(ENC_THREADS), 0, (cudaStream_t)stream, 
       indptr, indices, values, n_items, uid0, reinterpret_cast<const uint4*>(W_enc_bf16), b_q0, keep, seed, step, step_dev,
       reinterpret_cast<__nv_bfloat16*>(h1_bf16), ld_h1, coef, pre_ws, counters, slot_of_item, reinterpret_cast<__nv_bfloat16*>(xc_bf16), ld_xc,
       nullptr, 0, work);
@@ -661,7 +669,7 @@ extern "C" int ltg_enc_gather_partial(const int32_t* indptr, const int32_t* indi
   LTG_REQUIRE(xc_bf16 == nullptr || slot_of_item != nullptr);
   if (B <= 0) return LTG_OK;
   const int chunks = max_row_nnz <= ENC_CHUNK ? 1 : (max_row_nnz + ENC_CHUNK - 1) / ENC_CHUNK;
-  enc_gather_fwd_kernel<true><<<dim3(B, chunks), ENC_THREADS, 0, (cudaStream_t)stream>>>(
+  ltg_launch(enc_gather_fwd_kernel<true>, dim3(dim3(B, chunks)), dim3(ENC_THREADS), 0, (cudaStream_t)stream, 
       indptr, indices, nullptr, n_items_global, uid0, reinterpret_cast<const uint4*>(W_shard_bf16), nullptr, keep, seed, step, step_dev, nullptr, 0,
       coef, pre_sum, nullptr, slot_of_item, reinterpret_cast<__nv_bfloat16*>(xc_bf16), ld_xc, row_rnorm, item_offset, nullptr);
   LTG_CHECK_LAUNCH();
@@ -721,13 +729,13 @@ extern "C" int ltg_tanh_bwd(const float* dy, int ld_dy, int n_partials, int64_t 
                    (dx_f32 == nullptr || (ld_dxf % 4 == 0 && (reinterpret_cast<uintptr_t>(dx_f32) & 15) == 0));
   if (vec) {
     const int n4 = N / 4;
-    tanh_bwd4_kernel<<<dim3((B + TB4_ROWS - 1) / TB4_ROWS, (n4 + 159) / 160), 160, 0, (cudaStream_t)stream>>>(
+    ltg_launch(tanh_bwd4_kernel, dim3(dim3((B + TB4_ROWS - 1) / TB4_ROWS, (n4 + 159) / 160)), dim3(160), 0, (cudaStream_t)stream, 
         dy, ld_dy, n_partials, partial_stride, reinterpret_cast<const __nv_bfloat16*>(y_bf16), ld_y, B, N,
         reinterpret_cast<__nv_bfloat16*>(dx_bf16), ld_dxb, dx_f32, ld_dxf, dbias);
     LTG_CHECK_LAUNCH();
     return LTG_OK;
   }
-  tanh_bwd_kernel<<<dim3((B + 3) / 4, (N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+  ltg_launch(tanh_bwd_kernel, dim3(dim3((B + 3) / 4, (N + 127) / 128)), dim3(128), 0, (cudaStream_t)stream, 
       dy, ld_dy, n_partials, partial_stride, reinterpret_cast<const __nv_bfloat16*>(y_bf16), ld_y, B, N, reinterpret_cast<__nv_bfloat16*>(dx_bf16), ld_dxb, dx_f32,
       ld_dxf, dbias);
   LTG_CHECK_LAUNCH();
@@ -786,7 +794,7 @@ extern "C" int ltg_dec_row_bwd(const float* partial, int n_blocks, const void* l
   LTG_REQUIRE(partial && logits_bf16 && indptr && indices && lse && scal && dl_bf16);
   LTG_REQUIRE(ld % 8 == 0 && ld >= n_items);
   if (B <= 0) return LTG_OK;
-  dec_row_bwd_kernel<<<B, ROWBWD_THREADS, 0, (cudaStream_t)stream>>>(
+  ltg_launch(dec_row_bwd_kernel, dim3(B), dim3(ROWBWD_THREADS), 0, (cudaStream_t)stream, 
       reinterpret_cast<const float2*>(partial), n_blocks, reinterpret_cast<const __nv_bfloat16*>(logits_bf16), ld, B, n_items,
       1.0f / (float)B_global, lam, indptr, indices, values, samp_ptr, samp_items, samp_valid, lse, scal, reinterpret_cast<__nv_bfloat16*>(dl_bf16));
   LTG_CHECK_LAUNCH();
