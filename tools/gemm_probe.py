@@ -41,6 +41,17 @@ def main():
         t2 = graph_time(lambda: ops.gemm(A, B, M, N, K, bn=bn, out_bf16=out, act=1, keep=0.7, seed=1, rng_stream=3, rng_ld=out.stride(0)))
         print("M=%6d N=%6d K=%5d bn=%3d : plain %7.2f us   tanh+dropout %7.2f us   (%.0f GFLOP -> %.0f TFLOP/s)" %
               (M, N, K, bn, t, t2, 2e-9 * M * N * K, 2e-6 * M * N * K / t))
+    # decoder-forward shape: time against the catalog size at fixed batch 500 (fixed cost vs cost per column tile)
+    for bn in (128, 192, 256):
+        row = []
+        for N in (bn, 148 * bn // 4, 148 * bn // 2, 148 * bn, 2 * 148 * bn):   # 1 tile, quarter / half / one / two tiles per SM column-wise
+            M, K = 500, 600
+            A = torch.randn(M, 608, device=dev).bfloat16()
+            B = torch.randn(N, 600, device=dev).bfloat16()
+            out = torch.zeros(M, (N + 7) // 8 * 8, device=dev, dtype=torch.bfloat16)
+            t = graph_time(lambda: ops.gemm(A, B, M, N, K, bn=bn, out_bf16=out))
+            row.append("N=%6d %6.2f us" % (N, t))
+        print("M=500 K=600 bn=%3d : " % bn + "   ".join(row))
     # empty kernel launch floor inside a graph
     x = torch.zeros(1024, device=dev)
     t = graph_time(lambda: x.add_(1.0))
