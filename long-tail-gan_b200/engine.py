@@ -248,7 +248,10 @@ class GanEngine(object):
         # 98 us for forward + dz12 fused vs 65 + 36 us as two kernels, step 0.519 vs 0.513 ms -- the tile is bound by its epilogue warps
         # (tools/disc_trace.py: 30 of 40 us per tile are tanh/dropout/head/dact epilogues at IPC ~1.2), not by the GEMM it absorbs: off.
         self.fused_dz12 = os.environ.get("LTG_FUSED_DZ12", "0") != "0"
-        self.fused_mid = True   # fused 600->400->200->600 middle instead of two GEMMs + element-wise launches ...
+        self.is_dae = bool(getattr(vae, "is_dae", False))   # MultiDAE (MultiVAE.py:11-92): tanh middle, no KL, unfused GEMM chain
+        if self.is_dae:
+            assert self.world_size == 1, "MultiDAE runs on the single-GPU engine"
+        self.fused_mid = not self.is_dae   # fused 600->400->200->600 middle instead of two GEMMs + element-wise launches ...
         # ... on tcgen05 (mid_tc.cu: one CTA per 128 rows x column third) for large batches, where streaming the weights once per 128
         # rows pays; at batch 500 the 12 CTAs of that kernel are a serial L2-latency chain (38 us vs 16 us measured) and the mma.sync
         # kernels (mid_kernels.cu, 160 CTAs) win. LTG_MID_TC=0/1 forces either.
@@ -320,6 +323,7 @@ class GanEngine(object):
         self.dgrad_splits = ops.actual_splits(I, ops.pick_splits(B, H, I, 128))
         self.dh2_part = torch.zeros(self.dgrad_splits, B, H, **f32)
         self.dz = torch.zeros(B, L, **f32)
+        self.dzpre = torch.zeros(B, L, **bf)     # MultiDAE: gradient at the pre-activation of the 200-wide layer
         self.dh1 = torch.zeros(B, H, **f32)
         # split-K partials of the three discriminator weight-gradient GEMMs (summed by the Adam kernel)
         self.d_splits_max = 32
@@ -368,14 +372,22 @@ class GanEngine(object):
                             self.eps_inject if is_training else None, B, uid0, 1.0 if is_training else 0.0, self.seed, 0, wstep,
                             self.mulv, self.z, self.zmu, self.h2, scal, tc=self.mid_tc)
         else:
-            ops.gemm(self.h1, v.view("W_q1", "b"), B, 2 * L, H, b_mn=True, bn=64, out_f32=self.mulv, bias=v.view("b_q1"))
-            ops.latent_fwd(self.mulv, self.eps_inject if is_training else None, B, uid0, 1.0 if is_training else 0.0, self.seed, 0,
-                           wstep, self.z, self.zmu, scal)
-            ops.gemm(self.z, v.view("W_p0", "b"), B, H, L, b_mn=True, bn=64, out_bf16=self.h2, bias=v.view("b_p0"), act=1)
+            self._middle_unfused(B, uid0, 1.0 if is_training else 0.0, wstep, scal, self.eps_inject if is_training else None)
         # (phase A samples with Gumbel-top-k straight from the logits: the softmax statistics are computed by the G forward only)
         ops.dec_logits_fwd(self.h2, v.WdT_b, v.view("b_p1"), B, self.I, self.logits if stash else None,
                            self.partial if (is_training or not stash) else None)
         return indptr, indices
+
+    def _middle_unfused(self, B, uid0, is_training, wstep, scal, eps=None):
+        """h1 -> z -> h2 as GEMMs with fused epilogues. MultiVAE (MultiVAE.py:157-181): mu|logvar GEMM, latent head (KL,
+        reparameterisation), tanh GEMM. MultiDAE (MultiVAE.py:62-68): two tanh GEMMs."""
+        v = self.vae
+        if self.is_dae:
+            ops.gemm(self.h1, v.view("W_q1", "b"), B, L, H, b_mn=True, bn=64, out_bf16=self.z, bias=v.view("b_q1"), act=1)
+        else:
+            ops.gemm(self.h1, v.view("W_q1", "b"), B, 2 * L, H, b_mn=True, bn=64, out_f32=self.mulv, bias=v.view("b_q1"))
+            ops.latent_fwd(self.mulv, eps, B, uid0, is_training, self.seed, 0, wstep, self.z, self.zmu, scal)
+        ops.gemm(self.z, v.view("W_p0", "b"), B, H, L, b_mn=True, bn=64, out_bf16=self.h2, bias=v.view("b_p0"), act=1)
 
     def _disc_forward(self, pop, niche, label, P, backward, g_w4=None, g_b4=None):
         """discriminator.py:16-55 on P pairs (real and generated share the weights, so they run as one batch)."""
@@ -649,11 +661,16 @@ class GanEngine(object):
             with self._fork(self.s2):
                 ops.gemm(self.z, self.dh2pre, L, H, B, a_mn=True, b_mn=True, bn=64, out_f32=v.view("W_p0", "g"))
             ops.gemm(self.dh2pre, v.view("W_p0", "b"), B, L, H, bn=64, out_f32=self.dz)
-            ops.latent_bwd(self.dz, self.mulv, self.zmu, B, Bg, -1.0, self.scal, self.dmulv, v.view("b_q1", "g"))
+            if self.is_dae:   # through z = tanh(.) (MultiVAE.py:66-67); column sums -> db_1
+                ops.tanh_bwd(self.dz, self.z, B, L, dx_bf16=self.dzpre, dbias=v.view("b_q1", "g"))
+                dmid, q1 = self.dzpre, L
+            else:
+                ops.latent_bwd(self.dz, self.mulv, self.zmu, B, Bg, -1.0, self.scal, self.dmulv, v.view("b_q1", "g"))
+                dmid, q1 = self.dmulv, 2 * L
             self._join(self.s2)
             with self._fork(self.s2):
-                ops.gemm(self.h1, self.dmulv, H, 2 * L, B, a_mn=True, b_mn=True, bn=64, out_f32=v.view("W_q1", "g"))
-            ops.gemm(self.dmulv, v.view("W_q1", "b"), B, H, 2 * L, bn=64, out_f32=self.dh1)
+                ops.gemm(self.h1, dmid, H, q1, B, a_mn=True, b_mn=True, bn=64, out_f32=v.view("W_q1", "g"))
+            ops.gemm(dmid, v.view("W_q1", "b"), B, H, q1, bn=64, out_f32=self.dh1)
             ops.tanh_bwd(self.dh1, self.h1, B, H, dx_bf16=self.dh1pre_b, dx_f32=self.dh1pre, dbias=v.view("b_q0", "g"))
         # encoder weight gradient over the batch's active items as a tensor-core GEMM: G = Xc^T dh1pre   [n_active, 600]
         if not (self.world_size > 1 and getattr(self, "_dp_comm", False) and self.dp_tables is not None):
@@ -907,10 +924,20 @@ class GanEngine(object):
             self.vae.small_g, peer["small_g"] = sym(self.vae.small_g); peer["small_g_mc"] = mc[6]
             pads = torch.zeros(ops.PEER_SLOTS * 8, dtype=torch.int32, device=self.device)
             self._peer_pads, peer["pads"] = sym(pads)
+            failure = None
         except Exception as e:  # noqa: BLE001  -- no peer mapping on this system: NCCL collectives do the same exchange
-            if self.rank == 0:
-                import sys
-                print("long-tail-gan_b200: peer-memory exchange unavailable (%s); using NCCL collectives" % (e,), file=sys.stderr)
+            failure = e
+        # every rank must take the same path: the peer kernels spin on flags that only the peer path writes. A rank that failed says so
+        # itself (not only rank 0), and one failure anywhere sends all ranks to the NCCL collectives.
+        import sys
+        all_ok = torch.tensor([0 if failure is not None else 1], dtype=torch.int32, device=self.device)
+        dist.all_reduce(all_ok, op=dist.ReduceOp.MIN)
+        if failure is not None:
+            print("long-tail-gan_b200 [rank %d]: peer-memory exchange unavailable (%s); using NCCL collectives" % (self.rank, failure),
+                  file=sys.stderr)
+        if int(all_ok.item()) == 0:
+            if failure is None and self.rank == 0:
+                print("long-tail-gan_b200: another rank has no peer mapping; all ranks use NCCL collectives", file=sys.stderr)
             return
         I = self.I
         self.vae.WdT_b = self.WdT_b_full[:I]
@@ -1002,9 +1029,7 @@ class GanEngine(object):
             ip = trp[b0: b0 + B + 1]
             ops.enc_gather_fwd(ip, tri, None, B, self.I, uid_start + b0, v.W_q0_b, v.view("b_q0"), keep, self.seed, 0, self.words,
                                self.h1, coef, max_eval_nnz, self.enc_ws, self.enc_cnt)
-            ops.gemm(self.h1, v.view("W_q1", "b"), B, 2 * L, H, b_mn=True, bn=64, out_f32=self.mulv, bias=v.view("b_q1"))
-            ops.latent_fwd(self.mulv, None, B, uid_start + b0, 0.0, self.seed, 0, self.words, self.z, self.zmu, self.scal)
-            ops.gemm(self.z, v.view("W_p0", "b"), B, H, L, b_mn=True, bn=64, out_bf16=self.h2, bias=v.view("b_p0"), act=1)
+            self._middle_unfused(B, uid_start + b0, 0.0, self.words, self.scal)
             # fp32 logits: softmax is monotone per row, so ranking the logits equals ranking generator_out
             ops.gemm(self.h2, v.WdT_b, B, self.I, H, bn=256, out_f32=scores, bias=v.view("b_p1"))
             ops.topk_metrics(scores, B, self.I, ip, tri, tep[b0: b0 + B + 1], tei, k, recall_ks, None, dcg[b0:], hits[b0:])
@@ -1049,9 +1074,7 @@ class Session(object):
             ipb = ip[b0: b0 + B + 1]
             ops.enc_gather_fwd(ipb, idx, val, B, e.I, b0, v.W_q0_b, v.view("b_q0"), keep, e.seed, 0, e.words, e.h1, coef, max_nnz,
                                e.enc_ws, e.enc_cnt)
-            ops.gemm(e.h1, v.view("W_q1", "b"), B, 2 * L, H, b_mn=True, bn=64, out_f32=e.mulv, bias=v.view("b_q1"))
-            ops.latent_fwd(e.mulv, None, B, b0, is_training, e.seed, 0, e.words, e.z, e.zmu, e.scal)
-            ops.gemm(e.z, v.view("W_p0", "b"), B, H, L, b_mn=True, bn=64, out_bf16=e.h2, bias=v.view("b_p0"), act=1)
+            e._middle_unfused(B, b0, is_training, e.words, e.scal)
             ops.dec_logits_fwd(e.h2, v.WdT_b, v.view("b_p1"), B, e.I, e.logits, e.partial)
             ops.dec_row_stats(e.partial, ops.dec_logits_nblk(B, e.I), e.logits, B, ipb, idx, val, None, None, None, e.lse, e.xw, None, e.scal)
             ops.dec_probs(e.logits, e.lse, B, e.I, out_dev)

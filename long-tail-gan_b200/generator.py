@@ -48,6 +48,9 @@ def _pad4(n):
 
 
 class MultiVAE(object):
+    is_dae = False      # MultiDAE below: deterministic encoder (no mu/logvar split, no KL)
+    q1_out = 2 * L      # width of the second encoder layer: mu | logvar (MultiVAE.py:150,157-158)
+
     def __init__(self, p_dims, q_dims=None, lam=0.0, lr=1e-3, random_seed=None, device=None):
         # MultiVAE.py:12-31 (MultiDAE.__init__ / construct_placeholders) and 97-102
         assert len(p_dims) == 3 and p_dims[0] == L and p_dims[1] == H, "this build implements the VAE-CF 200-600-I generator"
@@ -75,7 +78,7 @@ class MultiVAE(object):
         self.WdT = torch.zeros(I, H, **f32); self.WdT_m = torch.zeros(I, H, **f32); self.WdT_v = torch.zeros(I, H, **f32)
         self.W_q0_b = torch.zeros(I, H, dtype=torch.bfloat16, device=dev)
         self.WdT_b = torch.zeros(I, H, dtype=torch.bfloat16, device=dev)
-        sizes = [("W_q1", H * 2 * L), ("W_p0", L * H), ("b_q0", H), ("b_q1", 2 * L), ("b_p0", H), ("b_p1", _pad4(I))]
+        sizes = [("W_q1", H * self.q1_out), ("W_p0", L * H), ("b_q0", H), ("b_q1", self.q1_out), ("b_p0", H), ("b_p1", _pad4(I))]
         self._small_off = {}
         off = 0
         for name, n in sizes:
@@ -94,7 +97,7 @@ class MultiVAE(object):
     # natural-shape views of the small parameters (fp32 master, gradient, bf16 shadow)
     def view(self, name, which="p"):
         arena = {"p": self.small, "m": self.small_m, "v": self.small_v, "g": self.small_g, "b": self.small_b}[which]
-        shapes = {"W_q1": (H, 2 * L), "W_p0": (L, H)}
+        shapes = {"W_q1": (H, self.q1_out), "W_p0": (L, H)}
         t = self._view(arena, name, shapes.get(name))
         if name == "b_p1":
             t = t[: self.n_items]
@@ -140,8 +143,8 @@ class MultiVAE(object):
             x = torch.randn(2 * n + 16, generator=g)
             return x[x.abs() <= 2.0][:n] * std
 
-        self.set_params([xavier(I, H), xavier(H, 2 * L), xavier(L, H), xavier(H, I), tn(H, 0.001), tn(2 * L, 0.001), tn(H, 0.001),
-                         tn(I, 0.001)])
+        self.set_params([xavier(I, H), xavier(H, self.q1_out), xavier(L, H), xavier(H, I), tn(H, 0.001), tn(self.q1_out, 0.001),
+                         tn(H, 0.001), tn(I, 0.001)])
         self.reset_optimizer()
 
     def build_graph(self):
@@ -161,7 +164,18 @@ class MultiVAE(object):
         self.refresh_shadows()
 
     def __repr__(self):
-        return "MultiVAE(p_dims=%s)" % (self.p_dims,)
+        return "%s(p_dims=%s)" % (type(self).__name__, self.p_dims)
+
+
+class MultiDAE(MultiVAE):
+    """The reference's other base recommender (Codes/Base_Recommender/MultiVAE.py:11-92): the same 4 dense layers without the
+    variational middle -- h = l2_normalize(x) -> dropout -> tanh(h W0 + b0) -> tanh(. W1 + b1) -> tanh(. W2 + b2) -> . W3 + b3
+    (MultiVAE.py:58-69: tanh on every layer but the last), loss = multinomial NLL (+ 2 * l2_regularizer(lam), MultiVAE.py:41-48).
+    Storage, parameter order [W0, W1, W2, W3, b0, b1, b2, b3] and the engine's kernels are the MultiVAE's; the second encoder layer is
+    200 wide instead of 400 and the latent head (mu/logvar, KL, reparameterisation) is replaced by a tanh epilogue. The L2 term is
+    accepted only as lam = 0.0 -- what a generator.py-style wrapper passes (generator.py:18 builds its model with lam=0.0)."""
+    is_dae = True
+    q1_out = L
 
 
 def count_items(pro_dir):
@@ -171,6 +185,16 @@ def count_items(pro_dir):
         for _ in f:
             n += 1
     return n
+
+
+def generator_DAECF(pro_dir):
+    """A generator.py-style wrapper (README.md:74-79 contract) around MultiDAE: (model, item probability distribution, loss, params,
+    p_dims, total_anneal_steps, anneal_cap); the last two are 0 (no KL term to anneal)."""
+    n_items = count_items(pro_dir)
+    p_dims = [200, 600, n_items]
+    dae = MultiDAE(p_dims, lam=0.0, random_seed=98765)
+    logits_var, loss_var, params = dae.build_graph()
+    return dae, logits_var, loss_var, params, p_dims, 0, 0.0
 
 
 def generator_VAECF(pro_dir):

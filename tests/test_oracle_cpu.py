@@ -166,3 +166,26 @@ def test_anneal_schedule():
     assert abs(orc.anneal_value(1000) - 0.05) < 1e-12
     assert orc.anneal_value(4000) == 0.2 and orc.anneal_value(10 ** 6) == 0.2
     assert orc.anneal_value(5, total_anneal_steps=0) == 0.2
+
+
+def test_dae_forward_matches_float64_numpy():
+    """oracle.dae_forward (MultiVAE.py:33-69: tanh on every layer but the last, NLL + lam * sum ||W||^2) against a float64 NumPy
+    re-derivation; with lam = 0 the loss equals the NLL."""
+    p = orc.init_dae_params(50, seed=3)
+    assert [tuple(t.shape) for t in p] == [(50, 600), (600, 200), (200, 600), (600, 50), (600,), (200,), (600,), (50,)]
+    X = (torch.rand(7, 50, generator=torch.Generator().manual_seed(1)) < 0.2).float()
+    X[:, 0] = 1
+    out = orc.dae_forward(p, X, None, 1.0, lam=0.01)
+    W = [t.double().numpy() for t in p]
+    x = X.double().numpy()
+    h = x / np.sqrt((x * x).sum(1, keepdims=True))
+    h = np.tanh(h @ W[0] + W[4]); h = np.tanh(h @ W[1] + W[5]); h = np.tanh(h @ W[2] + W[6])
+    lg = h @ W[3] + W[7]
+    mx = lg.max(1, keepdims=True)
+    ls = lg - mx - np.log(np.exp(lg - mx).sum(1, keepdims=True))
+    nll = -(ls * x).sum(1).mean()
+    reg = 0.01 * sum((w * w).sum() for w in W[:4])
+    assert abs(float(out["neg_ll"]) - nll) < 1e-4 * abs(nll) and abs(float(out["neg_ELBO"]) - (nll + reg)) < 1e-4 * (nll + reg)
+    out0 = orc.dae_forward(p, X, None, 1.0)
+    assert float(out0["neg_ELBO"]) == float(out0["neg_ll"]) and float(out0["KL"]) == 0.0
+    assert np.allclose(out0["probs"].sum(1).numpy(), 1.0, atol=1e-5)
