@@ -334,7 +334,8 @@ def run_x1m(args, rank, world, local_rank):
     tabs = syn.make_side_tables(indptr, indices, I, seed=7)
     data, vae, lo, hi = vp.build_shard(tabs, I, rank, world, BATCH)
     disc = dis.Discriminator(I, I, H0, H1, H2, H3, seed=4242)
-    engine = vp.CatalogShardedEngine(vae, disc, data.max_B, data.max_P, I, lo, rank, world, seed=2026, lr=LR, lam=LAM, max_active=data.max_active)
+    engine = vp.CatalogShardedEngine(vae, disc, data.max_B, data.max_P, I, lo, rank, world, seed=2026, lr=LR, lam=LAM, max_active=data.max_active,
+                                     use_graphs=not args.no_graphs)
     eng.pin_host_inputs(data)
 
     def barrier():
@@ -356,7 +357,7 @@ def run_x1m(args, rank, world, local_rank):
     while True:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
-        k0 = ops.kernel_launches
+        k0 = engine.kernels_launched
         e0.record()
         for i in range(args.steps):
             step(i)
@@ -366,7 +367,7 @@ def run_x1m(args, rank, world, local_rank):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         block_ms.append(float(t.item()))
-        launches = ops.kernel_launches - k0
+        launches = engine.kernels_launched - k0
         if sum(block_ms) >= MIN_TIMED_S * 1e3 or len(block_ms) >= MAX_REPEATS:
             break
     ms = sorted(block_ms)[len(block_ms) // 2]
@@ -402,6 +403,8 @@ def run_x1m(args, rank, world, local_rank):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item())
+    for i in range(nb):   # the timed steps ran one graph per batch; capture the per-phase graphs before timing them
+        engine.run_phase_a(data, i); engine.run_d_step(data, i); engine.run_g_step(data, i)
     t_a = timed(lambda i: engine.run_phase_a(data, i % nb), 8)
     t_d = timed(lambda i: engine.run_d_step(data, i % nb), 8)
     t_g = timed(lambda i: engine.run_g_step(data, i % nb), 8)
@@ -428,7 +431,7 @@ def run_x1m(args, rank, world, local_rank):
                             "GAN step = A + D + G" % (BENCH_CONFIGS[CONFIG]["label"], X1M_USERS, I, world, hi - lo, BATCH),
                    users=X1M_USERS, items=I, items_per_gpu=hi - lo, batch_per_gpu=BATCH, global_batch=BATCH, parallelism="vp%d" % world,
                    disc="h0..h3 = %d/%d/%d/%d" % (H0, H1, H2, H3), ganlambda=LAM,
-                   exchange="torch.distributed (NCCL) all-reduce of [B,600] activations x2, all-gather of per-row softmax statistics [B,4], "
+                   exchange=("inside the step's CUDA graph: " if not args.no_graphs else "") + "torch.distributed (NCCL) all-reduce of [B,600] activations x2, all-gather of per-row softmax statistics [B,4], "
                             "all-reduce of the candidate logits and of the 161 k discriminator gradients; no weight or weight-gradient traffic",
                    l2_policy="per-step working set (shard weights + Adam state, %.1f GB) exceeds the 126 MB L2; %d distinct batches" %
                              (30.0 * 1200 * (hi - lo) / 1e9, nb))
@@ -437,7 +440,7 @@ def run_x1m(args, rank, world, local_rank):
                     gpu_launches=launches, config=cfg, clocks=clocks,
                     e2e=dict(value=users / (ms_e2e * 1e-3), unit="users/s", h2d_bytes_per_step=h2d // args.steps, d2h_bytes_per_step=2 * ops.NSCAL * 4,
                              ms_per_step=ms_e2e / args.steps),
-                    phases_ms=dict(A=t_a, D=t_d, G=t_g), step_roofline=roof, graphs=False,
+                    phases_ms=dict(A=t_a, D=t_d, G=t_g), step_roofline=roof, graphs=not args.no_graphs,
                     roofline=dict(bound=roof["G"]["bound"], kernel="G update of the catalog shard (per GPU; SURVEY 8d model on the shard)",
                                   achieved=(roof["G"]["bytes"] / (t_g * 1e-3) / 1e9) if roof["G"]["bound"] == "hbm" else roof["G"]["flops"] / (t_g * 1e-3) / 1e12,
                                   peak=hb if roof["G"]["bound"] == "hbm" else tc, unit="GB/s" if roof["G"]["bound"] == "hbm" else "TFLOP/s",
@@ -656,15 +659,17 @@ def main():
         adam_bytes = 30.0 * n_par          # p,m,v read+write (24) + fp32 gradient read (4) + bf16 shadow write (2)
         enc_bytes = 26.0 * n_par           # same without a dense gradient read: the compact gradient rows are L2-resident
         traffic = None
-        try:  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full` capture
-            for rec in json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_adam_full.json"))):
-                if "adam_kernel" in rec["kernel"] and "enc_adam" not in rec["kernel"] and int(rec["grid"]) >= 1000:
-                    traffic = rec["dram_total_MB"] * 1e6
+        ncu_tab = []
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of one step
+            ncu_tab = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_step_table_v0.json")))   # (v0 holds the Adam sweeps too)
+            for rec in ncu_tab:
+                if "adam_kernel" in rec["kernel"] and "enc_adam" not in rec["kernel"] and rec.get("dram_MB", 0) > 100:
+                    traffic = rec["dram_MB"] * 1e6
         except Exception:
             traffic = None
         adam_roof = dict(bound="hbm", kernel="adam_kernel (fused TF-Adam + bf16 shadow over W_dec^T [I,600])",
                          achieved=adam_bytes / (t_adam * 1e-3) / 1e9, peak=peak, unit="GB/s", frac=adam_bytes / (t_adam * 1e-3) / 1e9 / peak,
-                         traffic=traffic, traffic_source="profiles/r1_ncu_adam_full.json (ncu --set full; writes still resident in L2 at kernel end are not counted)",
+                         traffic=traffic, traffic_source="profiles/r2_ncu_step_table_v0.json (ncu --set full; writes still resident in L2 at kernel end are not counted)",
                          peak_source=peak_src, algorithmic_bytes_per_launch=adam_bytes, ms_per_launch=t_adam, us_per_step=t_adam * 1e3,
                          how="CUDA events around 50 back-to-back launches on the launching stream after the timed region; each launch "
                              "touches 362 MB (> L2)")
@@ -688,18 +693,21 @@ def main():
             bytes_avg = 0.5 * (n_d * (by_pair + dsc.ld3 * 2) + n_g * by_pair)
             tr = None
             try:
-                tr = 0.5 * sum(float(x) for x in json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_disc_fused.json")))["dram_bytes_per_launch"])
+                df = [rec["dram_MB"] * 1e6 for rec in json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_step_table_v2.json")))
+                      if "disc_fused_kernel" in rec["kernel"]]
+                tr = sum(df) / len(df) if df else None
             except Exception:
                 tr = None
             roof = dict(bound="tensor", kernel="disc_fused_kernel (discriminator forward: 3 chained tcgen05 MMAs + tanh/dropout epilogues + head per 128 pairs)",
                         achieved=flops / (t_avg * 1e-3) / 1e12, peak=tpeak, unit="TFLOP/s", frac=flops / (t_avg * 1e-3) / 1e12 / tpeak,
-                        traffic=tr, traffic_source="profiles/r1_ncu_disc_fused.json (ncu --set full, mean of the D and the G launch)",
+                        traffic=tr, traffic_source="profiles/r2_ncu_step_table_v2.json (ncu --set full of one step, mean of the D and the G launch)",
                         peak_source=tsrc, algorithmic_flops_per_launch=flops, algorithmic_bytes_per_launch=bytes_avg,
                         ms_per_launch=t_avg, us_per_step=(t_df_d + t_df_g) * 1e3,
                         launches=dict(D=dict(pairs=n_d, ms=t_df_d), G=dict(pairs=n_g, ms=t_df_g)),
                         hbm_view=dict(achieved=bytes_avg / (t_avg * 1e-3) / 1e9, peak=peak, unit="GB/s", frac=bytes_avg / (t_avg * 1e-3) / 1e9 / peak),
-                        binding_limit="epilogue instruction issue (SFU tanh + integer hash dropout), not the tensor pipe or HBM: "
-                                      "profiles/r1_ncu_disc_fused.txt",
+                        binding_limit="its serial phases and the epilogue instruction stream (tanh + counter-hash dropout, 16 epilogue warps at IPC 1.3; "
+                                      "43% of stall samples are one role waiting for another), not the tensor pipe or HBM: "
+                                      "profiles/r2_ncu_step_table_v2.txt, profiles/r2_disc_fused_trace.txt",
                         how="CUDA events around 30 back-to-back launches of each of the step's two configurations on the launching stream",
                         others=[adam_roof, enc_roof])
             adam_roof.pop("others", None)

@@ -80,8 +80,9 @@ class CatalogShardedEngine(GanEngine):
 
     def __init__(self, vae, disc, max_B, max_P, n_items_global, item_lo, rank, world, group=None, **kw):
         kw.setdefault("use_graphs", False)
+        # use_graphs=True: phase A / D / G (or the whole step) of a batch are captured as CUDA graphs with their NCCL collectives inside
+        # (every rank captures and replays the same sequence); nothing in the step reads a device value back to the host
         super().__init__(vae, disc, max_B, max_P, world_size=1, rank=0, **kw)
-        assert not self.use_graphs, "the catalog-sharded step issues NCCL collectives between kernels and runs eagerly"
         self.vp_rank, self.vp_world, self.group = int(rank), int(world), group
         self.I_global, self.item_lo = int(n_items_global), int(item_lo)
         dev, B = self.device, self.max_B
@@ -193,7 +194,9 @@ class CatalogShardedEngine(GanEngine):
         st = self.stats[:B]
         st[:, 0] = self.lse[:B]; st[:, 1] = self.xw[:B]; st[:, 2] = self.su[:B] if K > 0 else 0.0
         if self.vp_world > 1:
-            sa = torch.empty(self.vp_world, B, 4, dtype=torch.float32, device=self.device)
+            sa = self.stats_all[:, :B]
+            if B != self.max_B:
+                sa = torch.empty(self.vp_world, B, 4, dtype=torch.float32, device=self.device)
             dist.all_gather_into_tensor(sa, st.contiguous(), group=self.group)
         else:
             sa = st[None]
@@ -236,16 +239,19 @@ class CatalogShardedEngine(GanEngine):
         ops.adam(v.small, v.small_m, v.small_v, v.small_g, v.small_b, scal=self.scal)
 
     def run_phase_a(self, data, bi):
-        self.phase_a(data, bi)
+        self._run(("vpa", id(data), bi), lambda: self.phase_a(data, bi))
 
     def run_d_step(self, data, bi):
-        self.d_step(data, bi)
+        self._run(("vpd", id(data), bi), lambda: self.d_step(data, bi))
 
     def run_g_step(self, data, bi):
-        self.g_step(data, bi)
+        self._run(("vpg", id(data), bi), lambda: self.g_step(data, bi))
+
+    def _step(self, data, bi):
+        self.phase_a(data, bi); self.d_step(data, bi); self.g_step(data, bi)
 
     def run_step(self, data, bi):
-        self.phase_a(data, bi); self.d_step(data, bi); self.g_step(data, bi)
+        self._run(("vpadg", id(data), bi), lambda: self._step(data, bi))
 
     def last_losses(self, B, B_global=None, reduce=False):
         """NLL is a sum over the shards (all-reduced here: a collective); KL, sum p, sum y, cnt, d_loss are already global/replicated."""

@@ -9,7 +9,7 @@ import torch
 H0, H1, H2, H3 = 100, 150, 250, 300
 
 
-def run_check(n_items, batch, rank, world, steps=2, seed=11, lr=1e-3, n_eval=96):
+def run_check(n_items, batch, rank, world, steps=2, seed=11, lr=1e-3, n_eval=96, use_graphs=False):
     import torch.distributed as dist
     pkg = __name__.rsplit(".", 1)[0]
     gen = importlib.import_module(pkg + ".generator"); dis = importlib.import_module(pkg + ".discriminator")
@@ -29,7 +29,8 @@ def run_check(n_items, batch, rank, world, steps=2, seed=11, lr=1e-3, n_eval=96)
     # ---- sharded run
     data, vae, lo, hi = vp.build_shard(tabs, I, rank, world, B, vae_params=params)
     disc = new_disc()
-    e = vp.CatalogShardedEngine(vae, disc, data.max_B, data.max_P, I, lo, rank, world, seed=seed, lr=lr, lam=1.0, keep_d=1.0, max_active=data.max_active)
+    e = vp.CatalogShardedEngine(vae, disc, data.max_B, data.max_P, I, lo, rank, world, seed=seed, lr=lr, lam=1.0, keep_d=1.0, max_active=data.max_active,
+                                use_graphs=use_graphs)
     for _ in range(steps):
         e.run_phase_a(data, 0); e.run_d_step(data, 0); e.run_g_step(data, 0)
     torch.cuda.synchronize()
@@ -53,7 +54,7 @@ def run_check(n_items, batch, rank, world, steps=2, seed=11, lr=1e-3, n_eval=96)
         dist.all_gather(outs, buf)
         return torch.cat(outs, 0)[:dim_len]
     WdT = gather(vae.WdT, I); Wq0 = gather(vae.W_q0, I)
-    out = dict(world=world, n_items=I, batch=B, steps=steps, losses_sharded={k: float(v) for k, v in L.items()})
+    out = dict(world=world, n_items=I, batch=B, steps=steps, graphs=bool(use_graphs), losses_sharded={k: float(v) for k, v in L.items()})
     if rank == 0:
         vae1 = gen.MultiVAE([200, 600, I], lam=0.0, random_seed=1); vae1.set_params(params); vae1.reset_optimizer()
         disc1 = new_disc()

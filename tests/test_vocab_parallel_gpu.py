@@ -26,9 +26,12 @@ def _check(res):
     assert res["eval_users"][0] == res["eval_users"][1] and abs(res["eval_ndcg"][0] - res["eval_ndcg"][1]) < 5e-3
 
 
-def test_one_shard_equals_single_gpu_engine():
+@pytest.mark.parametrize("graphs", [False, True])
+def test_one_shard_equals_single_gpu_engine(graphs):
     vpc = importlib.import_module("long-tail-gan_b200.vp_check")
-    _check(vpc.run_check(2400, 96, 0, 1))
+    res = vpc.run_check(2400, 96, 0, 1, use_graphs=graphs)
+    assert res["graphs"] == graphs
+    _check(res)
 
 
 def test_partial_gather_sums_to_full_encoder():
@@ -69,10 +72,13 @@ def test_partial_gather_sums_to_full_encoder():
 
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_two_shards_equal_single_gpu_engine(tmp_path):
+@pytest.mark.parametrize("graphs", [False, True])
+def test_two_shards_equal_single_gpu_engine(tmp_path, graphs):
+    """Two item shards on two GPUs against the single-GPU engine; with graphs=True the phases are CUDA graphs that hold the NCCL
+    collectives (first step eager + capture, second step a replay)."""
     out = str(tmp_path / "vp.json")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port",
-           "29621", os.path.join(ROOT, "tools", "vp_check.py"), out]
+           "29622" if graphs else "29621", os.path.join(ROOT, "tools", "vp_check.py"), out] + (["graphs"] if graphs else [])
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     res = json.load(open(out))

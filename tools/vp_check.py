@@ -20,8 +20,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     vpc = importlib.import_module("long-tail-gan_b200.vp_check")
     args = [a for a in sys.argv[1:] if not a.endswith(".json")]
+    graphs = "graphs" in args     # capture phase A / D / G (NCCL collectives inside) as CUDA graphs; the second step is a replay
+    args = [a for a in args if a != "graphs"]
     I = int(args[0]) if args else 2400
-    res = vpc.run_check(I, 96, rank, world)
+    res = vpc.run_check(I, 96, rank, world, use_graphs=graphs)
     if rank == 0:
         print(json.dumps(res, indent=1))
         for a in sys.argv[1:]:
