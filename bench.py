@@ -200,31 +200,48 @@ def step_roofline(n_items, batch, nnz_user, cand_user, pairs_real, pairs_gen, t_
     return out
 
 
+EVAL_USERS = {"ml20m": 10000, "netflix": 40000, "msd": 50000}   # held-out users per configuration
+
+
 def eval_throughput(engine, tabs, n_users=2000):
     """SURVEY 8d asks for evaluation users/s beside the training metric: fold-in forward (dropout on, F4) + exact top-100
-    NDCG@100 / Recall@20,50 (engine.evaluate = train.py:333-348 / test.py:138-173) on the first n_users synthetic users, 80/20
-    split of each user's items. Host CSR upload and metric read-back are inside the time."""
+    NDCG@100 / Recall@20,50 (engine.evaluate = train.py:333-348 / test.py:138-173). Synthetic configurations: SURVEY 8d's number
+    of held-out users (10 k / 40 k / 50 k) with an 80/20 fold-in / held-out split (synthetic.make_eval_split); the bundled real
+    dataset: its first n_users training users, every fifth item held out. Host CSR upload and metric read-back are inside the time."""
     import numpy as np
     import torch
-    indptr = np.asarray(tabs["indptr"], dtype=np.int64)
-    indices = np.asarray(tabs["indices"], dtype=np.int32)
-    n = int(min(n_users, len(indptr) - 1))
-    tr, te, trp, tep = [], [], [0], [0]
-    for u in range(n):
-        it = indices[indptr[u]: indptr[u + 1]]
-        held = np.zeros(len(it), dtype=bool)
-        held[4::5] = True
-        tr.append(it[~held]); te.append(it[held])
-        trp.append(trp[-1] + len(tr[-1])); tep.append(tep[-1] + len(te[-1]))
-    args = (np.asarray(trp, dtype=np.int64), np.concatenate(tr), np.asarray(tep, dtype=np.int64), np.concatenate(te))
-    engine.evaluate(*args)   # warm-up
+    if CONFIG in EVAL_USERS:
+        syn = importlib.import_module("long-tail-gan_b200.synthetic")
+        _, I, deg = syn.CONFIGS[CONFIG]
+        n = EVAL_USERS[CONFIG]
+        args = syn.make_eval_split(n, I, deg)
+        split = "80/20 random split of %d synthetic held-out users" % n
+    else:
+        indptr = np.asarray(tabs["indptr"], dtype=np.int64)
+        indices = np.asarray(tabs["indices"], dtype=np.int32)
+        n = int(min(n_users, len(indptr) - 1))
+        tr, te, trp, tep = [], [], [0], [0]
+        for u in range(n):
+            it = indices[indptr[u]: indptr[u + 1]]
+            held = np.zeros(len(it), dtype=bool)
+            held[4::5] = True
+            tr.append(it[~held]); te.append(it[held])
+            trp.append(trp[-1] + len(tr[-1])); tep.append(tep[-1] + len(te[-1]))
+        args = (np.asarray(trp, dtype=np.int64), np.concatenate(tr), np.asarray(tep, dtype=np.int64), np.concatenate(te))
+        split = "every fifth item of the first %d training users held out" % n
+    engine.evaluate(*args)   # warm-up (allocates the evaluation workspaces)
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    res = engine.evaluate(*args)
-    dt = time.perf_counter() - t0
+    dts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        res = engine.evaluate(*args)
+        dts.append(time.perf_counter() - t0)
+    dt = sorted(dts)[1]
     nd = res["ndcg@100"]
     return dict(users_per_sec=n / dt, users=n, ms=dt * 1e3, users_with_heldout=len(nd), ndcg_at_100_random_init=float(np.mean(nd)) if nd else None,
-                what="fold-in forward + exact top-100 NDCG@100 / Recall@20,50 per user; host CSR upload and metric read-back included")
+                split=split, batch=int(engine._eval_ws.rows), repeats_ms=[x * 1e3 for x in dts],
+                what="fold-in forward + exact top-100 NDCG@100 / Recall@20,50 per user; host CSR upload and metric read-back included; "
+                     "median of 3 calls")
 
 
 def cpu_baseline(tabs, n_steps, n_items):

@@ -88,6 +88,61 @@ adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
   }
 }
 
+// Adam whose gradient is the sum of split-K partials (the discriminator update: 161 k parameters, 16+ partials of the three
+// weight-gradient GEMMs), laid out so that EVERY load of the launch is issued in one round: a CTA owns 32 float4 and its eight
+// warps each fetch four partials of them (warp 0 also p, m, v and partial 0), fold them as (a+b)+(c+d) and hand the result over
+// through shared memory; warp 0 adds the eight sums in partial order and runs the update. adam_kernel's loop over rounds of four
+// partials waited for one full memory round trip per round -- on the critical chain of the step, beside HBM-saturating sweeps, that
+// was 29 us for 0.6 MB of parameters (timeline of round 2). Same operations in the same order as that loop: bit-identical result.
+constexpr int AP_WARPS = 8;
+constexpr int AP_MAX_PARTIALS = 1 + 4 * AP_WARPS;
+
+__global__ void __launch_bounds__(32 * AP_WARPS)
+adam_partials_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g, int n_partials,
+                     int64_t partial_stride, __nv_bfloat16* __restrict__ shadow, int64_t n, float lr_t, const float* __restrict__ scal,
+                     float b1, float b2, float eps) {
+  pdl_trigger();
+  pdl_wait_cta();
+  __shared__ float4 s_sum[AP_WARPS][32];
+  if (lr_t < 0.f) lr_t = scal[LTG_S_LR_T];
+  const int64_t n4 = n >> 2;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 32 + lane;
+  const bool ok = i < n4;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 pp = zero, mm = zero, vv = zero, gg = zero, o[4];
+  if (w == 0 && ok) { pp = ld_stream_f4(p + 4 * i); mm = ld_stream_f4(m + 4 * i); vv = ld_stream_f4(v + 4 * i); gg = ld_stream_f4(g + 4 * i); }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int sp = 1 + 4 * w + q;
+    o[q] = (ok && sp < n_partials) ? ld_stream_f4(g + (size_t)sp * partial_stride + 4 * i) : zero;
+  }
+  s_sum[w][lane] = make_float4((o[0].x + o[1].x) + (o[2].x + o[3].x), (o[0].y + o[1].y) + (o[2].y + o[3].y),
+                               (o[0].z + o[1].z) + (o[2].z + o[3].z), (o[0].w + o[1].w) + (o[2].w + o[3].w));
+  __syncthreads();
+  if (w == 0 && ok) {
+    for (int k = 0; 1 + 4 * k < n_partials; ++k) {
+      const float4 s = s_sum[k][lane];
+      gg.x += s.x; gg.y += s.y; gg.z += s.z; gg.w += s.w;
+    }
+    adam_update4(pp, mm, vv, gg, lr_t, b1, b2, eps);
+    *reinterpret_cast<float4*>(p + 4 * i) = pp; *reinterpret_cast<float4*>(m + 4 * i) = mm; *reinterpret_cast<float4*>(v + 4 * i) = vv;
+    if (shadow != nullptr) {
+      uint2 s; s.x = pack_bf16x2(pp.x, pp.y); s.y = pack_bf16x2(pp.z, pp.w);
+      *reinterpret_cast<uint2*>(shadow + 4 * i) = s;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {   // tail (n % 4)
+    const int64_t t = (n4 << 2) + threadIdx.x;
+    float gt = g[t];
+    for (int sp = 1; sp < n_partials; ++sp) gt += g[(size_t)sp * partial_stride + t];
+    float mt = m[t], vt = v[t], pt = p[t];
+    ltg_adam1(pt, mt, vt, gt, lr_t, b1, b2, eps);
+    m[t] = mt; v[t] = vt; p[t] = pt;
+    if (shadow != nullptr) shadow[t] = __float2bfloat16(pt);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Encoder weight W_q0 [I, 600]: its gradient X^T dh1pre is non-zero only on the items that occur in the batch
 // ("active" items, about a third of the catalog at B = 500). It is built compactly -- G[slot, :] for the active
@@ -249,6 +304,14 @@ extern "C" int ltg_adam(float* p, float* m, float* v, const float* g, int n_part
                 reinterpret_cast<uintptr_t>(g)) & 15) == 0);
   LTG_REQUIRE((reinterpret_cast<uintptr_t>(shadow_bf16) & 7) == 0);
   if (n <= 0) return LTG_OK;
+  static int one_round = -1;   // LTG_ADAM_ONE_ROUND=0: the loop over rounds of partials in adam_kernel (A/B switch)
+  if (one_round < 0) { const char* e = getenv("LTG_ADAM_ONE_ROUND"); one_round = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  if (one_round && n_partials > 1 && n_partials <= AP_MAX_PARTIALS) {
+    ltg_launch(adam_partials_kernel, dim3((unsigned)(((n >> 2) + 31) / 32 > 0 ? ((n >> 2) + 31) / 32 : 1)), dim3(32 * AP_WARPS), 0, (cudaStream_t)stream,
+        p, m, v, g, n_partials, partial_stride, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n, lr_t, scal, beta1, beta2, eps);
+    LTG_CHECK_LAUNCH();
+    return LTG_OK;
+  }
   ltg_launch(adam_kernel, dim3(grid_for(((n >> 2) + ADAM_UN - 1) / ADAM_UN, 256, 1 << 30)), dim3(256), n > (1 << 20) ? adam_throttle_smem() : 0, (cudaStream_t)stream, 
       p, m, v, g, n_partials, partial_stride, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n, lr_t, scal, beta1, beta2, eps);
   LTG_CHECK_LAUNCH();

@@ -177,6 +177,7 @@ topk_metrics_kernel(const void* __restrict__ scores, int64_t ld, int n_items,
 constexpr int TS_THREADS = 512;
 constexpr int TS_BINS = 2048;
 constexpr int TS_MAX_ITEMS = 49152;
+constexpr int TS_CAND = 2048;          // candidate list of the pre-filter (key << 32 | ~index)
 
 // block-wide: given per-thread `mine`, returns the sum over all threads with a HIGHER thread index (exclusive suffix sum)
 __device__ __forceinline__ uint32_t block_suffix_excl(uint32_t mine, uint32_t* s_warp) {
@@ -244,11 +245,15 @@ __global__ void __launch_bounds__(TS_THREADS)
 topk_staged_kernel(const void* __restrict__ scores, int64_t ld, int n_items,
                    const int32_t* __restrict__ seen_ptr, const int32_t* __restrict__ seen_items,
                    const int32_t* __restrict__ held_ptr, const int32_t* __restrict__ held_items,
-                   int k, int4 rk, int n_rk, int32_t* __restrict__ topk_idx, double* __restrict__ dcg, int32_t* __restrict__ hits) {
+                   int k, int4 rk, int n_rk, int32_t* __restrict__ topk_idx, double* __restrict__ dcg, int32_t* __restrict__ hits,
+                   bool use_prefilter) {
   extern __shared__ __align__(16) uint32_t s_keys[];   // [n_items rounded up to 8]
   __shared__ __align__(16) uint32_t s_hist[TS_BINS];
   __shared__ uint32_t s_warp[TS_THREADS / 32];
   __shared__ uint32_t s_sel[3];
+  __shared__ uint32_t s_lmax[TS_THREADS];
+  __shared__ unsigned long long s_cand[TS_CAND];
+  __shared__ int s_ncand;
   __shared__ unsigned long long s_win[TK_MAXK];
   __shared__ int s_nwin;
   __shared__ double s_dcg[TK_MAXK / 32];
@@ -257,7 +262,7 @@ topk_staged_kernel(const void* __restrict__ scores, int64_t ld, int n_items,
   const int u = blockIdx.x;
   const int tid = threadIdx.x;
   if (tid < TK_MAXK) s_win[tid] = 0ull;
-  if (tid == 0) s_nwin = 0;
+  if (tid == 0) { s_nwin = 0; s_ncand = 0; }
   if (tid < 4) s_hits[tid] = 0;
   // ---- the row, once, 16 bytes per load
   if (BF16) {
@@ -293,20 +298,48 @@ topk_staged_kernel(const void* __restrict__ scores, int64_t ld, int n_items,
   __syncthreads();
 
   const int kk = min(k, n_items);
+  // ---- candidate pre-filter. Every thread takes the maximum of its own (strided) elements: 512 DISTINCT elements of the row, so the
+  // kk-th largest of them is a lower bound of the row's kk-th largest key and only the elements >= that bound can be in the top kk
+  // (about 110 of 20 k for scores without structure). The exact selection below then runs over that short list instead of the row:
+  // the 3 histogram passes over all keys -- fp32 logits of one row share sign, exponent and leading mantissa bits, so their first
+  // digit lands in a handful of bins and the shared-memory atomics serialise -- shrink to one compare pass. Rows whose list overflows
+  // (massive ties, e.g. one score for the whole catalog) take the full-row path: same result either way.
+  if (use_prefilter) {
+    uint32_t lmax = 0u;   // (key 0 = a negative NaN: below every real score)
+    for (int i = tid; i < n_items; i += TS_THREADS) lmax = max(lmax, s_keys[i]);
+    s_lmax[tid] = lmax;
+    __syncthreads();
+    uint32_t c0 = 0, k0 = 0;
+    const uint32_t bound = radix_select11(TS_THREADS, (uint32_t)kk, [&](int i, uint32_t& v) { v = s_lmax[i]; return true; }, s_hist, s_warp,
+                                          s_sel, &c0, &k0);
+    for (int i = tid; i < n_items; i += TS_THREADS) {
+      const uint32_t key = s_keys[i];
+      if (key >= bound) {
+        const int slot = atomicAdd(&s_ncand, 1);
+        if (slot < TS_CAND) s_cand[slot] = ((unsigned long long)key << 32) | (unsigned long long)(~(uint32_t)i);
+      }
+    }
+    __syncthreads();
+  }
+  const bool use_cand = use_prefilter && s_ncand <= TS_CAND;   // uniform over the CTA
+  const int n_el = use_cand ? s_ncand : n_items;
+  auto key_of = [&](int i) -> uint32_t { return use_cand ? (uint32_t)(s_cand[i] >> 32) : s_keys[i]; };
+  auto inv_of = [&](int i) -> uint32_t { return use_cand ? (uint32_t)(s_cand[i] & 0xFFFFFFFFull) : ~(uint32_t)i; };
+
   uint32_t cnt_eq = 0, k_rem = 0;
-  const uint32_t T = radix_select11(n_items, (uint32_t)kk, [&](int i, uint32_t& v) { v = s_keys[i]; return true; }, s_hist, s_warp, s_sel,
+  const uint32_t T = radix_select11(n_el, (uint32_t)kk, [&](int i, uint32_t& v) { v = key_of(i); return true; }, s_hist, s_warp, s_sel,
                                     &cnt_eq, &k_rem);
   // ties at the threshold: keep the k_rem lowest indices among the cnt_eq elements equal to T
   uint32_t inv_thr = 0u;
   if (cnt_eq != k_rem) {
     uint32_t c2 = 0, k2 = 0;
-    inv_thr = radix_select11(n_items, k_rem, [&](int i, uint32_t& v) { v = ~(uint32_t)i; return s_keys[i] == T; }, s_hist, s_warp, s_sel, &c2, &k2);
+    inv_thr = radix_select11(n_el, k_rem, [&](int i, uint32_t& v) { v = inv_of(i); return key_of(i) == T; }, s_hist, s_warp, s_sel, &c2, &k2);
   }
-  for (int i = tid; i < n_items; i += TS_THREADS) {
-    const uint32_t key = s_keys[i];
-    if (key > T || (key == T && ~(uint32_t)i >= inv_thr)) {
+  for (int i = tid; i < n_el; i += TS_THREADS) {
+    const uint32_t key = key_of(i), inv = inv_of(i);
+    if (key > T || (key == T && inv >= inv_thr)) {
       const int slot = atomicAdd(&s_nwin, 1);
-      if (slot < TK_MAXK) s_win[slot] = ((unsigned long long)key << 32) | (unsigned long long)(~(uint32_t)i);
+      if (slot < TK_MAXK) s_win[slot] = ((unsigned long long)key << 32) | (unsigned long long)inv;
     }
   }
   __syncthreads();
@@ -376,7 +409,9 @@ extern "C" int ltg_topk_metrics(const void* scores, int is_bf16, int64_t ld, int
   const bool aligned = (reinterpret_cast<uintptr_t>(scores) & 15) == 0 && ((ld * (is_bf16 ? 2 : 4)) & 15) == 0;
   if (use_staged && n_items <= TS_MAX_ITEMS && aligned) {
     const size_t sm = (size_t)((n_items + 7) / 8 * 8) * 4;
-    static size_t opted_s[2] = {30 * 1024, 30 * 1024};   // the kernel has ~10 KB of static shared memory
+    static size_t opted_s[2] = {16 * 1024, 16 * 1024};   // the kernel has ~28 KB of static shared memory
+    static int prefilter = -1;   // LTG_TOPK_PREFILTER=0: select over the whole row (A/B switch)
+    if (prefilter < 0) { const char* e = getenv("LTG_TOPK_PREFILTER"); prefilter = (e != nullptr && e[0] == '0') ? 0 : 1; }
     if (sm > opted_s[is_bf16 ? 1 : 0]) {
       cudaError_t e = is_bf16 ? cudaFuncSetAttribute(topk_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)
                               : cudaFuncSetAttribute(topk_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
@@ -385,10 +420,10 @@ extern "C" int ltg_topk_metrics(const void* scores, int is_bf16, int64_t ld, int
     }
     if (is_bf16)
       topk_staged_kernel<true><<<n_rows, TS_THREADS, sm, (cudaStream_t)stream>>>(scores, ld, n_items, seen_ptr, seen_items, held_ptr, held_items, k, rk,
-                                                                                 n_rk, topk_idx, dcg, hits);
+                                                                                 n_rk, topk_idx, dcg, hits, prefilter != 0);
     else
       topk_staged_kernel<false><<<n_rows, TS_THREADS, sm, (cudaStream_t)stream>>>(scores, ld, n_items, seen_ptr, seen_items, held_ptr, held_items, k, rk,
-                                                                                  n_rk, topk_idx, dcg, hits);
+                                                                                  n_rk, topk_idx, dcg, hits, prefilter != 0);
     LTG_CHECK_LAUNCH();
     return LTG_OK;
   }

@@ -185,6 +185,10 @@ def upload_batch(bt):
     return bt["h2d_bytes"]
 
 
+class _EvalWorkspace(object):
+    """Activation buffers of GanEngine.evaluate (attribute names as in the engine: h1, mulv, z, zmu, h2, ...)."""
+
+
 class GanEngine(object):
     """Owns the workspaces and runs phase A / D / G / evaluation for one (vae, discriminator) pair."""
 
@@ -229,6 +233,8 @@ class GanEngine(object):
         self.s3 = mk(-3)   # run_step: the G update's VAE forward beside the D update
         self.s4 = mk(0)    # Adam over the encoder rows that get no gradient from this batch
         self.s5 = mk(-1)   # decoder Adam, chunk by chunk behind the weight-gradient GEMM of branch s1
+        self.s6 = mk(0)    # clearing Xc behind its consumer
+        self.small_adam_early = os.environ.get("LTG_SMALL_ADAM_EARLY", "1") != "0"
         self.dec_chunks = int(os.environ.get("LTG_DEC_CHUNKS", "1"))
         self._cap_stream = mk(-5) if prio else None
         self.overlap = True
@@ -248,6 +254,7 @@ class GanEngine(object):
         # 98 us for forward + dz12 fused vs 65 + 36 us as two kernels, step 0.519 vs 0.513 ms -- the tile is bound by its epilogue warps
         # (tools/disc_trace.py: 30 of 40 us per tile are tanh/dropout/head/dact epilogues at IPC ~1.2), not by the GEMM it absorbs: off.
         self.fused_dz12 = os.environ.get("LTG_FUSED_DZ12", "0") != "0"
+        self.reuse_gather = os.environ.get("LTG_REUSE_GATHER", "1") != "0"   # run_step: one embedding gather for the D and the G update
         self.is_dae = bool(getattr(vae, "is_dae", False))   # MultiDAE (MultiVAE.py:11-92): tanh middle, no KL, unfused GEMM chain
         if self.is_dae:
             assert self.world_size == 1, "MultiDAE runs on the single-GPU engine"
@@ -378,33 +385,64 @@ class GanEngine(object):
                            self.partial if (is_training or not stash) else None)
         return indptr, indices
 
-    def _middle_unfused(self, B, uid0, is_training, wstep, scal, eps=None):
+    def _middle_unfused(self, B, uid0, is_training, wstep, scal, eps=None, ws=None):
         """h1 -> z -> h2 as GEMMs with fused epilogues. MultiVAE (MultiVAE.py:157-181): mu|logvar GEMM, latent head (KL,
-        reparameterisation), tanh GEMM. MultiDAE (MultiVAE.py:62-68): two tanh GEMMs."""
+        reparameterisation), tanh GEMM. MultiDAE (MultiVAE.py:62-68): two tanh GEMMs. `ws`: the activation buffers (default: the
+        training workspaces of this engine; evaluation passes its own, larger ones)."""
         v = self.vae
+        ws = self if ws is None else ws
         if self.is_dae:
-            ops.gemm(self.h1, v.view("W_q1", "b"), B, L, H, b_mn=True, bn=64, out_bf16=self.z, bias=v.view("b_q1"), act=1)
+            ops.gemm(ws.h1, v.view("W_q1", "b"), B, L, H, b_mn=True, bn=64, out_bf16=ws.z, bias=v.view("b_q1"), act=1)
         else:
-            ops.gemm(self.h1, v.view("W_q1", "b"), B, 2 * L, H, b_mn=True, bn=64, out_f32=self.mulv, bias=v.view("b_q1"))
-            ops.latent_fwd(self.mulv, eps, B, uid0, is_training, self.seed, 0, wstep, self.z, self.zmu, scal)
-        ops.gemm(self.z, v.view("W_p0", "b"), B, H, L, b_mn=True, bn=64, out_bf16=self.h2, bias=v.view("b_p0"), act=1)
+            ops.gemm(ws.h1, v.view("W_q1", "b"), B, 2 * L, H, b_mn=True, bn=64, out_f32=ws.mulv, bias=v.view("b_q1"))
+            ops.latent_fwd(ws.mulv, eps, B, uid0, is_training, self.seed, 0, wstep, ws.z, ws.zmu, scal)
+        ops.gemm(ws.z, v.view("W_p0", "b"), B, H, L, b_mn=True, bn=64, out_bf16=ws.h2, bias=v.view("b_p0"), act=1)
 
-    def _disc_forward(self, pop, niche, label, P, backward, g_w4=None, g_b4=None):
-        """discriminator.py:16-55 on P pairs (real and generated share the weights, so they run as one batch)."""
+    def _eval_workspace(self, rows):
+        """Activation buffers of the ranking evaluation, allocated on first use and kept: evaluation is a pure forward, so its batch is
+        not tied to the training batch -- a few thousand users per launch instead of 500 (fewer launches per user, full waves in the
+        GEMM and one top-k CTA per row over many more rows than SMs)."""
+        ws = getattr(self, "_eval_ws", None)
+        if ws is not None and ws.rows >= rows:
+            return ws
+        dev = self.device
+        bf = dict(dtype=torch.bfloat16, device=dev); f32 = dict(dtype=torch.float32, device=dev)
+        ws = _EvalWorkspace()
+        ws.rows = int(rows)
+        ws.h1 = torch.zeros(rows, H, **bf)
+        ws.enc_ws = torch.zeros(rows, H, **f32)
+        ws.enc_cnt = torch.zeros(rows, dtype=torch.int32, device=dev)
+        ws.mulv = torch.zeros(rows, 2 * L, **f32)
+        ws.z = torch.zeros(rows, L, **bf)
+        ws.zmu = torch.zeros(rows, L, **f32)
+        ws.h2 = torch.zeros(rows, 608, **bf)
+        ws.h2[:, H] = 1.0
+        ws.scores = torch.zeros(rows, self.ld, **f32)
+        self._eval_ws = ws
+        return ws
+
+    def _disc_forward(self, pop, niche, label, P, backward, g_w4=None, g_b4=None, gathered_row0=None):
+        """discriminator.py:16-55 on P pairs (real and generated share the weights, so they run as one batch).
+        gathered_row0: the embedding rows of these pairs already sit in Xp / Xn from that row on (run_step: the D update gathered the
+        generated pairs behind the real ones, the G update reads the same rows instead of gathering them again)."""
         d = self.disc
         seed, kd = self.seed, self.keep_d
         st = ops.STREAM_DISC_DROPOUT
         words, scal = (self.w_d, self.scal_d) if backward else (self.w_g, self.scal)   # D update / G update
-        ops.disc_gather(d.E_b, pop, niche, P, self.Xp, self.Xn)
+        if gathered_row0 is None:
+            Xp, Xn = self.Xp, self.Xn
+            ops.disc_gather(d.E_b, pop, niche, P, Xp, Xn)
+        else:
+            Xp, Xn = self.Xp[gathered_row0:], self.Xn[gathered_row0:]
         if self.fused_disc:
-            ops.disc_fwd_fused(self.Xp, self.Xn, P, d, label, kd, seed, st, words, self.Hd, self.y, scal,
+            ops.disc_fwd_fused(Xp, Xn, P, d, label, kd, seed, st, words, self.Hd, self.y, scal,
                                self.dz3 if backward else None, g_w4 if backward else None, g_b4 if backward else None,
                                self.dz12 if (backward and self.fused_dz12) else None)
             return
         k1 = d.h0 + 1  # embedding columns + the ones column (bias row of W1 / W2)
-        ops.gemm(self.Xp, d.view("W1", "b"), P, d.h1, k1, lda=128, b_mn=True, bn=ops.pick_bn(P, d.h1), out_bf16=self.Hd, ld_bf16=d.k3,
+        ops.gemm(Xp, d.view("W1", "b"), P, d.h1, k1, lda=128, b_mn=True, bn=ops.pick_bn(P, d.h1), out_bf16=self.Hd, ld_bf16=d.k3,
                  act=1, keep=kd, seed=seed, rng_stream=st, rng_step_dev=words, rng_ld=d.ld1)
-        ops.gemm(self.Xn, d.view("W2", "b"), P, d.h2, k1, lda=128, b_mn=True, bn=ops.pick_bn(P, d.h2), out_bf16=self.Hd[:, d.off2:],
+        ops.gemm(Xn, d.view("W2", "b"), P, d.h2, k1, lda=128, b_mn=True, bn=ops.pick_bn(P, d.h2), out_bf16=self.Hd[:, d.off2:],
                  ld_bf16=d.k3, act=1, keep=kd, seed=seed, rng_stream=st + 1, rng_step_dev=words, rng_ld=d.ld2)
         ops.gemm(self.Hd, d.view("W3", "b"), P, d.h3, d.k3, b_mn=True, bn=ops.pick_bn(P, d.h3), out_bf16=self.Y3, act=1, keep=kd, seed=seed,
                  rng_stream=st + 2, rng_step_dev=words, rng_ld=d.ld3)
@@ -516,12 +554,13 @@ class GanEngine(object):
             ops.enc_adam(v.W_q0, v.W_q0_m, v.W_q0_v, v.W_q0_b, self.I, data.batches[bi]["slot_of_item"], self.G_enc, scal=self.scal, rows=1)
         self._early_done = True
 
-    def _g_disc_forward(self, data, bi):
+    def _g_disc_forward(self, data, bi, reuse_gather=False):
         # y_generated with fresh dropout masks (keep_prob 0.7 is fed in the G step too, train.py:326)
         bt = data.batches[bi]
         Pr, K = bt["Pr"], bt["K"]
         if K > 0:
-            self._disc_forward(bt["pair_pop"][Pr:], bt["pair_niche"][Pr:], bt["label"][Pr:], K, False)
+            self._disc_forward(bt["pair_pop"][Pr:], bt["pair_niche"][Pr:], bt["label"][Pr:], K, False,
+                               gathered_row0=Pr if (reuse_gather and self.reuse_gather) else None)
 
     def _g_forward(self, data, bi):
         bt = data.batches[bi]
@@ -675,8 +714,9 @@ class GanEngine(object):
         # encoder weight gradient over the batch's active items as a tensor-core GEMM: G = Xc^T dh1pre   [n_active, 600]
         if not (self.world_size > 1 and getattr(self, "_dp_comm", False) and self.dp_tables is not None):
             ops.gemm(self.Xc, self.dh1pre_b, bt["n_active"], H, B, a_mn=True, b_mn=True, bn=ops.pick_bn(bt["n_active"], H), out_f32=self.G_enc)
-        with self._fork(self.s2):
-            # self-cleaning, off the critical path: the next G forward scatters into an all-zero matrix
+        with self._fork(self.s6):
+            # self-cleaning, off the critical path (own branch: nothing of this step waits for it): the next G forward scatters into an
+            # all-zero matrix
             ops.enc_xc_clear(indptr, indices, B, bt["nnz"], bt["slot_of_item"], self.Xc)
         act_exchange = dp_comm and self.dp_tables is not None
         if self.world_size > 1 and not act_exchange:
@@ -712,6 +752,14 @@ class GanEngine(object):
             if self.nrows > 0:
                 r0, nr = self.row0, self.nrows
                 ops.adam(v.W_q0[r0:r0 + nr], v.W_q0_m[r0:r0 + nr], v.W_q0_v[r0:r0 + nr], self.g_enc_shard, self.Wq0_b_shard, scal=self.scal)
+        small_done = False
+        if fuse_update and self.overlap and self.small_adam_early:
+            # Every small gradient is final once the W_q1 weight-gradient GEMM (branch s2) and the decoder weight-gradient GEMM (branch s1:
+            # its aux column is db_p1) are: the small arena's Adam runs on s2 beside the encoder sweep below instead of behind it
+            self.s2.wait_stream(self.s1)
+            with torch.cuda.stream(self.s2):
+                ops.adam(v.small, v.small_m, v.small_v, v.small_g, v.small_b, scal=self.scal)
+            small_done = True
         if fuse_update:
             ops.enc_adam(v.W_q0, v.W_q0_m, v.W_q0_v, v.W_q0_b, self.I, bt["slot_of_item"], self.G_enc, scal=self.scal,
                          rows=2 if getattr(self, "_early_done", False) else 0)
@@ -722,8 +770,9 @@ class GanEngine(object):
         self._join(self.s1)
         if chunked:
             self._join(self.s5)
-        if fuse_update:
+        if fuse_update and not small_done:
             ops.adam(v.small, v.small_m, v.small_v, v.small_g, v.small_b, scal=self.scal)
+        self._join(self.s6)
 
     def _dec_chunk_rows(self):
         """Row chunks [(r0, n_rows)] of the decoder matrix for the pipelined weight gradient + Adam (multiples of 128 rows)."""
@@ -832,7 +881,9 @@ class GanEngine(object):
             self._d_update_dp()    # (its gradient exchange involves the peers; the G forward on branch s3 is rank-local)
         else:
             self._d_update()
-        self._g_disc_forward(data, bi)
+        # (the D update above gathered the embedding rows of all P pairs of THIS batch, the generated ones from row Pr on, and nothing
+        # has overwritten them: the frozen embedding, F5, makes the second gather of train.py:326 a copy of the first)
+        self._g_disc_forward(data, bi, reuse_gather=True)
         self._join(self.s3)
         if dp:
             self._g_rest_dp(data, bi)
@@ -1011,7 +1062,15 @@ class GanEngine(object):
         (ndcg@k, recall@rk...) over users with a non-empty held-out set, exactly like eval_functions.py."""
         dev = self.device
         N = len(tr_indptr) - 1
-        batch = self.max_B if batch is None else min(batch, self.max_B)
+        # default batch: up to 4,096 users, bounded by 1 GiB of fp32 scores (the reference's batch_size_vad / batch_size_test only bound
+        # its dense host arrays, train.py:333-337; every user is scored independently, dropout keyed by user id)
+        cap = max(1, min(4096, (1 << 30) // (4 * self.ld)))
+        if batch is None:
+            nbat = max(1, -(-N // cap))
+            batch = max(1, -(-N // nbat))          # equal batches (10,000 users -> 3 x 3,334, not 4,096 + 4,096 + 1,808)
+        else:
+            batch = max(1, min(int(batch), cap))
+        ws = self._eval_workspace(batch)
         keep = self.keep_vae if keep is None else keep
         trp = torch.as_tensor(np.ascontiguousarray(tr_indptr, dtype=np.int32)).to(dev)
         tri = torch.as_tensor(np.ascontiguousarray(tr_indices, dtype=np.int32)).to(dev)
@@ -1019,7 +1078,7 @@ class GanEngine(object):
         tei = torch.as_tensor(np.ascontiguousarray(te_indices if len(te_indices) else np.zeros(1), dtype=np.int32)).to(dev)
         coef = torch.zeros(max(1, len(tr_indices)), dtype=torch.float32, device=dev)
         max_eval_nnz = int(np.diff(np.asarray(tr_indptr, dtype=np.int64)).max()) if N > 0 else 0
-        scores = torch.zeros(batch, self.ld, dtype=torch.float32, device=dev)
+        scores = ws.scores
         dcg = torch.zeros(N, dtype=torch.float64, device=dev)
         hits = torch.zeros(N, len(recall_ks), dtype=torch.int32, device=dev)
         v = self.vae
@@ -1028,10 +1087,10 @@ class GanEngine(object):
             ops.step_advance(self.words, self.scal, 0, self.lr)
             ip = trp[b0: b0 + B + 1]
             ops.enc_gather_fwd(ip, tri, None, B, self.I, uid_start + b0, v.W_q0_b, v.view("b_q0"), keep, self.seed, 0, self.words,
-                               self.h1, coef, max_eval_nnz, self.enc_ws, self.enc_cnt)
-            self._middle_unfused(B, uid_start + b0, 0.0, self.words, self.scal)
+                               ws.h1, coef, max_eval_nnz, ws.enc_ws, ws.enc_cnt)
+            self._middle_unfused(B, uid_start + b0, 0.0, self.words, self.scal, ws=ws)
             # fp32 logits: softmax is monotone per row, so ranking the logits equals ranking generator_out
-            ops.gemm(self.h2, v.WdT_b, B, self.I, H, bn=256, out_f32=scores, bias=v.view("b_p1"))
+            ops.gemm(ws.h2, v.WdT_b, B, self.I, H, bn=256, out_f32=scores, bias=v.view("b_p1"))
             ops.topk_metrics(scores, B, self.I, ip, tri, tep[b0: b0 + B + 1], tei, k, recall_ks, None, dcg[b0:], hits[b0:])
         torch.cuda.synchronize()
         return metrics_from_counts(dcg.cpu().numpy(), hits.cpu().numpy(), np.diff(np.asarray(te_indptr, dtype=np.int64)), k, recall_ks)

@@ -243,8 +243,9 @@ def test_run_step_single_graph_equals_three_phases(setup):
 
     a = run(False)
     b = run(True)
-    # same counters; the one-graph step merges the three per-phase counter advances into one launch (2 launches less per step)
-    assert torch.equal(a[3], b[3]) and a[4] - b[4] == 2 * 3 * 2
+    # same counters; the one-graph step merges the three per-phase counter advances into one launch and gathers the embedding rows of
+    # the generated pairs once for the D and the G update (3 launches less per step)
+    assert torch.equal(a[3], b[3]) and a[4] - b[4] == 3 * 3 * 2
     W0 = torch.as_tensor(s["params"][3]).t().cuda()
     assert rel(b[0] - W0, a[0] - W0) < 2e-2
     assert (a[1] - b[1]).abs().max().item() < 1e-3
