@@ -305,6 +305,25 @@ int ltg_topk_metrics(const void* scores, int is_bf16, int64_t ld, int n_rows, in
                      const int32_t* seen_ptr, const int32_t* seen_items, const int32_t* held_ptr, const int32_t* held_items,
                      int k, const int32_t* rk_host, int n_rk, int32_t* topk_idx, double* dcg, int32_t* hits, void* stream);
 
+/* ---- a1 / f3: dataset ingestion on the host cores (data_processing.py:6-37: pandas.read_csv + scipy csr_matrix) -----------
+ * HOST entry points (no kernels, no stream): every pointer below is a host pointer.
+ * ltg_csv_open: memory-maps the CSV at `path_host`, finds the columns named `row_name_host` / `col_name_host` in its header line
+ * (tp['uid'], tp['sid'] at data_processing.py:8-15; further columns are ignored), parses the integer ids with n_threads threads
+ * (<= 0: all cores) and returns an opaque handle in *handle_host. stats_host (may be NULL) receives
+ * [n_pairs, row_min, row_max, col_min, col_max] -- what load_train_data / load_tr_te_data derive their shapes and uid offset from
+ * (uid.max() + 1, uid.min(); min/max over both files).
+ * ltg_csv_pairs: the parsed pairs in file order (load_user_items, data_processing.py:72-96), n_pairs int64 each.
+ * ltg_csv_to_csr: CSR of the pair list as scipy's csr_matrix((ones, (rows - row_offset, cols)), shape=(n_rows, n_cols)) followed by
+ * sort_indices builds it: duplicates summed into counts_host, column ids ascending within a row. indptr_host [n_rows + 1];
+ * indices_host / counts_host hold n_pairs entries (capacity), *nnz_host of them are written. An id outside the shape is an error.
+ * ltg_csv_close: frees the handle.                                                                                          */
+int ltg_csv_open(const char* path_host, const char* row_name_host, const char* col_name_host, int n_threads, void** handle_host,
+                 int64_t* stats_host);
+int ltg_csv_pairs(void* handle_host, int64_t* rows_host, int64_t* cols_host);
+int ltg_csv_to_csr(void* handle_host, int64_t row_offset, int64_t n_rows, int64_t n_cols, int n_threads, int32_t* indptr_host,
+                   int32_t* indices_host, float* counts_host, int64_t* nnz_host);
+int ltg_csv_close(void* handle_host);
+
 /* ---- misc ------------------------------------------------------------------------------------------------------------ */
 /* fp32 -> bf16 with optional re-pitch: dst[r*ld_dst + c] = src[r*ld_src + c]                                             */
 int ltg_cast_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows, int64_t cols, void* stream);

@@ -18,7 +18,7 @@ _SUFFIX = os.environ.get("LTG_LIB_SUFFIX", "")
 LIB_PATH = os.path.join(_HERE, "libltgan%s.so" % _SUFFIX)
 
 SOURCES = ["runtime.cu", "gemm_ops.cu", "vae_kernels.cu", "adam_kernels.cu", "sampler_kernels.cu", "disc_kernels.cu",
-           "topk_kernels.cu", "mid_kernels.cu", "mid_tc.cu", "disc_fused.cu", "peer_kernels.cu"]
+           "topk_kernels.cu", "mid_kernels.cu", "mid_tc.cu", "disc_fused.cu", "peer_kernels.cu", "ingest.cu"]
 HEADERS = ["ltg_common.cuh", "gemm_sm100.cuh"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
@@ -145,6 +145,10 @@ SIGNATURES = {
     "ltg_disc_head": (_I, [_P, _I, _I, _I, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P]),
     "ltg_topk_metrics": (_I, [_P, _I, _I64, _I, _I, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _P]),
     "ltg_cast_bf16": (_I, [_P, _I64, _P, _I64, _I64, _I64, _P]),
+    "ltg_csv_open": (_I, [_P, _P, _P, _I, _P, _P]),
+    "ltg_csv_pairs": (_I, [_P, _P, _P]),
+    "ltg_csv_to_csr": (_I, [_P, _I64, _I64, _I64, _I, _P, _P, _P, _P]),
+    "ltg_csv_close": (_I, [_P]),
 }
 
 _lib = None

@@ -29,8 +29,70 @@ def csr_from_pairs(rows, cols, n_rows, n_cols, dtype):
     return np.cumsum(indptr).astype(np.int32), (uniq % n_cols).astype(np.int32), counts.astype(dtype)
 
 
+class CsvPairs(object):
+    """A `uid,sid` interaction file parsed by the native multi-threaded reader (ltg_csv_open, csrc/ingest.cu): the stand-in for
+    `pd.read_csv(path)` followed by `csr_matrix((ones, (rows, cols)))` (data_processing.py:7-15, 21-35) on files with tens of
+    millions of rows. Context manager; the parsed pairs live in the library until close()."""
+
+    def __init__(self, path, row_name="uid", col_name="sid", n_threads=0):
+        import ctypes
+        from . import _lib
+        self._lib = _lib
+        self._h = ctypes.c_void_p()
+        stats = np.zeros(5, dtype=np.int64)
+        _lib.check(_lib.load().ltg_csv_open(str(path).encode(), row_name.encode(), col_name.encode(), int(n_threads), ctypes.byref(self._h),
+                                            stats.ctypes.data))
+        self.n_pairs, self.row_min, self.row_max, self.col_min, self.col_max = (int(x) for x in stats)
+        self.n_threads = int(n_threads)
+
+    def pairs(self):
+        """(rows, cols) int64 in file order."""
+        r = np.empty(self.n_pairs, dtype=np.int64); c = np.empty(self.n_pairs, dtype=np.int64)
+        self._lib.check(self._lib.load().ltg_csv_pairs(self._h, r.ctypes.data, c.ctypes.data))
+        return r, c
+
+    def to_csr(self, n_rows, n_cols, dtype, row_offset=0):
+        """scipy CSR [n_rows, n_cols] of the pairs (rows shifted by -row_offset), duplicates summed, indices sorted."""
+        indptr = np.empty(n_rows + 1, dtype=np.int32)
+        indices = np.empty(max(1, self.n_pairs), dtype=np.int32)
+        counts = np.empty(max(1, self.n_pairs), dtype=np.float32)
+        nnz = np.zeros(1, dtype=np.int64)
+        self._lib.check(self._lib.load().ltg_csv_to_csr(self._h, int(row_offset), int(n_rows), int(n_cols), self.n_threads, indptr.ctypes.data,
+                                                        indices.ctypes.data, counts.ctypes.data, nnz.ctypes.data))
+        k = int(nnz[0])
+        return sparse.csr_matrix((counts[:k].astype(dtype), indices[:k].copy(), indptr), shape=(n_rows, n_cols), dtype=dtype)
+
+    def close(self):
+        if self._h:
+            self._lib.load().ltg_csv_close(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
+
+
+def _native_csv():
+    """LTG_NATIVE_CSV=0 keeps the pandas + NumPy readers below (the comparison arm of tests/test_data_processing.py)."""
+    import os
+    return os.environ.get("LTG_NATIVE_CSV", "1") != "0"
+
+
 def load_train_data(csv_file, n_items):
     """data_processing.py:6-17: returns (CSR float32 [uid.max()+1, n_items], uid.min())."""
+    if _native_csv():
+        with CsvPairs(csv_file) as cp:
+            if cp.n_pairs == 0:
+                raise ValueError("%s holds no interactions" % csv_file)
+            return cp.to_csr(cp.row_max + 1, n_items, np.float32), cp.row_min
     tp = pd.read_csv(csv_file)
     n_users = int(tp["uid"].max()) + 1
     indptr, indices, data = csr_from_pairs(tp["uid"].to_numpy(), tp["sid"].to_numpy(), n_users, n_items, np.float32)
@@ -39,6 +101,13 @@ def load_train_data(csv_file, n_items):
 
 def load_tr_te_data(csv_file_tr, csv_file_te, n_items):
     """data_processing.py:20-37: fold-in / held-out CSR float64 with the uid offset removed."""
+    if _native_csv():
+        with CsvPairs(csv_file_tr) as tr, CsvPairs(csv_file_te) as te:
+            if tr.n_pairs == 0 or te.n_pairs == 0:
+                raise ValueError("%s / %s: a split holds no interactions" % (csv_file_tr, csv_file_te))
+            start_idx = min(tr.row_min, te.row_min)
+            n = max(tr.row_max, te.row_max) - start_idx + 1
+            return tr.to_csr(n, n_items, np.float64, start_idx), te.to_csr(n, n_items, np.float64, start_idx), start_idx
     tp_tr = pd.read_csv(csv_file_tr)
     tp_te = pd.read_csv(csv_file_te)
     start_idx = int(min(tp_tr["uid"].min(), tp_te["uid"].min()))
