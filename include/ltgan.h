@@ -281,7 +281,10 @@ int ltg_disc_gather(const void* E_bf16, const int32_t* pop_ids, const int32_t* n
  * (columns [0,off2) branch 1, [off2, off2+h2) branch 2, one3 = 1), y[P], the scal / dz3 / dw4 / db4 outputs of ltg_disc_head
  * (dz3 bf16 [P, ld3], NULL = forward only). dz12_bf16 (optional, needs dz3): the backward continues in the same tile with
  * dz12 [P, k3] = (dz3 W3^T) * d/da dropout(tanh(a)) recovered from Hd (autodiff of discriminator.py:25-44 under train.py:163), so
- * the separate backward GEMM is not needed. ltg_disc_fused_supported tells whether the sizes fit the kernel's fixed tiles.       */
+ * the separate backward GEMM is not needed. ltg_disc_fused_supported tells whether the sizes fit the kernel's fixed tiles.
+ * rng_row0: dropout-counter row of this launch's pair 0. A launch over pairs [r, r + P) of a larger batch (pointers advanced to
+ * row r) with rng_row0 = r draws exactly the masks the one launch over the whole batch draws for those rows (engine.run_step runs
+ * the real pairs of the D update, which do not depend on phase A, beside phase A, and the generated pairs behind the sampler).   */
 /* debug: device buffer (148*2*32 u64) that receives per-phase globaltimer stamps of the following launches; NULL switches it off */
 int ltg_disc_fused_set_trace(void* buf);
 int ltg_disc_fused_supported(int k1, int ld1, int ld2, int ld3, int off2, int one3, int h2, int k3);
@@ -289,7 +292,7 @@ int ltg_disc_fwd_fused(const void* Xp_bf16, const void* Xn_bf16, int P, int k1, 
                        int h2, const void* W3_bf16, int ld3, int k3, int off2, int one3, const float* w4, const float* b4,
                        const int32_t* label, float keep, uint64_t seed, uint32_t rng_stream, uint32_t rng_step,
                        const uint32_t* rng_step_dev, void* Hd_bf16, float* y, float* scal, void* dz3_bf16, float* dw4, float* db4,
-                       void* dz12_bf16, void* stream);
+                       void* dz12_bf16, int rng_row0, void* stream);
 /* Head: s = Y3*w4 + b4, y = sigmoid(s); label[row]: 0 real, 1 generated, <0 ignored.
  * Accumulates scal[D_LOSS], scal[SUM_Y] and scal[CNT] (generated rows), and when dz3 != NULL the backward seed:
  * dz3 bf16 [P, ld] = ds*w4*dact(Y3), dw4[h3] += Y3^T ds, *db4 += sum ds. (The fc1 bias gradient comes out of the

@@ -140,7 +140,8 @@ SIGNATURES = {
     "ltg_enc_adam_peer": (_I, [_P, _P, _P, _P, _P, _I64, _I, _P, _P, _I, _F, _P, _F, _F, _F, _P]),
     "ltg_disc_gather": (_I, [_P, _P, _P, _I, _P, _P, _P]),
     "ltg_disc_fused_supported": (_I, [_I, _I, _I, _I, _I, _I, _I, _I]),
-    "ltg_disc_fwd_fused": (_I, [_P, _P, _I, _I, _P, _I, _P, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P, _F, _U64, _U32, _U32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ltg_disc_fwd_fused": (_I, [_P, _P, _I, _I, _P, _I, _P, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P, _F, _U64, _U32, _U32, _P, _P, _P, _P, _P, _P, _P, _P,
+                                _I, _P]),
     "ltg_disc_fused_set_trace": (_I, [_P]),
     "ltg_disc_head": (_I, [_P, _I, _I, _I, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P]),
     "ltg_topk_metrics": (_I, [_P, _I, _I64, _I, _I, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _P]),

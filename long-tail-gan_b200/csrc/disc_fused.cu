@@ -44,6 +44,7 @@ static_assert(DF_W3_STAGE * 2 <= DF_R1 && DF_W3T_STAGE * 2 <= DF_R2 && DF_KB4 * 
 
 struct DiscFusedParams {
   int P, ld1, ld2, ld3, off2, one3, h2, k3, kb3;
+  int rng_row0;                // row index of pair 0 in the dropout counter space (a launch over a slice of a larger pair batch)
   const float* w4; const float* b4; const int32_t* label;
   float keep; uint64_t seed; uint32_t rng_stream, rng_step; const uint32_t* rng_step_dev;
   __nv_bfloat16* Hd; float* y; float* scal; __nv_bfloat16* dz3; float* dw4; float* db4; __nv_bfloat16* dz12;
@@ -326,7 +327,7 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmXp, const __grid_constan
         tmem_ld16(taddr + c, v);
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = tanh_approx(v[i]);
-        if (drop) drop16(v, key1, thr16, inv_keep, row, p.ld1, c);
+        if (drop) drop16(v, key1, thr16, inv_keep, p.rng_row0 + row, p.ld1, c);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int g0 = c + 8 * h;
@@ -347,7 +348,7 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmXp, const __grid_constan
         tmem_ld16(taddr + DF_N1 + c, v);
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = tanh_approx(v[i]);
-        if (drop) drop16(v, key2, thr16, inv_keep, row, p.ld2, c);
+        if (drop) drop16(v, key2, thr16, inv_keep, p.rng_row0 + row, p.ld2, c);
         if (c + 16 > p.h2) {                     // warp-uniform: only the last chunk(s) hold the ones column / padding
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -388,7 +389,7 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmXp, const __grid_constan
           tmem_ld16(taddr + c, v);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = tanh_approx(v[i]);
-          if (drop) drop16(v, key3, thr16, inv_keep, row, p.ld3, c);
+          if (drop) drop16(v, key3, thr16, inv_keep, p.rng_row0 + row, p.ld3, c);
           float w[16];
           load_w16(w, s_w4, c);
 #pragma unroll
@@ -575,8 +576,9 @@ extern "C" int ltg_disc_fwd_fused(const void* Xp_bf16, const void* Xn_bf16, int 
                                   int ld2, int h2, const void* W3_bf16, int ld3, int k3, int off2, int one3, const float* w4, const float* b4,
                                   const int32_t* label, float keep, uint64_t seed, uint32_t rng_stream, uint32_t rng_step,
                                   const uint32_t* rng_step_dev, void* Hd_bf16, float* y, float* scal, void* dz3_bf16, float* dw4, float* db4,
-                                  void* dz12_bf16, void* stream) {
+                                  void* dz12_bf16, int rng_row0, void* stream) {
   LTG_REQUIRE(Xp_bf16 && Xn_bf16 && W1_bf16 && W2_bf16 && W3_bf16 && w4 && b4 && label && Hd_bf16 && scal);
+  LTG_REQUIRE(rng_row0 >= 0);
   LTG_REQUIRE((reinterpret_cast<uintptr_t>(w4) & 15) == 0);
   LTG_REQUIRE(dz12_bf16 == nullptr || dz3_bf16 != nullptr);
   LTG_REQUIRE(ltg_disc_fused_supported(k1, ld1, ld2, ld3, off2, one3, h2, k3));
@@ -595,7 +597,7 @@ extern "C" int ltg_disc_fwd_fused(const void* Xp_bf16, const void* Xn_bf16, int 
   DiscFusedParams p;
   p.P = P; p.ld1 = ld1; p.ld2 = ld2; p.ld3 = ld3; p.off2 = off2; p.one3 = one3; p.h2 = h2; p.k3 = k3; p.kb3 = (k3 + 63) / 64;
   p.w4 = w4; p.b4 = b4; p.label = label; p.keep = keep; p.seed = seed; p.rng_stream = rng_stream; p.rng_step = rng_step;
-  p.rng_step_dev = rng_step_dev;
+  p.rng_step_dev = rng_step_dev; p.rng_row0 = rng_row0;
   p.Hd = reinterpret_cast<__nv_bfloat16*>(Hd_bf16); p.y = y; p.scal = scal; p.dz3 = reinterpret_cast<__nv_bfloat16*>(dz3_bf16);
   p.dw4 = dw4; p.db4 = db4; p.dz12 = reinterpret_cast<__nv_bfloat16*>(dz12_bf16); p.trace = g_df_trace;
   static bool opted = false;

@@ -234,6 +234,8 @@ class GanEngine(object):
         self.s4 = mk(0)    # Adam over the encoder rows that get no gradient from this batch
         self.s5 = mk(-1)   # decoder Adam, chunk by chunk behind the weight-gradient GEMM of branch s1
         self.s6 = mk(0)    # clearing Xc behind its consumer
+        self.s7 = mk(-2)   # run_step: the real pairs' half of the D forward beside phase A
+        self.split_d = int(os.environ.get("LTG_SPLIT_D", "0"))
         self.small_adam_early = os.environ.get("LTG_SMALL_ADAM_EARLY", "1") != "0"
         self.dec_chunks = int(os.environ.get("LTG_DEC_CHUNKS", "1"))
         self._cap_stream = mk(-5) if prio else None
@@ -358,8 +360,10 @@ class GanEngine(object):
         if self.overlap:
             torch.cuda.current_stream().wait_stream(side)
 
-    def _vae_forward(self, data, bt, is_training, keep, stash=True, indptr=None, indices=None, coef=None, uid0=None, B=None, max_nnz=None):
-        """MultiVAE.forward_pass (MultiVAE.py:175-186) up to the logits and their softmax statistics."""
+    def _vae_forward(self, data, bt, is_training, keep, stash=True, indptr=None, indices=None, coef=None, uid0=None, B=None, max_nnz=None,
+                     before_decoder=None):
+        """MultiVAE.forward_pass (MultiVAE.py:175-186) up to the logits and their softmax statistics. before_decoder: optional callable
+        issued between the middle and the decoder GEMM (run_step forks a side branch there)."""
         v = self.vae
         wstep = self.w_g if is_training else self.w_a
         scal = self.scal if is_training else self.scal_a
@@ -380,6 +384,8 @@ class GanEngine(object):
                             self.mulv, self.z, self.zmu, self.h2, scal, tc=self.mid_tc)
         else:
             self._middle_unfused(B, uid0, 1.0 if is_training else 0.0, wstep, scal, self.eps_inject if is_training else None)
+        if before_decoder is not None:
+            before_decoder()
         # (phase A samples with Gumbel-top-k straight from the logits: the softmax statistics are computed by the G forward only)
         ops.dec_logits_fwd(self.h2, v.WdT_b, v.view("b_p1"), B, self.I, self.logits if stash else None,
                            self.partial if (is_training or not stash) else None)
@@ -454,14 +460,16 @@ class GanEngine(object):
     # ------------------------------------------------------------------------------------------------------------
     # phase A: train.py:192-269
     # ------------------------------------------------------------------------------------------------------------
-    def phase_a(self, data, bi, advance=True):
+    def phase_a(self, data, bi, advance=True, before_decoder=None, before_sampler=None):
         bt = data.batches[bi]
         B = bt["B"]
         if advance:
             ops.step_advance(self.words, self.scal_a, 0, self.lr, anneal_cap=self.anneal_cap, total_anneal_steps=self.total_anneal_steps,
                              zero=bt["cnt"], snap=self.w_a)   # the sampler's per-user counters are cleared by the same launch
         # train.py:200: sess.run(generator_out) with default placeholders: dropout 0.75 (F4), is_training 0
-        self._vae_forward(data, bt, False, self.keep_vae)
+        self._vae_forward(data, bt, False, self.keep_vae, before_decoder=before_decoder)
+        if before_sampler is not None:
+            before_sampler()
         if bt["K"] > 0:
             Pr = bt["Pr"]
             ops.sample_pairs(self.logits, B, self.I, bt["uid0"], data.cand_ptr[bt["b0"]: bt["b0"] + B + 1], data.cand_items, bt["samp_ptr"],
@@ -481,7 +489,19 @@ class GanEngine(object):
         ops.step_advance(self.words, self.scal_d, 1, self.lr, anneal_cap=self.anneal_cap, total_anneal_steps=self.total_anneal_steps,
                          zero=self.arena_gp[0][d._off["w4"][0]:], snap=self.w_d)
 
-    def _d_fwd_bwd(self, data, bi, advance=True):
+    def _d_real_forward(self, data, bi):
+        """The REAL pairs of the D update (rows [0, Pr) of the batch's pair list): precomputed tables (train.py:223-224), independent of
+        phase A, so run_step issues them on a side branch beside it; _d_fwd_bwd(real_done=True) then runs the generated pairs only.
+        Same buffers, same rows, same dropout counters (rng_row0) as the one launch over all P pairs."""
+        bt = data.batches[bi]
+        d = self.disc
+        Pr = bt["Pr"]
+        gW = lambda name: self.arena_gp[0][d._off[name][0]: d._off[name][0] + d._off[name][1]]  # noqa: E731
+        ops.disc_gather(d.E_b, bt["pair_pop"], bt["pair_niche"], Pr, self.Xp, self.Xn)
+        ops.disc_fwd_fused(self.Xp, self.Xn, Pr, d, bt["label"], self.keep_d, self.seed, ops.STREAM_DISC_DROPOUT, self.w_d, self.Hd, self.y,
+                           self.scal_d, self.dz3, gW("w4"), gW("b4"), None, rng_row0=0)
+
+    def _d_fwd_bwd(self, data, bi, advance=True, real_done=False):
         bt = data.batches[bi]
         d = self.disc
         P = bt["P"]
@@ -505,7 +525,14 @@ class GanEngine(object):
             d.arena_g.zero_()
             gW = lambda name: d.view(name, "g")  # noqa: E731
             kw = dict(atomic=True)
-        self._disc_forward(bt["pair_pop"], bt["pair_niche"], bt["label"], P, True, g_w4=gW("w4"), g_b4=gW("b4"))
+        if real_done:
+            Pr = bt["Pr"]
+            ops.disc_gather(d.E_b, bt["pair_pop"][Pr:], bt["pair_niche"][Pr:], P - Pr, self.Xp[Pr:], self.Xn[Pr:])
+            ops.disc_fwd_fused(self.Xp[Pr:], self.Xn[Pr:], P - Pr, d, bt["label"][Pr:], self.keep_d, self.seed, ops.STREAM_DISC_DROPOUT, self.w_d,
+                               self.Hd[Pr:], self.y[Pr:], self.scal_d, self.dz3[Pr:], gW("w4"), gW("b4"), None, rng_row0=Pr)
+            self._join(self.s7)   # the real pairs' half (branch s7, issued beside phase A)
+        else:
+            self._disc_forward(bt["pair_pop"], bt["pair_niche"], bt["label"], P, True, g_w4=gW("w4"), g_b4=gW("b4"))
         with self._fork(self.s1):
             ops.gemm(self.Hd, self.dz3, d.k3, d.h3, P, a_mn=True, b_mn=True, splits=sp3, bn=bn3, out_f32=gW("W3"), ld_f32=d.ld3, **kw)  # dW3 (+db3)
         if not (self.fused_disc and self.fused_dz12):   # (the fused kernel has already produced dz12 as its fourth MMA)
@@ -871,12 +898,21 @@ class GanEngine(object):
         ops.step_advance3(self.words, self.scal_a, self.scal_d, self.scal, self.lr, bt["cnt"], self.arena_gp[0][d._off["w4"][0]:],
                           self.vae.small_g, self.w_a, self.w_d, self.w_g, anneal_cap=self.anneal_cap,
                           total_anneal_steps=self.total_anneal_steps)
-        self.phase_a(data, bi, advance=False)
+        # LTG_SPLIT_D = 1 / 2 / 3: the real pairs' half of the D forward starts beside phase A (after the advance / before the decoder
+        # GEMM / before the sampler) on branch s7; only the generated pairs' half waits for the sampler
+        split = self.split_d if (self.split_d and not dp and self.fused_disc and not self.fused_dz12 and bt["Pr"] > 0 and bt["K"] > 0) else 0
+
+        def real_half():
+            with self._fork(self.s7):
+                self._d_real_forward(data, bi)
+        if split == 1:
+            real_half()
+        self.phase_a(data, bi, advance=False, before_decoder=real_half if split == 2 else None, before_sampler=real_half if split == 3 else None)
         self._fuse_update = not dp
         self._g_early(data, bi)
         with self._fork(self.s3):
             self._vae_forward(data, bt, True, self.keep_vae)
-        self._d_fwd_bwd(data, bi, advance=False)
+        self._d_fwd_bwd(data, bi, advance=False, real_done=split > 0)
         if dp:
             self._d_update_dp()    # (its gradient exchange involves the peers; the G forward on branch s3 is rank-local)
         else:

@@ -356,13 +356,14 @@ def disc_fused_supported(d):
     return bool(lib().ltg_disc_fused_supported(d.h0 + 1, d.ld1, d.ld2, d.ld3, d.off2, d.one3, d.h2, d.k3))
 
 
-def disc_fwd_fused(Xp, Xn, P, d, label, keep, seed, rng_stream, rng_step_dev, Hd, y, scal, dz3=None, dw4=None, db4=None, dz12=None):
-    """discriminator.py:16-55 in one launch; `d` is the package's Discriminator (ones-row weight layout)."""
+def disc_fwd_fused(Xp, Xn, P, d, label, keep, seed, rng_stream, rng_step_dev, Hd, y, scal, dz3=None, dw4=None, db4=None, dz12=None, rng_row0=0):
+    """discriminator.py:16-55 in one launch; `d` is the package's Discriminator (ones-row weight layout). rng_row0: dropout-counter
+    row of pair 0 (a launch over a row slice of a larger pair batch)."""
     _count(1)
     check(lib().ltg_disc_fwd_fused(ptr(Xp), ptr(Xn), P, d.h0 + 1, ptr(d.view("W1", "b")), d.ld1, ptr(d.view("W2", "b")), d.ld2, d.h2,
                                    ptr(d.view("W3", "b")), d.ld3, d.k3, d.off2, d.one3, ptr(d.view("w4")), ptr(d.view("b4")), ptr(label),
                                    keep, seed, rng_stream, 0, ptr(rng_step_dev), ptr(Hd), ptr(y), ptr(scal), ptr(dz3), ptr(dw4), ptr(db4),
-                                   ptr(dz12), _stream()))
+                                   ptr(dz12), int(rng_row0), _stream()))
 
 
 def topk_metrics(scores, n_rows, n_items, seen_ptr, seen_items, held_ptr, held_items, k, rks, topk_idx, dcg, hits):

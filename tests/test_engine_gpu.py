@@ -217,9 +217,11 @@ def test_graph_replay_equals_eager(setup):
     assert (a[2] - b[2]).abs().max().item() < 1e-3
 
 
-def test_run_step_single_graph_equals_three_phases(setup):
+@pytest.mark.parametrize("split_d", [0, 1, 2, 3])
+def test_run_step_single_graph_equals_three_phases(setup, split_d):
     """engine.run_step (phase A + D + G of one batch captured as ONE graph, what bench.py times) against the three per-phase calls
-    run eagerly on a twin engine: same RNG counters, weights equal up to float-atomic summation order."""
+    run eagerly on a twin engine: same RNG counters, weights equal up to float-atomic summation order. split_d > 0: the real pairs'
+    half of the D forward runs as its own launch beside phase A (same dropout counters through rng_row0)."""
     s = setup
     eng = s["eng"]
     gen = importlib.import_module("long-tail-gan_b200.generator")
@@ -232,6 +234,7 @@ def test_run_step_single_graph_equals_three_phases(setup):
         disc.set_params(s["E"], s["dparams"])
         data = eng.TrainData(batch_size=BATCH, **s["tabs"])
         e = eng.GanEngine(vae, disc, data.max_B, data.max_P, seed=SEED, use_graphs=fused, max_active=data.max_active)
+        e.split_d = split_d
         for _ in range(3):          # first pass captures, later passes replay
             for bi in range(2):
                 if fused:
@@ -245,7 +248,8 @@ def test_run_step_single_graph_equals_three_phases(setup):
     b = run(True)
     # same counters; the one-graph step merges the three per-phase counter advances into one launch and gathers the embedding rows of
     # the generated pairs once for the D and the G update (3 launches less per step)
-    assert torch.equal(a[3], b[3]) and a[4] - b[4] == 3 * 3 * 2
+    # (... and 2 launches more when the D forward is split into its real and its generated half)
+    assert torch.equal(a[3], b[3]) and a[4] - b[4] == (3 - (2 if split_d else 0)) * 3 * 2
     W0 = torch.as_tensor(s["params"][3]).t().cuda()
     assert rel(b[0] - W0, a[0] - W0) < 2e-2
     assert (a[1] - b[1]).abs().max().item() < 1e-3

@@ -622,6 +622,52 @@ def test_disc_fused_forward_matches_unfused_chain(ops, P, backward, sizes):
     assert (yr - yf).abs().max().item() < 5e-3
 
 
+@pytest.mark.parametrize("P,Pr", [(1000, 333), (40000, 19001), (300, 128)])
+def test_disc_fused_row_slices_equal_one_launch(ops, P, Pr):
+    """ltg_disc_fwd_fused over rows [0, Pr) and [Pr, P) of a pair batch (pointers advanced, rng_row0 = first row) against ONE launch
+    over all P rows: every per-row output (hidden activation with its dropout pattern, y, dz3) bit-identical -- a row's result does not
+    depend on which 128-row tile it sits in --, the atomically accumulated sums equal up to summation order. This is what lets
+    engine.run_step run the real pairs' half of the D forward beside phase A."""
+    disc_mod = importlib.import_module("long-tail-gan_b200.discriminator")
+    I = 700
+    d = disc_mod.Discriminator(I, I, 100, 150, 250, 300, device="cuda", seed=5)
+    with torch.no_grad():
+        g = torch.Generator(device="cuda").manual_seed(3)
+        d.set_params(d.E, [p + 0.05 * torch.randn(p.shape, device="cuda", generator=g) for p in d.get_params()])
+    pop = torch.randint(0, I, (P,), dtype=torch.int32, device="cuda"); niche = torch.randint(0, I, (P,), dtype=torch.int32, device="cuda")
+    label = torch.randint(-1, 2, (P,), dtype=torch.int32, device="cuda")
+    bf = dict(device="cuda", dtype=torch.bfloat16)
+    Xp = torch.zeros(P, 128, **bf); Xn = torch.zeros(P, 128, **bf)
+    ops.disc_gather(d.E_b, pop, niche, P, Xp, Xn)
+    words = torch.tensor([11, 0, 0, 0], dtype=torch.int32, device="cuda")
+    keep, seed, st = 0.7, 99, ops.STREAM_DISC_DROPOUT
+
+    def run(slices):
+        Hd = torch.zeros(P, d.k3, **bf); y = torch.zeros(P, device="cuda"); scal = torch.zeros(16, device="cuda")
+        dz3 = torch.zeros(P, d.ld3, **bf); dw4 = torch.zeros(d.ld3, device="cuda"); db4 = torch.zeros(4, device="cuda")
+        for r0, r1 in slices:
+            ops.disc_fwd_fused(Xp[r0:], Xn[r0:], r1 - r0, d, label[r0:], keep, seed, st, words, Hd[r0:], y[r0:], scal, dz3[r0:], dw4, db4, None,
+                               rng_row0=r0)
+        torch.cuda.synchronize()
+        return Hd, y, scal, dz3, dw4, db4
+
+    one = run([(0, P)])
+    two = run([(0, Pr), (Pr, P)])
+    assert (one[0] != 0).any() and (one[0] == 0).float().mean().item() > 0.2     # dropout is on
+    assert torch.equal(one[0], two[0]) and torch.equal(one[1], two[1]) and torch.equal(one[3], two[3])
+    for slot in (ops.S_D_LOSS, ops.S_SUM_Y):
+        assert abs(one[2][slot].item() - two[2][slot].item()) < 1e-4 * max(1.0, abs(one[2][slot].item()))
+    assert one[2][ops.S_CNT].item() == two[2][ops.S_CNT].item()
+    assert (one[4] - two[4]).abs().max().item() < 1e-3 * max(1.0, one[4].abs().max().item())
+    assert abs(one[5][0].item() - two[5][0].item()) < 1e-3 * max(1.0, abs(one[5][0].item()))
+    # and without the row offset the second slice would draw different masks (the test can see the difference)
+    Hd_wrong = torch.zeros(P, d.k3, **bf)
+    ops.disc_fwd_fused(Xp[Pr:], Xn[Pr:], P - Pr, d, label[Pr:], keep, seed, st, words, Hd_wrong[Pr:], torch.zeros(P, device="cuda"),
+                       torch.zeros(16, device="cuda"), rng_row0=0)
+    torch.cuda.synchronize()
+    assert not torch.equal(Hd_wrong[Pr:] == 0, one[0][Pr:] == 0)
+
+
 def test_peer_exchange_kernels_on_one_device(ops):
     """peer_kernels.cu with pointer tables whose entries all live on this GPU (a table entry is just an address, so two "ranks"
     can be two local buffers): the pull-sum, the push, the Adam with fused reduce-scatter / all-gather, and the flag barrier with

@@ -1,7 +1,7 @@
 """Kernel timeline of one captured GAN step (ML-20M shape): replays engine.run_step under torch.profiler (CUPTI activity records
 carry device timestamps also for kernels launched from a CUDA graph) and prints, for the last replay, every kernel with its stream,
 start offset and duration -- the tool that shows which chain is the critical path and what overlaps what.
-    python tools/timeline.py [phase: step|a|d|g] [out.json]
+    python tools/timeline.py [phase: step|a|d|g|eval] [out.json]
 """
 import importlib
 import json
@@ -31,6 +31,29 @@ def main():
     vae = gen.MultiVAE([200, 600, I], lam=0.0, random_seed=98765); vae.init_weights(98765)
     disc = dis.Discriminator(I, I, bench.H0, bench.H1, bench.H2, bench.H3, seed=4242)
     e = eng.GanEngine(vae, disc, data.max_B, data.max_P, seed=2026, lr=bench.LR, lam=bench.LAM, max_active=data.max_active)
+    if phase == "eval":
+        # one engine.evaluate call over SURVEY 8d's 10 k held-out users: every kernel (and memcpy) of the call with its duration
+        ev_args = syn.make_eval_split(int(os.environ.get("LTG_TL_EVAL_USERS", "10000")), I, deg)
+        e.evaluate(*ev_args)
+        torch.cuda.synchronize()
+        import time
+        t0 = time.perf_counter(); e.evaluate(*ev_args); wall = time.perf_counter() - t0
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            e.evaluate(*ev_args)
+            torch.cuda.synchronize()
+        evs = [ev for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA]
+        evs.sort(key=lambda ev: ev.time_range.start)
+        t0 = evs[0].time_range.start
+        print("evaluate: %d device activities, %.1f us from first to last, %.1f us host wall without the profiler" %
+              (len(evs), max(ev.time_range.end for ev in evs) - t0, wall * 1e6))
+        agg = {}
+        for ev in evs:
+            print("%8.1f %7.1f  %s" % (ev.time_range.start - t0, ev.time_range.end - ev.time_range.start, ev.name[:90]))
+            a = agg.setdefault(ev.name[:60], [0, 0.0]); a[0] += 1; a[1] += ev.time_range.end - ev.time_range.start
+        print("---- totals")
+        for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            print("%9.1f us  x%-3d %s" % (t, n, k))
+        return
     fn = dict(step=e.run_step, a=e.run_phase_a, d=e.run_d_step, g=e.run_g_step)[phase]
     for r in range(3):
         for bi in range(nb):
