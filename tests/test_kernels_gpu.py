@@ -454,14 +454,20 @@ def test_sampler_distribution_chi_square(ops):
 # ----------------------------------------------------------------------------------------------------------------
 # top-k metrics
 # ----------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("dtype", ["f32", "bf16"])
-def test_topk_metrics_exact(ops, dtype):
+@pytest.mark.parametrize("dtype,I", [("f32", 2500), ("bf16", 2500), ("f32", 20108), ("bf16", 20108), ("f32", 333)])
+def test_topk_metrics_exact(ops, dtype, I):
+    """Exact top-k index lists (ties: lowest index first), DCG and hit counts against NumPy. The rows cover both selection paths of
+    the staged kernel: the candidate pre-filter (random rows; rows with a few hundred ties at the threshold) and its full-row path
+    (a fully tied row and a row with half the catalog tied at the top overflow the 2,048-entry candidate list)."""
     from scipy import sparse
     rng = np.random.RandomState(12)
-    n, I, k = 57, 2500, 100
+    n, k = 57, 100
     scores = rng.randn(n, I).astype(np.float32)
     scores[3, :] = 0.25           # a fully tied row
     scores[4, ::2] = 1.0          # half the row tied at the top
+    scores[5, 7::40] = 5.0        # a few ties above everything else, fewer than k for small catalogs
+    scores[6, :] = np.round(scores[6, :] * 4) / 4    # a coarse grid: hundreds of ties at every level, also at the threshold
+    scores[7, :] = -np.abs(scores[7, :])             # all negative
     t = dev(scores)
     if dtype == "bf16":
         t = t.bfloat16()
