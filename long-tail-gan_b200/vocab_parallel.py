@@ -49,6 +49,26 @@ def shard_tables(tabs, lo, hi):
     return out
 
 
+def combine_softmax_stats(sa):
+    """Per-shard softmax statistics -> global ones (MultiVAE.py:108,143 over a catalog split into shards). sa [R, B, >=3] holds, per
+    shard r and user, (lse_r = log sum_{i in shard} exp(logit_i), sum_{i in shard} x_i, sum over the user's sampled items in the
+    shard of exp(logit_i - lse_r)). Returns (lse [B] = log sum_r exp(lse_r), sum x [B], sum of sampled softmax probabilities [B] =
+    sum_r s_r exp(lse_r - lse))."""
+    lse = torch.logsumexp(sa[:, :, 0], dim=0)
+    w = torch.exp(sa[:, :, 0] - lse[None])
+    return lse, sa[:, :, 1].sum(0), (sa[:, :, 2] * w).sum(0)
+
+
+def merge_topk(vals, gids, k):
+    """Per-shard top-k lists side by side (vals / gids [B, R*k]: scores and GLOBAL item ids) -> the global top-k ids [B, k] ordered by
+    (score desc, id asc), the tie rule of ltg_topk_metrics (eval_functions.py:17-23 leaves ties to argpartition). Two stable sorts:
+    ascending id first, then descending score."""
+    o1 = torch.argsort(gids, dim=1, stable=True)
+    vals, gids = torch.gather(vals, 1, o1), torch.gather(gids, 1, o1)
+    o2 = torch.argsort(vals, dim=1, descending=True, stable=True)
+    return torch.gather(gids, 1, o2)[:, :k]
+
+
 class ShardData(TrainData):
     """TrainData over the shard-local CSR + per-batch catalog-shard structures (row norms, owned candidate positions)."""
 
@@ -200,11 +220,10 @@ class CatalogShardedEngine(GanEngine):
             dist.all_gather_into_tensor(sa, st.contiguous(), group=self.group)
         else:
             sa = st[None]
-        lse = torch.logsumexp(sa[:, :, 0], dim=0)
-        w = torch.exp(sa[:, :, 0] - lse[None])
+        lse, xw_g, su_g = combine_softmax_stats(sa)
         self.lse_g[:B] = lse
-        self.xw_g[:B] = sa[:, :, 1].sum(0)
-        self.su_g[:B] = (sa[:, :, 2] * w).sum(0)
+        self.xw_g[:B] = xw_g
+        self.su_g[:B] = su_g
         # NLL: the local pass used the local lse; -sum_i x (logit - lse) = local + sum x_r (lse - lse_r)
         self.scal[ops.S_NLL_SUM] += (self.xw[:B] * (lse - self.lse[:B])).sum()
         self.scal[ops.S_SUM_P] = self.su_g[:B].sum()
@@ -319,11 +338,7 @@ class CatalogShardedEngine(GanEngine):
                 vals, gids = torch.cat(vals, 1), torch.cat(gids, 1)
             else:
                 vals, gids = val_loc, gid_loc
-            # merge: ascending id first (stable), then descending score (stable) == (score desc, id asc), the kernel's tie rule
-            o1 = torch.argsort(gids, dim=1, stable=True)
-            vals, gids = torch.gather(vals, 1, o1), torch.gather(gids, 1, o1)
-            o2 = torch.argsort(vals, dim=1, descending=True, stable=True)
-            top_all[b0: b0 + B] = torch.gather(gids, 1, o2)[:, :k].cpu().numpy()
+            top_all[b0: b0 + B] = merge_topk(vals, gids, k).cpu().numpy()
         # metrics on the merged lists (eval_functions.py:25-30, 47-52), fp64 like NumPy
         n_held = np.diff(te_indptr)
         tp = 1.0 / np.log2(np.arange(2, k + 2))
