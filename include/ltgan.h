@@ -327,6 +327,28 @@ int ltg_csv_to_csr(void* handle_host, int64_t row_offset, int64_t n_rows, int64_
                    int32_t* indices_host, float* counts_host, int64_t* nnz_host);
 int ltg_csv_close(void* handle_host);
 
+/* ---- f1: GAN side tables on the host cores (data_processing.py:170-271) ------------------------------------------------
+ * HOST entry points. The overlap coefficients (data_processing.py:100-167) are read from the sparse co-occurrence counts
+ * C = X^T X: CSR with int64 row pointers, column ids sorted within a row (int32, or int64 when indices_are_64), int64 counts, and
+ * deg[i] = C[i,i]; overlap(a,b) = C[a,b] / min(deg[a], deg[b]) in float64, 0 where an item never occurs. Users are given as ragged
+ * lists in file order: un_ptr/un_items the niche items, up_ptr/up_items the popular items (load_user_items, 72-96); eligible[u] =
+ * the user appears in both (train.py:213-217).
+ * ltg_cand_sets = load_items_to_sample (170-224): per eligible user the own niche items plus the top max(2n, 10-n) other items of
+ * niche_sorted (ascending ids) by their best overlap with any own niche item (ties: ascending id), written sorted to
+ * out_items[out_ptr[u] ...] with the count in out_count[u]; out_ptr must reserve n + max(2n, 10-n) entries per user.
+ * ltg_real_pairs = load_vectors (227-271): per eligible user and niche item the user's popular item with the highest overlap (first
+ * maximum in list order), kept when both ids are valid (item_valid, = membership in ITEM_FEATURE_DICT, 258-262); pairs of user u
+ * are written from position un_ptr[u] of out_niche / out_pop, their number to out_count[u].                                  */
+int ltg_cand_sets(const int64_t* C_indptr_host, const void* C_indices_host, int indices_are_64, const int64_t* C_counts_host,
+                  const double* deg_host, int n_items, const int32_t* niche_sorted_host, int n_niche, const int64_t* un_ptr_host,
+                  const int32_t* un_items_host, const uint8_t* eligible_host, int64_t n_users, int n_threads,
+                  const int64_t* out_ptr_host, int32_t* out_items_host, int32_t* out_count_host);
+int ltg_real_pairs(const int64_t* C_indptr_host, const void* C_indices_host, int indices_are_64, const int64_t* C_counts_host,
+                   const double* deg_host, int n_items, const uint8_t* item_valid_host, const int64_t* un_ptr_host,
+                   const int32_t* un_items_host, const int64_t* up_ptr_host, const int32_t* up_items_host,
+                   const uint8_t* eligible_host, int64_t n_users, int n_threads, int32_t* out_niche_host, int32_t* out_pop_host,
+                   int32_t* out_count_host);
+
 /* ---- misc ------------------------------------------------------------------------------------------------------------ */
 /* fp32 -> bf16 with optional re-pitch: dst[r*ld_dst + c] = src[r*ld_src + c]                                             */
 int ltg_cast_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows, int64_t cols, void* stream);

@@ -18,7 +18,7 @@ _SUFFIX = os.environ.get("LTG_LIB_SUFFIX", "")
 LIB_PATH = os.path.join(_HERE, "libltgan%s.so" % _SUFFIX)
 
 SOURCES = ["runtime.cu", "gemm_ops.cu", "vae_kernels.cu", "adam_kernels.cu", "sampler_kernels.cu", "disc_kernels.cu",
-           "topk_kernels.cu", "mid_kernels.cu", "mid_tc.cu", "disc_fused.cu", "peer_kernels.cu", "ingest.cu"]
+           "topk_kernels.cu", "mid_kernels.cu", "mid_tc.cu", "disc_fused.cu", "peer_kernels.cu", "ingest.cu", "tables.cu"]
 HEADERS = ["ltg_common.cuh", "gemm_sm100.cuh"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
@@ -150,6 +150,8 @@ SIGNATURES = {
     "ltg_csv_pairs": (_I, [_P, _P, _P]),
     "ltg_csv_to_csr": (_I, [_P, _I64, _I64, _I64, _I, _P, _P, _P, _P]),
     "ltg_csv_close": (_I, [_P]),
+    "ltg_cand_sets": (_I, [_P, _P, _I, _P, _P, _I, _P, _I, _P, _P, _P, _I64, _I, _P, _P, _P]),
+    "ltg_real_pairs": (_I, [_P, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I64, _I, _P, _P, _P]),
 }
 
 _lib = None

@@ -236,10 +236,62 @@ def overlap_from_interactions(uidx, item, n_items):
     return OverlapCoeffs(C, C.diagonal())
 
 
-def load_items_to_sample(user_popular_data, user_niche_data, NICHE_TAGS, OVERLAP_COEFFS, N):
+def _native_tables():
+    """LTG_NATIVE_TABLES=0 keeps the NumPy loops of load_items_to_sample / load_vectors (the comparison arm of the tests)."""
+    import os
+    return os.environ.get("LTG_NATIVE_TABLES", "1") != "0"
+
+
+def _ragged_lists(d, N, eligible):
+    """dict user -> list of ids  ->  (ptr int64 [N+1], items int32) over the eligible users, list order kept."""
+    ptr = np.zeros(N + 1, dtype=np.int64)
+    chunks = []
+    for u in np.nonzero(eligible)[0].tolist():
+        v = np.asarray(d[u], dtype=np.int64)
+        chunks.append(v)
+        ptr[u + 1] = len(v)
+    items = np.concatenate(chunks) if chunks else np.zeros(0, dtype=np.int64)
+    return np.cumsum(ptr), np.ascontiguousarray(items, dtype=np.int32)
+
+
+def _cooc_args(OV):
+    """(indptr int64, indices, indices_are_64, counts int64, deg float64) of the sparse co-occurrence matrix for the C-ABI."""
+    C = OV.C
+    indptr = np.ascontiguousarray(C.indptr, dtype=np.int64)
+    is64 = C.indices.dtype == np.int64
+    indices = np.ascontiguousarray(C.indices, dtype=np.int64 if is64 else np.int32)
+    counts = np.ascontiguousarray(C.data, dtype=np.int64)
+    return indptr, indices, int(is64), counts, np.ascontiguousarray(OV.deg, dtype=np.float64)
+
+
+def _eligible_users(user_popular_data, user_niche_data, N):
+    el = np.zeros(N, dtype=np.uint8)
+    for u in user_niche_data:
+        if isinstance(u, (int, np.integer)) and 0 <= u < N and u in user_popular_data:
+            el[u] = 1
+    return el
+
+
+def load_items_to_sample(user_popular_data, user_niche_data, NICHE_TAGS, OVERLAP_COEFFS, N, n_threads=0):
     """data_processing.py:170-224: candidates = the user's niche items + the top max(2n, 10-n) other niche items ranked by
     their best overlap with any of the user's niche items (stable: ties keep ascending item id, which is the iteration
-    order of the reference's `NICHE_TAGS - curr_niche_tags` set of small ints)."""
+    order of the reference's `NICHE_TAGS - curr_niche_tags` set of small ints). Runs on all host cores through ltg_cand_sets
+    (csrc/tables.cu); the NumPy loop below is the same computation (LTG_NATIVE_TABLES=0)."""
+    if _native_tables() and isinstance(OVERLAP_COEFFS, OverlapCoeffs):
+        from . import _lib
+        el = _eligible_users(user_popular_data, user_niche_data, N)
+        un_ptr, un_items = _ragged_lists(user_niche_data, N, el)
+        n_u = np.diff(un_ptr)
+        out_ptr = np.concatenate([[0], np.cumsum(np.where(el > 0, n_u + np.maximum(2 * n_u, 10 - n_u), 0))]).astype(np.int64)
+        out_items = np.empty(max(1, int(out_ptr[-1])), dtype=np.int32)
+        out_count = np.zeros(max(1, N), dtype=np.int32)
+        niche_sorted = np.ascontiguousarray(sorted(NICHE_TAGS), dtype=np.int32)
+        indptr, indices, is64, counts, deg = _cooc_args(OVERLAP_COEFFS)
+        _lib.check(_lib.load().ltg_cand_sets(indptr.ctypes.data, indices.ctypes.data, is64, counts.ctypes.data, deg.ctypes.data,
+                                             OVERLAP_COEFFS.n_items, niche_sorted.ctypes.data, len(niche_sorted), un_ptr.ctypes.data,
+                                             un_items.ctypes.data, el.ctypes.data, N, int(n_threads), out_ptr.ctypes.data,
+                                             out_items.ctypes.data, out_count.ctypes.data))
+        return {u: out_items[out_ptr[u]: out_ptr[u] + out_count[u]].astype(np.int64) for u in np.nonzero(el)[0].tolist()}
     niche_sorted = np.asarray(sorted(NICHE_TAGS), dtype=np.int64)
     out = {}
     for user_idx in range(N):
@@ -255,9 +307,32 @@ def load_items_to_sample(user_popular_data, user_niche_data, NICHE_TAGS, OVERLAP
     return out
 
 
-def load_vectors(user_popular_data, user_niche_data, OVERLAP_COEFFS, ITEM_FEATURE_DICT, N):
+def load_vectors(user_popular_data, user_niche_data, OVERLAP_COEFFS, ITEM_FEATURE_DICT, N, n_threads=0):
     """data_processing.py:227-271: for each niche item of the user the popular item of the user with the highest overlap
-    (first maximum in list order), dropped when either id is not in ITEM_FEATURE_DICT."""
+    (first maximum in list order), dropped when either id is not in ITEM_FEATURE_DICT. Runs on all host cores through
+    ltg_real_pairs (csrc/tables.cu); the NumPy loop below is the same computation (LTG_NATIVE_TABLES=0)."""
+    if _native_tables() and isinstance(OVERLAP_COEFFS, OverlapCoeffs):
+        from . import _lib
+        el = _eligible_users(user_popular_data, user_niche_data, N)
+        un_ptr, un_items = _ragged_lists(user_niche_data, N, el)
+        up_ptr, up_items = _ragged_lists(user_popular_data, N, el)
+        n_items = OVERLAP_COEFFS.n_items
+        valid = np.zeros(n_items, dtype=np.uint8)
+        keys = np.asarray([k for k in ITEM_FEATURE_DICT.keys() if 0 <= k < n_items], dtype=np.int64)
+        valid[keys] = 1
+        out_n = np.empty(max(1, len(un_items)), dtype=np.int32); out_p = np.empty(max(1, len(un_items)), dtype=np.int32)
+        out_count = np.zeros(max(1, N), dtype=np.int32)
+        indptr, indices, is64, counts, deg = _cooc_args(OVERLAP_COEFFS)
+        _lib.check(_lib.load().ltg_real_pairs(indptr.ctypes.data, indices.ctypes.data, is64, counts.ctypes.data, deg.ctypes.data, n_items,
+                                              valid.ctypes.data, un_ptr.ctypes.data, un_items.ctypes.data, up_ptr.ctypes.data,
+                                              up_items.ctypes.data, el.ctypes.data, N, int(n_threads), out_n.ctypes.data, out_p.ctypes.data,
+                                              out_count.ctypes.data))
+        x_niche, x_pop = {}, {}
+        for u in np.nonzero(el)[0].tolist():
+            a, b = int(un_ptr[u]), int(un_ptr[u]) + int(out_count[u])
+            x_niche[u] = out_n[a:b].tolist()
+            x_pop[u] = out_p[a:b].tolist()
+        return x_niche, x_pop
     x_niche, x_pop = {}, {}
     for user_idx in range(N):
         if user_idx not in user_popular_data or user_idx not in user_niche_data:
