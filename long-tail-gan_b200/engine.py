@@ -1108,16 +1108,41 @@ class GanEngine(object):
             batch = max(1, min(int(batch), cap))
         ws = self._eval_workspace(batch)
         keep = self.keep_vae if keep is None else keep
-        trp = torch.as_tensor(np.ascontiguousarray(tr_indptr, dtype=np.int32)).to(dev)
-        tri = torch.as_tensor(np.ascontiguousarray(tr_indices, dtype=np.int32)).to(dev)
-        tep = torch.as_tensor(np.ascontiguousarray(te_indptr, dtype=np.int32)).to(dev)
-        tei = torch.as_tensor(np.ascontiguousarray(te_indices if len(te_indices) else np.zeros(1), dtype=np.int32)).to(dev)
-        coef = torch.zeros(max(1, len(tr_indices)), dtype=torch.float32, device=dev)
-        max_eval_nnz = int(np.diff(np.asarray(tr_indptr, dtype=np.int64)).max()) if N > 0 else 0
-        scores = ws.scores
-        dcg = torch.zeros(N, dtype=torch.float64, device=dev)
-        hits = torch.zeros(N, len(recall_ks), dtype=torch.int32, device=dev)
         v = self.vae
+        scores = ws.scores
+        tr_ptr_h = np.ascontiguousarray(tr_indptr, dtype=np.int32)
+        tr_idx_h = torch.from_numpy(np.ascontiguousarray(tr_indices if len(tr_indices) else np.zeros(1), dtype=np.int32))
+        max_eval_nnz = int(np.diff(tr_ptr_h.astype(np.int64)).max()) if N > 0 else 0
+        # Host set-up is a third of the call at 10 k users (profiles/r2_timeline_eval.txt: 0.88 of 2.5 ms before the first kernel), so only
+        # what the first batch's forward needs is uploaded before it is launched -- the row pointers and the first batch's fold-in items;
+        # the rest of the fold-in items and the held-out CSR follow on a copy stream while the GPU works on batch 0.
+        main = torch.cuda.current_stream()
+        up = getattr(self, "_eval_up_stream", None)
+        if up is None:
+            up = self._eval_up_stream = torch.cuda.Stream(device=dev)
+        trp = torch.as_tensor(tr_ptr_h).to(dev)
+        tri = torch.empty(tr_idx_h.numel(), dtype=torch.int32, device=dev)
+        coef = torch.empty(tr_idx_h.numel(), dtype=torch.float32, device=dev)   # written by the gather, not read by evaluation
+        first_end = int(tr_ptr_h[min(batch, N)]) if N > 0 else 0
+        if len(tr_indices) == 0:
+            tri.zero_()
+        elif first_end > 0:
+            tri[:first_end].copy_(tr_idx_h[:first_end], non_blocking=True)
+        ev_alloc = torch.cuda.Event()
+        ev_alloc.record(main)             # tri exists and its first rows are on their way: the copy stream may fill in the rest
+        state = {}
+
+        def upload_rest():
+            up.wait_event(ev_alloc)       # (not wait_stream: batch 0's forward is already queued on main, the copies run beside it)
+            with torch.cuda.stream(up):
+                if len(tr_indices) > first_end:
+                    tri[first_end:].copy_(tr_idx_h[first_end:], non_blocking=True)
+                state["tep"] = torch.as_tensor(np.ascontiguousarray(te_indptr, dtype=np.int32)).to(dev, non_blocking=True)
+                state["tei"] = torch.as_tensor(np.ascontiguousarray(te_indices if len(te_indices) else np.zeros(1), dtype=np.int32)).to(dev, non_blocking=True)
+                state["dcg"] = torch.zeros(N, dtype=torch.float64, device=dev)
+                state["hits"] = torch.zeros(N, max(1, len(recall_ks)), dtype=torch.int32, device=dev)
+            main.wait_stream(up)
+
         for b0 in range(0, N, batch):
             B = min(batch, N - b0)
             ops.step_advance(self.words, self.scal, 0, self.lr)
@@ -1127,7 +1152,13 @@ class GanEngine(object):
             self._middle_unfused(B, uid_start + b0, 0.0, self.words, self.scal, ws=ws)
             # fp32 logits: softmax is monotone per row, so ranking the logits equals ranking generator_out
             ops.gemm(ws.h2, v.WdT_b, B, self.I, H, bn=256, out_f32=scores, bias=v.view("b_p1"))
-            ops.topk_metrics(scores, B, self.I, ip, tri, tep[b0: b0 + B + 1], tei, k, recall_ks, None, dcg[b0:], hits[b0:])
+            if b0 == 0:
+                upload_rest()
+            ops.topk_metrics(scores, B, self.I, ip, tri, state["tep"][b0: b0 + B + 1], state["tei"], k, recall_ks, None, state["dcg"][b0:],
+                             state["hits"][b0:])
+        if N <= 0:
+            upload_rest()
+        dcg, hits = state["dcg"], state["hits"][:, :len(recall_ks)]
         torch.cuda.synchronize()
         return metrics_from_counts(dcg.cpu().numpy(), hits.cpu().numpy(), np.diff(np.asarray(te_indptr, dtype=np.int64)), k, recall_ks)
 
