@@ -323,6 +323,29 @@ def test_adam_matches_tf_formula(ops):
     assert abs(scal[ops.S_ANNEAL].item() - orc.anneal_value(2)) < 1e-9
 
 
+@pytest.mark.parametrize("n_partials", [2, 5, 16, 17, 33, 34])
+def test_adam_over_split_k_partials(ops, n_partials):
+    """ltg_adam whose gradient is a sum of split-K partials (the discriminator update): the one-round kernel (<= 33 partials: eight
+    warps x four partials per 32 float4, folded through shared memory) and the loop over rounds (34) against TF-Adam on the fp64
+    sum of the partials; n % 4 != 0 exercises the scalar tail."""
+    torch.manual_seed(20 + n_partials)
+    n = 161001                      # the discriminator's parameter count (SURVEY a11): 161001 % 4 == 1
+    stride = (n + 3) // 4 * 4 + 8
+    p = torch.randn(n, device="cuda"); m = torch.randn(n, device="cuda") * 0.01; v = torch.rand(n, device="cuda") * 1e-4
+    gp = torch.randn(n_partials, stride, device="cuda") * 0.1
+    p0, m0, v0 = p.cpu().clone(), m.cpu().clone(), v.cpu().clone()
+    sh = torch.zeros(stride, device="cuda", dtype=torch.bfloat16)[:n]
+    lr_t = orc.tf_adam_lr_t(1e-4, 5)
+    ops.adam(p, m, v, gp, sh, lr_t=lr_t, n_partials=n_partials, partial_stride=stride)
+    torch.cuda.synchronize()
+    g = gp[:, :n].double().sum(0).float().cpu()
+    orc.tf_adam_step(p0, m0, v0, g, lr_t)
+    assert (m.cpu() - m0).abs().max().item() < 1e-6          # (1 - b1) * |g_sum error|: fp32 summation order of up to 34 terms
+    assert (v.cpu() - v0).abs().max().item() < 1e-7
+    assert (p.cpu() - p0).abs().max().item() < 2e-6
+    assert (sh.float().cpu() - p0).abs().max().item() < 2e-2
+
+
 def test_enc_wgrad_and_enc_adam(ops):
     rng = np.random.RandomState(8)
     B, I = 50, 400
