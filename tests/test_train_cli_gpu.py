@@ -7,6 +7,7 @@ import sys
 
 import numpy as np
 import pytest
+import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -57,3 +58,29 @@ def test_train_and_test_cli_roundtrip(tmp_path, monkeypatch):
     assert os.path.exists(ck)
     n100, r20, r50 = test.test_GAN(output_path=ck, quiet=True, **cfg)
     assert abs(n100 - h[-1]["ndcg"]) < 0.03 and r50 > r20 > 0
+
+
+def test_resume_reproduces_uninterrupted_run(tmp_path, monkeypatch):
+    """to_restore = 1 (parsed and ignored by the reference, train.py:374): a run stopped after epoch 0 and resumed from its checkpoint
+    (weights, Adam moments, shared step counter, RNG step, shuffle sequence) ends where the uninterrupted 2-epoch run ends -- up to
+    the summation order of float atomics."""
+    train = importlib.import_module("long-tail-gan_b200.train")
+    cfg = dict(h0_size=100, h1_size=150, h2_size=250, h3_size=300, NUM_EPOCH=8, NUM_SUB_EPOCHS=1, BATCH_SIZE=100, DISPLAY_ITER=50,
+               LEARNING_RATE=1e-3, model_name="LT_GAN", dataset=GOLD, GANLAMBDA=1.0)
+    (tmp_path / "a").mkdir(); (tmp_path / "b").mkdir()
+    monkeypatch.chdir(tmp_path / "a")
+    full = train.train_GAN(max_epochs=2, quiet=True, seed=3, to_restore=0, **cfg)
+    monkeypatch.chdir(tmp_path / "b")
+    first = train.train_GAN(max_epochs=1, quiet=True, seed=3, to_restore=0, **cfg)
+    W_start = first["vae"].WdT.clone()
+    assert os.path.exists(os.path.join("chkpt", "askubuntu_sample_LT_GAN_1.0", "model_0"))
+    rest = train.train_GAN(max_epochs=2, quiet=True, seed=3, to_restore=1, **cfg)
+    assert [h["epoch"] for h in rest["history"]] == [1] and [h["epoch"] for h in full["history"]] == [0, 1]
+    assert torch.equal(rest["engine"].words.cpu()[:3], full["engine"].words.cpu()[:3])       # rng step, Adam t, G-update count
+    assert abs(rest["history"][0]["ndcg"] - full["history"][1]["ndcg"]) < 1e-2
+    moved = (full["vae"].WdT.float() - W_start.float()).norm().item()          # what epoch 1 did to the decoder weights
+    assert (full["vae"].WdT.float() - rest["vae"].WdT.float()).norm().item() < 0.1 * moved   # (lost Adam moments or dropout steps would show as tens of percent)
+    assert (full["vae"].W_q0.float() - rest["vae"].W_q0.float()).abs().max().item() < 5e-3
+    assert (full["disc"].arena - rest["disc"].arena).abs().max().item() < 5e-3
+    # (and the resumed epoch really continued from the checkpoint: it moved the weights of epoch 0 about as far as the full run's epoch 1)
+    assert (rest["vae"].WdT.float() - W_start.float()).norm().item() > 0
