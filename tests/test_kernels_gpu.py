@@ -340,9 +340,10 @@ def test_adam_over_split_k_partials(ops, n_partials):
     torch.cuda.synchronize()
     g = gp[:, :n].double().sum(0).float().cpu()
     orc.tf_adam_step(p0, m0, v0, g, lr_t)
-    assert (m.cpu() - m0).abs().max().item() < 1e-6          # (1 - b1) * |g_sum error|: fp32 summation order of up to 34 terms
-    assert (v.cpu() - v0).abs().max().item() < 1e-7
-    assert (p.cpu() - p0).abs().max().item() < 2e-6
+    # fp32 summation order of up to 34 terms with |sum| up to ~2.5: |g error| <~ 1e-5, so (1 - b1) dg ~ 1e-6 and (1 - b2) 2 g dg ~ 1e-7
+    assert (m.cpu() - m0).abs().max().item() < 3e-6
+    assert (v.cpu() - v0).abs().max().item() < 5e-7
+    assert (p.cpu() - p0).abs().max().item() < 1e-5
     assert (sh.float().cpu() - p0).abs().max().item() < 2e-2
 
 

@@ -67,20 +67,28 @@ def test_resume_reproduces_uninterrupted_run(tmp_path, monkeypatch):
     train = importlib.import_module("long-tail-gan_b200.train")
     cfg = dict(h0_size=100, h1_size=150, h2_size=250, h3_size=300, NUM_EPOCH=8, NUM_SUB_EPOCHS=1, BATCH_SIZE=100, DISPLAY_ITER=50,
                LEARNING_RATE=1e-3, model_name="LT_GAN", dataset=GOLD, GANLAMBDA=1.0)
+    # one initial state for both runs (the reference leaves the discriminator initialiser unseeded, discriminator.py:14-41)
+    gen = importlib.import_module("long-tail-gan_b200.generator")
+    dis = importlib.import_module("long-tail-gan_b200.discriminator")
+    vae0 = gen.MultiVAE([200, 600, 1000], lam=0.0, random_seed=98765); vae0.init_weights(98765)
+    disc0 = dis.Discriminator(1000, 1000, 100, 150, 250, 300, seed=11)
+    init = ([t.detach().clone().cpu() for t in vae0.params], disc0.E.detach().clone().cpu(), [t.cpu() for t in disc0.get_params()])
     (tmp_path / "a").mkdir(); (tmp_path / "b").mkdir()
     monkeypatch.chdir(tmp_path / "a")
-    full = train.train_GAN(max_epochs=2, quiet=True, seed=3, to_restore=0, **cfg)
+    full = train.train_GAN(max_epochs=2, quiet=True, seed=3, to_restore=0, init=init, **cfg)
     monkeypatch.chdir(tmp_path / "b")
-    first = train.train_GAN(max_epochs=1, quiet=True, seed=3, to_restore=0, **cfg)
-    W_start = first["vae"].WdT.clone()
+    first = train.train_GAN(max_epochs=1, quiet=True, seed=3, to_restore=0, init=init, **cfg)
+    W_start, Wq_start, D_start = first["vae"].WdT.clone(), first["vae"].W_q0.clone(), first["disc"].arena.clone()
     assert os.path.exists(os.path.join("chkpt", "askubuntu_sample_LT_GAN_1.0", "model_0"))
-    rest = train.train_GAN(max_epochs=2, quiet=True, seed=3, to_restore=1, **cfg)
+    rest = train.train_GAN(max_epochs=2, quiet=True, seed=3, to_restore=1, init=init, **cfg)   # (the checkpoint replaces `init`)
     assert [h["epoch"] for h in rest["history"]] == [1] and [h["epoch"] for h in full["history"]] == [0, 1]
     assert torch.equal(rest["engine"].words.cpu()[:3], full["engine"].words.cpu()[:3])       # rng step, Adam t, G-update count
     assert abs(rest["history"][0]["ndcg"] - full["history"][1]["ndcg"]) < 1e-2
     moved = (full["vae"].WdT.float() - W_start.float()).norm().item()          # what epoch 1 did to the decoder weights
     assert (full["vae"].WdT.float() - rest["vae"].WdT.float()).norm().item() < 0.1 * moved   # (lost Adam moments or dropout steps would show as tens of percent)
-    assert (full["vae"].W_q0.float() - rest["vae"].W_q0.float()).abs().max().item() < 5e-3
-    assert (full["disc"].arena - rest["disc"].arena).abs().max().item() < 5e-3
+    moved_q = (full["vae"].W_q0.float() - Wq_start.float()).norm().item()
+    assert (full["vae"].W_q0.float() - rest["vae"].W_q0.float()).norm().item() < 0.1 * moved_q
+    moved_d = (full["disc"].arena - D_start).norm().item()
+    assert (full["disc"].arena - rest["disc"].arena).norm().item() < 0.25 * moved_d
     # (and the resumed epoch really continued from the checkpoint: it moved the weights of epoch 0 about as far as the full run's epoch 1)
     assert (rest["vae"].WdT.float() - W_start.float()).norm().item() > 0
