@@ -148,7 +148,23 @@ def load_item_one_hot_features(item_list_path, SHOW2ID, n_items):
 
 
 def load_user_items(csv_file_path):
-    """data_processing.py:72-96: uid -> list of sids in file order."""
+    """data_processing.py:72-96: uid -> list of sids in file order (the first two columns of the file, whatever their names)."""
+    if _native_csv():
+        with open(csv_file_path, "r") as f:
+            names = [x.strip().strip('"') for x in f.readline().rstrip("\r\n").split(",")]
+        if len(names) >= 2 and names[0] != names[1]:
+            with CsvPairs(csv_file_path, names[0], names[1]) as cp:
+                u, s_ = cp.pairs()
+            order = np.argsort(u, kind="stable")             # users in ascending id, each user's items in file order
+            us, ss = u[order], s_[order]
+            cut = np.nonzero(np.diff(us))[0] + 1
+            starts = np.concatenate([[0], cut]).astype(np.int64)
+            keys = us[starts].tolist() if len(us) else []
+            vals = np.split(ss, cut) if len(us) else []
+            by_user = {k: v.tolist() for k, v in zip(keys, vals)}
+            # the reference's dict is filled in order of first appearance; keep that iteration order
+            first_seen = u[np.sort(np.unique(u, return_index=True)[1])].tolist() if len(u) else []
+            return {k: by_user[k] for k in first_seen}
     tp = pd.read_csv(csv_file_path)
     u = tp.iloc[:, 0].to_numpy()
     s = tp.iloc[:, 1].to_numpy()

@@ -236,6 +236,9 @@ class GanEngine(object):
         self.s6 = mk(0)    # clearing Xc behind its consumer
         self.s7 = mk(-2)   # run_step: the real pairs' half of the D forward beside phase A
         self.split_d = int(os.environ.get("LTG_SPLIT_D", "0"))
+        # split-K of the discriminator's weight-gradient GEMMs (their partials are summed by the Adam kernel; at most d_splits_max = 32)
+        self.d_sp3 = max(1, min(32, int(os.environ.get("LTG_D_SP3", "12"))))
+        self.d_sp = max(1, min(32, int(os.environ.get("LTG_D_SP", "16"))))
         self.small_adam_early = os.environ.get("LTG_SMALL_ADAM_EARLY", "1") != "0"
         self.dec_chunks = int(os.environ.get("LTG_DEC_CHUNKS", "1"))
         self._cap_stream = mk(-5) if prio else None
@@ -513,10 +516,9 @@ class GanEngine(object):
         k1 = d.h0 + 1
         part = True   # data parallel sums the partials into arena_g before the all-reduce (see _d_step_dp)
         bn3 = ops.pick_bn(d.k3, d.h3, True)
-        # fixed split counts (empty splits store zeros): dW3 has 8 output tiles -> 16 splits fill the machine; dW1/dW2 have one tile
-        import os
-        sp3 = int(os.environ.get("LTG_D_SP3", "12")) if part else ops.pick_splits(d.k3, d.h3, P, bn3)
-        sp = int(os.environ.get("LTG_D_SP", "16")) if part else ops.pick_splits(k1, d.h2, P, 256)
+        # fixed split counts (empty splits store zeros): dW3 has 8 output tiles -> 12 splits fill the machine; dW1/dW2 have one tile
+        sp3 = self.d_sp3 if part else ops.pick_splits(d.k3, d.h3, P, bn3)
+        sp = self.d_sp if part else ops.pick_splits(k1, d.h2, P, 256)
         self._d_parts = max(sp, sp3) if part else 1
         if part:
             gW = lambda name: self.arena_gp[0][d._off[name][0]: d._off[name][0] + d._off[name][1]]  # noqa: E731
