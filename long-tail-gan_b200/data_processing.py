@@ -232,6 +232,33 @@ def load_overlap_coeff(show2id_path, user_tag_matrix_path):
     """data_processing.py:110-167 as one sparse product: C = X^T X on the binary user x item matrix of item_counts.csv, kept sparse;
     coefficient = C[a,b] / min(C[a,a], C[b,b]) in float64 (the same division the reference performs), formed on demand."""
     SHOW2ID = _read_show2id(show2id_path)
+    n_items = int(max(int(v) for v in SHOW2ID.values())) + 1
+    if _native_csv():
+        # integer ids (every bundled / benchmark dataset): native parse of the first two columns + a lookup table for SHOW2ID
+        try:
+            keys = np.asarray([int(k) for k in SHOW2ID.keys()], dtype=np.int64)
+            vals = np.asarray([int(v) for v in SHOW2ID.values()], dtype=np.int64)
+            with open(user_tag_matrix_path, "r") as f:
+                names = [x.strip().strip('"') for x in f.readline().rstrip("\r\n").split(",")]
+            ok = len(keys) > 0 and keys.min() >= 0 and keys.max() < (1 << 26) and len(names) >= 2 and names[0] != names[1] and \
+                all(str(int(k)) == k for k in list(SHOW2ID.keys())[:1000])
+        except ValueError:
+            ok = False
+        if ok:
+            from . import _lib
+            try:
+                with CsvPairs(user_tag_matrix_path, names[0], names[1]) as cp:
+                    users, tags = cp.pairs()
+            except _lib.LtgError:
+                users = None      # ids that are not integers: the string path below
+            if users is not None:
+                lut = np.full(int(keys.max()) + 1, -1, dtype=np.int64)
+                lut[keys] = vals
+                inside = (tags >= 0) & (tags < len(lut))
+                item = np.where(inside, lut[np.clip(tags, 0, len(lut) - 1)], -1)
+                keep = item >= 0                      # tags without an entry in item2id.txt are skipped (data_processing.py:141-145)
+                _, uidx = np.unique(users[keep], return_inverse=True)
+                return overlap_from_interactions(uidx, item[keep], n_items)
     tp = pd.read_csv(user_tag_matrix_path, dtype=str)
     users = tp.iloc[:, 0].to_numpy()
     tags = tp.iloc[:, 1].to_numpy()
@@ -239,7 +266,6 @@ def load_overlap_coeff(show2id_path, user_tag_matrix_path):
     users, tags = users[keep], tags[keep]
     item = np.asarray([int(SHOW2ID[t]) for t in tags], dtype=np.int64)
     _, uidx = np.unique(users, return_inverse=True)
-    n_items = int(max(int(v) for v in SHOW2ID.values())) + 1
     return overlap_from_interactions(uidx, item, n_items)
 
 
