@@ -133,11 +133,13 @@ extern "C" int ltg_csv_open(const char* path_host, const char* row_name_host, co
   if (map == MAP_FAILED) { delete h; ltg_set_last_error("mmap failed", __FILE__, __LINE__); return LTG_ERR_ARG; }
   const char* base = static_cast<const char*>(map);
   const char* end = base + size;
-  // header: the positions of the two named columns (tp['uid'], tp['sid'] in data_processing.py:8-15)
-  const char* hnl = static_cast<const char*>(memchr(base, '\n', size));
+  // header: the positions of the two named columns (tp['uid'], tp['sid'] in data_processing.py:8-15); a UTF-8 byte-order mark in front
+  // of it is skipped like pandas does
+  const char* hb = (size >= 3 && (unsigned char)base[0] == 0xEF && (unsigned char)base[1] == 0xBB && (unsigned char)base[2] == 0xBF) ? base + 3 : base;
+  const char* hnl = static_cast<const char*>(memchr(hb, '\n', (size_t)(end - hb)));
   const char* he = hnl != nullptr ? hnl : end;
   int fr = -1, fc = -1, f = 0;
-  for (const char* p = base; p <= he; ++f) {
+  for (const char* p = hb; p <= he; ++f) {
     const char* comma = static_cast<const char*>(memchr(p, ',', (size_t)(he - p)));
     const char* fe = comma != nullptr ? comma : he;
     const std::string name = trim_field(p, fe);
