@@ -150,7 +150,7 @@ def load_item_one_hot_features(item_list_path, SHOW2ID, n_items):
 def load_user_items(csv_file_path):
     """data_processing.py:72-96: uid -> list of sids in file order (the first two columns of the file, whatever their names)."""
     if _native_csv():
-        with open(csv_file_path, "r") as f:
+        with open(csv_file_path, "r", encoding="utf-8-sig") as f:
             names = [x.strip().strip('"') for x in f.readline().rstrip("\r\n").split(",")]
         if len(names) >= 2 and names[0] != names[1]:
             with CsvPairs(csv_file_path, names[0], names[1]) as cp:
@@ -238,7 +238,7 @@ def load_overlap_coeff(show2id_path, user_tag_matrix_path):
         try:
             keys = np.asarray([int(k) for k in SHOW2ID.keys()], dtype=np.int64)
             vals = np.asarray([int(v) for v in SHOW2ID.values()], dtype=np.int64)
-            with open(user_tag_matrix_path, "r") as f:
+            with open(user_tag_matrix_path, "r", encoding="utf-8-sig") as f:
                 names = [x.strip().strip('"') for x in f.readline().rstrip("\r\n").split(",")]
             ok = len(keys) > 0 and keys.min() >= 0 and keys.max() < (1 << 26) and len(names) >= 2 and names[0] != names[1] and \
                 all(str(int(k)) == k for k in list(SHOW2ID.keys())[:1000])
